@@ -1,0 +1,283 @@
+"""ctypes binding of libvstab.so (include/vstab.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or no B200 is visible the
+import of the compute entry points fails loudly (``VstabNativeError``).  Host code above this
+module only ever hands CUDA torch tensors to it; torch is plumbing (device memory + streams).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libvstab.so")
+
+INTERP = {"bilinear": 0, "bicubic": 1}
+MASK_RULE_P = 0
+MASK_RULE_C = 1
+STAGE_AUTO = 0
+STAGE_GLOBAL = 1
+MODE_INDEX = {"translation": 0, "similarity": 1, "perspective": 2}
+MODE_NAMES = ("translation", "similarity", "perspective")
+
+
+class VstabNativeError(RuntimeError):
+    pass
+
+
+class FitResult(C.Structure):
+    _fields_ = [
+        ("matrix", C.c_float * 9),
+        ("confidence", C.c_float),
+        ("residual", C.c_float),
+        ("accepted", C.c_int32),
+        ("n_valid", C.c_int32),
+    ]
+
+
+FIT_RESULT_FLOATS = C.sizeof(FitResult) // 4  # 13 x 4-byte words
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library() -> C.CDLL:
+    """dlopen libvstab.so and declare every prototype of include/vstab.h."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise VstabNativeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        vp, i32, fp = C.c_void_p, C.c_int, C.POINTER(C.c_float)
+        lib.vstab_abi_version.restype = i32
+        lib.vstab_create.argtypes = [i32, C.POINTER(vp)]
+        lib.vstab_create.restype = i32
+        lib.vstab_destroy.argtypes = [vp]
+        lib.vstab_destroy.restype = None
+        lib.vstab_last_error.argtypes = [vp]
+        lib.vstab_last_error.restype = C.c_char_p
+        lib.vstab_launch_count.argtypes = [vp]
+        lib.vstab_launch_count.restype = C.c_uint64
+        lib.vstab_working_size.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32)]
+        lib.vstab_working_size.restype = i32
+        lib.vstab_gray_working.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp]
+        lib.vstab_gray_working.restype = i32
+        lib.vstab_warp_fused.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, fp, i32, i32, vp, vp, vp, vp]
+        lib.vstab_warp_fused.restype = i32
+        lib.vstab_common_coverage.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+        lib.vstab_common_coverage.restype = i32
+        if hasattr(lib, "vstab_dis_flow"):
+            lib.vstab_dis_flow.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp]
+            lib.vstab_dis_flow.restype = i32
+        if hasattr(lib, "vstab_fit_batch"):
+            lib.vstab_fit_batch.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+            lib.vstab_fit_batch.restype = i32
+        if lib.vstab_abi_version() != 1:
+            raise VstabNativeError("libvstab.so ABI version mismatch; rebuild it")
+        _lib = lib
+        return lib
+
+
+def working_size(width: int, height: int) -> tuple[int, int]:
+    """Host helper (no GPU needed): nodes/stabilizer_utils.py:248-268."""
+    lib = load_library()
+    w, h = C.c_int(), C.c_int()
+    rc = lib.vstab_working_size(int(width), int(height), C.byref(w), C.byref(h))
+    if rc != 0:
+        raise ValueError("invalid frame size")
+    return w.value, h.value
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _check_cuda(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise VstabNativeError(f"{name} must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise VstabNativeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise VstabNativeError(f"{name} must be contiguous")
+
+
+class Handle:
+    """One libvstab handle per (device, thread); kernels go to torch's current stream."""
+
+    def __init__(self, device: int | torch.device | None = None):
+        if not torch.cuda.is_available():
+            raise VstabNativeError("no CUDA device visible: libvstab needs a B200 (sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise VstabNativeError("libvstab needs a CUDA device")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        hp = C.c_void_p()
+        rc = self.lib.vstab_create(self.device.index, C.byref(hp))
+        if rc != 0:
+            raise VstabNativeError(self.lib.vstab_last_error(None).decode())
+        self._h = hp
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.vstab_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise VstabNativeError(f"libvstab error {rc}: {self.lib.vstab_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.vstab_launch_count(self._h))
+
+    # -- K1 + K2 ---------------------------------------------------------------------------------
+    def gray_working(self, rgb: torch.Tensor, work_size: tuple[int, int] | None = None) -> torch.Tensor:
+        """rgb [N,H,W,3] f32 cuda -> gray [N,h,w] u8 at the working (estimation) size."""
+        _check_cuda(rgb, torch.float32, "rgb")
+        n, h, w, c = rgb.shape
+        if c != 3:
+            raise VstabNativeError("rgb must have 3 channels")
+        ww, wh = work_size if work_size is not None else working_size(w, h)
+        out = torch.empty((n, wh, ww), dtype=torch.uint8, device=rgb.device)
+        self._check(self.lib.vstab_gray_working(self._h, rgb.data_ptr(), n, h, w, out.data_ptr(), wh, ww, _stream_ptr(rgb.device)))
+        return out
+
+    # -- K10 + K11 + K12 -------------------------------------------------------------------------
+    def warp_fused(
+        self,
+        src: torch.Tensor,
+        fwd: torch.Tensor,
+        out_size: tuple[int, int],
+        interp: str,
+        border: tuple[float, float, float],
+        *,
+        mask_rule: int = MASK_RULE_P,
+        stage_mode: int = STAGE_AUTO,
+        want_mask: bool = True,
+        want_pad_count: bool = False,
+        out: torch.Tensor | None = None,
+        mask_out: torch.Tensor | None = None,
+    ):
+        """src [N,H,W,3] f32, fwd [N,S,9] f32 forward matrices -> (dst [N,H',W',3], mask [N,H',W'] | None, pad_count [N] | None)."""
+        _check_cuda(src, torch.float32, "src")
+        _check_cuda(fwd, torch.float32, "fwd")
+        n, sh, sw, c = src.shape
+        if c != 3:
+            raise VstabNativeError("src must have 3 channels")
+        if fwd.dim() == 2:
+            fwd = fwd.view(n, 1, 9)
+        if fwd.shape[0] != n or fwd.shape[2] != 9:
+            raise VstabNativeError("fwd must be [N,S,9]")
+        samples = int(fwd.shape[1])
+        ow, oh = int(out_size[0]), int(out_size[1])
+        dst = out if out is not None else torch.empty((n, oh, ow, 3), dtype=torch.float32, device=src.device)
+        _check_cuda(dst, torch.float32, "out")
+        mask = None
+        if want_mask:
+            mask = mask_out if mask_out is not None else torch.empty((n, oh, ow), dtype=torch.float32, device=src.device)
+            _check_cuda(mask, torch.float32, "mask_out")
+        pad = torch.empty((n,), dtype=torch.int32, device=src.device) if want_pad_count else None
+        b = (C.c_float * 3)(*[float(x) for x in border])
+        self._check(
+            self.lib.vstab_warp_fused(
+                self._h, src.data_ptr(), n, sh, sw, fwd.data_ptr(), samples, INTERP[interp], oh, ow, b,
+                int(mask_rule), int(stage_mode), dst.data_ptr(), _ptr(mask), _ptr(pad), _stream_ptr(src.device),
+            )
+        )
+        return dst, mask, pad
+
+    def common_coverage(self, fwd: torch.Tensor, src_size, out_size, mask_rule: int = MASK_RULE_P) -> torch.Tensor:
+        _check_cuda(fwd, torch.float32, "fwd")
+        n = int(fwd.shape[0])
+        sw, sh = int(src_size[0]), int(src_size[1])
+        ow, oh = int(out_size[0]), int(out_size[1])
+        out = torch.empty((oh, ow), dtype=torch.uint8, device=fwd.device)
+        self._check(self.lib.vstab_common_coverage(self._h, fwd.data_ptr(), n, sh, sw, oh, ow, int(mask_rule), out.data_ptr(), _stream_ptr(fwd.device)))
+        return out
+
+    # -- K3 + K4 ---------------------------------------------------------------------------------
+    def dis_flow(self, gray: torch.Tensor, *, want_flow: bool = False, grid_step: int = 8):
+        """gray [N,h,w] u8 -> (flow [N-1,h,w,2] | None, grid [N-1,gh,gw,2] | None)."""
+        _check_cuda(gray, torch.uint8, "gray")
+        if not hasattr(self.lib, "vstab_dis_flow"):
+            raise VstabNativeError("libvstab.so was built without vstab_dis_flow")
+        n, h, w = gray.shape
+        npairs = max(n - 1, 0)
+        flow = torch.empty((npairs, h, w, 2), dtype=torch.float32, device=gray.device) if want_flow else None
+        grid = None
+        if grid_step > 0:
+            gh, gw = (h + grid_step - 1) // grid_step, (w + grid_step - 1) // grid_step
+            grid = torch.empty((npairs, gh, gw, 2), dtype=torch.float32, device=gray.device)
+        self._check(self.lib.vstab_dis_flow(self._h, gray.data_ptr(), n, h, w, _ptr(flow), _ptr(grid), int(max(grid_step, 0)), _stream_ptr(gray.device)))
+        return flow, grid
+
+    # -- K4 + K7..K9 -----------------------------------------------------------------------------
+    def fit_grid(self, grid_flow: torch.Tensor, grid_step: int, mode_mask: int = 7) -> torch.Tensor:
+        """grid_flow [P,gh,gw,2] sampled flow -> raw result words [P,3,13] (see FitResult)."""
+        _check_cuda(grid_flow, torch.float32, "grid_flow")
+        if not hasattr(self.lib, "vstab_fit_batch"):
+            raise VstabNativeError("libvstab.so was built without vstab_fit_batch")
+        p, gh, gw, _ = grid_flow.shape
+        out = torch.zeros((p, 3, FIT_RESULT_FLOATS), dtype=torch.float32, device=grid_flow.device)
+        self._check(self.lib.vstab_fit_batch(self._h, None, grid_flow.data_ptr(), p, gh * gw, gw, gh, int(grid_step), int(mode_mask), out.data_ptr(), _stream_ptr(grid_flow.device)))
+        return out
+
+    def fit_points(self, prev: torch.Tensor, curr: torch.Tensor, mode_mask: int = 7) -> torch.Tensor:
+        """prev/curr [P,K,2] correspondences (NaN rows = invalid) -> raw result words [P,3,13]."""
+        _check_cuda(prev, torch.float32, "prev")
+        _check_cuda(curr, torch.float32, "curr")
+        p, k, _ = prev.shape
+        out = torch.zeros((p, 3, FIT_RESULT_FLOATS), dtype=torch.float32, device=prev.device)
+        self._check(self.lib.vstab_fit_batch(self._h, prev.data_ptr(), curr.data_ptr(), p, k, 0, 0, 0, int(mode_mask), out.data_ptr(), _stream_ptr(prev.device)))
+        return out
+
+
+_handles: dict[tuple[int, int], Handle] = {}
+
+
+def get_handle(device: int | torch.device | None = None) -> Handle:
+    if not torch.cuda.is_available():
+        raise VstabNativeError("no CUDA device visible: libvstab needs a B200 (sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, threading.get_ident())
+    h = _handles.get(key)
+    if h is None:
+        h = Handle(torch.device("cuda", idx))
+        _handles[key] = h
+    return h
+
+
+def decode_fit_results(raw: torch.Tensor):
+    """raw [P,3,13] cuda/cpu float32 words -> dict of numpy arrays (matrix f32, conf, resid, accepted, n_valid)."""
+    import numpy as np
+
+    arr = raw.detach().cpu().numpy()
+    words = arr.view(np.int32)
+    return {
+        "matrix": arr[..., :9].reshape(arr.shape[0], 3, 3, 3).copy(),
+        "confidence": arr[..., 9].copy(),
+        "residual": arr[..., 10].copy(),
+        "accepted": words[..., 11].copy(),
+        "n_valid": words[..., 12].copy(),
+    }

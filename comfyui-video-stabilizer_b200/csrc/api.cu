@@ -1,0 +1,66 @@
+// api.cu -- handle lifecycle and error plumbing of libvstab.so (see include/vstab.h).
+#include "common.cuh"
+
+#include <stdlib.h>
+
+char g_vstab_err[512] = "";
+
+extern "C" int vstab_abi_version(void) { return VSTAB_ABI_VERSION; }
+
+extern "C" int vstab_create(int device, vstab_handle** out) {
+  if (!out) return vstab_fail(nullptr, VSTAB_ERR_INVALID, "vstab_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess)
+    return vstab_fail(nullptr, VSTAB_ERR_CUDA, "vstab_create: no CUDA device (%s)", cudaGetErrorString(e));
+  if (device < 0 || device >= count)
+    return vstab_fail(nullptr, VSTAB_ERR_INVALID, "vstab_create: device index out of range");
+  vstab_handle* h = (vstab_handle*)calloc(1, sizeof(vstab_handle));
+  if (!h) return vstab_fail(nullptr, VSTAB_ERR_NOMEM, "vstab_create: host allocation failed");
+  h->device = device;
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    free(h);
+    return vstab_fail(nullptr, VSTAB_ERR_CUDA, "vstab_create: cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  }
+  if (prop.major < 10) {
+    free(h);
+    return vstab_fail(nullptr, VSTAB_ERR_UNSUPPORTED,
+                      "vstab_create: libvstab is built for sm_100a (B200) only; device is %s", prop.name);
+  }
+  h->sm_count = prop.multiProcessorCount;
+  h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  *out = h;
+  return VSTAB_OK;
+}
+
+extern "C" void vstab_destroy(vstab_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->ws) cudaFree(h->ws);
+  for (int i = 0; i < h->n_area_cache; ++i)
+    if (h->area_cache[i].dev) cudaFree(h->area_cache[i].dev);
+  free(h);
+}
+
+extern "C" const char* vstab_last_error(const vstab_handle* h) { return h ? h->err : g_vstab_err; }
+
+extern "C" uint64_t vstab_launch_count(const vstab_handle* h) { return h ? h->launches : 0; }
+
+int vstab_workspace(vstab_handle* h, size_t bytes, void** out) {
+  if (bytes > h->ws_bytes) {
+    // grow-only; the old block may still be in use by enqueued work, so drain first
+    VSTAB_CUDA(h, cudaDeviceSynchronize());
+    if (h->ws) cudaFree(h->ws);
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+    const size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&h->ws, want);
+    if (e != cudaSuccess) return vstab_fail(h, VSTAB_ERR_NOMEM, "workspace cudaMalloc failed: %s", cudaGetErrorString(e));
+    h->ws_bytes = want;
+  }
+  *out = h->ws;
+  return VSTAB_OK;
+}

@@ -1,0 +1,519 @@
+// warp.cu -- fused inverse-map resampler (K10 + K11 + K12 of SURVEY.md section 2.1).
+//
+// One launch covers the whole batch: for every output pixel it evaluates, per shutter sample,
+// the inverse-mapped source coordinate in double, quantises it to 1/32 px (round half to even)
+// exactly like OpenCV's fixed-point remap, blends 2x2 (bilinear) or 4x4 (bicubic) taps with
+// cv2's float32 weight tables and per-tap BORDER_CONSTANT, accumulates the samples in float32
+// in sample order, and writes RGB (float4 stores through a per-warp shared-memory transpose),
+// the padding mask and the per-frame padded-pixel count in the same pass.
+//
+// Replaces nodes/video_stabilizer_flow.py:560-588, nodes/video_stabilizer_classic.py:491-519,
+// nodes/motion_apply.py:75-122 and :137-202 of the reference.
+//
+// Tiling: a CTA of 256 threads owns a 64x16 output tile.  Warp w owns rows w and w+8, lane l
+// owns columns l and l+32 (stride-1 lanes => conflict-free shared-memory gathers, 3-word
+// stride).  The source footprint of the tile (bounding box of the four projected corners over
+// all samples, plus the tap margin) is staged once into shared memory with 16-byte cp.async
+// copies; taps that fall outside the staged box (degenerate maps) fall back to a global load,
+// so the staging is a pure optimisation and never changes results.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TW = 64;
+constexpr int TH = 16;
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
+constexpr int MAX_SAMPLES = 33;
+constexpr int MINV_SLOTS = 34;  // 34*9*8 bytes keeps everything behind it 16-byte aligned
+constexpr int SCRATCH_FLOATS_PER_WARP = 2 * TW * 3;  // two rows of RGB
+
+struct WarpParams {
+  const float* __restrict__ src;
+  const float* __restrict__ fwd;
+  float* __restrict__ dst;
+  float* __restrict__ mask;
+  unsigned int* __restrict__ pad_count;
+  int n, sh, sw, oh, ow;
+  int samples;
+  int mask_rule;
+  int stage_mode;
+  int stage_capacity;  // floats available for the staged source tile
+  int vec_store;       // ow % 4 == 0 && dst 16B aligned
+  int vec_load;        // sw % 4 == 0 && src 16B aligned
+  float border[3];
+};
+
+__constant__ float c_cubic_tab[32][4];
+
+struct StagedTile {
+  const float* smem;  // staged box, row pitch = pitch floats
+  int x0, y0, x1, y1; // inclusive box in source pixel coordinates (already clipped to the image)
+  int pitch;
+  bool active;
+};
+
+// RGB of one tap (3 consecutive floats).
+__device__ __forceinline__ void fetch_rgb(const WarpParams& p, const float* __restrict__ frame,
+                                          const StagedTile& t, int y, int x, float& r, float& g,
+                                          float& b) {
+  if ((unsigned)x >= (unsigned)p.sw || (unsigned)y >= (unsigned)p.sh) {
+    r = p.border[0];
+    g = p.border[1];
+    b = p.border[2];
+    return;
+  }
+  if (t.active && x >= t.x0 && x <= t.x1 && y >= t.y0 && y <= t.y1) {
+    const float* s = t.smem + (y - t.y0) * t.pitch + (x - t.x0) * 3;
+    r = s[0];
+    g = s[1];
+    b = s[2];
+    return;
+  }
+  const float* s = frame + ((size_t)y * p.sw + x) * 3;
+  r = __ldg(s);
+  g = __ldg(s + 1);
+  b = __ldg(s + 2);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int INTERP>
+__global__ void __launch_bounds__(NTHREADS) warp_fused_kernel(const WarpParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_minv = reinterpret_cast<double*>(smem_raw);                       // [34][9], 16B multiple
+  float* s_scratch = reinterpret_cast<float*>(s_minv + MINV_SLOTS * 9);       // [8][384]
+  int* s_box = reinterpret_cast<int*>(s_scratch + NWARPS * SCRATCH_FLOATS_PER_WARP);  // 8 ints
+  float* s_tile = reinterpret_cast<float*>(s_box + 8);                        // staged source box
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int frame_idx = blockIdx.z;
+  const int tx0 = blockIdx.x * TW;
+  const int ty0 = blockIdx.y * TH;
+  const int S = p.samples;
+  const float* __restrict__ frame = p.src + (size_t)frame_idx * p.sh * p.sw * 3;
+
+  if (tid < S) vstab_invert3(p.fwd + ((size_t)frame_idx * S + tid) * 9, s_minv + tid * 9);
+  if (tid == 0) {
+    s_box[0] = INT_MAX;  // min x
+    s_box[1] = INT_MAX;  // min y
+    s_box[2] = INT_MIN;  // max x
+    s_box[3] = INT_MIN;  // max y
+    s_box[4] = 0;        // degenerate flag
+  }
+  __syncthreads();
+
+  // ---- source footprint of the tile: 4 corners x S samples ----------------------------------
+  StagedTile tile;
+  tile.smem = s_tile;
+  tile.active = false;
+  tile.x0 = tile.y0 = 0;
+  tile.x1 = tile.y1 = -1;
+  tile.pitch = 0;
+  if (p.stage_mode == VSTAB_STAGE_AUTO) {
+    const int txe = min(tx0 + TW, p.ow) - 1;
+    const int tye = min(ty0 + TH, p.oh) - 1;
+    for (int k = tid; k < 4 * S; k += NTHREADS) {
+      const double* m = s_minv + (k >> 2) * 9;
+      const double cx = (k & 1) ? (double)txe : (double)tx0;
+      const double cy = (k & 2) ? (double)tye : (double)ty0;
+      const double X = m[0] * cx + m[1] * cy + m[2];
+      const double Y = m[3] * cx + m[4] * cy + m[5];
+      const double W = m[6] * cx + m[7] * cy + m[8];
+      const double sx = X / W, sy = Y / W;
+      // Convexity of the projected tile needs W to keep one sign; positive is the sane case.
+      if (!(W > 1e-12) || !(fabs(sx) < 1e8) || !(fabs(sy) < 1e8)) {
+        atomicOr(&s_box[4], 1);
+      } else {
+        atomicMin(&s_box[0], (int)floor(sx));
+        atomicMin(&s_box[1], (int)floor(sy));
+        atomicMax(&s_box[2], (int)floor(sx));
+        atomicMax(&s_box[3], (int)floor(sy));
+      }
+    }
+    __syncthreads();
+    if (s_box[4] == 0) {
+      constexpr int LO = (INTERP == VSTAB_INTERP_BILINEAR) ? 1 : 2;
+      constexpr int HI = (INTERP == VSTAB_INTERP_BILINEAR) ? 2 : 3;
+      int bx0 = max(s_box[0] - LO, 0), by0 = max(s_box[1] - LO, 0);
+      int bx1 = min(s_box[2] + HI, p.sw - 1), by1 = min(s_box[3] + HI, p.sh - 1);
+      if (p.vec_load) {  // 16-byte granules: 4 pixels = 48 bytes keeps every row 16B aligned
+        bx0 &= ~3;
+        bx1 = min(bx1 | 3, p.sw - 1);
+      }
+      const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
+      if (bw > 0 && bh > 0 && (long long)bw * 3 * bh <= (long long)p.stage_capacity) {
+        tile.active = true;
+        tile.x0 = bx0;
+        tile.y0 = by0;
+        tile.x1 = bx1;
+        tile.y1 = by1;
+        tile.pitch = bw * 3;
+        const int row_floats = bw * 3;
+        if (p.vec_load) {
+          const int row_vec = row_floats >> 2;  // bw % 4 == 0 => exact
+          for (int r = warp; r < bh; r += NWARPS) {
+            const float* g = frame + ((size_t)(by0 + r) * p.sw + bx0) * 3;
+            float* s = s_tile + r * row_floats;
+            for (int v = lane; v < row_vec; v += 32) cp_async16(s + 4 * v, g + 4 * v);
+          }
+          cp_async_wait_all();
+        } else {
+          for (int r = warp; r < bh; r += NWARPS) {
+            const float* g = frame + ((size_t)(by0 + r) * p.sw + bx0) * 3;
+            float* s = s_tile + r * row_floats;
+            for (int v = lane; v < row_floats; v += 32) s[v] = __ldg(g + v);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- per-pixel resampling ------------------------------------------------------------------
+  const float fS = (float)S;
+  float* scratch = s_scratch + warp * SCRATCH_FLOATS_PER_WARP;
+  unsigned int padded = 0;
+
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int oy = ty0 + warp + rr * NWARPS;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int ox = tx0 + lane + cc * 32;
+      float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
+      int cover = 0;
+      if (oy < p.oh && ox < p.ow) {
+        const double dx = (double)ox, dy = (double)oy;
+        for (int s = 0; s < S; ++s) {
+          const double* m = s_minv + s * 9;
+          const double X = __dadd_rn(__dadd_rn(__dmul_rn(m[0], dx), __dmul_rn(m[1], dy)), m[2]);
+          const double Y = __dadd_rn(__dadd_rn(__dmul_rn(m[3], dx), __dmul_rn(m[4], dy)), m[5]);
+          const double W = __dadd_rn(__dadd_rn(__dmul_rn(m[6], dx), __dmul_rn(m[7], dy)), m[8]);
+          // -- coverage (INTER_NEAREST ones warp) on the continuous coordinate
+          {
+            double cxs = __ddiv_rn(X, W), cys = __ddiv_rn(Y, W);
+            if (p.mask_rule == VSTAB_MASK_RULE_C) {
+              cxs = rint(cxs);
+              cys = rint(cys);
+            }
+            const bool ok = (cxs >= 0.0) && (cxs <= (double)(p.sw - 1)) && (cys >= 0.0) &&
+                            (cys <= (double)(p.sh - 1));
+            cover += ok ? 1 : 0;
+          }
+          // -- 1/32-px fixed-point source coordinate
+          const double sc = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
+          double fx = __dmul_rn(X, sc), fy = __dmul_rn(Y, sc);
+          fx = fmax(-2147483648.0, fmin(2147483647.0, fx));
+          fy = fmax(-2147483648.0, fmin(2147483647.0, fy));
+          const int ix = __double2int_rn(fx), iy = __double2int_rn(fy);
+          int sx = ix >> 5, sy = iy >> 5;
+          sx = max(-32768, min(32767, sx));
+          sy = max(-32768, min(32767, sy));
+          const int ax = ix & 31, ay = iy & 31;
+          float vr, vg, vb;
+          if (INTERP == VSTAB_INTERP_BILINEAR) {
+            const float fx1 = (float)ax * 0.03125f, fy1 = (float)ay * 0.03125f;
+            const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
+            const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
+            const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
+            if (sx >= p.sw || sx + 1 < 0 || sy >= p.sh || sy + 1 < 0) {
+              // remapBilinear: footprint entirely outside the source => the border colour itself
+              vr = p.border[0];
+              vg = p.border[1];
+              vb = p.border[2];
+            } else {
+              float r0, g0, b0, r1, g1, b1, r2, g2, b2, r3, g3, b3;
+              fetch_rgb(p, frame, tile, sy, sx, r0, g0, b0);
+              fetch_rgb(p, frame, tile, sy, sx + 1, r1, g1, b1);
+              fetch_rgb(p, frame, tile, sy + 1, sx, r2, g2, b2);
+              fetch_rgb(p, frame, tile, sy + 1, sx + 1, r3, g3, b3);
+              vr = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0, w00), __fmul_rn(r1, w01)),
+                                       __fmul_rn(r2, w10)),
+                             __fmul_rn(r3, w11));
+              vg = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(g0, w00), __fmul_rn(g1, w01)),
+                                       __fmul_rn(g2, w10)),
+                             __fmul_rn(g3, w11));
+              vb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b0, w00), __fmul_rn(b1, w01)),
+                                       __fmul_rn(b2, w10)),
+                             __fmul_rn(b3, w11));
+            }
+          } else {
+            float wx[4], wy[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              wx[k] = c_cubic_tab[ax][k];
+              wy[k] = c_cubic_tab[ay][k];
+            }
+            const int bx = sx - 1, by = sy - 1;
+            if (bx >= 0 && bx < p.sw - 3 && by >= 0 && by < p.sh - 3) {
+              vr = vg = vb = 0.f;
+#pragma unroll
+              for (int k1 = 0; k1 < 4; ++k1) {
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) {
+                  const float w = __fmul_rn(wy[k1], wx[k2]);
+                  float r, g, b;
+                  fetch_rgb(p, frame, tile, by + k1, bx + k2, r, g, b);
+                  vr = __fadd_rn(vr, __fmul_rn(r, w));
+                  vg = __fadd_rn(vg, __fmul_rn(g, w));
+                  vb = __fadd_rn(vb, __fmul_rn(b, w));
+                }
+              }
+            } else {
+              // remapBicubic border branch: cv + sum over in-range taps of (S - cv) * w
+              vr = p.border[0];
+              vg = p.border[1];
+              vb = p.border[2];
+              if (!(bx >= p.sw || bx + 3 < 0 || by >= p.sh || by + 3 < 0)) {
+#pragma unroll
+                for (int k1 = 0; k1 < 4; ++k1) {
+#pragma unroll
+                  for (int k2 = 0; k2 < 4; ++k2) {
+                    const int yy = by + k1, xx = bx + k2;
+                    if ((unsigned)xx < (unsigned)p.sw && (unsigned)yy < (unsigned)p.sh) {
+                      const float w = __fmul_rn(wy[k1], wx[k2]);
+                      float r, g, b;
+                      fetch_rgb(p, frame, tile, yy, xx, r, g, b);
+                      vr = __fadd_rn(vr, __fmul_rn(__fsub_rn(r, p.border[0]), w));
+                      vg = __fadd_rn(vg, __fmul_rn(__fsub_rn(g, p.border[1]), w));
+                      vb = __fadd_rn(vb, __fmul_rn(__fsub_rn(b, p.border[2]), w));
+                    }
+                  }
+                }
+              }
+            }
+          }
+          acc_r = __fadd_rn(acc_r, vr);
+          acc_g = __fadd_rn(acc_g, vg);
+          acc_b = __fadd_rn(acc_b, vb);
+        }
+        if (S > 1) {
+          acc_r = __fdiv_rn(acc_r, fS);
+          acc_g = __fdiv_rn(acc_g, fS);
+          acc_b = __fdiv_rn(acc_b, fS);
+        }
+        // padding mask: 1 - (coverage > .5) for one sample, 1 - count/S for blur; <1e-3 -> 0
+        float mval;
+        if (S == 1) {
+          mval = cover ? 0.0f : 1.0f;
+        } else {
+          mval = __fsub_rn(1.0f, __fdiv_rn((float)cover, fS));
+          if (mval < 1e-3f) mval = 0.0f;
+        }
+        if (mval > 1e-3f) ++padded;
+        if (p.mask) p.mask[((size_t)frame_idx * p.oh + oy) * p.ow + ox] = mval;
+        if (!p.vec_store) {
+          float* d = p.dst + (((size_t)frame_idx * p.oh + oy) * p.ow + ox) * 3;
+          d[0] = acc_r;
+          d[1] = acc_g;
+          d[2] = acc_b;
+        }
+      }
+      if (p.vec_store) {
+        float* sc = scratch + rr * (TW * 3) + (lane + cc * 32) * 3;
+        sc[0] = acc_r;
+        sc[1] = acc_g;
+        sc[2] = acc_b;
+      }
+    }
+  }
+
+  if (p.vec_store) {
+    __syncwarp();
+    // 2 rows x 192 floats = 96 float4 per warp, 3 per lane, fully coalesced 16-byte stores.
+    const int valid_floats = (min(tx0 + TW, p.ow) - tx0) * 3;  // multiple of 4 when ow % 4 == 0
+#pragma unroll
+    for (int q3 = 0; q3 < 3; ++q3) {
+      const int q = lane + q3 * 32;
+      const int rr = q / 48, qi = q - rr * 48;
+      const int oy = ty0 + warp + rr * NWARPS;
+      if (oy < p.oh && qi * 4 < valid_floats) {
+        const float4 v = *reinterpret_cast<const float4*>(scratch + rr * (TW * 3) + qi * 4);
+        float* d = p.dst + (((size_t)frame_idx * p.oh + oy) * p.ow + tx0) * 3 + qi * 4;
+        *reinterpret_cast<float4*>(d) = v;
+      }
+    }
+  }
+
+  if (p.pad_count) {
+    for (int o = 16; o > 0; o >>= 1) padded += __shfl_down_sync(0xffffffffu, padded, o);
+    if (lane == 0 && padded) atomicAdd(p.pad_count + frame_idx, padded);
+  }
+}
+
+// AND-reduction of INTER_NEAREST coverage over n matrices (crop solvers).
+__global__ void __launch_bounds__(256) common_coverage_kernel(const float* __restrict__ fwd, int n,
+                                                              int sh, int sw, int oh, int ow,
+                                                              int mask_rule,
+                                                              unsigned char* __restrict__ common) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_minv = reinterpret_cast<double*>(smem_raw);  // [chunk][9]
+  const int ox = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  bool all_ok = true;
+  constexpr int CHUNK = 64;
+  for (int base = 0; base < n; base += CHUNK) {
+    const int cnt = min(CHUNK, n - base);
+    __syncthreads();
+    if ((int)threadIdx.x < cnt)
+      vstab_invert3(fwd + (size_t)(base + threadIdx.x) * 9, s_minv + threadIdx.x * 9);
+    __syncthreads();
+    if (ox < ow && oy < oh) {
+      const double dx = (double)ox, dy = (double)oy;
+      for (int k = 0; k < cnt; ++k) {
+        const double* m = s_minv + k * 9;
+        const double X = __dadd_rn(__dadd_rn(__dmul_rn(m[0], dx), __dmul_rn(m[1], dy)), m[2]);
+        const double Y = __dadd_rn(__dadd_rn(__dmul_rn(m[3], dx), __dmul_rn(m[4], dy)), m[5]);
+        const double W = __dadd_rn(__dadd_rn(__dmul_rn(m[6], dx), __dmul_rn(m[7], dy)), m[8]);
+        double cxs = __ddiv_rn(X, W), cys = __ddiv_rn(Y, W);
+        if (mask_rule == VSTAB_MASK_RULE_C) {
+          cxs = rint(cxs);
+          cys = rint(cys);
+        }
+        all_ok = all_ok && (cxs >= 0.0) && (cxs <= (double)(sw - 1)) && (cys >= 0.0) &&
+                 (cys <= (double)(sh - 1));
+      }
+    }
+  }
+  if (ox < ow && oy < oh) common[(size_t)oy * ow + ox] = all_ok ? 1 : 0;
+}
+
+bool g_cubic_tab_ready[64] = {false};
+
+void build_cubic_tab(float tab[32][4]) {
+  // cv::interpolateCubic with A = -0.75, float32 arithmetic in this exact order
+  const volatile float A = -0.75f;
+  for (int i = 0; i < 32; ++i) {
+    volatile float x = (float)i * (1.0f / 32.0f);
+    volatile float x1 = x + 1.0f;
+    volatile float t0 = A * x1;
+    volatile float t1 = t0 - 5.0f * A;
+    volatile float t2 = t1 * x1;
+    volatile float t3 = t2 + 8.0f * A;
+    volatile float t4 = t3 * x1;
+    volatile float c0 = t4 - 4.0f * A;
+    volatile float u0 = (A + 2.0f) * x;
+    volatile float u1 = u0 - (A + 3.0f);
+    volatile float u2 = u1 * x;
+    volatile float u3 = u2 * x;
+    volatile float c1 = u3 + 1.0f;
+    volatile float xm = 1.0f - x;
+    volatile float v0 = (A + 2.0f) * xm;
+    volatile float v1 = v0 - (A + 3.0f);
+    volatile float v2 = v1 * xm;
+    volatile float v3 = v2 * xm;
+    volatile float c2 = v3 + 1.0f;
+    volatile float w0 = 1.0f - c0;
+    volatile float w1 = w0 - c1;
+    volatile float c3 = w1 - c2;
+    tab[i][0] = c0;
+    tab[i][1] = c1;
+    tab[i][2] = c2;
+    tab[i][3] = c3;
+  }
+}
+
+}  // namespace
+
+extern "C" int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, int src_h, int src_w,
+                                const float* fwd_dev, int samples, int interp, int out_h,
+                                int out_w, const float* border_host, int mask_rule,
+                                int stage_mode, float* dst_dev, float* mask_dev,
+                                uint32_t* pad_count_dev, void* stream) {
+  if (!h) return vstab_fail(nullptr, VSTAB_ERR_INVALID, "vstab_warp_fused: null handle");
+  if (!src_dev || !fwd_dev || !dst_dev || !border_host)
+    return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_warp_fused: null pointer argument");
+  if (n < 0 || src_h <= 0 || src_w <= 0 || out_h <= 0 || out_w <= 0)
+    return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_warp_fused: bad dimensions");
+  if (samples < 1 || samples > MAX_SAMPLES)
+    return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_warp_fused: samples must be in 1..33");
+  if (interp != VSTAB_INTERP_BILINEAR && interp != VSTAB_INTERP_BICUBIC)
+    return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_warp_fused: unknown interpolation");
+  if (mask_rule != VSTAB_MASK_RULE_P && mask_rule != VSTAB_MASK_RULE_C)
+    return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_warp_fused: unknown mask rule");
+  if (src_w > 32767 || src_h > 32767)
+    return vstab_fail(h, VSTAB_ERR_UNSUPPORTED, "vstab_warp_fused: source larger than 32767 px");
+  if (n == 0) return VSTAB_OK;
+  if (n > 65535) return vstab_fail(h, VSTAB_ERR_UNSUPPORTED, "vstab_warp_fused: n > 65535 frames per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  VSTAB_CUDA(h, cudaSetDevice(h->device));
+
+  if (!g_cubic_tab_ready[h->device & 63]) {
+    float tab[32][4];
+    build_cubic_tab(tab);
+    VSTAB_CUDA(h, cudaMemcpyToSymbolAsync(c_cubic_tab, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st));
+    g_cubic_tab_ready[h->device & 63] = true;
+  }
+  if (pad_count_dev) VSTAB_CUDA(h, cudaMemsetAsync(pad_count_dev, 0, sizeof(uint32_t) * n, st));
+
+  WarpParams p;
+  p.src = src_dev;
+  p.fwd = fwd_dev;
+  p.dst = dst_dev;
+  p.mask = mask_dev;
+  p.pad_count = pad_count_dev;
+  p.n = n;
+  p.sh = src_h;
+  p.sw = src_w;
+  p.oh = out_h;
+  p.ow = out_w;
+  p.samples = samples;
+  p.mask_rule = mask_rule;
+  p.stage_mode = stage_mode;
+  p.vec_store = (out_w % 4 == 0) && (((uintptr_t)dst_dev & 15) == 0);
+  p.vec_load = (src_w % 4 == 0) && (((uintptr_t)src_dev & 15) == 0);
+  p.border[0] = border_host[0];
+  p.border[1] = border_host[1];
+  p.border[2] = border_host[2];
+
+  const size_t fixed = sizeof(double) * MINV_SLOTS * 9 + sizeof(float) * NWARPS * SCRATCH_FLOATS_PER_WARP + sizeof(int) * 8;
+  // Staged source box: (TW + margin) x (TH + margin) pixels for near-identity maps; blur and
+  // bicubic get a larger box.  Degenerate footprints gather from global memory instead.
+  int box_w = TW + 8, box_h = TH + 8;
+  if (samples > 1) {
+    box_w += 24;
+    box_h += 24;
+  }
+  size_t stage_bytes = (size_t)box_w * box_h * 3 * sizeof(float);
+  if (stage_mode == VSTAB_STAGE_GLOBAL) stage_bytes = 16;
+  p.stage_capacity = (int)(stage_bytes / sizeof(float));
+  const size_t smem = fixed + stage_bytes;
+
+  dim3 grid(vstab_ceil_div(out_w, TW), vstab_ceil_div(out_h, TH), n);
+  if (grid.y > 65535) return vstab_fail(h, VSTAB_ERR_UNSUPPORTED, "vstab_warp_fused: output too tall");
+  if (interp == VSTAB_INTERP_BILINEAR) {
+    VSTAB_CUDA(h, cudaFuncSetAttribute(warp_fused_kernel<VSTAB_INTERP_BILINEAR>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    warp_fused_kernel<VSTAB_INTERP_BILINEAR><<<grid, NTHREADS, smem, st>>>(p);
+  } else {
+    VSTAB_CUDA(h, cudaFuncSetAttribute(warp_fused_kernel<VSTAB_INTERP_BICUBIC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    warp_fused_kernel<VSTAB_INTERP_BICUBIC><<<grid, NTHREADS, smem, st>>>(p);
+  }
+  VSTAB_LAUNCH_CHECK(h, "warp_fused_kernel");
+  return VSTAB_OK;
+}
+
+extern "C" int vstab_common_coverage(vstab_handle* h, const float* fwd_dev, int n, int src_h,
+                                     int src_w, int out_h, int out_w, int mask_rule,
+                                     uint8_t* common_dev, void* stream) {
+  if (!h) return vstab_fail(nullptr, VSTAB_ERR_INVALID, "vstab_common_coverage: null handle");
+  if (!fwd_dev || !common_dev || n < 0 || src_h <= 0 || src_w <= 0 || out_h <= 0 || out_w <= 0)
+    return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_common_coverage: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  VSTAB_CUDA(h, cudaSetDevice(h->device));
+  dim3 grid(vstab_ceil_div(out_w, 32), vstab_ceil_div(out_h, 8));
+  common_coverage_kernel<<<grid, 256, sizeof(double) * 64 * 9, st>>>(fwd_dev, n, src_h, src_w, out_h,
+                                                                    out_w, mask_rule, common_dev);
+  VSTAB_LAUNCH_CHECK(h, "common_coverage_kernel");
+  return VSTAB_OK;
+}

@@ -1,0 +1,212 @@
+"""Host-side (O(N) scalars / 3x3 matrices) half of the stabilizer path, in float64 numpy.
+
+Mirrors the behaviour -- names, argument meaning, numeric types -- of the helpers in the
+reference's ``nodes/stabilizer_utils.py`` that sit between the estimation kernels and the warp
+kernel.  None of this touches pixels; pixels only ever live in HBM (see ``pipeline.py``).
+
+Reference anchors (file:line in the reference repository):
+  working size            nodes/stabilizer_utils.py:248-268
+  rescale to full         nodes/stabilizer_utils.py:279-297
+  matrix <-> params       nodes/stabilizer_utils.py:300-358
+  box smoothing           nodes/stabilizer_utils.py:361-383
+  expand transform        nodes/stabilizer_utils.py:386-406
+  padding colour parser   nodes/stabilizer_utils.py:843-873
+  warp meta builder       nodes/stabilizer_utils.py:876-896
+  bounding boxes / ratio  nodes/stabilizer_utils.py:1010-1052
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, Sequence, Tuple
+
+import numpy as np
+
+ESTIMATION_MAX_SIDE = 960
+DEFAULT_PADDING_RGB = (127, 127, 127)
+TRANSFORM_MODES = ("translation", "similarity", "perspective")
+FRAMING_MODES = ("crop", "crop_and_pad", "expand")
+MODE_LADDER = {
+    "perspective": ("perspective", "similarity", "translation"),
+    "similarity": ("similarity", "translation"),
+    "translation": ("translation",),
+}
+
+
+def working_estimation_size(width: int, height: int, max_side: int = ESTIMATION_MAX_SIDE):
+    """(w, h) of the estimation image, or None when the frame is used as is."""
+    longest = max(int(width), int(height))
+    if longest <= max_side:
+        return None
+    ratio = max_side / float(longest)
+    w = max(1, int(round(width * ratio)))
+    h = max(1, int(round(height * ratio)))
+    if w >= width or h >= height:
+        return None
+    return w, h
+
+
+def rescale_transform_to_full(matrix, source_size, working_size) -> np.ndarray:
+    """S^-1 @ M @ S in float64 -> float32, S = diag(work/src)."""
+    kx = working_size[0] / float(source_size[0])
+    ky = working_size[1] / float(source_size[1])
+    down = np.diag([kx, ky, 1.0]).astype(np.float64)
+    up = np.diag([1.0 / kx, 1.0 / ky, 1.0]).astype(np.float64)
+    return (up @ np.asarray(matrix).astype(np.float64) @ down).astype(np.float32)
+
+
+def matrix_to_params(matrix, base_mode: str) -> np.ndarray:
+    m = matrix
+    if base_mode == "translation":
+        return np.array([m[0, 2], m[1, 2]], dtype=np.float64)
+    if base_mode == "similarity":
+        a, c = m[0, 0], m[1, 0]
+        mag = math.sqrt(max(a * a + c * c, 1e-10))
+        return np.array([m[0, 2], m[1, 2], math.atan2(c, a), math.log(mag)], dtype=np.float64)
+    return np.array(
+        [m[0, 0] - 1.0, m[0, 1], m[0, 2], m[1, 0], m[1, 1] - 1.0, m[1, 2], m[2, 0], m[2, 1]],
+        dtype=np.float64,
+    )
+
+
+def params_to_matrix(params, base_mode: str) -> np.ndarray:
+    p = params
+    if base_mode == "translation":
+        rows = [[1.0, 0.0, p[0]], [0.0, 1.0, p[1]], [0.0, 0.0, 1.0]]
+    elif base_mode == "similarity":
+        k = math.exp(p[3])
+        cs, sn = math.cos(p[2]), math.sin(p[2])
+        rows = [[k * cs, -k * sn, p[0]], [k * sn, k * cs, p[1]], [0.0, 0.0, 1.0]]
+    else:
+        rows = [[p[0] + 1.0, p[1], p[2]], [p[3], p[4] + 1.0, p[5]], [p[6], p[7], 1.0]]
+    return np.array(rows, dtype=np.float32)
+
+
+def smoothing_window(smooth: float, fps: float) -> int:
+    fps = float(max(1.0, fps))
+    seconds = 3.0 / 16.0 + smooth * (13.0 / 16.0 - 3.0 / 16.0)
+    window = max(3, int(round(seconds * fps)))
+    return window + 1 if window % 2 == 0 else window
+
+
+def smooth_path(path: np.ndarray, smooth: float, fps: float) -> np.ndarray:
+    """Edge-padded odd box filter along time, per parameter column (float64)."""
+    smooth = float(np.clip(smooth, 0.0, 1.0))
+    if smooth <= 0.0 or len(path) <= 2:
+        return path.copy()
+    window = smoothing_window(smooth, fps)
+    half = window // 2
+    taps = np.ones(window, dtype=np.float64) / float(window)
+    out = np.zeros_like(path)
+    for col in range(path.shape[1]):
+        out[:, col] = np.convolve(np.pad(path[:, col], (half, half), mode="edge"), taps, mode="valid")
+    return out
+
+
+def compute_bounding_boxes(matrices: Sequence[np.ndarray], width: int, height: int):
+    corners = np.array(
+        [[0.0, float(width), 0.0, float(width)], [0.0, 0.0, float(height), float(height)], [1.0, 1.0, 1.0, 1.0]],
+        dtype=np.float64,
+    )
+    lo, hi = [], []
+    for m in matrices:
+        q = m @ corners
+        q /= q[2, :]
+        lo.append([q[0].min(), q[1].min()])
+        hi.append([q[0].max(), q[1].max()])
+    return np.array(lo), np.array(hi)
+
+
+def min_content_ratio(mins, maxs, width: int, height: int) -> float:
+    iw = max(0.0, np.min(maxs[:, 0]) - np.max(mins[:, 0]))
+    ih = max(0.0, np.min(maxs[:, 1]) - np.max(mins[:, 1]))
+    if iw <= 0.0 or ih <= 0.0:
+        return 1e-6
+    return max(1e-6, min(iw / width, ih / height))
+
+
+def prepare_expand_transform(mins, maxs):
+    x_lo, y_lo = float(np.min(mins[:, 0])), float(np.min(mins[:, 1]))
+    x_hi, y_hi = float(np.max(maxs[:, 0])), float(np.max(maxs[:, 1]))
+    shift = np.array([[1.0, 0.0, -x_lo], [0.0, 1.0, -y_lo], [0.0, 0.0, 1.0]], dtype=np.float32)
+    return shift, (max(int(math.ceil(x_hi - x_lo)), 1), max(int(math.ceil(y_hi - y_lo)), 1))
+
+
+def parse_padding_color(value) -> Tuple[int, int, int]:
+    """'#RRGGBB' | '#RGB' | 'r,g,b' | 'r/g/b' | 0xRRGGBB int -> (r, g, b); junk -> (127,127,127)."""
+    if isinstance(value, str):
+        text = value.strip()
+        if "," in text or "/" in text:
+            try:
+                nums = [int(tok) for tok in text.replace("/", ",").replace(" ", ",").split(",") if tok != ""]
+            except (TypeError, ValueError):
+                return DEFAULT_PADDING_RGB
+            if len(nums) == 1:
+                nums = nums * 3
+            if len(nums) != 3:
+                return DEFAULT_PADDING_RGB
+            return tuple(int(np.clip(v, 0, 255)) for v in nums)
+        digits = text.removeprefix("#")
+        if len(digits) == 3:
+            digits = "".join(ch * 2 for ch in digits)
+        if len(digits) != 6:
+            return DEFAULT_PADDING_RGB
+        try:
+            packed = int(digits, 16)
+        except (TypeError, ValueError):
+            return DEFAULT_PADDING_RGB
+    else:
+        try:
+            packed = int(value)
+        except (TypeError, ValueError):
+            return DEFAULT_PADDING_RGB
+    packed = int(np.clip(packed, 0, 0xFFFFFF))
+    return (packed >> 16) & 0xFF, (packed >> 8) & 0xFF, packed & 0xFF
+
+
+def border_value(padding_rgb) -> Tuple[float, float, float]:
+    """padding colour as float32/255, the borderValue of every warp (flow.py:547-548)."""
+    v = np.array(padding_rgb, dtype=np.float32) / 255.0
+    return tuple(float(x) for x in v)
+
+
+def build_stabilization_warp_meta(*, source_size, output_size, framing_mode, applied_matrices) -> Dict[str, Any]:
+    return {
+        "source_size": [int(source_size[0]), int(source_size[1])],
+        "output_size": [int(output_size[0]), int(output_size[1])],
+        "framing_mode": framing_mode,
+        "matrix_convention": "source_to_stabilized",
+        "per_frame": [
+            {"index": int(i), "applied_matrix": np.asarray(m, dtype=np.float32).tolist()}
+            for i, m in enumerate(applied_matrices)
+        ],
+    }
+
+
+def resolve_fps_for_stabilizer(frame_rate, context_fps):
+    """fps rule of Flow/Classic (flow.py:230-238): widget wins, then container fps, then 16."""
+
+    def ok(v):
+        return isinstance(v, (int, float)) and np.isfinite(v) and v > 0.0
+
+    candidate = frame_rate if ok(frame_rate) else (context_fps if ok(context_fps) else 16.0)
+    effective = float(max(1.0, candidate))
+    requested = float(frame_rate) if isinstance(frame_rate, (int, float)) and frame_rate > 0.0 else None
+    return effective, requested
+
+
+def padded_fraction(pad_count: int, pixels: int) -> float:
+    """float(mask.mean()) of a 0/1 float32 mask: numpy sums exactly (< 2^24), divides in f32."""
+    return float(np.float32(pad_count) / np.float32(pixels))
+
+
+# reference-compatible private names (the reference's tests and scripts import these)
+_working_estimation_size = working_estimation_size
+_rescale_transform_to_full = rescale_transform_to_full
+_matrix_to_params = matrix_to_params
+_params_to_matrix = params_to_matrix
+_smooth_path = smooth_path
+_compute_bounding_boxes = compute_bounding_boxes
+_min_content_ratio = min_content_ratio
+_prepare_expand_transform = prepare_expand_transform
+_parse_padding_color = parse_padding_color
+_build_stabilization_warp_meta = build_stabilization_warp_meta

@@ -1,0 +1,305 @@
+"""Clip container and host<->HBM plumbing for the node layer.
+
+The reference keeps a ``VideoContext`` holding a list of HWC float32 numpy frames
+(nodes/stabilizer_utils.py:62-72) filled by ``_normalize_video_input`` (:150-197) and packs the
+results back with ``_reconstruct_video`` / ``_convert_masks_for_output`` (:200-221, :1055-1077).
+Here the clip lives in HBM as one ``[N,H,W,3]`` float32 tensor; the adapter rules (uint8 or
+0..255 floats are divided by 255 per frame, CHW frames are transposed, 1 channel is repeated,
+alpha is dropped, dict inputs carry fps) are kept.  torch is used for device memory, streams and
+the copies only -- every pixel operation of the path runs in libvstab kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, Iterable, List, Literal, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native
+
+# frames per host->device / device->host copy chunk (keeps staging buffers ~0.8 GB at 1080p)
+CHUNK_BYTES = 768 << 20
+
+
+@dataclass
+class FrameAdapter:
+    dtype: Any
+    channel_first: bool
+    value_range: Literal["0_1", "0_255"]
+    origin: Literal["numpy", "torch"]
+    squeeze_last_dim: bool
+
+
+@dataclass
+class VideoContext:
+    frames: torch.Tensor  # [N,H,W,3] float32, CUDA, values 0..1
+    adapter: FrameAdapter
+    width: int
+    height: int
+    channels: int
+    fps: Optional[float]
+    template_kind: Literal["dict", "sequence"]
+    template_meta: Dict[str, Any] = field(default_factory=dict)
+
+    def __len__(self) -> int:
+        return int(self.frames.shape[0])
+
+    @property
+    def device(self) -> torch.device:
+        return self.frames.device
+
+
+def _require_device(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _native.VstabNativeError(
+            "no CUDA device visible: the stabilizer path runs on a B200 only; there is no CPU fallback"
+        )
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def frames_per_chunk(height: int, width: int, channels: int = 3) -> int:
+    return max(1, CHUNK_BYTES // (height * width * channels * 4))
+
+
+def _upload_batched(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    """CPU [N,H,W,C] tensor -> device, chunked so pinned sources overlap with later kernels."""
+    if t.is_cuda:
+        return t.to(device)
+    n = t.shape[0]
+    out = torch.empty(t.shape, dtype=t.dtype, device=device)
+    step = max(1, CHUNK_BYTES // max(1, t[0].numel() * t.element_size()))
+    for a in range(0, n, step):
+        out[a : a + step].copy_(t[a : a + step], non_blocking=True)
+    return out
+
+
+def _frame_to_hwc(arr: np.ndarray):
+    """Per-frame layout rules of _to_numpy_frame (stabilizer_utils.py:96-147), host slow path."""
+    channel_first = False
+    squeeze = False
+    if arr.ndim == 3 and arr.shape[0] in (1, 3, 4) and arr.shape[0] < arr.shape[-1]:
+        channel_first = True
+        arr = np.moveaxis(arr, 0, -1)
+    elif arr.ndim == 4 and arr.shape[0] == 1:
+        arr = arr[0]
+    if arr.ndim == 2:
+        arr = arr[..., None]
+        squeeze = True
+    elif arr.ndim == 3 and arr.shape[2] == 1:
+        squeeze = True
+    return arr, channel_first, squeeze
+
+
+def _ensure_rgb_host(arr: np.ndarray) -> np.ndarray:
+    c = arr.shape[2]
+    if c == 1:
+        return np.repeat(arr, 3, axis=2)
+    if c > 3:
+        return arr[..., :3]
+    return arr
+
+
+def normalize_video_input(value: Any, device=None) -> VideoContext:
+    """ComfyUI IMAGE (or list / dict of frames) -> clip resident in HBM.
+
+    Fast path: a 4-D torch tensor [B,H,W,C] (float32 / uint8) is uploaded as a whole and the
+    per-frame range test (max > 1.5 => /255) runs on the device.  Everything else (lists of
+    numpy / CHW / mixed frames) is normalised frame by frame on the host first.
+    """
+    device = _require_device(device)
+    if isinstance(value, dict):
+        seq = None
+        for key in ("frames", "images", "video"):
+            if key in value:
+                seq = value[key]
+                break
+        if seq is None:
+            raise ValueError("Video input dictionary must contain 'frames'.")
+        kind: Literal["dict", "sequence"] = "dict"
+        extra = {k: v for k, v in value.items() if k not in ("frames", "images", "video")}
+        fps = extra.get("fps")
+    else:
+        seq, kind, extra, fps = value, "sequence", {}, None
+
+    fast = (
+        isinstance(seq, torch.Tensor)
+        and seq.dim() == 4
+        and seq.shape[0] > 0
+        and seq.dtype in (torch.float32, torch.uint8)
+        # a [B,H,W,C] tensor whose frames would not be mistaken for CHW by the reference
+        and not (seq.shape[1] in (1, 3, 4) and seq.shape[1] < seq.shape[3])
+    )
+    if fast:
+        dev = _upload_batched(seq.contiguous(), device)
+        origin_dtype = np.uint8 if seq.dtype == torch.uint8 else np.float32
+        squeeze = dev.shape[3] == 1
+        if dev.dtype == torch.uint8:
+            frames = dev.to(torch.float32)
+            frames /= 255.0
+            value_range = "0_255"
+        else:
+            frames = dev
+            peaks = frames.reshape(frames.shape[0], -1).amax(dim=1)
+            big = peaks > 1.5
+            value_range = "0_255" if bool(big[0]) else "0_1"
+            if bool(big.any()):
+                if frames.data_ptr() == seq.data_ptr():
+                    frames = frames.clone()
+                frames[big] = frames[big] / 255.0
+        if frames.shape[3] == 1:
+            frames = frames.expand(-1, -1, -1, 3)
+        elif frames.shape[3] > 3:
+            frames = frames[..., :3]
+        elif frames.shape[3] == 2:
+            raise ValueError("2-channel frames are not supported.")
+        frames = frames.contiguous()
+        adapter = FrameAdapter(origin_dtype, False, value_range, "torch", bool(squeeze))
+    else:
+        host: List[np.ndarray] = []
+        adapter = None
+        for frame in seq:
+            origin = "torch" if isinstance(frame, torch.Tensor) else "numpy"
+            arr = frame.detach().cpu().numpy() if origin == "torch" else np.asarray(frame)
+            arr, channel_first, squeeze = _frame_to_hwc(arr)
+            dtype = arr.dtype
+            if dtype == np.uint8 or (arr.size and float(arr.max()) > 1.5):
+                arr = arr.astype(np.float32)
+                arr /= 255.0
+                value_range = "0_255"
+            else:
+                arr = np.ascontiguousarray(arr, dtype=np.float32)
+                value_range = "0_1"
+            this = FrameAdapter(dtype, channel_first, value_range, origin, squeeze)
+            if adapter is None:
+                adapter = this
+            elif this.channel_first != adapter.channel_first or this.origin != adapter.origin:
+                raise ValueError("Mixed tensor layouts within the same video sequence are not supported.")
+            host.append(_ensure_rgb_host(arr))
+        if not host:
+            raise ValueError("The input video sequence is empty.")
+        if host[0].shape[2] != 3:
+            raise ValueError("2-channel frames are not supported.")
+        stacked = torch.from_numpy(np.ascontiguousarray(np.stack(host, axis=0), dtype=np.float32))
+        frames = _upload_batched(stacked, device)
+
+    n, h, w, c = frames.shape
+    return VideoContext(frames, adapter, int(w), int(h), int(c), fps, kind, extra)
+
+
+def download(t: torch.Tensor, pin: bool = True) -> torch.Tensor:
+    """Device tensor -> CPU tensor (pinned when possible), chunked along dim 0."""
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=pin and torch.cuda.is_available())
+    n = t.shape[0]
+    if n == 0:
+        return out
+    step = max(1, CHUNK_BYTES // max(1, t[0].numel() * t.element_size()))
+    for a in range(0, n, step):
+        out[a : a + step].copy_(t[a : a + step], non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return out
+
+
+def reconstruct_video(frames: Any, context: VideoContext) -> Any:
+    """[N,H',W',3] float32 CPU tensor (or dict payload) following ComfyUI conventions."""
+    if isinstance(frames, np.ndarray):
+        frames = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.float32))
+    if frames.shape[0] == 0:
+        frames = torch.zeros((1, context.height, context.width, 3), dtype=torch.float32)
+    if frames.is_cuda:
+        frames = download(frames)
+    if context.template_kind == "dict":
+        payload = dict(context.template_meta)
+        payload["frames"] = frames
+        return payload
+    return frames
+
+
+def convert_masks_for_output(masks: Any) -> torch.Tensor:
+    """[N,H',W'] float32 CPU tensor, 1 = padding; empty -> zeros [1,1,1]."""
+    if isinstance(masks, np.ndarray):
+        masks = torch.from_numpy(np.ascontiguousarray(masks, dtype=np.float32))
+    if masks.shape[0] == 0:
+        return torch.zeros((1, 1, 1), dtype=torch.float32)
+    if masks.dim() == 4:
+        masks = masks[..., 0]
+    if masks.is_cuda:
+        masks = download(masks)
+    return masks.contiguous()
+
+
+def fused_warp(
+    context: VideoContext,
+    fwd: np.ndarray,
+    out_size: Tuple[int, int],
+    interpolation: str,
+    border: Tuple[float, float, float],
+    *,
+    want_mask: bool = True,
+    want_pad_count: bool = False,
+    mask_rule: int = _native.MASK_RULE_P,
+    output: Literal["host", "device"] = "host",
+):
+    """Run the fused resampler over the whole clip.
+
+    fwd: [N,S,9] float32 forward matrices (host).  Returns (frames, masks, pad_counts) where
+    frames is [N,H',W',3] and masks [N,H',W'] (None when want_mask is False).  With
+    output="host" the clip is processed in chunks: while chunk k is copied device->host on a
+    side stream, chunk k+1 is being resampled; the results land in pinned CPU tensors.
+    """
+    h = _native.get_handle(context.device)
+    dev = context.device
+    n = len(context)
+    ow, oh = int(out_size[0]), int(out_size[1])
+    fwd_t = torch.from_numpy(np.ascontiguousarray(fwd, dtype=np.float32)).to(dev, non_blocking=True)
+    if fwd_t.dim() == 2:
+        fwd_t = fwd_t.view(n, 1, 9)
+    if output == "device":
+        dst, mask, pad = h.warp_fused(
+            context.frames, fwd_t, (ow, oh), interpolation, border,
+            mask_rule=mask_rule, want_mask=want_mask, want_pad_count=want_pad_count,
+        )
+        return dst, mask, (pad.cpu().numpy().astype(np.int64) if pad is not None else None)
+
+    frames_cpu = torch.empty((n, oh, ow, 3), dtype=torch.float32, pin_memory=True)
+    masks_cpu = torch.empty((n, oh, ow), dtype=torch.float32, pin_memory=True) if want_mask else None
+    pads: List[torch.Tensor] = []
+    step = frames_per_chunk(oh, ow, 4)
+    main = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(dev)
+    bufs = [
+        (
+            torch.empty((min(step, n), oh, ow, 3), dtype=torch.float32, device=dev),
+            torch.empty((min(step, n), oh, ow), dtype=torch.float32, device=dev) if want_mask else None,
+        )
+        for _ in range(2 if n > step else 1)
+    ]
+    copied = [None] * len(bufs)
+    for k, a in enumerate(range(0, n, step)):
+        b = min(a + step, n)
+        dbuf, mbuf = bufs[k % len(bufs)]
+        if copied[k % len(bufs)] is not None:
+            main.wait_event(copied[k % len(bufs)])  # buffer free again
+        dst, mask, pad = h.warp_fused(
+            context.frames[a:b], fwd_t[a:b], (ow, oh), interpolation, border,
+            mask_rule=mask_rule, want_mask=want_mask, want_pad_count=want_pad_count,
+            out=dbuf[: b - a], mask_out=(mbuf[: b - a] if mbuf is not None else None),
+        )
+        if pad is not None:
+            pads.append(pad)
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            frames_cpu[a:b].copy_(dst, non_blocking=True)
+            if masks_cpu is not None:
+                masks_cpu[a:b].copy_(mask, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            copied[k % len(bufs)] = ev
+    copy_stream.synchronize()
+    main.synchronize()
+    pad_np = torch.cat(pads).cpu().numpy().astype(np.int64) if pads else None
+    return frames_cpu, masks_cpu, pad_np

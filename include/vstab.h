@@ -1,0 +1,179 @@
+/*
+ * vstab.h -- C ABI of libvstab.so, the B200 (sm_100a) hot path of ComfyUI-Video-Stabilizer.
+ *
+ * Every entry point replaces one OpenCV call site of the reference (file:line relative to the
+ * reference repository root) and is what a ctypes / cffi / pybind stub on the reference side
+ * would bind.
+ *
+ * Conventions
+ *   - plain C types only; no CUDA or torch types in any signature (`stream` is a cudaStream_t
+ *     passed as void*, NULL = legacy default stream);
+ *   - every pointer named *_dev is a DEVICE pointer owned by the caller; the library owns only
+ *     the workspace inside its handle.  *_host pointers are small host arrays read before the
+ *     call returns;
+ *   - all work is enqueued on the caller's stream; no entry point synchronises unless its
+ *     comment says so;
+ *   - return value 0 = VSTAB_OK, negative = error; vstab_last_error() gives the text.  Nothing
+ *     throws across the boundary;
+ *   - images are row-major, channel-interleaved: IMAGE = float32 [N][H][W][3] in 0..1
+ *     (ComfyUI IMAGE layout, nodes/stabilizer_utils.py:200-221), gray = uint8 [N][h][w].
+ */
+#ifndef VSTAB_H_
+#define VSTAB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSTAB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VSTAB_API __attribute__((visibility("default")))
+#else
+#define VSTAB_API
+#endif
+
+#define VSTAB_OK 0
+#define VSTAB_ERR_INVALID (-1)     /* bad argument */
+#define VSTAB_ERR_CUDA (-2)        /* CUDA runtime error, text in vstab_last_error */
+#define VSTAB_ERR_NOMEM (-3)       /* workspace allocation failed */
+#define VSTAB_ERR_UNSUPPORTED (-4) /* shape outside what the kernels were built for */
+
+/* interpolation (nodes/motion_apply.py:24-29 _interpolation_flag) */
+#define VSTAB_INTERP_BILINEAR 0 /* cv2.INTER_LINEAR */
+#define VSTAB_INTERP_BICUBIC 1  /* cv2.INTER_CUBIC  */
+
+/* padding-mask footprint rule of warpPerspective(ones, INTER_NEAREST) */
+#define VSTAB_MASK_RULE_P 0 /* closed rectangle on continuous coordinates (cv2 4.13 IPP HAL) */
+#define VSTAB_MASK_RULE_C 1 /* classic: round-half-even, then range check */
+
+/* source-tile staging of the fused resampler (debug / A-B switch) */
+#define VSTAB_STAGE_AUTO 0   /* shared-memory tile when the footprint fits, else global gather */
+#define VSTAB_STAGE_GLOBAL 1 /* always gather through L1 */
+
+/* transform models (nodes/stabilizer_utils.py:15 TransformMode) */
+#define VSTAB_MODE_TRANSLATION 0
+#define VSTAB_MODE_SIMILARITY 1
+#define VSTAB_MODE_PERSPECTIVE 2
+
+typedef struct vstab_handle vstab_handle;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+
+VSTAB_API int vstab_abi_version(void);
+
+/* One handle per (device, host thread).  Allocates nothing on the device until first use. */
+VSTAB_API int vstab_create(int device, vstab_handle** out);
+VSTAB_API void vstab_destroy(vstab_handle* h);
+
+/* Text of the last error recorded on this handle (or process-wide when h == NULL). */
+VSTAB_API const char* vstab_last_error(const vstab_handle* h);
+
+/* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
+VSTAB_API uint64_t vstab_launch_count(const vstab_handle* h);
+
+/* ---- K1 + K2 : gray + working-size downscale ------------------------------------------- */
+
+/*
+ * Working (estimation) size rule, nodes/stabilizer_utils.py:248-268 _working_estimation_size:
+ * longest side capped at 960.  Writes the size actually used (== input size when no resize
+ * happens).  Host-only helper.
+ */
+VSTAB_API int vstab_working_size(int width, int height, int* work_w, int* work_h);
+
+/*
+ * Replaces nodes/stabilizer_utils.py:236-242 (_make_gray: cv2.cvtColor(RGB2GRAY), *255, clip,
+ * truncating uint8 cast) and :271-276 (_make_gray_for_estimation: cv2.resize INTER_AREA).
+ * rgb_dev  [n][h][w][3] float32, gray_dev [n][work_h][work_w] uint8.
+ * Bit-exact against cv2 4.13: Y = fma(B,.114f, fma(R,.299f, G*.587f)); INTER_AREA x2
+ * ((a+b+c+d+2)>>2), integer xK (rint(sum/K^2)), and the general fractional-coverage path.
+ */
+VSTAB_API int vstab_gray_working(vstab_handle* h, const float* rgb_dev, int n, int height, int width,
+                       uint8_t* gray_dev, int work_h, int work_w, void* stream);
+
+/* ---- K10 + K11 + K12 : fused inverse-map resampler -------------------------------------- */
+
+/*
+ * Replaces, in ONE launch for the whole batch,
+ *   nodes/video_stabilizer_flow.py:560-588, nodes/video_stabilizer_classic.py:491-519,
+ *   nodes/motion_apply.py:75-122 (_warp_with_matrices) and :137-202 (_warp_with_motion_blur):
+ *     cv2.warpPerspective(frame, M, out, INTER_LINEAR|INTER_CUBIC, BORDER_CONSTANT, border)
+ *     cv2.warpPerspective(ones,  M, out, INTER_NEAREST, BORDER_CONSTANT, 0) -> >0.5 -> 1-x
+ *     and the S-sample f32 accumulate / S.
+ *
+ * src_dev      [n][src_h][src_w][3] float32
+ * fwd_dev      [n][samples][9] float32 FORWARD matrices exactly as the reference hands them to
+ *              cv2 (row-major 3x3).  The kernel inverts them in double by cofactors like
+ *              cv::invert, evaluates source coordinates in double, quantises to 1/32 px with
+ *              round-half-even and uses cv2's f32 weight tables and per-tap constant border.
+ * samples      1 (no blur) or 3..33 (motion_apply.py:166)
+ * border_host  3 floats = padding_rgb / 255 as float32 (motion_apply.py:70-72)
+ * dst_dev      [n][out_h][out_w][3] float32
+ * mask_dev     [n][out_h][out_w] float32, 1 = padding (0/1 when samples == 1, 1 - count/S
+ *              otherwise); may be NULL (masks_zero path of motion_apply.py:102-105)
+ * pad_count_dev [n] uint32, number of mask pixels > 1e-3 per frame (for padding_fraction_*,
+ *              video_stabilizer_flow.py:585-587); may be NULL; zeroed by the call.
+ */
+VSTAB_API int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, int src_h, int src_w,
+                     const float* fwd_dev, int samples, int interp, int out_h, int out_w,
+                     const float* border_host, int mask_rule, int stage_mode, float* dst_dev,
+                     float* mask_dev, uint32_t* pad_count_dev, void* stream);
+
+/*
+ * Coverage only (crop solvers, nodes/stabilizer_utils.py:604-656, :759-780 and
+ * nodes/motion_apply.py:205-228 _common_valid_mask): AND-reduces the INTER_NEAREST coverage of
+ * n matrices into common_dev [out_h][out_w] uint8 (1 = valid in every frame).
+ */
+VSTAB_API int vstab_common_coverage(vstab_handle* h, const float* fwd_dev, int n, int src_h, int src_w,
+                          int out_h, int out_w, int mask_rule, uint8_t* common_dev, void* stream);
+
+/* ---- K3 + K4 : DIS dense optical flow, batched over frame pairs ------------------------- */
+
+/*
+ * Replaces nodes/video_stabilizer_flow.py:76-87 (_create_flow_backend: PRESET_MEDIUM with
+ * finest_scale 2, patch 8, stride 4, 25 GD iterations, 5 variational-refinement iterations,
+ * mean normalisation, spatial propagation) and :140 backend.calc(prev, curr) for all pairs
+ * (i, i+1), i in [0, n_frames-1), plus the 8-px grid sampling of :141-147.
+ *
+ * gray_dev   [n_frames][h][w] uint8 working-size frames (h, w <= 960 longest side)
+ * flow_dev   [n_frames-1][h][w][2] float32 full working-size flow (cv2 layout) or NULL
+ * grid_dev   [n_frames-1][gh][gw][2] float32 flow sampled at (x, y) = (gx*step, gy*step),
+ *            gw = ceil(w/step), gh = ceil(h/step); or NULL
+ */
+VSTAB_API int vstab_dis_flow(vstab_handle* h, const uint8_t* gray_dev, int n_frames, int height, int width,
+                   float* flow_dev, float* grid_dev, int grid_step, void* stream);
+
+/* ---- K4 + K7 + K8 + K9 : robust model fit, batched over frame pairs --------------------- */
+
+typedef struct vstab_fit_result {
+  float matrix[9];  /* float32 3x3 prev->curr at working resolution */
+  float confidence; /* inliers / valid (similarity, perspective) or valid / total */
+  float residual;   /* mean |affine(prev) - curr| over both axes, flow.py:174,189,207 */
+  int32_t accepted; /* 1 if this candidate passes the reference's acceptance test */
+  int32_t n_valid;  /* finite correspondences */
+} vstab_fit_result;
+
+/*
+ * Replaces nodes/video_stabilizer_flow.py:148-210 for every pair: finite filter, then ALL
+ * three candidate models (translation = per-axis median, similarity =
+ * estimateAffinePartial2D RANSAC 2.0 px / 2000 / 0.992, perspective = findHomography RANSAC
+ * 2.5 px / 2000 / 0.992).  The sticky mode ladder (:161, :338-339) is replayed by the caller
+ * over the table so that frame-range shards agree.
+ *
+ * prev_dev / curr_dev  [n_pairs][n_pts][2] float32 correspondences; prev_dev may be NULL with
+ *                      grid_w/grid_h/grid_step > 0, meaning the regular sampling grid and
+ *                      curr = prev + flow where curr_dev then holds the sampled FLOW.
+ * mode_mask            bit VSTAB_MODE_* set = compute that candidate
+ * out_dev              [n_pairs][3] results indexed by VSTAB_MODE_*
+ */
+VSTAB_API int vstab_fit_batch(vstab_handle* h, const float* prev_dev, const float* curr_dev, int n_pairs,
+                    int n_pts, int grid_w, int grid_h, int grid_step, int mode_mask,
+                    vstab_fit_result* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSTAB_H_ */

@@ -1,0 +1,111 @@
+"""Generates tests/golden/* by running the UNMODIFIED reference from /root/reference.
+
+Run in the build container only:  python scripts/make_golden.py [--only NAME]
+The fixtures are small (selected patches / per-frame sums for the big shapes) and committed; the
+GPU box has no /root/reference, so `-m gpu` tests check the CUDA path against these files.
+Inputs are regenerated from seeds by tests/cases.py on both sides.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+from tests import cases, ref_import  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _summaries(frames: np.ndarray, masks: np.ndarray, patches):
+    out = {
+        "frame_sum": frames.reshape(frames.shape[0], -1).astype(np.float64).sum(axis=1),
+        "mask_sum": masks.reshape(masks.shape[0], -1).astype(np.float64).sum(axis=1),
+        "shape": np.array(frames.shape),
+    }
+    for k, (f, y, x, hh, ww) in enumerate(patches):
+        out[f"patch{k}"] = frames[f, y : y + hh, x : x + ww].copy()
+        out[f"mpatch{k}"] = masks[f, y : y + hh, x : x + ww, 0].copy()
+        out[f"patch{k}_at"] = np.array([f, y, x, hh, ww])
+    return out
+
+
+def gen_motion_apply(ref):
+    """Motion Apply on small clips (full outputs) and on BASELINE config 1 / 4 shapes (summaries)."""
+    for case in cases.MOTION_APPLY_CASES:
+        frames = cases.make_frames(case)
+        meta = cases.make_motion_meta(case, ref)
+        ctx = ref.stabilizer_utils._normalize_video_input([f for f in frames])
+        res = ref.motion_apply.apply_motion(
+            ctx, meta, case["padding_rgb"], framing_mode=case["framing"], interpolation=case["interp"],
+            motion_blur=case["blur"], motion_blur_samples=case["samples"],
+        )
+        name = case["name"]
+        with open(os.path.join(GOLDEN, f"apply_{name}_meta.json"), "w") as fh:
+            json.dump(meta, fh)
+        if case["store"] == "full":
+            np.savez_compressed(os.path.join(GOLDEN, f"apply_{name}.npz"), frames=res.frames, masks=res.masks)
+        else:
+            np.savez_compressed(os.path.join(GOLDEN, f"apply_{name}.npz"), **_summaries(res.frames, res.masks, case["patches"]))
+        print("apply", name, res.frames.shape, res.meta["motion_apply"])
+
+
+def gen_estimators(ref):
+    """Flow / Classic stabilizers: per-pair matrices, paths and final matrices (+ small outputs)."""
+    import cv2
+
+    for case in cases.STABILIZER_CASES:
+        frames = cases.make_frames(case)
+        mod = ref.video_stabilizer_flow if case["node"] == "flow" else ref.video_stabilizer_classic
+        ctx = ref.stabilizer_utils._normalize_video_input([f for f in frames])
+        res = mod._stabilize_frames(
+            ctx, case["framing"], case["mode"], case["camera_lock"], case["strength"], case["smooth"],
+            case["keep_fov"], case["padding_rgb"], case["fps"],
+        )
+        name = case["name"]
+        meta = res.meta
+        with open(os.path.join(GOLDEN, f"stab_{name}_meta.json"), "w") as fh:
+            json.dump(meta, fh)
+        out_frames = np.asarray(res.frames, dtype=np.float32)
+        out_masks = np.asarray(res.masks, dtype=np.float32)
+        payload = _summaries(out_frames, out_masks, case["patches"])
+        if case["store"] == "full":
+            payload["frames"] = out_frames
+            payload["masks"] = out_masks
+        payload["cv2_threads"] = np.array([cv2.getNumThreads()])
+        np.savez_compressed(os.path.join(GOLDEN, f"stab_{name}.npz"), **payload)
+        print("stab", name, out_frames.shape, meta.get("transform_mode_applied"))
+
+
+def gen_dis(ref):
+    """Raw cv2.DISOpticalFlow (reference configuration) on working-size gray pairs."""
+    be = ref.video_stabilizer_flow._create_flow_backend("DIS")
+    for case in cases.DIS_CASES:
+        prev, curr = cases.make_gray_pair(case)
+        flow = be.calc(prev, curr, None)
+        grid = flow[::8, ::8].copy()
+        np.savez_compressed(os.path.join(GOLDEN, f"dis_{case['name']}.npz"), grid=grid,
+                            flow_mean=flow.reshape(-1, 2).mean(axis=0), flow=flow if case["store"] == "full" else np.zeros(0))
+        print("dis", case["name"], flow.shape, flow.reshape(-1, 2).mean(axis=0))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref = ref_import.load_reference()
+    gens = {"apply": gen_motion_apply, "stab": gen_estimators, "dis": gen_dis}
+    for key, fn in gens.items():
+        if args.only in (None, key):
+            fn(ref)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,101 @@
+"""Seeded test cases shared by scripts/make_golden.py (reference side) and the parity tests.
+
+Inputs are pure functions of the case dict, so the golden generator (build container, real
+reference) and the GPU tests (no reference) see identical bytes.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+PAD = (127, 127, 127)
+
+
+def make_frames(case) -> np.ndarray:
+    """[N,H,W,3] float32 in 0..1."""
+    n, w, h = case["n"], case["w"], case["h"]
+    kind = case.get("frames", "noise")
+    if kind == "noise":  # white noise: worst case for resampling parity (gradient ~1/px)
+        rng = np.random.default_rng(case["seed"])
+        return rng.random((n, h, w, 3), dtype=np.float32)
+    if kind == "texture":  # smooth trackable texture rendered through shake matrices
+        import synth
+
+        base = synth.base_texture(case["seed"], w, h).numpy()
+        mats = synth.shake_matrices(n, case["seed"], w, h, perspective=case.get("perspective", False),
+                                    amount=case.get("amount", 1.0))
+        return synth.render_clip_numpy(base, mats, w, h)
+    raise ValueError(kind)
+
+
+def make_motion_meta(case, ref=None):
+    """motion_meta for Motion Apply cases.  'shake' needs the reference (generator); the
+    resulting JSON is committed beside the golden outputs, tests read it from there."""
+    n, w, h = case["n"], case["w"], case["h"]
+    if case["meta"] == "shake":
+        block = ref.shake_noise.generate_shake_motion_meta(
+            recipe=ref.shake_noise.STYLES[case.get("style", "handheld")], frame_count=n, width=w, height=h,
+            fps=16.0, amount=case.get("amount", 1.0), speed=1.0, seed=case["seed"], node="shake_generator",
+            style=case.get("style", "handheld"),
+        )
+        return {"motion_meta": block}
+    raise ValueError(case["meta"])
+
+
+MOTION_APPLY_CASES = [
+    dict(name="small_bilinear_pad", n=6, w=121, h=73, seed=11, meta="shake", amount=2.0, framing="crop_and_pad",
+         interp="bilinear", blur=0.0, samples=9, padding_rgb=PAD, store="full", patches=[]),
+    dict(name="small_bicubic_expand_blur", n=6, w=121, h=73, seed=12, meta="shake", amount=2.0, framing="expand",
+         interp="bicubic", blur=0.5, samples=5, padding_rgb=(10, 200, 90), store="full", patches=[]),
+    dict(name="small_bilinear_crop", n=6, w=120, h=72, seed=13, meta="shake", amount=1.0, framing="crop",
+         interp="bilinear", blur=0.0, samples=9, padding_rgb=PAD, store="full", patches=[]),
+    dict(name="small_bilinear_pad_blur", n=5, w=64, h=48, seed=14, meta="shake", amount=3.0, framing="crop_and_pad",
+         interp="bilinear", blur=1.0, samples=33, padding_rgb=PAD, store="full", patches=[]),
+    # BASELINE config 1: Shake Generator (handheld, seed 0) -> Motion Apply bilinear crop_and_pad, 81x832x480
+    dict(name="cfg1_832x480", n=81, w=832, h=480, seed=0, meta="shake", amount=1.0, framing="crop_and_pad",
+         interp="bilinear", blur=0.0, samples=9, padding_rgb=PAD, store="summary",
+         patches=[(0, 0, 0, 48, 64), (40, 200, 400, 48, 64), (80, 432, 768, 48, 64)]),
+    # BASELINE config 4 shape, shortened to 3 frames: bicubic expand, blur 0.5, Ultra (33 samples), 1080p
+    dict(name="cfg4_1080p_x3", n=3, w=1920, h=1080, seed=4, meta="shake", amount=1.0, framing="expand",
+         interp="bicubic", blur=0.5, samples=33, padding_rgb=PAD, store="summary",
+         patches=[(0, 0, 0, 48, 64), (1, 500, 900, 48, 64), (2, 1030, 1850, 48, 64)]),
+]
+
+STABILIZER_CASES = [
+    dict(name="flow_sim_pad_480p", node="flow", n=9, w=832, h=480, seed=21, frames="texture", framing="crop_and_pad",
+         mode="similarity", camera_lock=False, strength=0.7, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=16.0,
+         store="summary", patches=[(4, 100, 300, 48, 64)]),
+    dict(name="flow_sim_pad_1080p", node="flow", n=7, w=1920, h=1080, seed=22, frames="texture", framing="crop_and_pad",
+         mode="similarity", camera_lock=False, strength=0.7, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=16.0,
+         store="summary", patches=[(3, 500, 900, 48, 64)]),
+    dict(name="flow_trans_expand_480p", node="flow", n=7, w=832, h=480, seed=23, frames="texture", framing="expand",
+         mode="translation", camera_lock=False, strength=1.0, smooth=1.0, keep_fov=0.6, padding_rgb=(0, 0, 0), fps=24.0,
+         store="summary", patches=[(3, 100, 300, 48, 64)]),
+    dict(name="flow_persp_lock_1080p", node="flow", n=6, w=1920, h=1080, seed=24, frames="texture", perspective=True,
+         framing="crop_and_pad", mode="perspective", camera_lock=True, strength=0.7, smooth=0.5, keep_fov=0.6,
+         padding_rgb=PAD, fps=16.0, store="summary", patches=[(3, 500, 900, 48, 64)]),
+    dict(name="classic_sim_pad_720p", node="classic", n=7, w=1280, h=720, seed=25, frames="texture", framing="crop_and_pad",
+         mode="similarity", camera_lock=False, strength=0.7, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=16.0,
+         store="summary", patches=[(3, 300, 600, 48, 64)]),
+    dict(name="classic_trans_pad_720p", node="classic", n=7, w=1280, h=720, seed=26, frames="texture", framing="crop_and_pad",
+         mode="translation", camera_lock=False, strength=0.7, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=16.0,
+         store="summary", patches=[(3, 300, 600, 48, 64)]),
+]
+
+
+def make_gray_pair(case):
+    """Working-size uint8 pair for raw DIS parity: smooth texture + known similarity jitter."""
+    import synth
+    from oracle.gray_np import gray_u8
+
+    w, h = case["w"], case["h"]
+    base = synth.base_texture(case["seed"], w, h).numpy()
+    mats = synth.shake_matrices(2, case["seed"], w, h, amount=case.get("amount", 1.0))
+    clip = synth.render_clip_numpy(base, mats, w, h)
+    return gray_u8(clip[0]), gray_u8(clip[1])
+
+
+DIS_CASES = [
+    dict(name="pair_960x540", w=960, h=540, seed=31, store="grid"),
+    dict(name="pair_832x480", w=832, h=480, seed=32, store="grid"),
+    dict(name="pair_320x180", w=320, h=180, seed=33, store="full"),
+]

@@ -1,0 +1,165 @@
+"""CUDA fused resampler (vstab_warp_fused) vs the numpy oracle and the reference goldens.
+
+Tolerances are north_star's: pixels <= 1e-3 (bilinear) / 2e-3 (bicubic) max-abs on float32 [0,1],
+padding mask bit-exact.  The asserted bounds are much tighter because the kernel reproduces cv2's
+arithmetic: bilinear is expected bit-exact against the oracle, bicubic to float32 rounding.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import apply_np, resample_np as R
+from tests import cases
+from tests.conftest import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"bilinear": 1e-3, "bicubic": 2e-3}      # north_star
+TIGHT = {"bilinear": 0.0, "bicubic": 0.0}      # same op order as the oracle => identical bits
+
+
+def _rand_matrix(rng, kind, shift=15.0):
+    th, s = rng.normal(0, 0.01), 1 + rng.normal(0, 0.01)
+    tx, ty = rng.normal(0, shift, 2)
+    m = np.array([[s * np.cos(th), -s * np.sin(th), tx], [s * np.sin(th), s * np.cos(th), ty], [0, 0, 1]])
+    if kind == "persp":
+        m[2, :2] = rng.normal(0, 2e-5, 2)
+    return m.astype(np.float32)
+
+
+def _run(handle, src, mats, out_size, interp, border, **kw):
+    from vstab_b200 import _native
+
+    dev = torch.device("cuda", 0)
+    s = torch.from_numpy(np.ascontiguousarray(src)).to(dev)
+    f = torch.from_numpy(np.ascontiguousarray(mats, dtype=np.float32)).to(dev)
+    dst, mask, pad = handle.warp_fused(s, f, out_size, interp, border, want_pad_count=True, **kw)
+    torch.cuda.synchronize()
+    return dst.cpu().numpy(), mask.cpu().numpy(), pad.cpu().numpy()
+
+
+@pytest.mark.parametrize("size", [(121, 73), (320, 200), (832, 480)])
+@pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
+@pytest.mark.parametrize("stage", [0, 1])
+def test_single_sample_matches_oracle(handle, size, interp, stage):
+    rng = np.random.default_rng(7)
+    w, h = size
+    n = 4
+    src = rng.random((n, h, w, 3), dtype=np.float32)
+    border = (0.5, 0.25, 0.75)
+    for out_size in [(w, h), (w + 10, h + 8)]:
+        mats = np.stack([_rand_matrix(rng, "sim" if i % 2 == 0 else "persp") for i in range(n)])
+        got, mask, pad = _run(handle, src, mats.reshape(n, 1, 9), out_size, interp, border, stage_mode=stage)
+        for i in range(n):
+            want = R.warp_np(src[i], mats[i], out_size, interp, border)
+            err = float(np.abs(got[i] - want).max())
+            assert err <= TOL[interp]
+            assert err <= TIGHT[interp] + 1e-7, (interp, out_size, i, err)
+            want_mask = R.mask_np(mats[i], (w, h), out_size, R.RULE_P)
+            assert np.array_equal(mask[i], want_mask)
+            assert int(pad[i]) == int(want_mask.sum())
+
+
+@pytest.mark.parametrize("rule", [R.RULE_P, R.RULE_C])
+def test_mask_rules_and_ties(handle, rule):
+    """Integer and half-pixel translations put whole rows/columns exactly on the rule boundary."""
+    w, h = 200, 120
+    src = np.random.default_rng(1).random((1, h, w, 3), dtype=np.float32)
+    for t in [(3.0, -2.0), (0.5, 0.5), (-7.5, 4.0), (0.0, 0.0), (w - 1.0, 0.0), (-(w - 1.0) - 0.5, 1.5)]:
+        m = np.array([[1, 0, t[0]], [0, 1, t[1]], [0, 0, 1]], np.float32)
+        _, mask, _ = _run(handle, src, m.reshape(1, 1, 9), (w, h), "bilinear", (0, 0, 0), mask_rule=rule)
+        assert np.array_equal(mask[0], R.mask_np(m, (w, h), (w, h), rule)), t
+
+
+def test_degenerate_matrices_do_not_crash(handle):
+    """Singular / horizon-crossing maps: the staged-tile path must fall back, results = oracle."""
+    w, h = 160, 96
+    src = np.random.default_rng(2).random((1, h, w, 3), dtype=np.float32)
+    mats = [
+        np.array([[1, 0, 0], [0, 1, 0], [0.02, 0.0, 1]], np.float32),      # horizon inside the frame
+        np.array([[3.0, 0, -100], [0, 3.0, -50], [0, 0, 1]], np.float32),  # 3x zoom in
+        np.array([[0.2, 0, 30], [0, 0.2, 20], [0, 0, 1]], np.float32),     # 5x zoom out: huge footprint
+        np.array([[0, -1, 100], [1, 0, 0], [0, 0, 1]], np.float32),        # 90 degree rotation
+    ]
+    for m in mats:
+        got, mask, _ = _run(handle, src, m.reshape(1, 1, 9), (w, h), "bilinear", (0.1, 0.2, 0.3))
+        want = R.warp_np(src[0], m, (w, h), "bilinear", (0.1, 0.2, 0.3))
+        assert float(np.abs(got[0] - want).max()) <= 1e-6
+        assert np.array_equal(mask[0], R.mask_np(m, (w, h), (w, h)))
+
+
+@pytest.mark.parametrize("interp,samples", [("bilinear", 5), ("bicubic", 9), ("bilinear", 33)])
+def test_motion_blur_matches_oracle(handle, interp, samples):
+    from vstab_b200.motion_apply import sample_matrices
+
+    rng = np.random.default_rng(9)
+    w, h, n = 160, 96, 3
+    src = rng.random((n, h, w, 3), dtype=np.float32)
+    mats = [_rand_matrix(rng, "sim", 6.0).astype(np.float64) for _ in range(n)]
+    fwd = sample_matrices(mats, 0.5, samples)
+    got, mask, _ = _run(handle, src, fwd, (w + 4, h + 2), interp, (0.5, 0.5, 0.5))
+    for i in range(n):
+        want, want_mask = R.warp_blur_np(src[i], mats, i, (w + 4, h + 2), interp, (0.5, 0.5, 0.5), 0.5, samples)
+        assert float(np.abs(got[i] - want).max()) <= 1e-6
+        assert float(np.abs(mask[i] - want_mask).max()) <= 1e-7
+
+
+FULL = [c for c in cases.MOTION_APPLY_CASES]
+
+
+@pytest.mark.parametrize("case", FULL, ids=[c["name"] for c in FULL])
+def test_apply_motion_matches_reference_golden(case):
+    """apply_motion (public driver) vs outputs of the real reference (tests/golden)."""
+    from vstab_b200 import motion_apply, pipeline
+
+    gold = np.load(os.path.join(GOLDEN_DIR, f"apply_{case['name']}.npz"))
+    with open(os.path.join(GOLDEN_DIR, f"apply_{case['name']}_meta.json")) as fh:
+        meta = json.load(fh)
+    frames = cases.make_frames(case)
+    ctx = pipeline.normalize_video_input(torch.from_numpy(frames))
+    res = motion_apply.apply_motion(ctx, meta, case["padding_rgb"], framing_mode=case["framing"],
+                                    interpolation=case["interp"], motion_blur=case["blur"],
+                                    motion_blur_samples=case["samples"])
+    tol = TOL[case["interp"]]
+    tight = 1e-7 if case["interp"] == "bilinear" and case["blur"] == 0.0 else 2e-6
+    if case["store"] == "full":
+        assert res.frames.shape == gold["frames"].shape
+        err = float(np.abs(res.frames - gold["frames"]).max())
+        assert err <= tol and err <= tight, err
+        if case["blur"] == 0.0:
+            assert np.array_equal(res.masks, gold["masks"])
+        else:
+            assert float(np.abs(res.masks - gold["masks"]).max()) <= 1e-6
+    else:
+        assert tuple(res.frames.shape) == tuple(gold["shape"])
+        fs = res.frames.reshape(res.frames.shape[0], -1).astype(np.float64).sum(axis=1)
+        ms = res.masks.reshape(res.masks.shape[0], -1).astype(np.float64).sum(axis=1)
+        assert np.allclose(fs, gold["frame_sum"], rtol=0, atol=tight * res.frames[0].size)
+        assert np.allclose(ms, gold["mask_sum"], rtol=0, atol=1e-3)
+        for k in range(3):
+            f, y, x, hh, ww = gold[f"patch{k}_at"]
+            err = float(np.abs(res.frames[f, y:y + hh, x:x + ww] - gold[f"patch{k}"]).max())
+            assert err <= tol and err <= tight, (k, err)
+            assert float(np.abs(res.masks[f, y:y + hh, x:x + ww, 0] - gold[f"mpatch{k}"]).max()) <= 1e-6
+
+
+def test_full_size_properties_1080p(handle):
+    """BASELINE-size checks that need no oracle: identity is exact, translation by whole pixels is a
+    shifted copy, mask count equals the uncovered area."""
+    dev = torch.device("cuda", 0)
+    w, h, n = 1920, 1080, 4
+    g = torch.Generator(device="cpu").manual_seed(3)
+    src = torch.rand((n, h, w, 3), generator=g).to(dev)
+    eye = torch.eye(3, dtype=torch.float32).reshape(1, 1, 9).repeat(n, 1, 1).to(dev)
+    dst, mask, pad = handle.warp_fused(src, eye, (w, h), "bilinear", (0.5, 0.5, 0.5), want_pad_count=True)
+    assert torch.equal(dst, src) and int(mask.sum()) == 0 and int(pad.sum()) == 0
+    dst, mask, pad = handle.warp_fused(src, eye, (w, h), "bicubic", (0.5, 0.5, 0.5), want_pad_count=True)
+    assert float((dst - src).abs().max()) <= 1e-6
+    shift = torch.tensor([[1, 0, 7.0], [0, 1, -5.0], [0, 0, 1]], dtype=torch.float32).reshape(1, 1, 9).repeat(n, 1, 1).to(dev)
+    dst, mask, pad = handle.warp_fused(src, shift, (w, h), "bilinear", (0.25, 0.5, 0.75), want_pad_count=True)
+    assert torch.equal(dst[:, : h - 5, 7:], src[:, 5:, : w - 7])
+    assert int(pad[0]) == w * h - (w - 7) * (h - 5)
+    assert torch.equal(mask[:, : h - 5, 7:], torch.zeros_like(mask[:, : h - 5, 7:]))
