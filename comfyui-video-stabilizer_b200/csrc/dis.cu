@@ -1,0 +1,737 @@
+// dis.cu -- K3 + K4: Dense Inverse Search optical flow, batched over all frame pairs of a clip.
+//
+// Replaces nodes/video_stabilizer_flow.py:76-87 (_create_flow_backend) and :140
+// (cv2.DISOpticalFlow.calc) plus the 8-px grid sampling of :141-147.  The algorithm is OpenCV's
+// DIS (Kroeger et al. 2016) in the configuration the reference sets: finest scale 2, 8x8 patches
+// on a stride-4 grid, 2 x 12 inverse-compositional iterations with spatial propagation inside 8
+// fixed horizontal stripes, mean-normalised residuals, densification, and 5 x 5 red-black SOR
+// variational refinement (alpha 20, delta 5, gamma 10, eps 0.01, omega 1.6).
+//
+// Design for B200: every frame pair of the clip is independent, so each stage is ONE launch over
+// all pairs (a 121-frame clip = 120 pairs keeps ~1000 warps in flight even at the 30x16 coarsest
+// level).  Pyramids, gradients and structure tensors are built once per FRAME and shared by the
+// two pairs that use it.  The sequential raster-order propagation of the patch search is run as
+// an anti-diagonal wavefront: one warp per (pair, stripe), 8 patch rows x 4 lanes, where the 4
+// lanes of a quad reproduce OpenCV's 4-wide SIMD accumulators and their reduction order
+// ((a0+a2)+(a1+a3)), so the float results are bit-identical to the CPU reference and so are all
+// the discrete decisions (candidate choice, early stop).  This file is compiled with
+// -fmad=false: no multiply-add contraction anywhere except where the reference itself fuses.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace {
+
+constexpr int kBorder = 16;
+constexpr int kPatch = 8;
+constexpr int kStride = 4;
+constexpr int kStripes = 8;
+constexpr int kFinest = 2;
+constexpr int kGdIter = 25;
+constexpr int kVrIter = 5;
+constexpr int kSorIter = 5;
+constexpr float kEps = 0.001f;
+constexpr float kInf = 1e10f;
+constexpr float kAlpha = 20.f, kDelta = 5.f, kGamma = 10.f, kEpsilon = 0.01f, kOmega = 1.6f;
+constexpr int kMaxLevels = 8;
+
+struct Level {
+  int w, h, ws, hs;
+  // per frame
+  unsigned char* I;    // [F][h][w]
+  unsigned char* Iext; // [F][h+32][w+32]
+  short* Ix;           // [F][h][w]
+  short* Iy;
+  float* T;            // [F][5][hs][ws]  xx, yy, xy, x, y
+  // per pair
+  float* Ux;           // [P][h][w]
+  float* Uy;
+  float* Sx;           // [P][hs][ws]
+  float* Sy;
+};
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+  return p;
+}
+
+// Sobel 3x3 (cv::spatialGradient, reflect-101) + 16-px replicate border of the same image.
+__global__ void __launch_bounds__(256) grad_border_kernel(const unsigned char* __restrict__ I, int h, int w,
+                                                          short* __restrict__ gx, short* __restrict__ gy,
+                                                          unsigned char* __restrict__ E) {
+  const int f = blockIdx.z;
+  const unsigned char* img = I + (size_t)f * h * w;
+  const int we = w + 2 * kBorder, he = h + 2 * kBorder;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x < we && y < he) {
+    const int sy = min(max(y - kBorder, 0), h - 1), sx = min(max(x - kBorder, 0), w - 1);
+    E[(size_t)f * he * we + (size_t)y * we + x] = img[sy * w + sx];
+  }
+  if (x < w && y < h) {
+    const int ym = reflect101(y - 1, h), yp = reflect101(y + 1, h);
+    const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+    const int a = img[ym * w + xm], b = img[ym * w + x], c = img[ym * w + xp];
+    const int d = img[y * w + xm], e = img[y * w + xp];
+    const int g = img[yp * w + xm], hh = img[yp * w + x], i = img[yp * w + xp];
+    gx[(size_t)f * h * w + y * w + x] = (short)((c + 2 * e + i) - (a + 2 * d + g));
+    gy[(size_t)f * h * w + y * w + x] = (short)((g + 2 * hh + i) - (a + 2 * b + c));
+  }
+}
+
+// Structure tensor, horizontal running sums: one thread per (frame, row); float running sums in
+// OpenCV's order (precomputeStructureTensor) so that large sums round identically.
+__global__ void tensor_rows_kernel(const short* __restrict__ gx, const short* __restrict__ gy, int F, int h, int w,
+                                   int ws, float* __restrict__ aux /* [F][5][h][ws] */) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= F * h) return;
+  const int f = idx / h, i = idx - f * h;
+  const short* xr = gx + ((size_t)f * h + i) * w;
+  const short* yr = gy + ((size_t)f * h + i) * w;
+  float* o = aux + (size_t)f * 5 * h * ws + (size_t)i * ws;
+  const size_t plane = (size_t)h * ws;
+  float sxx = 0, syy = 0, sxy = 0, sx = 0, sy = 0;
+  for (int j = 0; j < kPatch; j++) {
+    const int a = xr[j], b = yr[j];
+    sxx += (float)(a * a); syy += (float)(b * b); sxy += (float)(a * b); sx += (float)a; sy += (float)b;
+  }
+  o[0] = sxx; o[plane] = syy; o[2 * plane] = sxy; o[3 * plane] = sx; o[4 * plane] = sy;
+  int js = 1;
+  for (int j = kPatch; j < w; j++) {
+    const int a = xr[j], b = yr[j], a0 = xr[j - kPatch], b0 = yr[j - kPatch];
+    sxx += (float)(a * a - a0 * a0); syy += (float)(b * b - b0 * b0); sxy += (float)(a * b - a0 * b0);
+    sx += (float)(a - a0); sy += (float)(b - b0);
+    if ((j - kPatch + 1) % kStride == 0) {
+      o[js] = sxx; o[plane + js] = syy; o[2 * plane + js] = sxy; o[3 * plane + js] = sx; o[4 * plane + js] = sy;
+      js++;
+    }
+  }
+}
+
+// Structure tensor, vertical running sums: one thread per (frame, component, patch column).
+__global__ void tensor_cols_kernel(const float* __restrict__ aux, int F, int h, int ws, int hs,
+                                   float* __restrict__ T /* [F][5][hs][ws] */) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= F * 5 * ws) return;
+  const int fc = idx / ws, j = idx - fc * ws;  // fc = frame * 5 + component
+  const float* a = aux + (size_t)fc * h * ws + j;
+  float* o = T + (size_t)fc * hs * ws + j;
+  float s = 0.f;
+  for (int i = 0; i < kPatch; i++) s += a[(size_t)i * ws];
+  o[0] = s;
+  int is = 1;
+  for (int i = kPatch; i < h; i++) {
+    s += (a[(size_t)i * ws] - a[(size_t)(i - kPatch) * ws]);
+    if ((i - kPatch + 1) % kStride == 0) {
+      o[(size_t)is * ws] = s;
+      is++;
+    }
+  }
+}
+
+// ---- patch inverse search ----------------------------------------------------------------------
+
+struct Bil {
+  float w00, w01, w10, w11;
+  int off;  // offset of the top-left sample in the bordered image
+};
+
+__device__ __forceinline__ Bil bil_weights(float i, float j, float Ux, float Uy, int w, int h, int we) {
+  const float i_lo = kBorder - kPatch + 1.0f, i_hi = kBorder + h - 1.0f;
+  const float j_lo = kBorder - kPatch + 1.0f, j_hi = kBorder + w - 1.0f;
+  const float iI = fminf(fmaxf(i + Uy + kBorder, i_lo), i_hi);
+  const float jI = fminf(fmaxf(j + Ux + kBorder, j_lo), j_hi);
+  const float di = iI - floorf(iI), dj = jI - floorf(jI);
+  Bil b;
+  b.w11 = di * dj;
+  b.w10 = di * (1 - dj);
+  b.w01 = (1 - di) * dj;
+  b.w00 = (1 - di) * (1 - dj);
+  b.off = (int)iI * we + (int)jI;
+  return b;
+}
+
+// (a0 + a2) + (a1 + a3) across the 4 lanes of a quad; every lane gets the same bits.
+__device__ __forceinline__ float quad_reduce(float v, unsigned mask) {
+  const float t = v + __shfl_xor_sync(mask, v, 2);
+  return t + __shfl_xor_sync(mask, t, 1);
+}
+
+// One 8x8 patch evaluation by a quad: lane l handles pixel columns l and l+4 of every row.
+// kind 0: mean-normalised SSD only; kind 1: SSD + gradient-weighted sums (processPatchMeanNorm).
+template <int KIND>
+__device__ __forceinline__ float patch_eval(const unsigned char* __restrict__ I0p, const unsigned char* __restrict__ I1p,
+                                            const short* __restrict__ gxp, const short* __restrict__ gyp, int s0, int s1,
+                                            const Bil& b, int l, float xgs, float ygs, float& dUx, float& dUy,
+                                            unsigned mask) {
+  float sd = 0.f, sq = 0.f, mx = 0.f, my = 0.f;
+  float a0 = I1p[l], a1 = I1p[l + 1], a4 = I1p[l + 4], a5 = I1p[l + 5];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const unsigned char* nb = I1p + (r + 1) * s1;
+    const float b0 = nb[l], b1 = nb[l + 1], b4 = nb[l + 4], b5 = nb[l + 5];
+    const float z0 = I0p[r * s0 + l], z4 = I0p[r * s0 + l + 4];
+    const float dl = b.w00 * a0 + b.w01 * a1 + b.w10 * b0 + b.w11 * b1 - z0;
+    const float dr = b.w00 * a4 + b.w01 * a5 + b.w10 * b4 + b.w11 * b5 - z4;
+    if (KIND == 1) {
+      const float px0 = gxp[r * s0 + l], px4 = gxp[r * s0 + l + 4];
+      const float py0 = gyp[r * s0 + l], py4 = gyp[r * s0 + l + 4];
+      mx = mx + (dl * px0 + dr * px4);
+      my = my + (dl * py0 + dr * py4);
+    }
+    sq = sq + (dl * dl + dr * dr);
+    sd = sd + (dl + dr);
+    a0 = b0; a1 = b1; a4 = b4; a5 = b5;
+  }
+  const float sum_diff = quad_reduce(sd, mask);
+  const float sum_sq = quad_reduce(sq, mask);
+  if (KIND == 1) {
+    const float smx = quad_reduce(mx, mask), smy = quad_reduce(my, mask);
+    dUx = smx - sum_diff * xgs / 64.f;
+    dUy = smy - sum_diff * ygs / 64.f;
+  }
+  return sum_sq - sum_diff * sum_diff / 64.f;
+}
+
+// One warp per (pair, stripe): 8 patch rows x 4 lanes, anti-diagonal wavefront over the columns.
+__global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P) {
+  const int pair = blockIdx.x;
+  const int stripe = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int row_in_stripe = lane >> 2;
+  const int l = lane & 3;
+  const int w = L.w, h = L.h, ws = L.ws, hs = L.hs, we = w + 2 * kBorder;
+  const int stripe_sz = (hs + kStripes - 1) / kStripes;  // ceil(hs / 8)  (<= 8 for working sizes <= 960)
+  const int lo = min(stripe * stripe_sz, hs), hi = min((stripe + 1) * stripe_sz, hs);
+  const int rows = hi - lo;
+  if (rows <= 0) return;  // whole warp exits together
+
+  const size_t npx = (size_t)h * w;
+  const unsigned char* I0 = L.I + (size_t)pair * npx;                                     // frame `pair`
+  const unsigned char* I1e = L.Iext + (size_t)(pair + 1) * (h + 2 * kBorder) * we;        // frame `pair + 1`
+  const short* gx = L.Ix + (size_t)pair * npx;
+  const short* gy = L.Iy + (size_t)pair * npx;
+  const float* T = L.T + (size_t)pair * 5 * hs * ws;
+  const size_t tp = (size_t)hs * ws;
+  const float* Ux = L.Ux + (size_t)pair * npx;
+  const float* Uy = L.Uy + (size_t)pair * npx;
+  volatile float* Sx = L.Sx + (size_t)pair * tp;
+  volatile float* Sy = L.Sy + (size_t)pair * tp;
+  const int inner = kGdIter / 2;  // floor(25 / 2 passes) = 12
+  const unsigned qmask = 0xFu << (lane & ~3);
+
+  for (int iter = 0; iter < 2; iter++) {
+    const int dir = iter == 0 ? 1 : -1;
+    const int nsteps = ws + rows - 1;
+    for (int step = 0; step < nsteps; step++) {
+      const int c = step - row_in_stripe;  // column counted in processing order
+      const bool active = row_in_stripe < rows && c >= 0 && c < ws;
+      if (active) {
+        const int is = dir == 1 ? lo + row_in_stripe : hi - 1 - row_in_stripe;
+        const int js = dir == 1 ? c : ws - 1 - c;
+        const int i = is * kStride, j = js * kStride;
+        const int k = is * ws + js;
+        float sx, sy;
+        if (iter == 0) {
+          sx = Ux[(i + kPatch / 2) * w + j + kPatch / 2];
+          sy = Uy[(i + kPatch / 2) * w + j + kPatch / 2];
+        } else {
+          sx = Sx[k];
+          sy = Sy[k];
+        }
+        const unsigned char* I0p = I0 + i * w + j;
+        float dux, duy;
+        // spatial propagation: own / previous column / previous row of this pass
+        Bil b = bil_weights((float)i, (float)j, sx, sy, w, h, we);
+        float min_ssd = patch_eval<0>(I0p, I1e + b.off, nullptr, nullptr, w, we, b, l, 0.f, 0.f, dux, duy, qmask);
+        if (c > 0) {
+          const float cx = Sx[k - dir], cy = Sy[k - dir];
+          b = bil_weights((float)i, (float)j, cx, cy, w, h, we);
+          const float s = patch_eval<0>(I0p, I1e + b.off, nullptr, nullptr, w, we, b, l, 0.f, 0.f, dux, duy, qmask);
+          if (s < min_ssd) { min_ssd = s; sx = cx; sy = cy; }
+        }
+        if (row_in_stripe > 0) {
+          const float cx = Sx[k - dir * ws], cy = Sy[k - dir * ws];
+          b = bil_weights((float)i, (float)j, cx, cy, w, h, we);
+          const float s = patch_eval<0>(I0p, I1e + b.off, nullptr, nullptr, w, we, b, l, 0.f, 0.f, dux, duy, qmask);
+          if (s < min_ssd) { min_ssd = s; sx = cx; sy = cy; }
+        }
+        float cur_Ux = sx, cur_Uy = sy;
+        const float xx = T[k], yy = T[tp + k], xy = T[2 * tp + k];
+        const float xgs = T[3 * tp + k], ygs = T[4 * tp + k];
+        float detH = xx * yy - xy * xy;
+        if (fabsf(detH) < kEps) detH = kEps;
+        const float invH11 = yy / detH, invH12 = -xy / detH, invH22 = xx / detH;
+        float prev_ssd = kInf;
+        for (int t = 0; t < inner; t++) {
+          b = bil_weights((float)i, (float)j, cur_Ux, cur_Uy, w, h, we);
+          const float ssd = patch_eval<1>(I0p, I1e + b.off, gx + i * w + j, gy + i * w + j, w, we, b, l, xgs, ygs, dux,
+                                          duy, qmask);
+          const float dx = invH11 * dux + invH12 * duy;
+          const float dy = invH12 * dux + invH22 * duy;
+          cur_Ux -= dx;
+          cur_Uy -= dy;
+          if (ssd >= prev_ssd) break;
+          prev_ssd = ssd;
+        }
+        const float ex = cur_Ux - sx, ey = cur_Uy - sy;
+        const double nrm = sqrt((double)ex * ex + (double)ey * ey);
+        if (nrm <= (double)kPatch) { sx = cur_Ux; sy = cur_Uy; }
+        if (l == 0) { Sx[k] = sx; Sy[k] = sy; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ---- densification -----------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) densify_kernel(Level L, int P) {
+  const int pair = blockIdx.z;
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int w = L.w, h = L.h, ws = L.ws, hs = L.hs;
+  if (j >= w || i >= h) return;
+  const size_t npx = (size_t)h * w;
+  const unsigned char* I0 = L.I + (size_t)pair * npx;
+  const unsigned char* I1 = L.I + (size_t)(pair + 1) * npx;
+  const float* Sx = L.Sx + (size_t)pair * hs * ws;
+  const float* Sy = L.Sy + (size_t)pair * hs * ws;
+  // set of patches overlapping (i, j): OpenCV's incremental start/end bookkeeping in closed form
+  const int e_is = min(i / kStride, hs - 1), e_js = min(j / kStride, ws - 1);
+  const int s_is = min(i >= kPatch ? (i - kPatch) / kStride + 1 : 0, e_is);
+  const int s_js = min(j >= kPatch ? (j - kPatch) / kStride + 1 : 0, e_js);
+  float sum_coef = 0.f, sum_Ux = 0.f, sum_Uy = 0.f;
+  for (int is = s_is; is <= e_is; is++)
+    for (int js = s_js; js <= e_js; js++) {
+      const float sx = Sx[is * ws + js], sy = Sy[is * ws + js];
+      const float j_m = fminf(fmaxf(j + sx, 0.0f), w - 1.0f - kEps);
+      const float i_m = fminf(fmaxf(i + sy, 0.0f), h - 1.0f - kEps);
+      const int j_l = (int)j_m, j_u = j_l + 1, i_l = (int)i_m, i_u = i_l + 1;
+      const float diff = (j_m - j_l) * (i_m - i_l) * I1[i_u * w + j_u] + (j_u - j_m) * (i_m - i_l) * I1[i_u * w + j_l] +
+                         (j_m - j_l) * (i_u - i_m) * I1[i_l * w + j_u] + (j_u - j_m) * (i_u - i_m) * I1[i_l * w + j_l] -
+                         I0[i * w + j];
+      const float coef = 1 / fmaxf(1.0f, fabsf(diff));
+      sum_Ux += coef * sx;
+      sum_Uy += coef * sy;
+      sum_coef += coef;
+    }
+  L.Ux[(size_t)pair * npx + i * w + j] = sum_Ux / sum_coef;
+  L.Uy[(size_t)pair * npx + i * w + j] = sum_Uy / sum_coef;
+}
+
+// ---- variational refinement --------------------------------------------------------------------
+
+struct VrBuf {  // all [P][h][w] float
+  float *avg, *Iz, *Ix, *Iy, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz;
+  float *A11, *A12, *A22, *b1, *b2, *wgt, *tu, *tv, *du, *dv;
+};
+
+#define PIXEL_INDEX()                                         \
+  const int pair = blockIdx.z;                                \
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);         \
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);          \
+  const int w = L.w, h = L.h;                                 \
+  if (x >= w || y >= h) return;                               \
+  const size_t base = (size_t)pair * h * w;                   \
+  const size_t k = base + (size_t)y * w + x;
+
+// warp I1 by the current flow (cv::remap INTER_LINEAR, BORDER_REPLICATE, 1/32 px), average, Iz
+__global__ void __launch_bounds__(256) vr_warp_kernel(Level L, VrBuf B) {
+  PIXEL_INDEX();
+  const unsigned char* I0 = L.I + (size_t)pair * h * w;
+  const unsigned char* I1 = L.I + (size_t)(pair + 1) * h * w;
+  const float mx = x + L.Ux[k], my = y + L.Uy[k];
+  const int ix = __float2int_rn(mx * 32.f), iy = __float2int_rn(my * 32.f);
+  int sx = ix >> 5, sy = iy >> 5;
+  const int ax = ix & 31, ay = iy & 31;
+  sx = min(max(sx, -32768), 32767);
+  sy = min(max(sy, -32768), 32767);
+  const float fx1 = ax * (1.f / 32.f), fy1 = ay * (1.f / 32.f), fx0 = 1.f - fx1, fy0 = 1.f - fy1;
+  const float w00 = fy0 * fx0, w01 = fy0 * fx1, w10 = fy1 * fx0, w11 = fy1 * fx1;
+  const int x0 = min(max(sx, 0), w - 1), x1 = min(max(sx + 1, 0), w - 1);
+  const int y0 = min(max(sy, 0), h - 1), y1 = min(max(sy + 1, 0), h - 1);
+  const float warped = (float)I1[y0 * w + x0] * w00 + (float)I1[y0 * w + x1] * w01 + (float)I1[y1 * w + x0] * w10 +
+                       (float)I1[y1 * w + x1] * w11;
+  const float i0 = (float)I0[y * w + x];
+  B.avg[k] = 0.5f * (i0 + warped);
+  B.Iz[k] = warped - i0;
+  B.tu[k] = L.Ux[k];
+  B.tv[k] = L.Uy[k];
+  B.du[k] = 0.f;
+  B.dv[k] = 0.f;
+}
+
+__device__ __forceinline__ float at_clamped(const float* p, size_t base, int y, int x, int h, int w) {
+  return p[base + (size_t)min(max(y, 0), h - 1) * w + min(max(x, 0), w - 1)];
+}
+
+// first derivatives of avg and of Iz (central differences without the 1/2, replicate border)
+__global__ void __launch_bounds__(256) vr_deriv1_kernel(Level L, VrBuf B) {
+  PIXEL_INDEX();
+  B.Ix[k] = at_clamped(B.avg, base, y, x + 1, h, w) - at_clamped(B.avg, base, y, x - 1, h, w);
+  B.Iy[k] = at_clamped(B.avg, base, y + 1, x, h, w) - at_clamped(B.avg, base, y - 1, x, h, w);
+  B.Ixz[k] = at_clamped(B.Iz, base, y, x + 1, h, w) - at_clamped(B.Iz, base, y, x - 1, h, w);
+  B.Iyz[k] = at_clamped(B.Iz, base, y + 1, x, h, w) - at_clamped(B.Iz, base, y - 1, x, h, w);
+}
+
+__global__ void __launch_bounds__(256) vr_deriv2_kernel(Level L, VrBuf B) {
+  PIXEL_INDEX();
+  B.Ixx[k] = at_clamped(B.Ix, base, y, x + 1, h, w) - at_clamped(B.Ix, base, y, x - 1, h, w);
+  B.Ixy[k] = at_clamped(B.Ix, base, y + 1, x, h, w) - at_clamped(B.Ix, base, y - 1, x, h, w);
+  B.Iyy[k] = at_clamped(B.Iy, base, y + 1, x, h, w) - at_clamped(B.Iy, base, y - 1, x, h, w);
+}
+
+// smoothness weight of the current flow (forward differences, replicate border)
+__global__ void __launch_bounds__(256) vr_weight_kernel(Level L, VrBuf B) {
+  PIXEL_INDEX();
+  const size_t kr = base + (size_t)y * w + min(x + 1, w - 1), kd = base + (size_t)min(y + 1, h - 1) * w + x;
+  const float ux = B.tu[kr] - B.tu[k], vx = B.tv[kr] - B.tv[k], uy = B.tu[kd] - B.tu[k], vy = B.tv[kd] - B.tv[k];
+  const float eps2 = kEpsilon * kEpsilon;
+  B.wgt[k] = (kAlpha / 2) / sqrtf(ux * ux + vx * vx + uy * uy + vy * vy + eps2);
+}
+
+// data term + smoothness term of the linear system, accumulated per pixel in the order OpenCV's
+// red/black scatter passes touch it (see oracle/dis_ref.c: red = (x + y) even goes first).
+__global__ void __launch_bounds__(256) vr_system_kernel(Level L, VrBuf B) {
+  PIXEL_INDEX();
+  const float zeta2 = 0.1f * 0.1f, eps2 = kEpsilon * kEpsilon, gamma2 = kGamma / 2, delta2 = kDelta / 2;
+  const float ix = B.Ix[k], iy = B.Iy[k], iz = B.Iz[k], ixx = B.Ixx[k], ixy = B.Ixy[k], iyy = B.Iyy[k];
+  const float ixz = B.Ixz[k], iyz = B.Iyz[k], dU = B.du[k], dV = B.dv[k];
+  float derivNorm = ix * ix + iy * iy + zeta2;
+  const float Ik1z = iz + ix * dU + iy * dV;
+  float weight = (delta2 / sqrtf(Ik1z * Ik1z / derivNorm + eps2)) / derivNorm;
+  float a11 = weight * (ix * ix) + zeta2;
+  float a12 = weight * (ix * iy);
+  float a22 = weight * (iy * iy) + zeta2;
+  float bb1 = -weight * (iz * ix);
+  float bb2 = -weight * (iz * iy);
+  derivNorm = ixx * ixx + ixy * ixy + zeta2;
+  const float derivNorm2 = iyy * iyy + ixy * ixy + zeta2;
+  const float Ik1zx = ixz + ixx * dU + ixy * dV;
+  const float Ik1zy = iyz + ixy * dU + iyy * dV;
+  weight = gamma2 / sqrtf(Ik1zx * Ik1zx / derivNorm + Ik1zy * Ik1zy / derivNorm2 + eps2);
+  a11 += weight * (ixx * ixx / derivNorm + ixy * ixy / derivNorm2);
+  a12 += weight * (ixx * ixy / derivNorm + ixy * iyy / derivNorm2);
+  a22 += weight * (ixy * ixy / derivNorm + iyy * iyy / derivNorm2);
+  bb1 += -weight * (ixx * ixz / derivNorm + ixy * iyz / derivNorm2);
+  bb2 += -weight * (ixy * ixz / derivNorm + iyy * iyz / derivNorm2);
+
+  const float* u0 = L.Ux;
+  const float* v0 = L.Uy;
+  const bool red = ((x + y) & 1) == 0;
+  const float wc = B.wgt[k];
+  // horizontal: own forward term (x < w-1) and the left neighbour's forward term (x > 0)
+  const bool own_h = x < w - 1, left_h = x > 0;
+  float own_ux = 0.f, own_vx = 0.f, left_ux = 0.f, left_vx = 0.f, wl = 0.f;
+  if (own_h) { own_ux = wc * (u0[k + 1] - u0[k]); own_vx = wc * (v0[k + 1] - v0[k]); }
+  if (left_h) { wl = B.wgt[k - 1]; left_ux = wl * (u0[k] - u0[k - 1]); left_vx = wl * (v0[k] - v0[k - 1]); }
+#define ADD_OWN_H() if (own_h) { bb1 += own_ux; a11 += wc; bb2 += own_vx; a22 += wc; }
+#define ADD_LEFT_H() if (left_h) { bb1 -= left_ux; a11 += wl; bb2 -= left_vx; a22 += wl; }
+  if (red) { ADD_OWN_H(); ADD_LEFT_H(); } else { ADD_LEFT_H(); ADD_OWN_H(); }
+  // vertical: own forward term (y < h-1) and the upper neighbour's forward term (y > 0)
+  const bool own_v = y < h - 1, up_v = y > 0;
+  float own_uy = 0.f, own_vy = 0.f, up_uy = 0.f, up_vy = 0.f, wu = 0.f;
+  if (own_v) { own_uy = wc * (u0[k + w] - u0[k]); own_vy = wc * (v0[k + w] - v0[k]); }
+  if (up_v) { wu = B.wgt[k - w]; up_uy = wu * (u0[k] - u0[k - w]); up_vy = wu * (v0[k] - v0[k - w]); }
+#define ADD_OWN_V() if (own_v) { bb1 += own_uy; a11 += wc; bb2 += own_vy; a22 += wc; }
+#define ADD_UP_V() if (up_v) { bb1 -= up_uy; a11 += wu; bb2 -= up_vy; a22 += wu; }
+  if (red) { ADD_OWN_V(); ADD_UP_V(); } else { ADD_UP_V(); ADD_OWN_V(); }
+  B.A11[k] = a11; B.A12[k] = a12; B.A22[k] = a22; B.b1[k] = bb1; B.b2[k] = bb2;
+}
+
+// one colour of one red-black SOR sweep on the flow increment (zero outside the image)
+__global__ void __launch_bounds__(256) vr_sor_kernel(Level L, VrBuf B, int colour) {
+  const int pair = blockIdx.z;
+  const int xh = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int w = L.w, h = L.h;
+  if (y >= h) return;
+  const int x = 2 * xh + ((y + colour) & 1);
+  if (x >= w) return;
+  const size_t k = (size_t)pair * h * w + (size_t)y * w + x;
+  const float wl = x > 0 ? B.wgt[k - 1] : 0.f, dul = x > 0 ? B.du[k - 1] : 0.f, dvl = x > 0 ? B.dv[k - 1] : 0.f;
+  const float dur = x + 1 < w ? B.du[k + 1] : 0.f, dvr = x + 1 < w ? B.dv[k + 1] : 0.f;
+  const float wu = y > 0 ? B.wgt[k - w] : 0.f, duu = y > 0 ? B.du[k - w] : 0.f, dvu = y > 0 ? B.dv[k - w] : 0.f;
+  const float dud = y + 1 < h ? B.du[k + w] : 0.f, dvd = y + 1 < h ? B.dv[k + w] : 0.f;
+  const float wc = B.wgt[k];
+  const float sigmaU = wl * dul + wc * dur + wu * duu + wc * dud;
+  const float sigmaV = wl * dvl + wc * dvr + wu * dvu + wc * dvd;
+  float du = B.du[k], dv = B.dv[k];
+  du += kOmega * ((sigmaU + B.b1[k] - dv * B.A12[k]) / B.A11[k] - du);
+  dv += kOmega * ((sigmaV + B.b2[k] - du * B.A12[k]) / B.A22[k] - dv);
+  B.du[k] = du;
+  B.dv[k] = dv;
+}
+
+// tempW = W + dW ; last == 1 also writes the refined flow back into the level
+__global__ void __launch_bounds__(256) vr_update_kernel(Level L, VrBuf B, int last) {
+  PIXEL_INDEX();
+  const float u = L.Ux[k] + B.du[k], v = L.Uy[k] + B.dv[k];
+  B.tu[k] = u;
+  B.tv[k] = v;
+  if (last) { L.Ux[k] = u; L.Uy[k] = v; }
+}
+
+// ---- flow upsampling ---------------------------------------------------------------------------
+
+// next level = 2 * resize(linear) in the arithmetic of the 1-channel float path of the wheel (IPP):
+// fraction in double -> float, fma(S1 - S0, f, S0), horizontal then vertical.
+__device__ __forceinline__ void ipp_coord(int d, double scale, int ssize, int& s, float& f) {
+  double v = (d + 0.5) * scale - 0.5;
+  int si = (int)floor(v);
+  v -= si;
+  if (si < 0) { v = 0; si = 0; }
+  if (si >= ssize - 1) { v = 0; si = ssize - 1; }
+  s = si;
+  f = (float)v;
+}
+
+__global__ void __launch_bounds__(256) upsample_kernel(Level src, Level dst) {
+  const int pair = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= dst.w || y >= dst.h) return;
+  int sx, sy;
+  float fx, fy;
+  ipp_coord(x, (double)src.w / dst.w, src.w, sx, fx);
+  ipp_coord(y, (double)src.h / dst.h, src.h, sy, fy);
+  const int sx1 = min(sx + 1, src.w - 1), sy1 = min(sy + 1, src.h - 1);
+  const size_t sb = (size_t)pair * src.h * src.w;
+  const size_t dk = (size_t)pair * dst.h * dst.w + (size_t)y * dst.w + x;
+#define UP1(F)                                                                             \
+  {                                                                                        \
+    const float p00 = src.F[sb + sy * src.w + sx], p01 = src.F[sb + sy * src.w + sx1];     \
+    const float p10 = src.F[sb + sy1 * src.w + sx], p11 = src.F[sb + sy1 * src.w + sx1];   \
+    const float r0 = fmaf(p01 - p00, fx, p00), r1 = fmaf(p11 - p10, fx, p10);              \
+    dst.F[dk] = fmaf(r1 - r0, fy, r0) * 2.f;                                               \
+  }
+  UP1(Ux)
+  UP1(Uy)
+#undef UP1
+}
+
+// final x(2^finest) upsampling in OpenCV's own 2-channel float path:
+// f = (float)((d+.5)*scale-.5); s = floor(f); f -= s; out = S0*(1-f) + S1*f, horizontal then vertical
+__device__ __forceinline__ void cv_coord_x(int d, double scale, int ssize, int& s, float& f) {
+  f = (float)((d + 0.5) * scale - 0.5);
+  s = (int)floorf(f);
+  f -= s;
+  if (s < 0) { f = 0; s = 0; }
+  if (s >= ssize - 1) { f = 0; s = ssize - 1; }
+}
+
+__device__ __forceinline__ void final_sample(const Level& L, int pair, int x, int y, int W, int H, float mul, float& ox,
+                                             float& oy) {
+  int sx, sy;
+  float fx, fy;
+  cv_coord_x(x, 1. / ((double)W / L.w), L.w, sx, fx);
+  fy = (float)((y + 0.5) * (1. / ((double)H / L.h)) - 0.5);
+  sy = (int)floorf(fy);
+  fy -= sy;
+  const int y0 = min(max(sy, 0), L.h - 1), y1 = min(max(sy + 1, 0), L.h - 1);
+  const int sx1 = min(sx + 1, L.w - 1);
+  const size_t b = (size_t)pair * L.h * L.w;
+#define FIN1(F, out)                                                                     \
+  {                                                                                      \
+    const float r0 = L.F[b + y0 * L.w + sx] * (1.f - fx) + L.F[b + y0 * L.w + sx1] * fx; \
+    const float r1 = L.F[b + y1 * L.w + sx] * (1.f - fx) + L.F[b + y1 * L.w + sx1] * fx; \
+    out = (r0 * (1.f - fy) + r1 * fy) * mul;                                             \
+  }
+  FIN1(Ux, ox)
+  FIN1(Uy, oy)
+#undef FIN1
+}
+
+__global__ void __launch_bounds__(256) final_flow_kernel(Level L, int W, int H, float mul, float* __restrict__ flow) {
+  const int pair = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  float ox, oy;
+  if (L.w == W && L.h == H) {
+    const size_t k = (size_t)pair * H * W + (size_t)y * W + x;
+    ox = L.Ux[k] * mul;
+    oy = L.Uy[k] * mul;
+  } else {
+    final_sample(L, pair, x, y, W, H, mul, ox, oy);
+  }
+  float* o = flow + (((size_t)pair * H + y) * W + x) * 2;
+  o[0] = ox;
+  o[1] = oy;
+}
+
+__global__ void __launch_bounds__(256) final_grid_kernel(Level L, int W, int H, float mul, int step, int gw, int gh,
+                                                         float* __restrict__ grid) {
+  const int pair = blockIdx.z;
+  const int gx = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int gy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (gx >= gw || gy >= gh) return;
+  float ox, oy;
+  if (L.w == W && L.h == H) {
+    const size_t k = (size_t)pair * H * W + (size_t)(gy * step) * W + gx * step;
+    ox = L.Ux[k] * mul;
+    oy = L.Uy[k] * mul;
+  } else {
+    final_sample(L, pair, gx * step, gy * step, W, H, mul, ox, oy);
+  }
+  float* o = grid + (((size_t)pair * gh + gy) * gw + gx) * 2;
+  o[0] = ox;
+  o[1] = oy;
+}
+
+__global__ void zero_kernel(float* p, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int coarsest_scale(int h, int w) {
+  const int mx = w > h ? w : h, mn = w < h ? w : h;
+  const int a = (int)(log(mx / (4.0 * kPatch)) / log(2.0) + 0.5);
+  const int b = (int)(log((double)(mn / kPatch)) / log(2.0));
+  return a < b ? a : b;
+}
+
+}  // namespace
+
+// Pairs are processed in chunks so the workspace stays bounded (about 6.5 MB per pair at 960x540).
+extern "C" int vstab_dis_flow(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width,
+                              float* flow_dev, float* grid_dev, int grid_step, void* stream) {
+  if (!hnd) return vstab_fail(nullptr, VSTAB_ERR_INVALID, "vstab_dis_flow: null handle");
+  if (!gray_dev || n_frames < 0 || height <= 0 || width <= 0)
+    return vstab_fail(hnd, VSTAB_ERR_INVALID, "vstab_dis_flow: bad argument");
+  if (grid_dev && grid_step <= 0) return vstab_fail(hnd, VSTAB_ERR_INVALID, "vstab_dis_flow: grid_step must be > 0");
+  if (n_frames < 2) return VSTAB_OK;
+  const int coarsest = coarsest_scale(height, width);
+  if (coarsest < kFinest || coarsest >= kMaxLevels)
+    return vstab_fail(hnd, VSTAB_ERR_UNSUPPORTED,
+                      "vstab_dis_flow: frame too small for finest scale 2 (OpenCV's automatic scale selection is not implemented)");
+  if (((height >> kFinest) - kPatch) / kStride + 1 > 8 * kStripes)
+    return vstab_fail(hnd, VSTAB_ERR_UNSUPPORTED, "vstab_dis_flow: working image taller than 960 px is not supported");
+  cudaStream_t st = (cudaStream_t)stream;
+  VSTAB_CUDA(hnd, cudaSetDevice(hnd->device));
+
+  const int kChunk = 256;  // pairs per pass
+  for (int p0 = 0; p0 < n_frames - 1; p0 += kChunk) {
+    const int P = (n_frames - 1 - p0) < kChunk ? (n_frames - 1 - p0) : kChunk;
+    const int F = P + 1;
+    const uint8_t* gray = gray_dev + (size_t)p0 * height * width;
+
+    // ---- carve the workspace ----
+    Level L[kMaxLevels];
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+    size_t o_I[kMaxLevels], o_E[kMaxLevels], o_gx[kMaxLevels], o_gy[kMaxLevels], o_T[kMaxLevels], o_Ux[kMaxLevels],
+        o_Uy[kMaxLevels], o_Sx[kMaxLevels], o_Sy[kMaxLevels];
+    int fraction = 1 << kFinest;
+    for (int i = kFinest; i <= coarsest; i++) {
+      if (i == kFinest) { L[i].h = height / fraction; L[i].w = width / fraction; }
+      else { L[i].h = L[i - 1].h / 2; L[i].w = L[i - 1].w / 2; }
+      L[i].ws = 1 + (L[i].w - kPatch) / kStride;
+      L[i].hs = 1 + (L[i].h - kPatch) / kStride;
+      const size_t n = (size_t)L[i].h * L[i].w, t = (size_t)L[i].hs * L[i].ws;
+      o_I[i] = take(n * F);
+      o_E[i] = take((size_t)(L[i].h + 2 * kBorder) * (L[i].w + 2 * kBorder) * F);
+      o_gx[i] = take(n * 2 * F);
+      o_gy[i] = take(n * 2 * F);
+      o_T[i] = take(t * 5 * 4 * F);
+      o_Ux[i] = take(n * 4 * P);
+      o_Uy[i] = take(n * 4 * P);
+      o_Sx[i] = take(t * 4 * P);
+      o_Sy[i] = take(t * 4 * P);
+    }
+    const size_t nf = (size_t)L[kFinest].h * L[kFinest].w;
+    const size_t o_aux = take((size_t)L[kFinest].h * L[kFinest].ws * 5 * 4 * F);
+    size_t o_vr[19];
+    for (int k = 0; k < 19; k++) o_vr[k] = take(nf * 4 * P);
+    void* wsp = nullptr;
+    int rc = vstab_workspace(hnd, off, &wsp);
+    if (rc != VSTAB_OK) return rc;
+    unsigned char* base = (unsigned char*)wsp;
+    for (int i = kFinest; i <= coarsest; i++) {
+      L[i].I = base + o_I[i];
+      L[i].Iext = base + o_E[i];
+      L[i].Ix = (short*)(base + o_gx[i]);
+      L[i].Iy = (short*)(base + o_gy[i]);
+      L[i].T = (float*)(base + o_T[i]);
+      L[i].Ux = (float*)(base + o_Ux[i]);
+      L[i].Uy = (float*)(base + o_Uy[i]);
+      L[i].Sx = (float*)(base + o_Sx[i]);
+      L[i].Sy = (float*)(base + o_Sy[i]);
+    }
+    float* aux = (float*)(base + o_aux);
+    VrBuf B;
+    {
+      float** f = (float**)&B;
+      for (int k = 0; k < 19; k++) f[k] = (float*)(base + o_vr[k]);
+    }
+
+    // ---- per-frame pyramid, gradients, bordered copies, structure tensors ----
+    for (int i = kFinest; i <= coarsest; i++) {
+      if (i == kFinest) rc = vstab_area_u8(hnd, gray, F, height, width, L[i].I, L[i].h, L[i].w, st);
+      else rc = vstab_area_u8(hnd, L[i - 1].I, F, L[i - 1].h, L[i - 1].w, L[i].I, L[i].h, L[i].w, st);
+      if (rc != VSTAB_OK) return rc;
+      dim3 ge(vstab_ceil_div(L[i].w + 2 * kBorder, 32), vstab_ceil_div(L[i].h + 2 * kBorder, 8), F);
+      grad_border_kernel<<<ge, 256, 0, st>>>(L[i].I, L[i].h, L[i].w, L[i].Ix, L[i].Iy, L[i].Iext);
+      VSTAB_LAUNCH_CHECK(hnd, "grad_border_kernel");
+      tensor_rows_kernel<<<vstab_ceil_div(F * L[i].h, 128), 128, 0, st>>>(L[i].Ix, L[i].Iy, F, L[i].h, L[i].w, L[i].ws, aux);
+      VSTAB_LAUNCH_CHECK(hnd, "tensor_rows_kernel");
+      tensor_cols_kernel<<<vstab_ceil_div(F * 5 * L[i].ws, 128), 128, 0, st>>>(aux, F, L[i].h, L[i].ws, L[i].hs, L[i].T);
+      VSTAB_LAUNCH_CHECK(hnd, "tensor_cols_kernel");
+    }
+
+    // ---- coarse-to-fine ----
+    {
+      const size_t n = (size_t)L[coarsest].h * L[coarsest].w * P;
+      zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L[coarsest].Ux, n);
+      zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L[coarsest].Uy, n);
+      hnd->launches += 2;
+    }
+    for (int i = coarsest; i >= kFinest; i--) {
+      dim3 gp(vstab_ceil_div(L[i].w, 32), vstab_ceil_div(L[i].h, 8), P);
+      patch_search_kernel<<<P, 256, 0, st>>>(L[i], P);
+      VSTAB_LAUNCH_CHECK(hnd, "patch_search_kernel");
+      densify_kernel<<<gp, 256, 0, st>>>(L[i], P);
+      VSTAB_LAUNCH_CHECK(hnd, "densify_kernel");
+      // variational refinement
+      vr_warp_kernel<<<gp, 256, 0, st>>>(L[i], B);
+      vr_deriv1_kernel<<<gp, 256, 0, st>>>(L[i], B);
+      vr_deriv2_kernel<<<gp, 256, 0, st>>>(L[i], B);
+      hnd->launches += 3;
+      dim3 gs(vstab_ceil_div((L[i].w + 1) / 2, 32), vstab_ceil_div(L[i].h, 8), P);
+      for (int it = 0; it < kVrIter; it++) {
+        vr_weight_kernel<<<gp, 256, 0, st>>>(L[i], B);
+        vr_system_kernel<<<gp, 256, 0, st>>>(L[i], B);
+        for (int s = 0; s < kSorIter; s++) {
+          vr_sor_kernel<<<gs, 256, 0, st>>>(L[i], B, 0);
+          vr_sor_kernel<<<gs, 256, 0, st>>>(L[i], B, 1);
+        }
+        vr_update_kernel<<<gp, 256, 0, st>>>(L[i], B, it == kVrIter - 1 ? 1 : 0);
+        hnd->launches += 3 + 2 * kSorIter;
+      }
+      VSTAB_LAUNCH_CHECK(hnd, "variational refinement kernels");
+      if (i > kFinest) {
+        dim3 gu(vstab_ceil_div(L[i - 1].w, 32), vstab_ceil_div(L[i - 1].h, 8), P);
+        upsample_kernel<<<gu, 256, 0, st>>>(L[i], L[i - 1]);
+        VSTAB_LAUNCH_CHECK(hnd, "upsample_kernel");
+      }
+    }
+    const float mul = (float)(1 << kFinest);
+    if (flow_dev) {
+      dim3 gf(vstab_ceil_div(width, 32), vstab_ceil_div(height, 8), P);
+      final_flow_kernel<<<gf, 256, 0, st>>>(L[kFinest], width, height, mul, flow_dev + (size_t)p0 * height * width * 2);
+      VSTAB_LAUNCH_CHECK(hnd, "final_flow_kernel");
+    }
+    if (grid_dev) {
+      const int gw = vstab_ceil_div(width, grid_step), gh = vstab_ceil_div(height, grid_step);
+      dim3 gg(vstab_ceil_div(gw, 32), vstab_ceil_div(gh, 8), P);
+      final_grid_kernel<<<gg, 256, 0, st>>>(L[kFinest], width, height, mul, grid_step, gw, gh,
+                                            grid_dev + (size_t)p0 * gh * gw * 2);
+      VSTAB_LAUNCH_CHECK(hnd, "final_grid_kernel");
+    }
+  }
+  return VSTAB_OK;
+}
