@@ -31,15 +31,16 @@ class VstabNativeError(RuntimeError):
 
 class FitResult(C.Structure):
     _fields_ = [
-        ("matrix", C.c_float * 9),
-        ("confidence", C.c_float),
-        ("residual", C.c_float),
-        ("accepted", C.c_int32),
+        ("matrix", C.c_double * 9),
+        ("residual", C.c_double),
+        ("n_inliers", C.c_int32),
         ("n_valid", C.c_int32),
+        ("n_total", C.c_int32),
+        ("ok", C.c_int32),
     ]
 
 
-FIT_RESULT_FLOATS = C.sizeof(FitResult) // 4  # 13 x 4-byte words
+FIT_RESULT_DOUBLES = C.sizeof(FitResult) // 8  # 12 x 8-byte words
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -233,21 +234,21 @@ class Handle:
 
     # -- K4 + K7..K9 -----------------------------------------------------------------------------
     def fit_grid(self, grid_flow: torch.Tensor, grid_step: int, mode_mask: int = 7) -> torch.Tensor:
-        """grid_flow [P,gh,gw,2] sampled flow -> raw result words [P,3,13] (see FitResult)."""
+        """grid_flow [P,gh,gw,2] sampled flow -> raw result words [P,3,12] float64 (see FitResult)."""
         _check_cuda(grid_flow, torch.float32, "grid_flow")
         if not hasattr(self.lib, "vstab_fit_batch"):
             raise VstabNativeError("libvstab.so was built without vstab_fit_batch")
         p, gh, gw, _ = grid_flow.shape
-        out = torch.zeros((p, 3, FIT_RESULT_FLOATS), dtype=torch.float32, device=grid_flow.device)
+        out = torch.zeros((p, 3, FIT_RESULT_DOUBLES), dtype=torch.float64, device=grid_flow.device)
         self._check(self.lib.vstab_fit_batch(self._h, None, grid_flow.data_ptr(), p, gh * gw, gw, gh, int(grid_step), int(mode_mask), out.data_ptr(), _stream_ptr(grid_flow.device)))
         return out
 
     def fit_points(self, prev: torch.Tensor, curr: torch.Tensor, mode_mask: int = 7) -> torch.Tensor:
-        """prev/curr [P,K,2] correspondences (NaN rows = invalid) -> raw result words [P,3,13]."""
+        """prev/curr [P,K,2] correspondences (NaN rows = invalid) -> raw result words [P,3,12] float64."""
         _check_cuda(prev, torch.float32, "prev")
         _check_cuda(curr, torch.float32, "curr")
         p, k, _ = prev.shape
-        out = torch.zeros((p, 3, FIT_RESULT_FLOATS), dtype=torch.float32, device=prev.device)
+        out = torch.zeros((p, 3, FIT_RESULT_DOUBLES), dtype=torch.float64, device=prev.device)
         self._check(self.lib.vstab_fit_batch(self._h, prev.data_ptr(), curr.data_ptr(), p, k, 0, 0, 0, int(mode_mask), out.data_ptr(), _stream_ptr(prev.device)))
         return out
 
@@ -269,15 +270,16 @@ def get_handle(device: int | torch.device | None = None) -> Handle:
 
 
 def decode_fit_results(raw: torch.Tensor):
-    """raw [P,3,13] cuda/cpu float32 words -> dict of numpy arrays (matrix f32, conf, resid, accepted, n_valid)."""
+    """raw [P,3,12] float64 words -> dict of numpy arrays indexed [pair, mode]."""
     import numpy as np
 
-    arr = raw.detach().cpu().numpy()
-    words = arr.view(np.int32)
+    arr = np.ascontiguousarray(raw.detach().cpu().numpy())
+    ints = arr[..., 10:12].copy().view(np.int32)  # [P,3,4]
     return {
         "matrix": arr[..., :9].reshape(arr.shape[0], 3, 3, 3).copy(),
-        "confidence": arr[..., 9].copy(),
-        "residual": arr[..., 10].copy(),
-        "accepted": words[..., 11].copy(),
-        "n_valid": words[..., 12].copy(),
+        "residual": arr[..., 9].copy(),
+        "n_inliers": ints[..., 0].copy(),
+        "n_valid": ints[..., 1].copy(),
+        "n_total": ints[..., 2].copy(),
+        "ok": ints[..., 3].copy(),
     }

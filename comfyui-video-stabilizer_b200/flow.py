@@ -1,0 +1,71 @@
+"""Video Stabilizer Flow driver: DIS dense optical flow -> candidate models, all on the GPU.
+
+Mirrors nodes/video_stabilizer_flow.py of the reference: ``_create_flow_backend`` (:76-87, the DIS
+configuration is compiled into libvstab's dis.cu), ``_estimate_motion_flow`` (:133-210) and
+``_stabilize_frames`` (:213-640, body shared with Classic in stabilizer_core.py).  The TV-L1 and
+phase-correlation fallbacks of the reference (:77-80, :110-130) are unreachable with the cv2 wheel
+it pins (no cv2.optflow) and are not provided: this path has exactly one backend.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native
+from .pipeline import VideoContext
+from .stabilizer_core import PairCandidates, StabilizationResult, stabilize_frames as _core
+
+SAMPLE_STEP = 8  # flow.py:138 sample_step
+
+
+def mode_mask_for(requested: str) -> int:
+    """Candidates the ladder can reach from `requested` (flow.py:156-160)."""
+    bits = {"translation": 0b001, "similarity": 0b011, "perspective": 0b111}
+    return bits[requested]
+
+
+def estimate_candidates(context: VideoContext, work_w: int, work_h: int, requested_mode: str,
+                        first_pair: int = 0, last_pair: Optional[int] = None) -> PairCandidates:
+    """K1/K2 -> K3 -> K4/K7-K9 for pairs [first_pair, last_pair) of the clip held by `context`
+    (pair i = frames i, i+1).  Everything stays on the device until the [P,3] result table."""
+    h = _native.get_handle(context.device)
+    n = len(context)
+    last_pair = n - 1 if last_pair is None else last_pair
+    frames = context.frames[first_pair : last_pair + 1]
+    gray = h.gray_working(frames, (work_w, work_h))
+    _, grid = h.dis_flow(gray, want_flow=False, grid_step=SAMPLE_STEP)
+    raw = h.fit_grid(grid, SAMPLE_STEP, mode_mask_for(requested_mode))
+    d = _native.decode_fit_results(raw)
+    return PairCandidates(d["matrix"], d["residual"], d["n_inliers"], d["n_valid"], d["n_total"], d["ok"], min_points=12)
+
+
+def stabilize_frames(
+    context: VideoContext,
+    framing_mode: str,
+    transform_mode: str,
+    camera_lock: bool,
+    strength: float,
+    smooth: float,
+    keep_fov: float,
+    padding_rgb: Tuple[int, int, int],
+    frame_rate: float,
+    *,
+    progress_bar: Any = None,
+    interrupt_check: Optional[Callable[[], None]] = None,
+    output: str = "host",
+    shard=None,
+) -> StabilizationResult:
+    if shard is not None:
+        estimator = shard.wrap_estimator(estimate_candidates)
+    else:
+        estimator = estimate_candidates
+    return _core(
+        context, framing_mode, transform_mode, camera_lock, strength, smooth, keep_fov, padding_rgb, frame_rate,
+        estimator=estimator, flavour="flow", progress_bar=progress_bar, interrupt_check=interrupt_check,
+        output=output, shard=shard,
+    )
+
+
+_stabilize_frames = stabilize_frames  # reference-compatible private name

@@ -1,0 +1,347 @@
+"""Shared pipeline body of the Flow and Classic stabilizers on the CUDA hot path.
+
+Behavioural mirror of ``_stabilize_frames`` in the reference
+(nodes/video_stabilizer_flow.py:213-640 and nodes/video_stabilizer_classic.py:163-567, which are
+near-verbatim copies of each other): fps resolution, early outs, per-pair estimation, sticky mode
+ladder, path cumsum + box smoothing, framing (crop_and_pad recentring / expand / crop), warp +
+padding mask, and the ``meta`` dictionary whose key set is part of the drop-in contract.
+
+Where the reference loops over frames calling cv2, this module launches batched kernels:
+  estimation   gray+area (K1/K2) -> DIS or GFTT+LK (K3 | K5/K6) -> all candidate models (K7-K9)
+  ladder       replayed on the host over the candidate table (tiny; also what makes frame-range
+               sharding exact, see sharding.py)
+  warp         one fused launch per chunk (K10-K12) with per-frame padded-pixel counts
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native, hostmath as hm
+from .motion_meta import applied_motion_meta_from_stabilization_warp
+from .pipeline import VideoContext, fused_warp
+
+MODE_NAMES = _native.MODE_NAMES
+
+
+@dataclass
+class StabilizationResult:
+    frames: Any  # [N,H',W',3] float32 (numpy view of a pinned CPU tensor, or CUDA tensor)
+    masks: Any   # [N,H',W',1] float32
+    meta: Dict[str, Any]
+
+
+@dataclass
+class PairCandidates:
+    """Candidate models of every frame pair, indexed [pair, mode] with mode = VSTAB_MODE_*."""
+    matrix: np.ndarray      # [P,3,3,3] float64 (pre-float32-cast)
+    residual: np.ndarray    # [P,3] float64
+    n_inliers: np.ndarray   # [P,3] int
+    n_valid: np.ndarray     # [P,3] int
+    n_total: np.ndarray     # [P,3] int
+    ok: np.ndarray          # [P,3] int
+    min_points: int = 12    # Flow: 12 finite grid points; Classic: 8 tracked features
+    detected: Optional[np.ndarray] = None  # Classic: corners found per pair (<12 => identity)
+
+    def to_array(self) -> np.ndarray:
+        """Flat float64 [P, 3*14 + 1] table (what shards all-gather)."""
+        p = self.matrix.shape[0]
+        cols = [self.matrix.reshape(p, 27), self.residual, self.n_inliers, self.n_valid, self.n_total, self.ok]
+        det = self.detected if self.detected is not None else np.full((p,), -1)
+        return np.concatenate([np.asarray(c, dtype=np.float64).reshape(p, -1) for c in cols] + [det.reshape(p, 1).astype(np.float64)], axis=1)
+
+    @staticmethod
+    def from_array(arr: np.ndarray, min_points: int) -> "PairCandidates":
+        p = arr.shape[0]
+        ints = lambda a: np.rint(a).astype(np.int64)
+        det = ints(arr[:, 42])
+        return PairCandidates(
+            matrix=arr[:, :27].reshape(p, 3, 3, 3).copy(), residual=arr[:, 27:30].copy(), n_inliers=ints(arr[:, 30:33]),
+            n_valid=ints(arr[:, 33:36]), n_total=ints(arr[:, 36:39]), ok=ints(arr[:, 39:42]), min_points=min_points,
+            detected=None if (det < 0).all() else det,
+        )
+
+
+Estimator = Callable[[VideoContext, int, int, str], PairCandidates]
+
+
+def replay_mode_ladder(cands: PairCandidates, requested_mode: str, *, with_residual: bool):
+    """The reference's per-pair fallback ladder with its clip-wide sticky downgrade
+    (flow.py:156-210 + :324-339; classic.py:104-158 + :264-272), replayed over the table."""
+    active = requested_mode
+    out = []
+    eye = np.eye(3, dtype=np.float32)
+    for p in range(cands.matrix.shape[0]):
+        n_valid = int(cands.n_valid[p].max())
+        chosen = None
+        too_few = n_valid < cands.min_points
+        if cands.detected is not None and int(cands.detected[p]) < 12:
+            too_few = True
+        if not too_few:
+            for mode in hm.MODE_LADDER[active]:
+                k = _native.MODE_INDEX[mode]
+                ok = bool(cands.ok[p, k])
+                if mode == "perspective" and n_valid >= 4 and ok:
+                    conf = float(cands.n_inliers[p, k]) / float(n_valid)
+                    if conf >= 0.15:
+                        chosen = (cands.matrix[p, k].astype(np.float32), mode, conf, float(cands.residual[p, k]))
+                        break
+                elif mode == "similarity" and n_valid >= 3 and ok:
+                    conf = float(cands.n_inliers[p, k]) / float(n_valid)
+                    if conf >= 0.1:
+                        chosen = (cands.matrix[p, k].astype(np.float32), mode, conf, float(cands.residual[p, k]))
+                        break
+                elif mode == "translation":
+                    denom = int(cands.detected[p]) if cands.detected is not None else int(cands.n_total[p, k])
+                    conf = float(n_valid) / float(denom)
+                    chosen = (cands.matrix[p, k].astype(np.float32), mode, conf, float(cands.residual[p, k]))
+                    break
+        if chosen is None:
+            chosen = (eye.copy(), "translation", 0.0, 0.0)
+        matrix, used, conf, resid = chosen
+        if used != active:
+            active = used
+        out.append((matrix, used, conf, resid if with_residual else None))
+    return out, active
+
+
+class _Progress:
+    """update_absolute every 10 items, like the reference's progress_stride bookkeeping."""
+
+    def __init__(self, bar, total: int):
+        self.bar, self.total, self.done = bar, total, 0
+
+    def advance(self, count: int, stride: int = 10) -> None:
+        if self.bar is None or count <= 0:
+            self.done += max(count, 0)
+            return
+        left = count
+        while left > 0:
+            step = min(stride, left)
+            self.done += step
+            left -= step
+            self.bar.update_absolute(self.done, self.total)
+
+    def finish(self) -> None:
+        if self.bar is not None:
+            self.bar.update_absolute(self.total, self.total)
+
+
+def stabilize_frames(
+    context: VideoContext,
+    framing_mode: str,
+    transform_mode: str,
+    camera_lock: bool,
+    strength: float,
+    smooth: float,
+    keep_fov: float,
+    padding_rgb: Tuple[int, int, int],
+    frame_rate: float,
+    *,
+    estimator: Estimator,
+    flavour: str,  # "flow" | "classic": selects meta keys and motion_meta source
+    progress_bar: Any = None,
+    interrupt_check: Optional[Callable[[], None]] = None,
+    output: str = "host",
+    shard=None,
+) -> StabilizationResult:
+    is_flow = flavour == "flow"
+    total_frames = len(context)
+    width, height = context.width, context.height
+    fps_effective, fps_requested = hm.resolve_fps_for_stabilizer(frame_rate, context.fps)
+    flow_keys = {"flow_backend": "DIS", "flow_fallback_reason": None} if is_flow else {}
+    source_tag = "estimated_flow" if is_flow else "estimated_classic"
+
+    def attach(meta):
+        try:
+            meta["motion_meta"] = applied_motion_meta_from_stabilization_warp(
+                meta["stabilization_warp"], fps=fps_effective, source=source_tag
+            )
+        except (KeyError, TypeError, ValueError, np.linalg.LinAlgError):
+            pass
+        return meta
+
+    def check():
+        if interrupt_check is not None:
+            interrupt_check()
+
+    if shard is not None:
+        total_frames = shard.total_frames
+    estimation_steps = max(0, total_frames - 1)
+    progress = _Progress(progress_bar, estimation_steps + total_frames)
+
+    if total_frames == 1:
+        meta = {
+            "frames": 1,
+            "note": "Single-frame input; bypassed stabilization.",
+            "transform_mode": transform_mode,
+            "framing_mode": framing_mode,
+            **({"keep_fov_applied": False} if is_flow else {}),
+            **flow_keys,
+            "stabilization_warp": hm.build_stabilization_warp_meta(
+                source_size=(width, height), output_size=(width, height), framing_mode=framing_mode,
+                applied_matrices=[np.eye(3, dtype=np.float32)],
+            ),
+            "fps_requested": fps_requested,
+            "fps_effective": fps_effective,
+        }
+        progress.finish()
+        frames = context.frames
+        masks = torch.zeros((1, height, width, 1), dtype=torch.float32, device=frames.device)
+        if output == "host":
+            return StabilizationResult(frames.cpu().numpy(), masks.cpu().numpy(), attach(meta))
+        return StabilizationResult(frames, masks, attach(meta))
+
+    # ---- estimation: all candidate models of every pair -----------------------------------------
+    work = hm.working_estimation_size(width, height)
+    work_w, work_h = work if work is not None else (width, height)
+    cands = estimator(context, work_w, work_h, transform_mode)
+    if shard is not None:
+        cands = shard.gather_candidates(cands)
+    chosen, active_mode = replay_mode_ladder(cands, transform_mode, with_residual=is_flow)
+    progress.advance(estimation_steps)
+    check()
+
+    base_mode = transform_mode
+    matrices: List[np.ndarray] = []
+    delta_params: List[np.ndarray] = []
+    for matrix, _, _, _ in chosen:
+        if work is not None:
+            matrix = hm.rescale_transform_to_full(matrix, (width, height), work)
+        matrices.append(matrix)
+        delta_params.append(hm.matrix_to_params(matrix, base_mode))
+
+    path = np.zeros((total_frames, delta_params[0].shape[0]), dtype=np.float64)
+    for i, delta in enumerate(delta_params, start=1):
+        path[i] = path[i - 1] + delta
+
+    strength = float(np.clip(strength, 0.0, 1.0))
+    smooth = float(np.clip(smooth, 0.0, 1.0))
+    if camera_lock:
+        smooth = max(smooth, 0.85)
+        target_path = np.zeros_like(path)
+    else:
+        target_path = path + strength * (hm.smooth_path(path, smooth, fps_effective) - path)
+    diffs = target_path - path
+    delta_full = [d.copy() for d in diffs]
+
+    keep_fov_clamped = float(np.clip(keep_fov, 0.0, 1.0))
+    keep_fov_applied = framing_mode == "crop" and keep_fov_clamped > 1e-6
+    stabilization_scale = 1.0
+
+    if framing_mode == "crop":
+        from .crop import solve_crop_framing  # deferred: the crop solvers are their own module
+
+        crop = solve_crop_framing(
+            context, base_mode, delta_full, path, target_path, keep_fov_clamped, transform_mode, camera_lock,
+            strength, smooth, fps_requested, fps_effective, padding_rgb, flow_keys, is_flow, attach, progress,
+            check, output,
+        )
+        if isinstance(crop, StabilizationResult):
+            return crop
+        final_matrices, apply_matrices, crop_meta, stabilization_scale = crop
+        output_size = (width, height)
+    else:
+        apply_matrices = [hm.params_to_matrix(d, base_mode) for d in delta_full]
+        final_matrices = apply_matrices
+        output_size = (width, height)
+        crop_meta = None
+
+    mins, maxs = hm.compute_bounding_boxes(apply_matrices, width, height)
+    framing_meta: Dict[str, Any] = {
+        "mode": framing_mode,
+        "input_size": [width, height],
+        "padding_color_rgb": [int(c) for c in padding_rgb],
+        "min_content_ratio": hm.min_content_ratio(mins, maxs, width, height),
+    }
+    if framing_mode == "crop":
+        framing_meta.update(crop_meta)
+        if keep_fov_applied:
+            framing_meta["keep_fov_requested"] = keep_fov_clamped
+        note = framing_meta.pop("_keep_fov_note", None)
+        if note:
+            framing_meta["keep_fov_note"] = note
+    elif framing_mode == "crop_and_pad":
+        x0, y0 = float(np.max(mins[:, 0])), float(np.max(mins[:, 1]))
+        x1, y1 = float(np.min(maxs[:, 0])), float(np.min(maxs[:, 1]))
+        iw, ih = max(1.0, x1 - x0), max(1.0, y1 - y0)
+        off_x = width * 0.5 - (x0 + x1) * 0.5
+        off_y = height * 0.5 - (y0 + y1) * 0.5
+        shift = np.array([[1.0, 0.0, off_x], [0.0, 1.0, off_y], [0.0, 0.0, 1.0]], dtype=np.float32)
+        final_matrices = [shift @ m for m in apply_matrices]
+        framing_meta.update(
+            {
+                "safe_region_origin": [x0, y0],
+                "safe_region_size": [iw, ih],
+                "actual_content_ratio": min(iw / width, ih / height),
+                "center_offset": [off_x, off_y],
+            }
+        )
+    else:
+        shift, output_size = hm.prepare_expand_transform(mins, maxs)
+        final_matrices = [shift @ m for m in apply_matrices]
+        framing_meta["expanded_size"] = list(output_size)
+
+    effective_diffs = (
+        np.array([hm.matrix_to_params(m, base_mode) for m in apply_matrices]) if framing_mode == "crop" else np.array(delta_full)
+    )
+    stabilization_scale = float(np.clip(stabilization_scale, 0.0, 1.0))
+    strength_effective = strength * stabilization_scale
+    effective_target_path = path + effective_diffs
+
+    # ---- warp + mask: one fused launch per chunk -------------------------------------------------
+    lo, hi = (0, total_frames) if shard is None else shard.frame_range
+    fwd = np.stack([np.asarray(m, dtype=np.float32).reshape(9) for m in final_matrices[lo:hi]], axis=0)[:, None, :]
+    frames_out, masks_out, pad_counts = fused_warp(
+        context if shard is None else shard.owned_context(context), fwd, output_size, "bilinear",
+        hm.border_value(padding_rgb), want_mask=True, want_pad_count=True, output=output,
+    )
+    if shard is not None:
+        pad_counts = shard.gather_pad_counts(pad_counts)
+    pixels = int(output_size[0]) * int(output_size[1])
+    padded_ratios = [hm.padded_fraction(int(c), pixels) for c in pad_counts]
+    framing_meta["padding_detected"] = bool(np.any(np.asarray(pad_counts) > 0))
+    progress.advance(total_frames)
+    check()
+
+    per_transition = []
+    for i, (_, mode, conf, resid) in enumerate(chosen):
+        entry = {"index": i, "mode": mode, "confidence": conf}
+        if is_flow:
+            entry["residual"] = resid
+        entry["matrix"] = matrices[i].astype(np.float32).tolist()
+        per_transition.append(entry)
+
+    meta = {
+        "frames": total_frames,
+        "transform_mode_requested": transform_mode,
+        "transform_mode_applied": active_mode,
+        "camera_lock": camera_lock,
+        "strength": strength,
+        "strength_effective": strength_effective,
+        "smooth": smooth,
+        "fps_requested": fps_requested,
+        "fps_effective": fps_effective,
+        "framing": framing_meta,
+        "keep_fov_applied": keep_fov_applied,
+        "padding_color_rgb": [int(c) for c in padding_rgb],
+        **flow_keys,
+        "stabilization_warp": hm.build_stabilization_warp_meta(
+            source_size=(width, height), output_size=output_size, framing_mode=framing_mode,
+            applied_matrices=final_matrices,
+        ),
+        "estimated_motion": {
+            "per_transition": per_transition,
+            "path": path.tolist(),
+            "target_path": target_path.tolist(),
+            "target_path_effective": effective_target_path.tolist(),
+        },
+        "padding_fraction_mean": float(np.mean(padded_ratios)),
+        "padding_fraction_max": float(np.max(padded_ratios)),
+    }
+    if output == "host":
+        return StabilizationResult(frames_out.numpy(), masks_out.numpy()[..., None], attach(meta))
+    return StabilizationResult(frames_out, masks_out[..., None], attach(meta))

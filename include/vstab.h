@@ -149,11 +149,12 @@ VSTAB_API int vstab_dis_flow(vstab_handle* h, const uint8_t* gray_dev, int n_fra
 /* ---- K4 + K7 + K8 + K9 : robust model fit, batched over frame pairs --------------------- */
 
 typedef struct vstab_fit_result {
-  float matrix[9];  /* float32 3x3 prev->curr at working resolution */
-  float confidence; /* inliers / valid (similarity, perspective) or valid / total */
-  float residual;   /* mean |affine(prev) - curr| over both axes, flow.py:174,189,207 */
-  int32_t accepted; /* 1 if this candidate passes the reference's acceptance test */
-  int32_t n_valid;  /* finite correspondences */
+  double matrix[9];  /* 3x3 prev->curr at working resolution, before the reference's float32 cast */
+  double residual;   /* mean |affine(prev) - curr| over both axes, flow.py:174,189,207 */
+  int32_t n_inliers; /* RANSAC consensus size (similarity, perspective) or n_valid (translation) */
+  int32_t n_valid;   /* finite correspondences */
+  int32_t n_total;   /* correspondences offered */
+  int32_t ok;        /* 1 = the estimator returned a model (cv2 result not None) */
 } vstab_fit_result;
 
 /*
@@ -166,8 +167,9 @@ typedef struct vstab_fit_result {
  * prev_dev / curr_dev  [n_pairs][n_pts][2] float32 correspondences; prev_dev may be NULL with
  *                      grid_w/grid_h/grid_step > 0, meaning the regular sampling grid and
  *                      curr = prev + flow where curr_dev then holds the sampled FLOW.
- * mode_mask            bit VSTAB_MODE_* set = compute that candidate
- * out_dev              [n_pairs][3] results indexed by VSTAB_MODE_*
+ * mode_mask            bit (1 << VSTAB_MODE_*) set = compute that candidate
+ * out_dev              [n_pairs][3] results indexed by VSTAB_MODE_*.  confidence is left to the
+ *                      caller: n_inliers / n_valid (similarity, perspective) or n_valid / n_total
  */
 VSTAB_API int vstab_fit_batch(vstab_handle* h, const float* prev_dev, const float* curr_dev, int n_pairs,
                     int n_pts, int grid_w, int grid_h, int grid_step, int mode_mask,
