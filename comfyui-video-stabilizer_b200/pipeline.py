@@ -21,6 +21,24 @@ from . import _native
 # frames per host->device / device->host copy chunk (keeps staging buffers ~0.8 GB at 1080p)
 CHUNK_BYTES = 768 << 20
 
+# bench.py sets this to a list to collect (start_event, end_event, frames, algorithmic_bytes) of
+# every vstab_warp_fused launch, recorded on the launching stream.
+WARP_LAUNCH_LOG = None
+
+
+def _timed_warp(h, src, fwd, out_size, interp, border, **kw):
+    if WARP_LAUNCH_LOG is None:
+        return h.warp_fused(src, fwd, out_size, interp, border, **kw)
+    st = torch.cuda.current_stream(src.device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    res = h.warp_fused(src, fwd, out_size, interp, border, **kw)
+    e1.record(st)
+    n, sh, sw, _ = src.shape
+    ow, oh = int(out_size[0]), int(out_size[1])
+    WARP_LAUNCH_LOG.append((e0, e1, int(n), int(n) * (12 * sh * sw + 12 * oh * ow + (4 * oh * ow if kw.get("want_mask", True) else 0))))
+    return res
+
 
 @dataclass
 class FrameAdapter:
@@ -257,8 +275,8 @@ def fused_warp(
     if fwd_t.dim() == 2:
         fwd_t = fwd_t.view(n, 1, 9)
     if output == "device":
-        dst, mask, pad = h.warp_fused(
-            context.frames, fwd_t, (ow, oh), interpolation, border,
+        dst, mask, pad = _timed_warp(
+            h, context.frames, fwd_t, (ow, oh), interpolation, border,
             mask_rule=mask_rule, want_mask=want_mask, want_pad_count=want_pad_count,
         )
         return dst, mask, (pad.cpu().numpy().astype(np.int64) if pad is not None else None)
@@ -282,8 +300,8 @@ def fused_warp(
         dbuf, mbuf = bufs[k % len(bufs)]
         if copied[k % len(bufs)] is not None:
             main.wait_event(copied[k % len(bufs)])  # buffer free again
-        dst, mask, pad = h.warp_fused(
-            context.frames[a:b], fwd_t[a:b], (ow, oh), interpolation, border,
+        dst, mask, pad = _timed_warp(
+            h, context.frames[a:b], fwd_t[a:b], (ow, oh), interpolation, border,
             mask_rule=mask_rule, want_mask=want_mask, want_pad_count=want_pad_count,
             out=dbuf[: b - a], mask_out=(mbuf[: b - a] if mbuf is not None else None),
         )

@@ -1,0 +1,126 @@
+"""Frame-range sharding of one clip across the GPUs of a node (one process per GPU).
+
+The reference is a single process; its only cross-frame couplings on this path are
+  (1) the clip-wide sticky mode downgrade of the fit ladder (flow.py:324-339),
+  (2) the O(N) trajectory smoothing / framing solve over ALL per-pair matrices (flow.py:356-533),
+  (3) padding_fraction_mean/max over all frames (flow.py:636-637).
+So the path shards by contiguous frame range with exactly one exchange: every rank estimates ALL
+candidate models for its own pairs (it loads one halo frame before its range; no pixels cross
+ranks), the per-pair candidate table (344 B per pair) is all-gathered over NCCL/NVLink, every rank
+replays the ladder and the smoothing/framing solve redundantly and bit-identically, and warps only
+its own frames.  A second tiny all-gather collects the per-frame padded-pixel counts for the meta.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .stabilizer_core import PairCandidates
+
+TABLE_COLS = 43
+
+
+def split_range(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Balanced contiguous split of [0, total): the first `total % world` ranks get one extra."""
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+@dataclass
+class FrameShard:
+    rank: int
+    world: int
+    total_frames: int
+    group: Optional[dist.ProcessGroup] = None
+    device: Optional[torch.device] = None  # device of the communication buffers (cuda for NCCL)
+
+    @property
+    def frame_range(self) -> Tuple[int, int]:
+        return split_range(self.total_frames, self.world, self.rank)
+
+    @property
+    def load_range(self) -> Tuple[int, int]:
+        """Frames this rank must hold: its own range plus one halo frame before it."""
+        lo, hi = self.frame_range
+        return max(lo - 1, 0), hi
+
+    @property
+    def pair_range(self) -> Tuple[int, int]:
+        """Global pair indices (pair p = frames p, p+1) estimated by this rank: those ENDING in its range."""
+        lo, hi = self.frame_range
+        return max(lo, 1) - 1, max(hi - 1, max(lo, 1) - 1)
+
+    def pair_counts(self) -> List[int]:
+        out = []
+        for r in range(self.world):
+            lo, hi = split_range(self.total_frames, self.world, r)
+            a = max(lo, 1) - 1
+            out.append(max(hi - 1, a) - a)
+        return out
+
+    # -- hooks used by stabilizer_core.stabilize_frames ------------------------------------------
+    def wrap_estimator(self, estimate: Callable) -> Callable:
+        """The local context holds frames load_range; every consecutive local pair is ours."""
+
+        def run(context, work_w, work_h, requested_mode):
+            if len(context) < 2:
+                z = np.zeros
+                return PairCandidates(z((0, 3, 3, 3)), z((0, 3)), z((0, 3), int), z((0, 3), int), z((0, 3), int), z((0, 3), int))
+            return estimate(context, work_w, work_h, requested_mode)
+
+        return run
+
+    def _all_gather_rows(self, local: np.ndarray, counts: List[int]) -> np.ndarray:
+        width = local.shape[1] if local.ndim == 2 else 1
+        cap = max(max(counts), 1)
+        dev = self.device if self.device is not None else torch.device("cpu")
+        send = torch.zeros((cap, width), dtype=torch.float64, device=dev)
+        if local.shape[0]:
+            send[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local.reshape(local.shape[0], width))).to(dev)
+        recv = torch.empty((self.world, cap, width), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(recv.view(-1, width), send, group=self.group)
+        host = recv.cpu().numpy()
+        return np.concatenate([host[r, : counts[r]] for r in range(self.world)], axis=0)
+
+    def gather_candidates(self, local: PairCandidates) -> PairCandidates:
+        counts = self.pair_counts()
+        if local.matrix.shape[0] != counts[self.rank]:
+            raise RuntimeError(f"rank {self.rank}: estimated {local.matrix.shape[0]} pairs, expected {counts[self.rank]}")
+        table = self._all_gather_rows(local.to_array() if counts[self.rank] else np.zeros((0, TABLE_COLS)), counts)
+        return PairCandidates.from_array(table, local.min_points)
+
+    def owned_context(self, context):
+        """Drop the halo frame so frame k of the result is global frame frame_range[0] + k."""
+        import dataclasses
+
+        lo, _ = self.frame_range
+        halo = lo - self.load_range[0]
+        if halo == 0:
+            return context
+        return dataclasses.replace(context, frames=context.frames[halo:])
+
+    def gather_pad_counts(self, local_counts) -> np.ndarray:
+        counts = [split_range(self.total_frames, self.world, r) for r in range(self.world)]
+        sizes = [hi - lo for lo, hi in counts]
+        rows = np.asarray(local_counts, dtype=np.float64).reshape(-1, 1)
+        return np.rint(self._all_gather_rows(rows, sizes)[:, 0]).astype(np.int64)
+
+
+def init_from_env(total_frames: int, backend: Optional[str] = None) -> FrameShard:
+    """torchrun-style bootstrap (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT)."""
+    import os
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    use_cuda = torch.cuda.is_available()
+    if use_cuda:
+        torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group(backend or ("nccl" if use_cuda else "gloo"), rank=rank, world_size=world)
+    return FrameShard(rank, world, total_frames, None, torch.device("cuda", local) if use_cuda else torch.device("cpu"))

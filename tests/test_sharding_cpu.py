@@ -1,0 +1,89 @@
+"""World-size-2 gloo test of the frame-range sharding host logic (no GPU, no pixels):
+the gathered candidate table and the ladder replayed on it must equal the single-process result."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import vstab_loader
+
+vstab_loader.load()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _fake_candidates(total_frames, seed=0):
+    """A table with a sticky downgrade in the middle: pair 7 has a failing similarity fit."""
+    from vstab_b200.stabilizer_core import PairCandidates
+
+    rng = np.random.default_rng(seed)
+    p = total_frames - 1
+    m = np.tile(np.eye(3), (p, 3, 1, 1)).astype(np.float64)
+    m[:, :, :2, 2] = rng.normal(0, 3, (p, 3, 2))
+    n_valid = np.full((p, 3), 8160)
+    n_inl = np.full((p, 3), 8000)
+    n_inl[7, 1] = 300  # confidence 0.037 < 0.10 => similarity rejected => sticky translation afterwards
+    return PairCandidates(m, rng.random((p, 3)), n_inl, n_valid, np.full((p, 3), 8160), np.ones((p, 3), int))
+
+
+def _worker(rank, world, port, total, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import vstab_loader
+
+    vstab_loader.load()
+    from vstab_b200.sharding import FrameShard
+    from vstab_b200.stabilizer_core import PairCandidates, replay_mode_ladder
+
+    shard = FrameShard(rank, world, total, None, torch.device("cpu"))
+    full = _fake_candidates(total)
+    a, b = shard.pair_range
+    local = PairCandidates.from_array(full.to_array()[a:b], 12)
+    gathered = shard.gather_candidates(local)
+    chosen, active = replay_mode_ladder(gathered, "similarity", with_residual=True)
+    pads = shard.gather_pad_counts(np.arange(*shard.frame_range) * 10)
+    out[rank] = (gathered.to_array(), [c[1] for c in chosen], active, pads, shard.frame_range, shard.load_range)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_equals_single_process():
+    from vstab_b200.stabilizer_core import replay_mode_ladder
+
+    total, world = 23, 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), total, out), nprocs=world, join=True)
+    full = _fake_candidates(total)
+    chosen, active = replay_mode_ladder(full, "similarity", with_residual=True)
+    modes = [c[1] for c in chosen]
+    assert modes[6] == "similarity" and modes[7] == "translation" and modes[-1] == "translation" and active == "translation"
+    for r in range(world):
+        table, rmodes, ractive, pads, frange, lrange = out[r]
+        assert np.array_equal(table, full.to_array())
+        assert rmodes == modes and ractive == active
+        assert np.array_equal(pads, np.arange(total) * 10)
+    assert out[0][4] == (0, 12) and out[1][4] == (12, 23) and out[1][5] == (11, 23)
+
+
+def test_split_covers_everything():
+    from vstab_b200.sharding import FrameShard, split_range
+
+    for total in (1, 2, 7, 121, 2000):
+        for world in (1, 2, 3, 8):
+            ranges = [split_range(total, world, r) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == total
+            assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+            pairs = []
+            for r in range(world):
+                a, b = FrameShard(r, world, total).pair_range
+                pairs += list(range(a, b))
+            assert pairs == list(range(max(total - 1, 0)))
