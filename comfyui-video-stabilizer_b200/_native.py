@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libvstab.so")
+LIB_PATH = os.environ.get("VSTAB_LIB") or os.path.join(_PKG_DIR, "libvstab.so")  # VSTAB_LIB: A/B builds of the same ABI
 
 INTERP = {"bilinear": 0, "bicubic": 1}
 MASK_RULE_P = 0

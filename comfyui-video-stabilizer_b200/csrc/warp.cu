@@ -24,6 +24,10 @@ constexpr int TW = 64;
 constexpr int TH = 16;
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
+#ifndef VSTAB_WARP_MIN_CTAS
+#define VSTAB_WARP_MIN_CTAS 4
+#endif
+constexpr int MIN_CTAS = VSTAB_WARP_MIN_CTAS;
 constexpr int MAX_SAMPLES = 33;
 constexpr int MINV_SLOTS = 34;  // 34*9*8 bytes keeps everything behind it 16-byte aligned
 constexpr int SCRATCH_FLOATS_PER_WARP = 2 * TW * 3;  // two rows of RGB
@@ -41,6 +45,7 @@ struct WarpParams {
   int stage_capacity;  // floats available for the staged source tile
   int vec_store;       // ow % 4 == 0 && dst 16B aligned
   int vec_load;        // sw % 4 == 0 && src 16B aligned
+  int vec_mask;        // ow % 4 == 0 && mask 16B aligned
   float border[3];
 };
 
@@ -85,12 +90,13 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 template <int INTERP>
-__global__ void __launch_bounds__(NTHREADS) warp_fused_kernel(const WarpParams p) {
+__global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const WarpParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_minv = reinterpret_cast<double*>(smem_raw);                       // [34][9], 16B multiple
   float* s_scratch = reinterpret_cast<float*>(s_minv + MINV_SLOTS * 9);       // [8][384]
   int* s_box = reinterpret_cast<int*>(s_scratch + NWARPS * SCRATCH_FLOATS_PER_WARP);  // 8 ints
-  float* s_tile = reinterpret_cast<float*>(s_box + 8);                        // staged source box
+  float* s_cubic = reinterpret_cast<float*>(s_box + 8);                       // [32][4] bicubic coefficients
+  float* s_tile = s_cubic + 128;                                              // staged source box
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -102,6 +108,7 @@ __global__ void __launch_bounds__(NTHREADS) warp_fused_kernel(const WarpParams p
   const float* __restrict__ frame = p.src + (size_t)frame_idx * p.sh * p.sw * 3;
 
   if (tid < S) vstab_invert3(p.fwd + ((size_t)frame_idx * S + tid) * 9, s_minv + tid * 9);
+  if (INTERP == VSTAB_INTERP_BICUBIC && tid < 128) s_cubic[tid] = c_cubic_tab[tid >> 2][tid & 3];
   if (tid == 0) {
     s_box[0] = INT_MAX;  // min x
     s_box[1] = INT_MAX;  // min y
@@ -118,6 +125,7 @@ __global__ void __launch_bounds__(NTHREADS) warp_fused_kernel(const WarpParams p
   tile.x0 = tile.y0 = 0;
   tile.x1 = tile.y1 = -1;
   tile.pitch = 0;
+  bool interior = false;
   if (p.stage_mode == VSTAB_STAGE_AUTO) {
     const int txe = min(tx0 + TW, p.ow) - 1;
     const int tye = min(ty0 + TH, p.oh) - 1;
@@ -152,6 +160,11 @@ __global__ void __launch_bounds__(NTHREADS) warp_fused_kernel(const WarpParams p
       const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
       if (bw > 0 && bh > 0 && (long long)bw * 3 * bh <= (long long)p.stage_capacity) {
         tile.active = true;
+        // Interior tile: the whole (unclipped) footprint lies >= 1 px inside the source, so every
+        // tap is in the staged box and every pixel is covered: no per-tap or per-pixel tests.
+        interior = (S == 1) && (INTERP == VSTAB_INTERP_BILINEAR) && (tx0 + TW <= p.ow) && (ty0 + TH <= p.oh) &&
+                   (s_box[0] - LO >= 1) && (s_box[1] - LO >= 1) && (s_box[2] + HI <= p.sw - 2) &&
+                   (s_box[3] + HI <= p.sh - 2);
         tile.x0 = bx0;
         tile.y0 = by0;
         tile.x1 = bx1;
@@ -178,152 +191,289 @@ __global__ void __launch_bounds__(NTHREADS) warp_fused_kernel(const WarpParams p
     __syncthreads();
   }
 
+  // ---- interior tiles: branch-free bilinear, single sample ---------------------------------------
+  if (interior) {
+    float* scratch = s_scratch + warp * SCRATCH_FLOATS_PER_WARP;
+    const double* m = s_minv;
+    const double m2 = m[2], m5 = m[5], m8 = m[8];
+    const bool affine = (m[6] == 0.0) && (m[7] == 0.0);
+    const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
+    const int t_x0 = tile.x0, t_y0 = tile.y0, t_pitch = tile.pitch;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const double dy = (double)(ty0 + warp + rr * NWARPS);
+      const double bx = __dmul_rn(m[1], dy), by = __dmul_rn(m[4], dy), bw = __dmul_rn(m[7], dy);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const double dx = (double)(tx0 + lane + cc * 32);
+        const double X = __dadd_rn(__dadd_rn(__dmul_rn(m[0], dx), bx), m2);
+        const double Y = __dadd_rn(__dadd_rn(__dmul_rn(m[3], dx), by), m5);
+        double sc = sc_affine;
+        if (!affine) {
+          const double W = __dadd_rn(__dadd_rn(__dmul_rn(m[6], dx), bw), m8);
+          sc = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
+        }
+        // |coordinates| < 2^15 here, so cv2's INT_MIN/INT_MAX and short saturation are no-ops
+        const int ix = __double2int_rn(__dmul_rn(X, sc)), iy = __double2int_rn(__dmul_rn(Y, sc));
+        const int sx = ix >> 5, sy = iy >> 5;
+        const float fx1 = (float)(ix & 31) * 0.03125f, fy1 = (float)(iy & 31) * 0.03125f;
+        const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
+        const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
+        const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
+        const float* s0 = s_tile + (sy - t_y0) * t_pitch + (sx - t_x0) * 3;
+        const float* s1 = s0 + t_pitch;
+        float* sc_out = scratch + rr * (TW * 3) + (lane + cc * 32) * 3;
+        float* gd = p.dst + (((size_t)frame_idx * p.oh + (ty0 + warp + rr * NWARPS)) * p.ow + (tx0 + lane + cc * 32)) * 3;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s0[ch], w00), __fmul_rn(s0[3 + ch], w01)),
+                                              __fmul_rn(s1[ch], w10)),
+                                    __fmul_rn(s1[3 + ch], w11));
+          if (p.vec_store) sc_out[ch] = v; else gd[ch] = v;
+        }
+      }
+    }
+    if (p.mask) {  // fully covered tile: mask = 0; 64x16 floats = one 16-byte store per thread
+      float* mrow = p.mask + ((size_t)frame_idx * p.oh + ty0 + (tid >> 4)) * p.ow + tx0 + (tid & 15) * 4;
+      if (p.vec_mask) {
+        *reinterpret_cast<float4*>(mrow) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        mrow[0] = 0.f; mrow[1] = 0.f; mrow[2] = 0.f; mrow[3] = 0.f;
+      }
+    }
+    if (p.vec_store) {
+      __syncwarp();
+#pragma unroll
+      for (int q3 = 0; q3 < 3; ++q3) {
+        const int q = lane + q3 * 32;
+        const int rr = q / 48, qi = q - rr * 48;
+        const float4 v = *reinterpret_cast<const float4*>(scratch + rr * (TW * 3) + qi * 4);
+        float* d = p.dst + (((size_t)frame_idx * p.oh + (ty0 + warp + rr * NWARPS)) * p.ow + tx0) * 3 + qi * 4;
+        *reinterpret_cast<float4*>(d) = v;
+      }
+    }
+    return;
+  }
+
   // ---- per-pixel resampling ------------------------------------------------------------------
+  // Sample-outer loop: the per-sample row/column products of the inverse matrix are hoisted out of
+  // the 4 pixels a thread owns; the float32 accumulation per pixel is still in sample order.
   const float fS = (float)S;
   float* scratch = s_scratch + warp * SCRATCH_FLOATS_PER_WARP;
   unsigned int padded = 0;
+  float acc[4][3];
+  int cover[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
+    cover[q] = 0;
+  }
+  const double dxs[2] = {(double)(tx0 + lane), (double)(tx0 + lane + 32)};
+  const double dys[2] = {(double)(ty0 + warp), (double)(ty0 + warp + NWARPS)};
+  const double x_hi = (double)(p.sw - 1), y_hi = (double)(p.sh - 1);
+  const bool t_on = tile.active;
+  const int t_x0 = tile.x0, t_y0 = tile.y0, t_x1 = tile.x1, t_y1 = tile.y1, t_pitch = tile.pitch;
 
+  for (int s = 0; s < S; ++s) {
+    const double* m = s_minv + s * 9;
+    const double m2 = m[2], m5 = m[5], m8 = m[8];
+    double ax[2], ay[2], aw[2], bx[2], by[2], bw[2];
 #pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int oy = ty0 + warp + rr * NWARPS;
+    for (int k = 0; k < 2; ++k) {
+      ax[k] = __dmul_rn(m[0], dxs[k]);
+      ay[k] = __dmul_rn(m[3], dxs[k]);
+      aw[k] = __dmul_rn(m[6], dxs[k]);
+      bx[k] = __dmul_rn(m[1], dys[k]);
+      by[k] = __dmul_rn(m[4], dys[k]);
+      bw[k] = __dmul_rn(m[7], dys[k]);
+    }
+    // affine maps (last row 0 0 w): W is the same double for every pixel => one division per CTA
+    const bool affine = (m[6] == 0.0) && (m[7] == 0.0);
+    const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      const int ox = tx0 + lane + cc * 32;
-      float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
-      int cover = 0;
-      if (oy < p.oh && ox < p.ow) {
-        const double dx = (double)ox, dy = (double)oy;
-        for (int s = 0; s < S; ++s) {
-          const double* m = s_minv + s * 9;
-          const double X = __dadd_rn(__dadd_rn(__dmul_rn(m[0], dx), __dmul_rn(m[1], dy)), m[2]);
-          const double Y = __dadd_rn(__dadd_rn(__dmul_rn(m[3], dx), __dmul_rn(m[4], dy)), m[5]);
-          const double W = __dadd_rn(__dadd_rn(__dmul_rn(m[6], dx), __dmul_rn(m[7], dy)), m[8]);
-          // -- coverage (INTER_NEAREST ones warp) on the continuous coordinate
-          {
-            double cxs = __ddiv_rn(X, W), cys = __ddiv_rn(Y, W);
-            if (p.mask_rule == VSTAB_MASK_RULE_C) {
-              cxs = rint(cxs);
-              cys = rint(cys);
-            }
-            const bool ok = (cxs >= 0.0) && (cxs <= (double)(p.sw - 1)) && (cys >= 0.0) &&
-                            (cys <= (double)(p.sh - 1));
-            cover += ok ? 1 : 0;
+    for (int q = 0; q < 4; ++q) {
+      const int rr = q >> 1, cc = q & 1;
+      const int oy = ty0 + warp + rr * NWARPS, ox = tx0 + lane + cc * 32;
+      if (oy >= p.oh || ox >= p.ow) continue;
+      const double X = __dadd_rn(__dadd_rn(ax[cc], bx[rr]), m2);
+      const double Y = __dadd_rn(__dadd_rn(ay[cc], by[rr]), m5);
+      double W, sc;
+      if (affine) {
+        W = m8;
+        sc = sc_affine;
+      } else {
+        W = __dadd_rn(__dadd_rn(aw[cc], bw[rr]), m8);
+        sc = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
+      }
+      // -- coverage (INTER_NEAREST ones warp): fl(X/W), fl(Y/W) inside the closed source rectangle.
+      //    X * fl(1/W) decides everything that is not within 1e-6 px of a boundary; only those
+      //    pixels pay for the exact divisions.
+      {
+        bool ok;
+        const double rw = sc * 0.03125;  // fl(32/W)/32 == fl(1/W): scaling by 2^-5 is exact
+        const double qx = X * rw, qy = Y * rw;
+        const double band = 1e-6;
+        if (p.mask_rule == VSTAB_MASK_RULE_P && qx > band && qx < x_hi - band && qy > band && qy < y_hi - band) {
+          ok = true;
+        } else if (p.mask_rule == VSTAB_MASK_RULE_P && (qx < -band || qx > x_hi + band || qy < -band || qy > y_hi + band)) {
+          ok = false;
+        } else {
+          double cxs = __ddiv_rn(X, W), cys = __ddiv_rn(Y, W);
+          if (p.mask_rule == VSTAB_MASK_RULE_C) {
+            cxs = rint(cxs);
+            cys = rint(cys);
           }
-          // -- 1/32-px fixed-point source coordinate
-          const double sc = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
-          double fx = __dmul_rn(X, sc), fy = __dmul_rn(Y, sc);
-          fx = fmax(-2147483648.0, fmin(2147483647.0, fx));
-          fy = fmax(-2147483648.0, fmin(2147483647.0, fy));
-          const int ix = __double2int_rn(fx), iy = __double2int_rn(fy);
-          int sx = ix >> 5, sy = iy >> 5;
-          sx = max(-32768, min(32767, sx));
-          sy = max(-32768, min(32767, sy));
-          const int ax = ix & 31, ay = iy & 31;
-          float vr, vg, vb;
-          if (INTERP == VSTAB_INTERP_BILINEAR) {
-            const float fx1 = (float)ax * 0.03125f, fy1 = (float)ay * 0.03125f;
-            const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
-            const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
-            const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
-            if (sx >= p.sw || sx + 1 < 0 || sy >= p.sh || sy + 1 < 0) {
-              // remapBilinear: footprint entirely outside the source => the border colour itself
-              vr = p.border[0];
-              vg = p.border[1];
-              vb = p.border[2];
-            } else {
-              float r0, g0, b0, r1, g1, b1, r2, g2, b2, r3, g3, b3;
-              fetch_rgb(p, frame, tile, sy, sx, r0, g0, b0);
-              fetch_rgb(p, frame, tile, sy, sx + 1, r1, g1, b1);
-              fetch_rgb(p, frame, tile, sy + 1, sx, r2, g2, b2);
-              fetch_rgb(p, frame, tile, sy + 1, sx + 1, r3, g3, b3);
-              vr = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0, w00), __fmul_rn(r1, w01)),
-                                       __fmul_rn(r2, w10)),
-                             __fmul_rn(r3, w11));
-              vg = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(g0, w00), __fmul_rn(g1, w01)),
-                                       __fmul_rn(g2, w10)),
-                             __fmul_rn(g3, w11));
-              vb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b0, w00), __fmul_rn(b1, w01)),
-                                       __fmul_rn(b2, w10)),
-                             __fmul_rn(b3, w11));
+          ok = (cxs >= 0.0) && (cxs <= x_hi) && (cys >= 0.0) && (cys <= y_hi);
+        }
+        cover[q] += ok ? 1 : 0;
+      }
+      // -- 1/32-px fixed-point source coordinate
+      double fx = __dmul_rn(X, sc), fy = __dmul_rn(Y, sc);
+      fx = fmax(-2147483648.0, fmin(2147483647.0, fx));
+      fy = fmax(-2147483648.0, fmin(2147483647.0, fy));
+      const int ix = __double2int_rn(fx), iy = __double2int_rn(fy);
+      int sx = ix >> 5, sy = iy >> 5;
+      sx = max(-32768, min(32767, sx));
+      sy = max(-32768, min(32767, sy));
+      const int fxi = ix & 31, fyi = iy & 31;
+      float vr, vg, vb;
+      if (INTERP == VSTAB_INTERP_BILINEAR) {
+        const float fx1 = (float)fxi * 0.03125f, fy1 = (float)fyi * 0.03125f;
+        const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
+        const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
+        const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
+        float r0, g0, b0, r1, g1, b1, r2, g2, b2, r3, g3, b3;
+        bool have = true;
+        if (t_on && sx >= t_x0 && sx < t_x1 && sy >= t_y0 && sy < t_y1) {
+          // whole 2x2 footprint inside the staged (in-image) box: 12 conflict-free LDS
+          const float* s0 = s_tile + (sy - t_y0) * t_pitch + (sx - t_x0) * 3;
+          const float* s1 = s0 + t_pitch;
+          r0 = s0[0]; g0 = s0[1]; b0 = s0[2]; r1 = s0[3]; g1 = s0[4]; b1 = s0[5];
+          r2 = s1[0]; g2 = s1[1]; b2 = s1[2]; r3 = s1[3]; g3 = s1[4]; b3 = s1[5];
+        } else if (sx >= p.sw || sx + 1 < 0 || sy >= p.sh || sy + 1 < 0) {
+          // remapBilinear: footprint entirely outside the source => the border colour itself
+          have = false;
+          r0 = g0 = b0 = r1 = g1 = b1 = r2 = g2 = b2 = r3 = g3 = b3 = 0.f;
+        } else {
+          fetch_rgb(p, frame, tile, sy, sx, r0, g0, b0);
+          fetch_rgb(p, frame, tile, sy, sx + 1, r1, g1, b1);
+          fetch_rgb(p, frame, tile, sy + 1, sx, r2, g2, b2);
+          fetch_rgb(p, frame, tile, sy + 1, sx + 1, r3, g3, b3);
+        }
+        if (have) {
+          vr = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0, w00), __fmul_rn(r1, w01)), __fmul_rn(r2, w10)), __fmul_rn(r3, w11));
+          vg = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(g0, w00), __fmul_rn(g1, w01)), __fmul_rn(g2, w10)), __fmul_rn(g3, w11));
+          vb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b0, w00), __fmul_rn(b1, w01)), __fmul_rn(b2, w10)), __fmul_rn(b3, w11));
+        } else {
+          vr = p.border[0];
+          vg = p.border[1];
+          vb = p.border[2];
+        }
+      } else {
+        float wx[4], wy[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          wx[k] = s_cubic[fxi * 4 + k];
+          wy[k] = s_cubic[fyi * 4 + k];
+        }
+        const int bxs = sx - 1, bys = sy - 1;
+        if (bxs >= 0 && bxs < p.sw - 3 && bys >= 0 && bys < p.sh - 3) {
+          vr = vg = vb = 0.f;
+          if (t_on && bxs >= t_x0 && bxs + 3 <= t_x1 && bys >= t_y0 && bys + 3 <= t_y1) {
+            const float* s0 = s_tile + (bys - t_y0) * t_pitch + (bxs - t_x0) * 3;
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1) {
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const float w = __fmul_rn(wy[k1], wx[k2]);
+                const float* t = s0 + k1 * t_pitch + k2 * 3;
+                vr = __fadd_rn(vr, __fmul_rn(t[0], w));
+                vg = __fadd_rn(vg, __fmul_rn(t[1], w));
+                vb = __fadd_rn(vb, __fmul_rn(t[2], w));
+              }
             }
           } else {
-            float wx[4], wy[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              wx[k] = c_cubic_tab[ax][k];
-              wy[k] = c_cubic_tab[ay][k];
+            for (int k1 = 0; k1 < 4; ++k1) {
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const float w = __fmul_rn(wy[k1], wx[k2]);
+                float r, g, b;
+                fetch_rgb(p, frame, tile, bys + k1, bxs + k2, r, g, b);
+                vr = __fadd_rn(vr, __fmul_rn(r, w));
+                vg = __fadd_rn(vg, __fmul_rn(g, w));
+                vb = __fadd_rn(vb, __fmul_rn(b, w));
+              }
             }
-            const int bx = sx - 1, by = sy - 1;
-            if (bx >= 0 && bx < p.sw - 3 && by >= 0 && by < p.sh - 3) {
-              vr = vg = vb = 0.f;
+          }
+        } else {
+          // remapBicubic border branch: cv + sum over in-range taps of (S - cv) * w
+          vr = p.border[0];
+          vg = p.border[1];
+          vb = p.border[2];
+          if (!(bxs >= p.sw || bxs + 3 < 0 || bys >= p.sh || bys + 3 < 0)) {
 #pragma unroll
-              for (int k1 = 0; k1 < 4; ++k1) {
+            for (int k1 = 0; k1 < 4; ++k1) {
 #pragma unroll
-                for (int k2 = 0; k2 < 4; ++k2) {
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const int yy = bys + k1, xx = bxs + k2;
+                if ((unsigned)xx < (unsigned)p.sw && (unsigned)yy < (unsigned)p.sh) {
                   const float w = __fmul_rn(wy[k1], wx[k2]);
                   float r, g, b;
-                  fetch_rgb(p, frame, tile, by + k1, bx + k2, r, g, b);
-                  vr = __fadd_rn(vr, __fmul_rn(r, w));
-                  vg = __fadd_rn(vg, __fmul_rn(g, w));
-                  vb = __fadd_rn(vb, __fmul_rn(b, w));
-                }
-              }
-            } else {
-              // remapBicubic border branch: cv + sum over in-range taps of (S - cv) * w
-              vr = p.border[0];
-              vg = p.border[1];
-              vb = p.border[2];
-              if (!(bx >= p.sw || bx + 3 < 0 || by >= p.sh || by + 3 < 0)) {
-#pragma unroll
-                for (int k1 = 0; k1 < 4; ++k1) {
-#pragma unroll
-                  for (int k2 = 0; k2 < 4; ++k2) {
-                    const int yy = by + k1, xx = bx + k2;
-                    if ((unsigned)xx < (unsigned)p.sw && (unsigned)yy < (unsigned)p.sh) {
-                      const float w = __fmul_rn(wy[k1], wx[k2]);
-                      float r, g, b;
-                      fetch_rgb(p, frame, tile, yy, xx, r, g, b);
-                      vr = __fadd_rn(vr, __fmul_rn(__fsub_rn(r, p.border[0]), w));
-                      vg = __fadd_rn(vg, __fmul_rn(__fsub_rn(g, p.border[1]), w));
-                      vb = __fadd_rn(vb, __fmul_rn(__fsub_rn(b, p.border[2]), w));
-                    }
-                  }
+                  fetch_rgb(p, frame, tile, yy, xx, r, g, b);
+                  vr = __fadd_rn(vr, __fmul_rn(__fsub_rn(r, p.border[0]), w));
+                  vg = __fadd_rn(vg, __fmul_rn(__fsub_rn(g, p.border[1]), w));
+                  vb = __fadd_rn(vb, __fmul_rn(__fsub_rn(b, p.border[2]), w));
                 }
               }
             }
           }
-          acc_r = __fadd_rn(acc_r, vr);
-          acc_g = __fadd_rn(acc_g, vg);
-          acc_b = __fadd_rn(acc_b, vb);
-        }
-        if (S > 1) {
-          acc_r = __fdiv_rn(acc_r, fS);
-          acc_g = __fdiv_rn(acc_g, fS);
-          acc_b = __fdiv_rn(acc_b, fS);
-        }
-        // padding mask: 1 - (coverage > .5) for one sample, 1 - count/S for blur; <1e-3 -> 0
-        float mval;
-        if (S == 1) {
-          mval = cover ? 0.0f : 1.0f;
-        } else {
-          mval = __fsub_rn(1.0f, __fdiv_rn((float)cover, fS));
-          if (mval < 1e-3f) mval = 0.0f;
-        }
-        if (mval > 1e-3f) ++padded;
-        if (p.mask) p.mask[((size_t)frame_idx * p.oh + oy) * p.ow + ox] = mval;
-        if (!p.vec_store) {
-          float* d = p.dst + (((size_t)frame_idx * p.oh + oy) * p.ow + ox) * 3;
-          d[0] = acc_r;
-          d[1] = acc_g;
-          d[2] = acc_b;
         }
       }
-      if (p.vec_store) {
-        float* sc = scratch + rr * (TW * 3) + (lane + cc * 32) * 3;
-        sc[0] = acc_r;
-        sc[1] = acc_g;
-        sc[2] = acc_b;
+      if (S == 1) {  // _warp_with_matrices copies the warp; only the blur path accumulates from zero
+        acc[q][0] = vr;
+        acc[q][1] = vg;
+        acc[q][2] = vb;
+      } else {
+        acc[q][0] = __fadd_rn(acc[q][0], vr);
+        acc[q][1] = __fadd_rn(acc[q][1], vg);
+        acc[q][2] = __fadd_rn(acc[q][2], vb);
       }
+    }
+  }
+
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int rr = q >> 1, cc = q & 1;
+    const int oy = ty0 + warp + rr * NWARPS, ox = tx0 + lane + cc * 32;
+    if (oy < p.oh && ox < p.ow) {
+      if (S > 1) {
+        acc[q][0] = __fdiv_rn(acc[q][0], fS);
+        acc[q][1] = __fdiv_rn(acc[q][1], fS);
+        acc[q][2] = __fdiv_rn(acc[q][2], fS);
+      }
+      // padding mask: 1 - (coverage > .5) for one sample, 1 - count/S for blur; <1e-3 -> 0
+      float mval;
+      if (S == 1) {
+        mval = cover[q] ? 0.0f : 1.0f;
+      } else {
+        mval = __fsub_rn(1.0f, __fdiv_rn((float)cover[q], fS));
+        if (mval < 1e-3f) mval = 0.0f;
+      }
+      if (mval > 1e-3f) ++padded;
+      if (p.mask) p.mask[((size_t)frame_idx * p.oh + oy) * p.ow + ox] = mval;
+      if (!p.vec_store) {
+        float* d = p.dst + (((size_t)frame_idx * p.oh + oy) * p.ow + ox) * 3;
+        d[0] = acc[q][0];
+        d[1] = acc[q][1];
+        d[2] = acc[q][2];
+      }
+    }
+    if (p.vec_store) {
+      float* sc = scratch + rr * (TW * 3) + (lane + cc * 32) * 3;
+      sc[0] = acc[q][0];
+      sc[1] = acc[q][1];
+      sc[2] = acc[q][2];
     }
   }
 
@@ -471,11 +621,12 @@ extern "C" int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, in
   p.stage_mode = stage_mode;
   p.vec_store = (out_w % 4 == 0) && (((uintptr_t)dst_dev & 15) == 0);
   p.vec_load = (src_w % 4 == 0) && (((uintptr_t)src_dev & 15) == 0);
+  p.vec_mask = (out_w % 4 == 0) && (((uintptr_t)mask_dev & 15) == 0);
   p.border[0] = border_host[0];
   p.border[1] = border_host[1];
   p.border[2] = border_host[2];
 
-  const size_t fixed = sizeof(double) * MINV_SLOTS * 9 + sizeof(float) * NWARPS * SCRATCH_FLOATS_PER_WARP + sizeof(int) * 8;
+  const size_t fixed = sizeof(double) * MINV_SLOTS * 9 + sizeof(float) * NWARPS * SCRATCH_FLOATS_PER_WARP + sizeof(int) * 8 + sizeof(float) * 128;
   // Staged source box: (TW + margin) x (TH + margin) pixels for near-identity maps; blur and
   // bicubic get a larger box.  Degenerate footprints gather from global memory instead.
   int box_w = TW + 8, box_h = TH + 8;
