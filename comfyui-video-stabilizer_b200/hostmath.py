@@ -54,6 +54,16 @@ def rescale_transform_to_full(matrix, source_size, working_size) -> np.ndarray:
     return (up @ np.asarray(matrix).astype(np.float64) @ down).astype(np.float32)
 
 
+def rescale_transforms_to_full(matrices: np.ndarray, source_size, working_size) -> np.ndarray:
+    """Stacked variant of rescale_transform_to_full ([P,3,3] float32 in, float32 out).  The two
+    diagonal products have a single non-zero term per element, so this is bit-identical."""
+    kx = working_size[0] / float(source_size[0])
+    ky = working_size[1] / float(source_size[1])
+    down = np.diag([kx, ky, 1.0]).astype(np.float64)
+    up = np.diag([1.0 / kx, 1.0 / ky, 1.0]).astype(np.float64)
+    return (up @ np.asarray(matrices).astype(np.float64) @ down).astype(np.float32)
+
+
 def matrix_to_params(matrix, base_mode: str) -> np.ndarray:
     m = matrix
     if base_mode == "translation":
@@ -107,13 +117,22 @@ def compute_bounding_boxes(matrices: Sequence[np.ndarray], width: int, height: i
         [[0.0, float(width), 0.0, float(width)], [0.0, 0.0, float(height), float(height)], [1.0, 1.0, 1.0, 1.0]],
         dtype=np.float64,
     )
-    lo, hi = [], []
-    for m in matrices:
-        q = m @ corners
-        q /= q[2, :]
-        lo.append([q[0].min(), q[1].min()])
-        hi.append([q[0].max(), q[1].max()])
-    return np.array(lo), np.array(hi)
+    # one 3x3 @ 3x4 product per matrix, evaluated term by term in the order of a dot product so the
+    # stacked form returns the same bits as the reference's per-matrix `matrix @ corners`
+    if any(np.asarray(x).dtype != np.float32 for x in matrices):
+        # float64 @ float64 goes through BLAS (fused multiply-adds): keep the per-matrix product
+        lo, hi = [], []
+        for mat in matrices:
+            q = mat @ corners
+            q /= q[2, :]
+            lo.append([q[0].min(), q[1].min()])
+            hi.append([q[0].max(), q[1].max()])
+        return np.array(lo), np.array(hi)
+    # float32 @ float64 promotes the float32 operand and multiplies without FMA (verified bit-equal)
+    m = np.stack([np.asarray(x) for x in matrices], axis=0).astype(np.float64)
+    q = m[:, :, 0:1] * corners[0][None, None, :] + m[:, :, 1:2] * corners[1][None, None, :] + m[:, :, 2:3] * corners[2][None, None, :]
+    q = q / q[:, 2:3, :]
+    return np.stack([q[:, 0].min(axis=1), q[:, 1].min(axis=1)], axis=1), np.stack([q[:, 0].max(axis=1), q[:, 1].max(axis=1)], axis=1)
 
 
 def min_content_ratio(mins, maxs, width: int, height: int) -> float:

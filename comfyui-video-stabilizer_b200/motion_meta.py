@@ -63,6 +63,21 @@ def _matrix_entry(owner: str, entry: Any, position: int, key: str) -> np.ndarray
     return m
 
 
+def _matrix_entries(owner: str, entries: list, key: str) -> List[np.ndarray]:
+    """All per_frame matrices, validated.  Vectorised happy path (one stacked isfinite + inv);
+    any irregularity re-runs the per-entry checks so the first offending entry is reported with
+    exactly the reference's message."""
+    try:
+        if all(isinstance(e, dict) and e.get("index") == i and key in e for i, e in enumerate(entries)):
+            stack = np.asarray([e[key] for e in entries], dtype=np.float64)
+            if stack.shape == (len(entries), 3, 3) and np.isfinite(stack).all():
+                np.linalg.inv(stack)
+                return list(stack)
+    except (ValueError, TypeError, np.linalg.LinAlgError):
+        pass
+    return [_matrix_entry(owner, e, i, key) for i, e in enumerate(entries)]
+
+
 def validate_motion_meta(block: Dict[str, Any]) -> None:
     if not isinstance(block, dict):
         raise ValueError("motion_meta must be an object.")
@@ -96,8 +111,7 @@ def validate_motion_meta(block: Dict[str, Any]) -> None:
         raise ValueError(
             "motion_meta.frame_count mismatch: " f"frame_count is {count}, per_frame has {len(entries)} entry/entries."
         )
-    for i, entry in enumerate(entries):
-        _matrix_entry("motion_meta", entry, i, "matrix")
+    _matrix_entries("motion_meta", entries, "matrix")
     if source == "generated_shake" and not isinstance(block.get("generator"), dict):
         raise ValueError("motion_meta.generator is required when source is 'generated_shake'.")
 
@@ -181,7 +195,7 @@ def motion_meta_from_stabilization_warp(warp_meta, fps: float, source: str):
 def applied_motion_meta_from_stabilization_warp(warp_meta, fps: float, source: str):
     """Forward (source -> stabilized) motion block: the matrices exactly as applied."""
     src, out, entries = _warp_header(warp_meta)
-    applied = [_matrix_entry("stabilization_warp", e, i, "applied_matrix") for i, e in enumerate(entries)]
+    applied = _matrix_entries("stabilization_warp", entries, "applied_matrix")
     return build_motion_meta_v2(
         source=source, frame_count=len(applied), fps=fps, input_size=src, output_size=out, matrices=applied
     )

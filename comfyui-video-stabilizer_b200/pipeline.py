@@ -248,6 +248,23 @@ def convert_masks_for_output(masks: Any) -> torch.Tensor:
     return masks.contiguous()
 
 
+_POOL: Dict[Any, torch.Tensor] = {}
+
+
+def _pooled(shape, device, tag: str) -> torch.Tensor:
+    """Device-resident result buffers are reused from call to call (output="device" hands out views
+    of them: consume a result before asking for the next one).  Avoids re-allocating gigabytes per
+    clip; host results always get fresh pinned tensors."""
+    key = (tag, tuple(shape), str(device))
+    buf = _POOL.get(key)
+    if buf is None:
+        for k in [k for k in _POOL if k[0] == tag and k[2] == str(device)]:
+            del _POOL[k]
+        buf = torch.empty(shape, dtype=torch.float32, device=device)
+        _POOL[key] = buf
+    return buf
+
+
 def fused_warp(
     context: VideoContext,
     fwd: np.ndarray,
@@ -259,8 +276,14 @@ def fused_warp(
     want_pad_count: bool = False,
     mask_rule: int = _native.MASK_RULE_P,
     output: Literal["host", "device"] = "host",
+    defer: bool = False,
 ):
     """Run the fused resampler over the whole clip.
+
+    With defer=True everything is enqueued and a callable is returned; calling it waits for the
+    GPU and yields (frames, masks, pad_counts).  The caller can build its host-side results while
+    the kernels and copies are in flight.
+
 
     fwd: [N,S,9] float32 forward matrices (host).  Returns (frames, masks, pad_counts) where
     frames is [N,H',W',3] and masks [N,H',W'] (None when want_mask is False).  With
@@ -275,11 +298,17 @@ def fused_warp(
     if fwd_t.dim() == 2:
         fwd_t = fwd_t.view(n, 1, 9)
     if output == "device":
+        dst_buf = _pooled((n, oh, ow, 3), dev, "warp_dst")
+        mask_buf = _pooled((n, oh, ow), dev, "warp_mask") if want_mask else None
         dst, mask, pad = _timed_warp(
             h, context.frames, fwd_t, (ow, oh), interpolation, border,
-            mask_rule=mask_rule, want_mask=want_mask, want_pad_count=want_pad_count,
+            mask_rule=mask_rule, want_mask=want_mask, want_pad_count=want_pad_count, out=dst_buf, mask_out=mask_buf,
         )
-        return dst, mask, (pad.cpu().numpy().astype(np.int64) if pad is not None else None)
+
+        def finish_device():
+            return dst, mask, (pad.cpu().numpy().astype(np.int64) if pad is not None else None)
+
+        return finish_device if defer else finish_device()
 
     frames_cpu = torch.empty((n, oh, ow, 3), dtype=torch.float32, pin_memory=True)
     masks_cpu = torch.empty((n, oh, ow), dtype=torch.float32, pin_memory=True) if want_mask else None
@@ -317,7 +346,10 @@ def fused_warp(
             ev = torch.cuda.Event()
             ev.record(copy_stream)
             copied[k % len(bufs)] = ev
-    copy_stream.synchronize()
-    main.synchronize()
-    pad_np = torch.cat(pads).cpu().numpy().astype(np.int64) if pads else None
-    return frames_cpu, masks_cpu, pad_np
+    def finish_host():
+        copy_stream.synchronize()
+        main.synchronize()
+        pad_np = torch.cat(pads).cpu().numpy().astype(np.int64) if pads else None
+        return frames_cpu, masks_cpu, pad_np
+
+    return finish_host if defer else finish_host()

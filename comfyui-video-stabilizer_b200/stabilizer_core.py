@@ -206,13 +206,11 @@ def stabilize_frames(
     check()
 
     base_mode = transform_mode
-    matrices: List[np.ndarray] = []
-    delta_params: List[np.ndarray] = []
-    for matrix, _, _, _ in chosen:
-        if work is not None:
-            matrix = hm.rescale_transform_to_full(matrix, (width, height), work)
-        matrices.append(matrix)
-        delta_params.append(hm.matrix_to_params(matrix, base_mode))
+    stacked = np.stack([c[0] for c in chosen], axis=0)
+    if work is not None:
+        stacked = hm.rescale_transforms_to_full(stacked, (width, height), work)
+    matrices: List[np.ndarray] = [stacked[i] for i in range(stacked.shape[0])]
+    delta_params: List[np.ndarray] = [hm.matrix_to_params(m, base_mode) for m in matrices]
 
     path = np.zeros((total_frames, delta_params[0].shape[0]), dtype=np.float64)
     for i, delta in enumerate(delta_params, start=1):
@@ -295,18 +293,12 @@ def stabilize_frames(
     # ---- warp + mask: one fused launch per chunk -------------------------------------------------
     lo, hi = (0, total_frames) if shard is None else shard.frame_range
     fwd = np.stack([np.asarray(m, dtype=np.float32).reshape(9) for m in final_matrices[lo:hi]], axis=0)[:, None, :]
-    frames_out, masks_out, pad_counts = fused_warp(
+    pending = fused_warp(
         context if shard is None else shard.owned_context(context), fwd, output_size, "bilinear",
-        hm.border_value(padding_rgb), want_mask=True, want_pad_count=True, output=output,
+        hm.border_value(padding_rgb), want_mask=True, want_pad_count=True, output=output, defer=True,
     )
-    if shard is not None:
-        pad_counts = shard.gather_pad_counts(pad_counts)
-    pixels = int(output_size[0]) * int(output_size[1])
-    padded_ratios = [hm.padded_fraction(int(c), pixels) for c in pad_counts]
-    framing_meta["padding_detected"] = bool(np.any(np.asarray(pad_counts) > 0))
-    progress.advance(total_frames)
-    check()
 
+    # the kernels above are in flight: build the meta tree on the host meanwhile
     per_transition = []
     for i, (_, mode, conf, resid) in enumerate(chosen):
         entry = {"index": i, "mode": mode, "confidence": conf}
@@ -314,6 +306,25 @@ def stabilize_frames(
             entry["residual"] = resid
         entry["matrix"] = matrices[i].astype(np.float32).tolist()
         per_transition.append(entry)
+
+    warp_meta = hm.build_stabilization_warp_meta(
+        source_size=(width, height), output_size=output_size, framing_mode=framing_mode, applied_matrices=final_matrices,
+    )
+    motion_block = None
+    try:
+        motion_block = applied_motion_meta_from_stabilization_warp(warp_meta, fps=fps_effective, source=source_tag)
+    except (KeyError, TypeError, ValueError, np.linalg.LinAlgError):
+        pass
+    path_list, target_list, effective_list = path.tolist(), target_path.tolist(), effective_target_path.tolist()
+
+    frames_out, masks_out, pad_counts = pending()
+    if shard is not None:
+        pad_counts = shard.gather_pad_counts(pad_counts)
+    pixels = int(output_size[0]) * int(output_size[1])
+    padded_ratios = [hm.padded_fraction(int(c), pixels) for c in pad_counts]
+    framing_meta["padding_detected"] = bool(np.any(np.asarray(pad_counts) > 0))
+    progress.advance(total_frames)
+    check()
 
     meta = {
         "frames": total_frames,
@@ -329,19 +340,18 @@ def stabilize_frames(
         "keep_fov_applied": keep_fov_applied,
         "padding_color_rgb": [int(c) for c in padding_rgb],
         **flow_keys,
-        "stabilization_warp": hm.build_stabilization_warp_meta(
-            source_size=(width, height), output_size=output_size, framing_mode=framing_mode,
-            applied_matrices=final_matrices,
-        ),
+        "stabilization_warp": warp_meta,
         "estimated_motion": {
             "per_transition": per_transition,
-            "path": path.tolist(),
-            "target_path": target_path.tolist(),
-            "target_path_effective": effective_target_path.tolist(),
+            "path": path_list,
+            "target_path": target_list,
+            "target_path_effective": effective_list,
         },
         "padding_fraction_mean": float(np.mean(padded_ratios)),
         "padding_fraction_max": float(np.max(padded_ratios)),
     }
+    if motion_block is not None:
+        meta["motion_meta"] = motion_block
     if output == "host":
-        return StabilizationResult(frames_out.numpy(), masks_out.numpy()[..., None], attach(meta))
-    return StabilizationResult(frames_out, masks_out[..., None], attach(meta))
+        return StabilizationResult(frames_out.numpy(), masks_out.numpy()[..., None], meta)
+    return StabilizationResult(frames_out, masks_out[..., None], meta)
