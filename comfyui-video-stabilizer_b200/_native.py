@@ -79,6 +79,9 @@ def load_library() -> C.CDLL:
         if hasattr(lib, "vstab_dis_flow"):
             lib.vstab_dis_flow.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp]
             lib.vstab_dis_flow.restype = i32
+        if hasattr(lib, "vstab_gftt_lk"):
+            lib.vstab_gftt_lk.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+            lib.vstab_gftt_lk.restype = i32
         if hasattr(lib, "vstab_fit_batch"):
             lib.vstab_fit_batch.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
             lib.vstab_fit_batch.restype = i32
@@ -231,6 +234,21 @@ class Handle:
             grid = torch.empty((npairs, gh, gw, 2), dtype=torch.float32, device=gray.device)
         self._check(self.lib.vstab_dis_flow(self._h, gray.data_ptr(), n, h, w, _ptr(flow), _ptr(grid), int(max(grid_step, 0)), _stream_ptr(gray.device)))
         return flow, grid
+
+    # -- K5 + K6 ---------------------------------------------------------------------------------
+    def gftt_lk(self, gray: torch.Tensor, max_corners: int = 400):
+        """gray [N,h,w] u8 -> (prev [N-1,K,2], curr [N-1,K,2] with NaN rows for missing / lost, detected [N-1] int32)."""
+        _check_cuda(gray, torch.uint8, "gray")
+        if not hasattr(self.lib, "vstab_gftt_lk"):
+            raise VstabNativeError("libvstab.so was built without vstab_gftt_lk")
+        n, h, w = gray.shape
+        p = max(n - 1, 0)
+        prev = torch.empty((p, max_corners, 2), dtype=torch.float32, device=gray.device)
+        curr = torch.empty((p, max_corners, 2), dtype=torch.float32, device=gray.device)
+        det = torch.zeros((p,), dtype=torch.int32, device=gray.device)
+        self._check(self.lib.vstab_gftt_lk(self._h, gray.data_ptr(), n, h, w, int(max_corners), prev.data_ptr(), curr.data_ptr(),
+                                           det.data_ptr(), _stream_ptr(gray.device)))
+        return prev, curr, det
 
     # -- K4 + K7..K9 -----------------------------------------------------------------------------
     def fit_grid(self, grid_flow: torch.Tensor, grid_step: int, mode_mask: int = 7) -> torch.Tensor:

@@ -1,0 +1,465 @@
+// classic.cu -- K5 + K6: Shi-Tomasi corners and pyramidal Lucas-Kanade, batched over a clip.
+//
+// Replaces nodes/video_stabilizer_classic.py:76-83 (cv2.goodFeaturesToTrack: 400 corners, quality
+// 0.01, minDistance 7, blockSize 21) and :88-100 (cv2.calcOpticalFlowPyrLK: 31x31 window, 3 pyramid
+// levels, 50 iterations / eps 0.01, status filter) for every pair (i, i+1) of the clip.
+//
+// GFTT arithmetic follows cv2 4.13 bit for bit (see oracle/classic_ref.c): fused Sobel forms,
+// unnormalised 21x21 box filter with DOUBLE running sums (one thread per row, then one per
+// column -- the running sums are sequential by construction, the parallelism is rows x frames),
+// min-eigenvalue, threshold at 0.01 * max, 3x3 local maxima, 64-bit (value, address) keys sorted by
+// a per-frame bitonic network, and the greedy minimum-distance pass as one warp per frame (the 9
+// neighbour cells of the 7-px grid are probed by 9 lanes).  LK is one warp per (pair, feature):
+// fixed-point bilinear windows exactly like OpenCV (14-bit weights, x32 intensities), 2x2 normal
+// equations reduced with warp shuffles.  Compiled with -fmad=false; fmaf() only where cv2 fuses.
+#include "common.cuh"
+
+#include <float.h>
+#include <math.h>
+
+namespace {
+
+constexpr int kBlock = 21;
+constexpr int kRadius = kBlock / 2;
+constexpr int kWin = 31;
+constexpr int kMaxLevel = 3;
+constexpr int kMaxIter = 50;
+constexpr int kCellCap = 4;
+constexpr int kCell = 7;
+constexpr float kMinDist2 = 49.0f;
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+  return p;
+}
+
+// ---- GFTT ---------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) gftt_cov_kernel(const unsigned char* __restrict__ gray, int h, int w, float s, float s2,
+                                                       float* __restrict__ cov /* [F][h][w][3] */) {
+  const int f = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const unsigned char* img = gray + (size_t)f * h * w;
+  const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+  const int ym = reflect101(y - 1, h), yp = reflect101(y + 1, h);
+  auto smooth_row = [&](int yy) {  // row filter [s 2s s], fused chain like cv2's AVX2 row filter
+    const float a = img[yy * w + xm], b = img[yy * w + x], c = img[yy * w + xp];
+    return fmaf(s, c, fmaf(s2, b, s * a));
+  };
+  auto diff_row = [&](int yy) { return (float)((int)img[yy * w + xp] - (int)img[yy * w + xm]); };
+  const float dy = smooth_row(yp) - smooth_row(ym);
+  const float dx = fmaf(diff_row(ym) + diff_row(yp), s, diff_row(y) * s2);
+  float* o = cov + (((size_t)f * h + y) * w + x) * 3;
+  o[0] = dx * dx;
+  o[1] = dx * dy;
+  o[2] = dy * dy;
+}
+
+// horizontal running sums in double: one thread per (frame, row)
+__global__ void gftt_box_rows_kernel(const float* __restrict__ cov, int F, int h, int w, double* __restrict__ rows /* [F][h][w][3] */) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= F * h) return;
+  const float* c = cov + (size_t)idx * w * 3;
+  double* o = rows + (size_t)idx * w * 3;
+  double a0 = 0, a1 = 0, a2 = 0;
+  for (int i = 0; i < kBlock; i++) {
+    const int x = reflect101(i - kRadius, w);
+    a0 += (double)c[x * 3];
+    a1 += (double)c[x * 3 + 1];
+    a2 += (double)c[x * 3 + 2];
+  }
+  o[0] = a0; o[1] = a1; o[2] = a2;
+  for (int x = 1; x < w; x++) {
+    const int xn = reflect101(x + kBlock - 1 - kRadius, w), xo = reflect101(x - 1 - kRadius, w);
+    a0 += (double)c[xn * 3] - (double)c[xo * 3];
+    a1 += (double)c[xn * 3 + 1] - (double)c[xo * 3 + 1];
+    a2 += (double)c[xn * 3 + 2] - (double)c[xo * 3 + 2];
+    o[x * 3] = a0; o[x * 3 + 1] = a1; o[x * 3 + 2] = a2;
+  }
+}
+
+// vertical running sums in double + minimum eigenvalue: one thread per (frame, column)
+__global__ void gftt_box_cols_kernel(const double* __restrict__ rows, int F, int h, int w, float* __restrict__ eig,
+                                     unsigned int* __restrict__ max_bits /* [F], float bits of the max (eig > 0) */) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= F * w) return;
+  const int f = idx / w, x = idx - f * w;
+  const double* R = rows + (size_t)f * h * w * 3 + (size_t)x * 3;
+  const size_t rs = (size_t)w * 3;
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int i = 0; i < kBlock - 1; i++) {
+    const int y = reflect101(i - kRadius, h);
+    s0 += R[y * rs]; s1 += R[y * rs + 1]; s2 += R[y * rs + 2];
+  }
+  float best = 0.f;
+  for (int y = 0; y < h; y++) {
+    const int yn = reflect101(y + kBlock - 1 - kRadius, h), yo = reflect101(y - kRadius, h);
+    const double t0 = s0 + R[yn * rs], t1 = s1 + R[yn * rs + 1], t2 = s2 + R[yn * rs + 2];
+    const float a = (float)t0 * 0.5f, b = (float)t1, c = (float)t2 * 0.5f;
+    const float e = (a + c) - sqrtf((a - c) * (a - c) + b * b);
+    eig[((size_t)f * h + y) * w + x] = e;
+    best = fmaxf(best, e);
+    s0 = t0 - R[yo * rs]; s1 = t1 - R[yo * rs + 1]; s2 = t2 - R[yo * rs + 2];
+  }
+  atomicMax(max_bits + f, __float_as_uint(best));  // non-negative floats order like their bit patterns
+}
+
+// thresholded 3x3 local maxima -> 64-bit keys (value bits << 32 | pixel index), appended per frame
+__global__ void __launch_bounds__(256) gftt_candidates_kernel(const float* __restrict__ eig, int h, int w,
+                                                              const unsigned int* __restrict__ max_bits, double quality,
+                                                              unsigned long long* __restrict__ keys, int cap,
+                                                              int* __restrict__ counts) {
+  const int f = blockIdx.z;
+  const int x = 1 + blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = 1 + blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w - 1 || y >= h - 1) return;
+  const float* e = eig + (size_t)f * h * w;
+  const float thr = (float)((double)__uint_as_float(max_bits[f]) * quality);
+  const float v = e[y * w + x];
+  if (!(v > thr)) return;
+  float m = v;
+#pragma unroll
+  for (int j = -1; j <= 1; j++)
+#pragma unroll
+    for (int i = -1; i <= 1; i++) m = fmaxf(m, e[(y + j) * w + x + i]);
+  if (v != m) return;
+  const int slot = atomicAdd(counts + f, 1);
+  if (slot < cap) keys[(size_t)f * cap + slot] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
+}
+
+// descending bitonic sort of each frame's keys in global memory (one CTA per frame)
+__global__ void __launch_bounds__(1024) gftt_sort_kernel(unsigned long long* __restrict__ keys, int cap, const int* __restrict__ counts) {
+  const int f = blockIdx.x;
+  unsigned long long* k = keys + (size_t)f * cap;
+  const int n = min(counts[f], cap);
+  int m = 1;
+  while (m < n) m <<= 1;
+  for (int i = n + threadIdx.x; i < m; i += blockDim.x) k[i] = 0ull;  // pads sort to the end
+  __syncthreads();
+  for (int size = 2; size <= m; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const unsigned long long a = k[i], b = k[j];
+          const bool desc = (i & size) == 0;
+          if ((a < b) == desc) { k[i] = b; k[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// greedy minimum-distance selection: one warp per frame, 9 lanes probe the 3x3 neighbour cells
+__global__ void gftt_select_kernel(const unsigned long long* __restrict__ keys, int cap, const int* __restrict__ counts, int h, int w,
+                                   int max_corners, short* __restrict__ cells /* [F][gh*gw][kCellCap][2] */,
+                                   unsigned char* __restrict__ cell_cnt /* [F][gh*gw], zeroed */, float* __restrict__ feats /* [F][max][2] */,
+                                   int* __restrict__ n_feats) {
+  const int f = blockIdx.x;
+  const int lane = threadIdx.x;
+  const int gw = (w + kCell - 1) / kCell, gh = (h + kCell - 1) / kCell;
+  short* cl = cells + (size_t)f * gw * gh * kCellCap * 2;
+  unsigned char* cc = cell_cnt + (size_t)f * gw * gh;
+  const unsigned long long* k = keys + (size_t)f * cap;
+  const int n = min(counts[f], cap);
+  int accepted = 0;
+  for (int i = 0; i < n && accepted < max_corners; i++) {
+    const int idx = (int)(k[i] & 0xffffffffu);
+    const int y = idx / w, x = idx - y * w;
+    const int xc = x / kCell, yc = y / kCell;
+    bool bad = false;
+    if (lane < 9) {
+      const int cx = xc + lane % 3 - 1, cy = yc + lane / 3 - 1;
+      if (cx >= 0 && cy >= 0 && cx < gw && cy < gh) {
+        const int c = cy * gw + cx;
+        const int cn = cc[c];
+        for (int j = 0; j < cn; j++) {
+          const float dx = (float)(x - cl[(c * kCellCap + j) * 2]), dy = (float)(y - cl[(c * kCellCap + j) * 2 + 1]);
+          if (dx * dx + dy * dy < kMinDist2) bad = true;
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, bad)) continue;
+    if (lane == 0) {
+      const int c = yc * gw + xc;
+      const int cn = cc[c];
+      if (cn < kCellCap) {
+        cl[(c * kCellCap + cn) * 2] = (short)x;
+        cl[(c * kCellCap + cn) * 2 + 1] = (short)y;
+        cc[c] = (unsigned char)(cn + 1);
+      }
+      feats[((size_t)f * max_corners + accepted) * 2] = (float)x;
+      feats[((size_t)f * max_corners + accepted) * 2 + 1] = (float)y;
+    }
+    accepted++;
+    __syncwarp();
+  }
+  if (lane == 0) n_feats[f] = accepted;
+}
+
+// ---- pyramidal Lucas-Kanade ---------------------------------------------------------------------
+
+// cv::pyrDown for 8-bit images: [1 4 6 4 1] x [1 4 6 4 1], (sum + 128) >> 8, reflect-101
+__global__ void __launch_bounds__(256) pyr_down_kernel(const unsigned char* __restrict__ src, int sh, int sw,
+                                                       unsigned char* __restrict__ dst, int dh, int dw) {
+  const int f = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= dw || y >= dh) return;
+  const unsigned char* s = src + (size_t)f * sh * sw;
+  int cx[5], cy[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) { cx[k] = reflect101(2 * x + k - 2, sw); cy[k] = reflect101(2 * y + k - 2, sh); }
+  const int wk[5] = {1, 4, 6, 4, 1};
+  int sum = 0;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const unsigned char* r = s + (size_t)cy[j] * sw;
+    const int row = r[cx[0]] + 4 * r[cx[1]] + 6 * r[cx[2]] + 4 * r[cx[3]] + r[cx[4]];
+    sum += wk[j] * row;
+  }
+  dst[((size_t)f * dh + y) * dw + x] = (unsigned char)((sum + 128) >> 8);
+}
+
+// Scharr derivatives (dx, dy) interleaved int16, reflect-101 inside the image
+__global__ void __launch_bounds__(256) scharr_kernel(const unsigned char* __restrict__ img, int h, int w, short2* __restrict__ d) {
+  const int f = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const unsigned char* I = img + (size_t)f * h * w;
+  const unsigned char* r0 = I + (size_t)reflect101(y - 1, h) * w;
+  const unsigned char* r1 = I + (size_t)y * w;
+  const unsigned char* r2 = I + (size_t)reflect101(y + 1, h) * w;
+  const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+  const int t0p = (r0[xp] + r2[xp]) * 3 + r1[xp] * 10, t0m = (r0[xm] + r2[xm]) * 3 + r1[xm] * 10;
+  const int t1m = r2[xm] - r0[xm], t1c = r2[x] - r0[x], t1p = r2[xp] - r0[xp];
+  d[((size_t)f * h + y) * w + x] = make_short2((short)(t0p - t0m), (short)((t1p + t1m) * 3 + t1c * 10));
+}
+
+struct LkLevel {
+  const unsigned char* img;  // [F][h][w]
+  const short2* deriv;       // [F][h][w]
+  int h, w;
+};
+struct LkPyr {
+  LkLevel lv[kMaxLevel + 1];
+  int levels;  // highest level index
+};
+
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per (pair, feature).  8 warps per CTA share nothing but the launch.
+__global__ void __launch_bounds__(256) lk_track_kernel(LkPyr P, int n_pairs, int max_corners, const float* __restrict__ feats,
+                                                       const int* __restrict__ n_feats, float* __restrict__ prev_out,
+                                                       float* __restrict__ curr_out) {
+  extern __shared__ short s_win[];  // [8 warps][961][3]: I, Ix, Iy of the template window
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = blockIdx.x * 8 + warp;
+  if (gid >= n_pairs * max_corners) return;
+  const int pair = gid / max_corners, fi = gid - pair * max_corners;
+  const float qnan = __int_as_float(0x7fc00000);
+  float* po = prev_out + (size_t)gid * 2;
+  float* co = curr_out + (size_t)gid * 2;
+  if (fi >= n_feats[pair]) {
+    if (lane == 0) { po[0] = qnan; po[1] = qnan; co[0] = qnan; co[1] = qnan; }
+    return;
+  }
+  const float fx = feats[((size_t)pair * max_corners + fi) * 2], fy = feats[((size_t)pair * max_corners + fi) * 2 + 1];
+  short* win = s_win + warp * (kWin * kWin * 3);
+  const float half = (kWin - 1) * 0.5f;
+  const float FLT_SCALE = 1.f / (1 << 20);
+  const int W_BITS = 14;
+  bool status = true;
+  float nx = 0.f, ny = 0.f;
+  for (int level = P.levels; level >= 0; level--) {
+    const LkLevel L = P.lv[level];
+    const unsigned char* I = L.img + (size_t)pair * L.h * L.w;
+    const unsigned char* J = L.img + (size_t)(pair + 1) * L.h * L.w;
+    const short2* D = L.deriv + (size_t)pair * L.h * L.w;
+    const int lh = L.h, lw = L.w;
+    float px = fx * (float)(1. / (1 << level)), py = fy * (float)(1. / (1 << level));
+    if (level == P.levels) { nx = px; ny = py; } else { nx = nx * 2.f; ny = ny * 2.f; }
+    px -= half; py -= half;
+    const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+    if (ipx < -kWin || ipx >= lw || ipy < -kWin || ipy >= lh) { if (level == 0) status = false; continue; }
+    float a = px - ipx, b = py - ipy;
+    int iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS)), iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
+    int iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS)), iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+    float A11 = 0, A12 = 0, A22 = 0;
+    __syncwarp();
+    for (int k = lane; k < kWin * kWin; k += 32) {
+      const int y = k / kWin, x = k - y * kWin;
+      const int sy = ipy + y, sx = ipx + x;
+      const int y0 = reflect101(sy, lh), y1 = reflect101(sy + 1, lh), x0 = reflect101(sx, lw), x1 = reflect101(sx + 1, lw);
+      const int ival = descale(I[y0 * lw + x0] * iw00 + I[y0 * lw + x1] * iw01 + I[y1 * lw + x0] * iw10 + I[y1 * lw + x1] * iw11, W_BITS - 5);
+      const bool in00 = sx >= 0 && sy >= 0 && sx < lw && sy < lh, in01 = sx + 1 >= 0 && sy >= 0 && sx + 1 < lw && sy < lh;
+      const bool in10 = sx >= 0 && sy + 1 >= 0 && sx < lw && sy + 1 < lh, in11 = sx + 1 >= 0 && sy + 1 >= 0 && sx + 1 < lw && sy + 1 < lh;
+      const short2 zero = make_short2(0, 0);
+      const short2 d00 = in00 ? D[sy * lw + sx] : zero, d01 = in01 ? D[sy * lw + sx + 1] : zero;
+      const short2 d10 = in10 ? D[(sy + 1) * lw + sx] : zero, d11 = in11 ? D[(sy + 1) * lw + sx + 1] : zero;
+      const int ixval = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, W_BITS);
+      const int iyval = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, W_BITS);
+      win[k * 3] = (short)ival; win[k * 3 + 1] = (short)ixval; win[k * 3 + 2] = (short)iyval;
+      A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval);
+    }
+    A11 = warp_sum(A11) * FLT_SCALE; A12 = warp_sum(A12) * FLT_SCALE; A22 = warp_sum(A22) * FLT_SCALE;
+    __syncwarp();
+    float Dd = A11 * A22 - A12 * A12;
+    const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (2 * kWin * kWin);
+    if (minEig < 1e-4f || Dd < FLT_EPSILON) { if (level == 0) status = false; continue; }
+    Dd = 1.f / Dd;
+    float wx = nx - half, wy = ny - half;
+    float pdx = 0, pdy = 0;
+    for (int j = 0; j < kMaxIter; j++) {
+      const int inx = (int)floorf(wx), iny = (int)floorf(wy);
+      if (inx < -kWin || inx >= lw || iny < -kWin || iny >= lh) { if (level == 0) status = false; break; }
+      a = wx - inx; b = wy - iny;
+      iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS)); iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
+      iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS)); iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+      float b1 = 0, b2 = 0;
+      for (int k = lane; k < kWin * kWin; k += 32) {
+        const int y = k / kWin, x = k - y * kWin;
+        const int y0 = reflect101(iny + y, lh), y1 = reflect101(iny + y + 1, lh), x0 = reflect101(inx + x, lw), x1 = reflect101(inx + x + 1, lw);
+        const int diff = descale(J[y0 * lw + x0] * iw00 + J[y0 * lw + x1] * iw01 + J[y1 * lw + x0] * iw10 + J[y1 * lw + x1] * iw11, W_BITS - 5) - win[k * 3];
+        b1 += (float)(diff * win[k * 3 + 1]);
+        b2 += (float)(diff * win[k * 3 + 2]);
+      }
+      b1 = warp_sum(b1) * FLT_SCALE; b2 = warp_sum(b2) * FLT_SCALE;
+      const float ddx = (A12 * b2 - A22 * b1) * Dd, ddy = (A12 * b1 - A11 * b2) * Dd;
+      wx += ddx; wy += ddy;
+      nx = wx + half; ny = wy + half;
+      if ((double)ddx * ddx + (double)ddy * ddy <= 1e-4) break;
+      if (j > 0 && fabsf(ddx + pdx) < 0.01f && fabsf(ddy + pdy) < 0.01f) {
+        nx -= ddx * 0.5f; ny -= ddy * 0.5f;
+        break;
+      }
+      pdx = ddx; pdy = ddy;
+    }
+    if (status && level == 0) {
+      const int ix = (int)floorf(nx - half), iy = (int)floorf(ny - half);
+      if (ix < -kWin || ix >= lw || iy < -kWin || iy >= lh) status = false;
+    }
+  }
+  if (lane == 0) {
+    po[0] = fx; po[1] = fy;
+    co[0] = status ? nx : qnan;
+    co[1] = status ? ny : qnan;
+  }
+}
+
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width, int max_corners,
+                             float* prev_dev, float* curr_dev, int32_t* detected_dev, void* stream) {
+  if (!hnd) return vstab_fail(nullptr, VSTAB_ERR_INVALID, "vstab_gftt_lk: null handle");
+  if (!gray_dev || !prev_dev || !curr_dev || !detected_dev || n_frames < 0 || height < 3 || width < 3 || max_corners <= 0)
+    return vstab_fail(hnd, VSTAB_ERR_INVALID, "vstab_gftt_lk: bad argument");
+  if (n_frames < 2) return VSTAB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  VSTAB_CUDA(hnd, cudaSetDevice(hnd->device));
+  const int h = height, w = width;
+  const int kChunk = 32;  // frames per pass of the corner detector (bounds the double row-sum buffer)
+  int cap = 1024;  // per-frame candidate capacity: power of two >= h*w/4 (a 3x3 local maximum needs its own 2x2 block)
+  while (cap < (h * w) / 4) cap <<= 1;
+  const int gw = (w + kCell - 1) / kCell, gh = (h + kCell - 1) / kCell;
+  const int P = n_frames - 1;
+
+  // ---- workspace ----
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  const size_t o_cov = take(sizeof(float) * 3 * (size_t)kChunk * h * w);
+  const size_t o_rows = take(sizeof(double) * 3 * (size_t)kChunk * h * w);
+  const size_t o_eig = take(sizeof(float) * (size_t)kChunk * h * w);
+  const size_t o_max = take(sizeof(unsigned) * kChunk);
+  const size_t o_keys = take(sizeof(unsigned long long) * (size_t)kChunk * cap);
+  const size_t o_cnt = take(sizeof(int) * kChunk);
+  const size_t o_cells = take(sizeof(short) * 2 * kCellCap * (size_t)kChunk * gw * gh);
+  const size_t o_ccnt = take((size_t)kChunk * gw * gh);
+  const size_t o_feats = take(sizeof(float) * 2 * (size_t)P * max_corners);
+  LkPyr pyr;
+  size_t o_img[kMaxLevel + 1], o_der[kMaxLevel + 1];
+  int lh = h, lw = w;
+  pyr.levels = 0;
+  for (int l = 0; l <= kMaxLevel; l++) {
+    if (l > 0) {
+      const int dh = (lh + 1) / 2, dw = (lw + 1) / 2;
+      if (dw <= kWin || dh <= kWin) break;
+      lh = dh; lw = dw;
+      o_img[l] = take((size_t)n_frames * lh * lw);
+      pyr.levels = l;
+    }
+    pyr.lv[l].h = lh; pyr.lv[l].w = lw;
+    o_der[l] = take(sizeof(short2) * (size_t)n_frames * lh * lw);
+  }
+  void* wsp = nullptr;
+  int rc = vstab_workspace(hnd, off, &wsp);
+  if (rc != VSTAB_OK) return rc;
+  unsigned char* base = (unsigned char*)wsp;
+  float* cov = (float*)(base + o_cov);
+  double* rows = (double*)(base + o_rows);
+  float* eig = (float*)(base + o_eig);
+  unsigned* maxb = (unsigned*)(base + o_max);
+  unsigned long long* keys = (unsigned long long*)(base + o_keys);
+  int* cnt = (int*)(base + o_cnt);
+  short* cells = (short*)(base + o_cells);
+  unsigned char* ccnt = base + o_ccnt;
+  float* feats = (float*)(base + o_feats);
+
+  const double scale_d = 1.0 / ((double)(1 << 2) * kBlock * 255.0);
+  const float s = (float)scale_d, s2 = s * 2.0f;
+  // ---- corners of frames 0 .. n-2 ----
+  for (int f0 = 0; f0 < P; f0 += kChunk) {
+    const int F = (P - f0) < kChunk ? (P - f0) : kChunk;
+    const unsigned char* g = gray_dev + (size_t)f0 * h * w;
+    dim3 gp(vstab_ceil_div(w, 32), vstab_ceil_div(h, 8), F);
+    gftt_cov_kernel<<<gp, 256, 0, st>>>(g, h, w, s, s2, cov);
+    VSTAB_LAUNCH_CHECK(hnd, "gftt_cov_kernel");
+    gftt_box_rows_kernel<<<vstab_ceil_div(F * h, 128), 128, 0, st>>>(cov, F, h, w, rows);
+    VSTAB_LAUNCH_CHECK(hnd, "gftt_box_rows_kernel");
+    VSTAB_CUDA(hnd, cudaMemsetAsync(maxb, 0, sizeof(unsigned) * kChunk, st));
+    VSTAB_CUDA(hnd, cudaMemsetAsync(cnt, 0, sizeof(int) * kChunk, st));
+    VSTAB_CUDA(hnd, cudaMemsetAsync(ccnt, 0, (size_t)kChunk * gw * gh, st));
+    gftt_box_cols_kernel<<<vstab_ceil_div(F * w, 128), 128, 0, st>>>(rows, F, h, w, eig, maxb);
+    VSTAB_LAUNCH_CHECK(hnd, "gftt_box_cols_kernel");
+    dim3 gc(vstab_ceil_div(w - 2, 32), vstab_ceil_div(h - 2, 8), F);
+    gftt_candidates_kernel<<<gc, 256, 0, st>>>(eig, h, w, maxb, 0.01, keys, cap, cnt);
+    VSTAB_LAUNCH_CHECK(hnd, "gftt_candidates_kernel");
+    gftt_sort_kernel<<<F, 1024, 0, st>>>(keys, cap, cnt);
+    VSTAB_LAUNCH_CHECK(hnd, "gftt_sort_kernel");
+    gftt_select_kernel<<<F, 32, 0, st>>>(keys, cap, cnt, h, w, max_corners, cells, ccnt, feats + (size_t)f0 * max_corners * 2,
+                                          detected_dev + f0);
+    VSTAB_LAUNCH_CHECK(hnd, "gftt_select_kernel");
+  }
+  // ---- pyramids + Scharr derivatives of every frame ----
+  pyr.lv[0].img = gray_dev;
+  for (int l = 0; l <= pyr.levels; l++) {
+    if (l > 0) {
+      unsigned char* dst = base + o_img[l];
+      dim3 gd(vstab_ceil_div(pyr.lv[l].w, 32), vstab_ceil_div(pyr.lv[l].h, 8), n_frames);
+      pyr_down_kernel<<<gd, 256, 0, st>>>(pyr.lv[l - 1].img, pyr.lv[l - 1].h, pyr.lv[l - 1].w, dst, pyr.lv[l].h, pyr.lv[l].w);
+      VSTAB_LAUNCH_CHECK(hnd, "pyr_down_kernel");
+      pyr.lv[l].img = dst;
+    }
+    short2* der = (short2*)(base + o_der[l]);
+    dim3 gs(vstab_ceil_div(pyr.lv[l].w, 32), vstab_ceil_div(pyr.lv[l].h, 8), n_frames);
+    scharr_kernel<<<gs, 256, 0, st>>>(pyr.lv[l].img, pyr.lv[l].h, pyr.lv[l].w, der);
+    VSTAB_LAUNCH_CHECK(hnd, "scharr_kernel");
+    pyr.lv[l].deriv = der;
+  }
+  // ---- track ----
+  const size_t smem = sizeof(short) * 8 * kWin * kWin * 3;
+  VSTAB_CUDA(hnd, cudaFuncSetAttribute(lk_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lk_track_kernel<<<vstab_ceil_div(P * max_corners, 8), 256, smem, st>>>(pyr, P, max_corners, feats, detected_dev, prev_dev, curr_dev);
+  VSTAB_LAUNCH_CHECK(hnd, "lk_track_kernel");
+  return VSTAB_OK;
+}

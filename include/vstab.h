@@ -146,6 +146,26 @@ VSTAB_API int vstab_common_coverage(vstab_handle* h, const float* fwd_dev, int n
 VSTAB_API int vstab_dis_flow(vstab_handle* h, const uint8_t* gray_dev, int n_frames, int height, int width,
                    float* flow_dev, float* grid_dev, int grid_step, void* stream);
 
+/* ---- K5 + K6 : Shi-Tomasi corners + pyramidal Lucas-Kanade, batched over frame pairs ---- */
+
+/*
+ * Replaces nodes/video_stabilizer_classic.py:76-83 (cv2.goodFeaturesToTrack(prev, maxCorners=400,
+ * qualityLevel=0.01, minDistance=7, blockSize=21)) and :88-100 (cv2.calcOpticalFlowPyrLK(prev, curr,
+ * features, winSize=(31,31), maxLevel=3, criteria=(EPS|COUNT, 50, 0.01)) + the status == 1 filter) for
+ * all pairs (i, i+1), i in [0, n_frames-1).
+ *
+ * gray_dev      [n_frames][h][w] uint8 working-size frames
+ * prev_dev      [n_frames-1][max_corners][2] float32 corner positions in frame i (NaN beyond the
+ *               number of corners found)
+ * curr_dev      [n_frames-1][max_corners][2] float32 tracked positions in frame i+1 (NaN when the
+ *               track was lost: cv2 status 0); feed both to vstab_fit_batch
+ * detected_dev  [n_frames-1] int32 number of corners found in frame i (classic.py:84 `< 12` test and
+ *               the translation confidence tracked / detected of :157)
+ */
+VSTAB_API int vstab_gftt_lk(vstab_handle* h, const uint8_t* gray_dev, int n_frames, int height, int width,
+                            int max_corners, float* prev_dev, float* curr_dev, int32_t* detected_dev,
+                            void* stream);
+
 /* ---- K4 + K7 + K8 + K9 : robust model fit, batched over frame pairs --------------------- */
 
 typedef struct vstab_fit_result {

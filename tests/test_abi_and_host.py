@@ -1,0 +1,177 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/vstab.h declares, the
+host helpers match the unmodified reference (when present), the node schema is the reference's."""
+import ctypes
+import json
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import pytest
+
+import vstab_loader
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+vstab_loader.load()
+from vstab_b200 import _native, hostmath as hm, motion_meta as mm  # noqa: E402
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "vstab.h")).read()
+    declared = sorted(set(re.findall(r"VSTAB_API\s+[\w\s\*]+?\b(vstab_\w+)\s*\(", header)))
+    assert len(declared) >= 10, declared
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    missing = [name for name in declared if not hasattr(lib, name)]
+    assert not missing, missing
+    assert lib.vstab_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_native.VstabNativeError):
+        _native.get_handle()
+    from vstab_b200 import pipeline
+
+    with pytest.raises(_native.VstabNativeError):
+        pipeline.normalize_video_input(torch.zeros((2, 8, 8, 3)))
+    lib = _native.load_library()
+    h = ctypes.c_void_p()
+    assert lib.vstab_create(0, ctypes.byref(h)) != 0  # no device => error code + message, no handle
+    assert lib.vstab_last_error(None)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "comfyui-video-stabilizer_b200")
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            text = open(os.path.join(pkg, name)).read()
+            assert "oracle" not in text.replace("oracle/dis_ref.c", ""), name
+            assert "import cv2" not in text, name
+
+
+def test_working_size_matches_host_rule():
+    for w, h in [(1920, 1080), (3840, 2160), (1280, 720), (832, 480), (1080, 1920), (961, 541), (2000, 300)]:
+        ws = hm.working_estimation_size(w, h)
+        assert _native.working_size(w, h) == (ws if ws is not None else (w, h))
+
+
+def test_padding_color_parser():
+    assert hm.parse_padding_color("#7F7F7F") == (127, 127, 127)
+    assert hm.parse_padding_color("#abc") == (0xAA, 0xBB, 0xCC)
+    assert hm.parse_padding_color("10, 300,-4") == (10, 255, 0)
+    assert hm.parse_padding_color("12") == (127, 127, 127)  # not 3 or 6 hex digits
+    assert hm.parse_padding_color("zzz") == (127, 127, 127)
+    assert hm.parse_padding_color(0x102030) == (0x10, 0x20, 0x30)
+
+
+def test_motion_meta_contract_messages():
+    block = mm.build_motion_meta_v2(source="x", frame_count=2, fps=16.0, input_size=(8, 6), output_size=(8, 6),
+                                    matrices=[np.eye(3), np.eye(3)])
+    assert mm.resolve_motion_meta({"motion_meta": block}).frame_count == 2
+    bad = json.loads(json.dumps(block))
+    bad["per_frame"][1]["matrix"][2] = [0, 0, 0]
+    with pytest.raises(ValueError, match=r"motion_meta.per_frame\[1\].matrix is not invertible."):
+        mm.validate_motion_meta(bad)
+    bad = json.loads(json.dumps(block))
+    bad["per_frame"][1]["index"] = 5
+    with pytest.raises(ValueError, match=r"per_frame\[1\].index must be 1, got 5"):
+        mm.validate_motion_meta(bad)
+    with pytest.raises(ValueError, match="version must be 2"):
+        mm.validate_motion_meta({"version": 1})
+    with pytest.raises(ValueError, match="meta must contain motion_meta or stabilization_warp"):
+        mm.resolve_motion_meta({})
+
+
+@pytest.mark.reference
+def test_host_helpers_equal_reference(reference_nodes):
+    ref = reference_nodes.stabilizer_utils
+    rng = np.random.default_rng(0)
+    for mode in ("translation", "similarity", "perspective"):
+        for _ in range(50):
+            th, s = rng.normal(0, 0.02), 1 + rng.normal(0, 0.02)
+            m = np.array([[s * np.cos(th), -s * np.sin(th), rng.normal(0, 9)], [s * np.sin(th), s * np.cos(th), rng.normal(0, 9)],
+                          [rng.normal(0, 1e-5), rng.normal(0, 1e-5), 1]], dtype=np.float32)
+            full = hm.rescale_transform_to_full(m, (1920, 1080), (960, 540))
+            assert np.array_equal(full, ref._rescale_transform_to_full(m, (1920, 1080), (960, 540)))
+            p = hm.matrix_to_params(full, mode)
+            assert np.array_equal(p, ref._matrix_to_params(full, mode))
+            assert np.array_equal(hm.params_to_matrix(p * 0.3, mode), ref._params_to_matrix(p * 0.3, mode))
+    path = np.cumsum(rng.normal(0, 2, (121, 4)), axis=0)
+    for smooth, fps in [(0.5, 16.0), (1.0, 24.0), (0.05, 1.0), (0.0, 30.0)]:
+        assert np.array_equal(hm.smooth_path(path, smooth, fps), ref._smooth_path(path, smooth, fps))
+    mats = [hm.params_to_matrix(r, "similarity") for r in rng.normal(0, 0.01, (30, 4)) * np.array([300, 300, 1, 1])]
+    for a, b in zip(hm.compute_bounding_boxes(mats, 1920, 1080), ref._compute_bounding_boxes(mats, 1920, 1080)):
+        assert np.array_equal(a, b)
+    lo, hi = ref._compute_bounding_boxes(mats, 1920, 1080)
+    assert hm.min_content_ratio(lo, hi, 1920, 1080) == ref._min_content_ratio(lo, hi, 1920, 1080)
+    t1, s1 = hm.prepare_expand_transform(lo, hi)
+    t2, s2 = ref._prepare_expand_transform(lo, hi)
+    assert np.array_equal(t1, t2) and s1 == s2
+    for text in ["#404040", "1,2,3", "#12", 99999999, "0x10"]:
+        assert hm.parse_padding_color(text) == ref._parse_padding_color(text)
+
+
+@pytest.mark.reference
+def test_motion_meta_equals_reference(reference_nodes):
+    ref = reference_nodes.motion_meta
+    mats = [np.array([[1.01, 0.02, 3.0], [-0.02, 0.99, -2.0], [1e-5, 0, 1.0]]) * (1 + 0.01 * i) for i in range(5)]
+    warp = hm.build_stabilization_warp_meta(source_size=(64, 48), output_size=(70, 50), framing_mode="expand", applied_matrices=mats)
+    assert warp == reference_nodes.stabilizer_utils._build_stabilization_warp_meta(
+        source_size=(64, 48), output_size=(70, 50), framing_mode="expand", applied_matrices=mats)
+    assert mm.applied_motion_meta_from_stabilization_warp(warp, 16.0, "s") == ref.applied_motion_meta_from_stabilization_warp(warp, 16.0, "s")
+    assert mm.motion_meta_from_stabilization_warp(warp, 24.0, "s") == ref.motion_meta_from_stabilization_warp(warp, 24.0, "s")
+
+
+def _install_comfy_stubs():
+    class _Socket:
+        def __init__(self, *a, **k):
+            self.args, self.kwargs = a, k
+
+    class _Kind:
+        Input = Output = _Socket
+
+    io = types.SimpleNamespace(
+        ComfyNode=type("ComfyNode", (), {}), Custom=lambda name: _Kind, Image=_Kind, Mask=_Kind, Float=_Kind, Combo=_Kind,
+        Boolean=_Kind, Color=_Kind, Int=_Kind, String=_Kind, NumberDisplay=types.SimpleNamespace(slider="slider"),
+        Schema=type("Schema", (), {"__init__": lambda self, **k: self.__dict__.update(k)}),
+        NodeOutput=lambda *a: a,
+    )
+    latest = types.ModuleType("comfy_api.latest")
+    latest.ComfyExtension = type("ComfyExtension", (), {})
+    latest.io = io
+    sys.modules.setdefault("comfy_api", types.ModuleType("comfy_api"))
+    sys.modules["comfy_api.latest"] = latest
+    comfy = types.ModuleType("comfy")
+    comfy.__path__ = []
+    utils = types.ModuleType("comfy.utils")
+    utils.ProgressBar = type("ProgressBar", (), {"__init__": lambda self, total: None, "update_absolute": lambda self, *a, **k: None})
+    sys.modules["comfy"] = comfy
+    sys.modules["comfy.utils"] = utils
+
+
+def test_node_schema_matches_reference_contract():
+    """ids / display names / socket names and order pinned by the reference's scripts/check_node_schema.py:11-64."""
+    _install_comfy_stubs()
+    sys.modules.pop("vstab_b200.nodes", None)
+    from vstab_b200 import nodes
+
+    stab_inputs = ["frames", "frame_rate", "framing_mode", "transform_mode", "camera_lock", "strength", "smooth", "keep_fov", "padding_color"]
+    expected = {
+        nodes.VideoStabilizerClassic: ("video_stabilizer_classic", "Video Stabilizer Classic", stab_inputs, ["frames_stabilized", "padding_mask", "meta"]),
+        nodes.VideoStabilizerFlow: ("video_stabilizer_flow", "Video Stabilizer Flow", stab_inputs, ["frames_stabilized", "padding_mask", "meta"]),
+        nodes.VideoStabilizerMotionApply: ("video_stabilizer_motion_apply", "Video Stabilizer Motion Apply",
+                                           ["frames", "motion_meta", "framing_mode", "interpolation", "padding_color", "motion_blur", "motion_blur_quality"],
+                                           ["frames", "padding_mask", "meta"]),
+    }
+    for cls, (node_id, display, ins, outs) in expected.items():
+        schema = cls.define_schema()
+        assert schema.node_id == node_id and schema.display_name == display
+        assert [s.args[0] for s in schema.inputs] == ins
+        assert [s.args[0] for s in schema.outputs] == outs
+    defaults = {s.args[0]: s.kwargs.get("default") for s in nodes.VideoStabilizerFlow.define_schema().inputs}
+    assert defaults["frame_rate"] == 16.0 and defaults["framing_mode"] == "crop_and_pad" and defaults["transform_mode"] == "similarity"
+    assert defaults["strength"] == 0.7 and defaults["smooth"] == 0.5 and defaults["keep_fov"] == 0.6 and defaults["padding_color"] == "#7F7F7F"

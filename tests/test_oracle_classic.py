@@ -1,0 +1,36 @@
+"""Pins oracle/classic_ref.c (Shi-Tomasi corners + pyramidal LK) against live cv2."""
+import numpy as np
+import pytest
+
+from oracle import classic_ref as CR
+from tests import cases
+
+cv2 = pytest.importorskip("cv2")
+
+
+@pytest.mark.parametrize("size", [(960, 540), (832, 480), (640, 360)])
+def test_gftt_identical_and_lk_close(size):
+    w, h = size
+    p, c = cases.make_gray_pair(dict(w=w, h=h, seed=w + 1, amount=1.5))
+    assert np.array_equal(cv2.cornerMinEigenVal(p, 21, ksize=3), CR.min_eigen(p))
+    f = cv2.goodFeaturesToTrack(p, maxCorners=400, qualityLevel=0.01, minDistance=7, blockSize=21).reshape(-1, 2)
+    g = CR.good_features(p)
+    assert np.array_equal(f, g)  # same corners in the same order
+    nxt, st, _ = cv2.calcOpticalFlowPyrLK(p, c, f.reshape(-1, 1, 2), None, winSize=(31, 31), maxLevel=3,
+                                          criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 50, 0.01))
+    mine, ms = CR.pyr_lk(p, c, f)
+    st = st.ravel()
+    assert int((st != ms).sum()) == 0
+    ok = st == 1
+    assert float(np.abs(nxt.reshape(-1, 2)[ok] - mine[ok]).max()) <= 2e-3  # float accumulation order only
+
+
+def test_lk_loses_points_that_leave_the_frame():
+    w, h = 320, 180
+    p, _ = cases.make_gray_pair(dict(w=w, h=h, seed=3, amount=1.0))
+    c = np.roll(p, (0, 60), (0, 1))  # 60 px shift: far beyond what 3 levels of a 31-px window recover at the edge
+    f = cv2.goodFeaturesToTrack(p, maxCorners=100, qualityLevel=0.01, minDistance=7, blockSize=21).reshape(-1, 2)
+    nxt, st, _ = cv2.calcOpticalFlowPyrLK(p, c, f.reshape(-1, 1, 2), None, winSize=(31, 31), maxLevel=3,
+                                          criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 50, 0.01))
+    mine, ms = CR.pyr_lk(p, c, f)
+    assert int((st.ravel() != ms).sum()) <= 1
