@@ -595,7 +595,6 @@ __device__ __forceinline__ void vr_px_sor(const Level& L, const VrBuf& B, int pa
 }
 
 __device__ __forceinline__ void cluster_barrier() {
-  __threadfence();  // make this CTA's global writes visible device-wide before the cluster barrier
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }

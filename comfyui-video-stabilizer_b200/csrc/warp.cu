@@ -21,11 +21,15 @@
 namespace {
 
 constexpr int TW = 64;
-constexpr int TH = 16;
+#ifndef VSTAB_WARP_GROUPS
+#define VSTAB_WARP_GROUPS 2
+#endif
+constexpr int GROUPS = VSTAB_WARP_GROUPS;  // row groups of 16 output rows per CTA
+constexpr int TH = 16 * GROUPS;
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
 #ifndef VSTAB_WARP_MIN_CTAS
-#define VSTAB_WARP_MIN_CTAS 4
+#define VSTAB_WARP_MIN_CTAS 3
 #endif
 constexpr int MIN_CTAS = VSTAB_WARP_MIN_CTAS;
 constexpr int MAX_SAMPLES = 33;
@@ -89,6 +93,104 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
+// Interior tile, single sample, bilinear: every tap is inside the staged box and every pixel is
+// covered, so the loop body is coordinates -> 12 shared-memory loads -> blend, nothing else.
+// Column / row products of the inverse matrix are hoisted (2 columns x 2 rows per thread).
+template <bool AFFINE, bool VEC>
+__device__ __forceinline__ void interior_tile(const double* __restrict__ s_minv, const float* __restrict__ tile0, int pitch,
+                                              int tx0, int ty0, int warp, int lane, int tid, int ow,
+                                              float* __restrict__ scratch, float* __restrict__ dst_tile,
+                                              float* __restrict__ mask_tile, int vec_mask) {
+  const double m0 = s_minv[0], m1 = s_minv[1], m2 = s_minv[2], m3 = s_minv[3], m4 = s_minv[4], m5 = s_minv[5];
+  const double m6 = s_minv[6], m7 = s_minv[7], m8 = s_minv[8];
+  const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
+  double ax[2], ay[2], aw[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double dx = (double)(tx0 + lane + 32 * k);
+    ax[k] = __dmul_rn(m0, dx);
+    ay[k] = __dmul_rn(m3, dx);
+    if (!AFFINE) aw[k] = __dmul_rn(m6, dx);
+  }
+  int ixs[4 * GROUPS], iys[4 * GROUPS];
+#pragma unroll
+  for (int g = 0; g < GROUPS; ++g) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const double dy = (double)(ty0 + g * 16 + warp + NWARPS * rr);
+      const double bx = __dmul_rn(m1, dy), by = __dmul_rn(m4, dy);
+      double bw = 0.0;
+      if (!AFFINE) bw = __dmul_rn(m7, dy);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const double X = __dadd_rn(__dadd_rn(ax[cc], bx), m2);
+        const double Y = __dadd_rn(__dadd_rn(ay[cc], by), m5);
+        double sc = sc_affine;
+        if (!AFFINE) {
+          const double W = __dadd_rn(__dadd_rn(aw[cc], bw), m8);
+          sc = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
+        }
+        // |coordinates| < 2^15 here, so cv2's INT_MIN/INT_MAX and short saturation are no-ops
+        ixs[g * 4 + rr * 2 + cc] = __double2int_rn(__dmul_rn(X, sc));
+        iys[g * 4 + rr * 2 + cc] = __double2int_rn(__dmul_rn(Y, sc));
+      }
+    }
+  }
+  if (mask_tile) {  // fully covered tile: mask = 0; 64 x 16*GROUPS floats = GROUPS 16-byte stores per thread
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g) {
+      float* mrow = mask_tile + (size_t)(g * 16 + (tid >> 4)) * ow + (tid & 15) * 4;
+      if (vec_mask) {
+        *reinterpret_cast<float4*>(mrow) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        mrow[0] = 0.f; mrow[1] = 0.f; mrow[2] = 0.f; mrow[3] = 0.f;
+      }
+    }
+  }
+  // the source box has been streaming into shared memory meanwhile
+  cp_async_wait_all();
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < GROUPS; ++g) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int ix = ixs[g * 4 + rr * 2 + cc], iy = iys[g * 4 + rr * 2 + cc];
+        const float fx1 = (float)(ix & 31) * 0.03125f, fy1 = (float)(iy & 31) * 0.03125f;
+        const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
+        const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
+        const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
+        const float* s0 = tile0 + (iy >> 5) * pitch + (ix >> 5) * 3;
+        const float* s1 = s0 + pitch;
+        float v[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+          v[ch] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s0[ch], w00), __fmul_rn(s0[3 + ch], w01)), __fmul_rn(s1[ch], w10)),
+                            __fmul_rn(s1[3 + ch], w11));
+        if (VEC) {
+          float* o = scratch + rr * (TW * 3) + (lane + cc * 32) * 3;
+          o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+        } else {
+          float* o = dst_tile + ((size_t)(g * 16 + warp + rr * NWARPS) * ow + lane + cc * 32) * 3;
+          o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+        }
+      }
+    }
+    if (VEC) {
+      __syncwarp();
+#pragma unroll
+      for (int q3 = 0; q3 < 3; ++q3) {
+        const int q = lane + q3 * 32;
+        const int rr = q >= 48 ? 1 : 0, qi = q - rr * 48;
+        const float4 val = *reinterpret_cast<const float4*>(scratch + rr * (TW * 3) + qi * 4);
+        *reinterpret_cast<float4*>(dst_tile + (size_t)(g * 16 + warp + rr * NWARPS) * ow * 3 + qi * 4) = val;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 template <int INTERP>
 __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const WarpParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -107,18 +209,9 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
   const int S = p.samples;
   const float* __restrict__ frame = p.src + (size_t)frame_idx * p.sh * p.sw * 3;
 
-  if (tid < S) vstab_invert3(p.fwd + ((size_t)frame_idx * S + tid) * 9, s_minv + tid * 9);
   if (INTERP == VSTAB_INTERP_BICUBIC && tid < 128) s_cubic[tid] = c_cubic_tab[tid >> 2][tid & 3];
-  if (tid == 0) {
-    s_box[0] = INT_MAX;  // min x
-    s_box[1] = INT_MAX;  // min y
-    s_box[2] = INT_MIN;  // max x
-    s_box[3] = INT_MIN;  // max y
-    s_box[4] = 0;        // degenerate flag
-  }
-  __syncthreads();
 
-  // ---- source footprint of the tile: 4 corners x S samples ----------------------------------
+  // ---- inverse matrices + source footprint of the tile (4 corners x S samples) ---------------
   StagedTile tile;
   tile.smem = s_tile;
   tile.active = false;
@@ -126,28 +219,64 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
   tile.x1 = tile.y1 = -1;
   tile.pitch = 0;
   bool interior = false;
-  if (p.stage_mode == VSTAB_STAGE_AUTO) {
-    const int txe = min(tx0 + TW, p.ow) - 1;
-    const int tye = min(ty0 + TH, p.oh) - 1;
-    for (int k = tid; k < 4 * S; k += NTHREADS) {
-      const double* m = s_minv + (k >> 2) * 9;
-      const double cx = (k & 1) ? (double)txe : (double)tx0;
-      const double cy = (k & 2) ? (double)tye : (double)ty0;
-      const double X = m[0] * cx + m[1] * cy + m[2];
-      const double Y = m[3] * cx + m[4] * cy + m[5];
-      const double W = m[6] * cx + m[7] * cy + m[8];
+  const int txe = min(tx0 + TW, p.ow) - 1;
+  const int tye = min(ty0 + TH, p.oh) - 1;
+  if (S == 1) {
+    // single sample: warp 0 inverts, projects the 4 corners (lane & 3) and reduces with shuffles;
+    // no atomics and one barrier less than the general path
+    if (warp == 0) {
+      double mi[9];
+      vstab_invert3(p.fwd + (size_t)frame_idx * 9, mi);
+      const double cx = (lane & 1) ? (double)txe : (double)tx0;
+      const double cy = (lane & 2) ? (double)tye : (double)ty0;
+      const double X = mi[0] * cx + mi[1] * cy + mi[2];
+      const double Y = mi[3] * cx + mi[4] * cy + mi[5];
+      const double W = mi[6] * cx + mi[7] * cy + mi[8];
       const double sx = X / W, sy = Y / W;
-      // Convexity of the projected tile needs W to keep one sign; positive is the sane case.
-      if (!(W > 1e-12) || !(fabs(sx) < 1e8) || !(fabs(sy) < 1e8)) {
-        atomicOr(&s_box[4], 1);
-      } else {
-        atomicMin(&s_box[0], (int)floor(sx));
-        atomicMin(&s_box[1], (int)floor(sy));
-        atomicMax(&s_box[2], (int)floor(sx));
-        atomicMax(&s_box[3], (int)floor(sy));
+      const bool bad = !(W > 1e-12) || !(fabs(sx) < 1e8) || !(fabs(sy) < 1e8);
+      const int fx = bad ? 0 : (int)floor(sx), fy = bad ? 0 : (int)floor(sy);
+      const int mnx = __reduce_min_sync(0xffffffffu, fx), mny = __reduce_min_sync(0xffffffffu, fy);
+      const int mxx = __reduce_max_sync(0xffffffffu, fx), mxy = __reduce_max_sync(0xffffffffu, fy);
+      const bool any_bad = __any_sync(0xffffffffu, bad);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s_minv[k] = mi[k];
+        s_box[0] = mnx; s_box[1] = mny; s_box[2] = mxx; s_box[3] = mxy; s_box[4] = any_bad ? 1 : 0;
       }
     }
+  } else {
+    if (tid < S) vstab_invert3(p.fwd + ((size_t)frame_idx * S + tid) * 9, s_minv + tid * 9);
+    if (tid == 0) {
+      s_box[0] = INT_MAX;  // min x
+      s_box[1] = INT_MAX;  // min y
+      s_box[2] = INT_MIN;  // max x
+      s_box[3] = INT_MIN;  // max y
+      s_box[4] = 0;        // degenerate flag
+    }
     __syncthreads();
+    if (p.stage_mode == VSTAB_STAGE_AUTO) {
+      for (int k = tid; k < 4 * S; k += NTHREADS) {
+        const double* m = s_minv + (k >> 2) * 9;
+        const double cx = (k & 1) ? (double)txe : (double)tx0;
+        const double cy = (k & 2) ? (double)tye : (double)ty0;
+        const double X = m[0] * cx + m[1] * cy + m[2];
+        const double Y = m[3] * cx + m[4] * cy + m[5];
+        const double W = m[6] * cx + m[7] * cy + m[8];
+        const double sx = X / W, sy = Y / W;
+        // Convexity of the projected tile needs W to keep one sign; positive is the sane case.
+        if (!(W > 1e-12) || !(fabs(sx) < 1e8) || !(fabs(sy) < 1e8)) {
+          atomicOr(&s_box[4], 1);
+        } else {
+          atomicMin(&s_box[0], (int)floor(sx));
+          atomicMin(&s_box[1], (int)floor(sy));
+          atomicMax(&s_box[2], (int)floor(sx));
+          atomicMax(&s_box[3], (int)floor(sy));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (p.stage_mode == VSTAB_STAGE_AUTO) {
     if (s_box[4] == 0) {
       constexpr int LO = (INTERP == VSTAB_INTERP_BILINEAR) ? 1 : 2;
       constexpr int HI = (INTERP == VSTAB_INTERP_BILINEAR) ? 2 : 3;
@@ -178,7 +307,6 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
             float* s = s_tile + r * row_floats;
             for (int v = lane; v < row_vec; v += 32) cp_async16(s + 4 * v, g + 4 * v);
           }
-          cp_async_wait_all();
         } else {
           for (int r = warp; r < bh; r += NWARPS) {
             const float* g = frame + ((size_t)(by0 + r) * p.sw + bx0) * 3;
@@ -188,72 +316,28 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
         }
       }
     }
-    __syncthreads();
   }
 
   // ---- interior tiles: branch-free bilinear, single sample ---------------------------------------
+  // (the 16-byte cp.async copies of the source box are still in flight: the interior path computes
+  //  its coordinates and weights first and only then waits for them)
   if (interior) {
     float* scratch = s_scratch + warp * SCRATCH_FLOATS_PER_WARP;
-    const double* m = s_minv;
-    const double m2 = m[2], m5 = m[5], m8 = m[8];
-    const bool affine = (m[6] == 0.0) && (m[7] == 0.0);
-    const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
-    const int t_x0 = tile.x0, t_y0 = tile.y0, t_pitch = tile.pitch;
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const double dy = (double)(ty0 + warp + rr * NWARPS);
-      const double bx = __dmul_rn(m[1], dy), by = __dmul_rn(m[4], dy), bw = __dmul_rn(m[7], dy);
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const double dx = (double)(tx0 + lane + cc * 32);
-        const double X = __dadd_rn(__dadd_rn(__dmul_rn(m[0], dx), bx), m2);
-        const double Y = __dadd_rn(__dadd_rn(__dmul_rn(m[3], dx), by), m5);
-        double sc = sc_affine;
-        if (!affine) {
-          const double W = __dadd_rn(__dadd_rn(__dmul_rn(m[6], dx), bw), m8);
-          sc = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
-        }
-        // |coordinates| < 2^15 here, so cv2's INT_MIN/INT_MAX and short saturation are no-ops
-        const int ix = __double2int_rn(__dmul_rn(X, sc)), iy = __double2int_rn(__dmul_rn(Y, sc));
-        const int sx = ix >> 5, sy = iy >> 5;
-        const float fx1 = (float)(ix & 31) * 0.03125f, fy1 = (float)(iy & 31) * 0.03125f;
-        const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
-        const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
-        const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
-        const float* s0 = s_tile + (sy - t_y0) * t_pitch + (sx - t_x0) * 3;
-        const float* s1 = s0 + t_pitch;
-        float* sc_out = scratch + rr * (TW * 3) + (lane + cc * 32) * 3;
-        float* gd = p.dst + (((size_t)frame_idx * p.oh + (ty0 + warp + rr * NWARPS)) * p.ow + (tx0 + lane + cc * 32)) * 3;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s0[ch], w00), __fmul_rn(s0[3 + ch], w01)),
-                                              __fmul_rn(s1[ch], w10)),
-                                    __fmul_rn(s1[3 + ch], w11));
-          if (p.vec_store) sc_out[ch] = v; else gd[ch] = v;
-        }
-      }
-    }
-    if (p.mask) {  // fully covered tile: mask = 0; 64x16 floats = one 16-byte store per thread
-      float* mrow = p.mask + ((size_t)frame_idx * p.oh + ty0 + (tid >> 4)) * p.ow + tx0 + (tid & 15) * 4;
-      if (p.vec_mask) {
-        *reinterpret_cast<float4*>(mrow) = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-        mrow[0] = 0.f; mrow[1] = 0.f; mrow[2] = 0.f; mrow[3] = 0.f;
-      }
-    }
+    const bool affine = (s_minv[6] == 0.0) && (s_minv[7] == 0.0);
+    float* dst_tile = p.dst + (((size_t)frame_idx * p.oh + ty0) * p.ow + tx0) * 3;
+    float* mask_tile = p.mask ? p.mask + ((size_t)frame_idx * p.oh + ty0) * p.ow + tx0 : nullptr;
+    const float* tile0 = s_tile - (tile.y0 * tile.pitch + tile.x0 * 3);  // so that tile0[sy*pitch + sx*3] is the texel
     if (p.vec_store) {
-      __syncwarp();
-#pragma unroll
-      for (int q3 = 0; q3 < 3; ++q3) {
-        const int q = lane + q3 * 32;
-        const int rr = q / 48, qi = q - rr * 48;
-        const float4 v = *reinterpret_cast<const float4*>(scratch + rr * (TW * 3) + qi * 4);
-        float* d = p.dst + (((size_t)frame_idx * p.oh + (ty0 + warp + rr * NWARPS)) * p.ow + tx0) * 3 + qi * 4;
-        *reinterpret_cast<float4*>(d) = v;
-      }
+      if (affine) interior_tile<true, true>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
+      else interior_tile<false, true>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
+    } else {
+      if (affine) interior_tile<true, false>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
+      else interior_tile<false, false>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
     }
     return;
   }
+  cp_async_wait_all();
+  __syncthreads();
 
   // ---- per-pixel resampling ------------------------------------------------------------------
   // Sample-outer loop: the per-sample row/column products of the inverse matrix are hoisted out of
@@ -261,6 +345,13 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
   const float fS = (float)S;
   float* scratch = s_scratch + warp * SCRATCH_FLOATS_PER_WARP;
   unsigned int padded = 0;
+  const double x_hi = (double)(p.sw - 1), y_hi = (double)(p.sh - 1);
+  const bool t_on = tile.active;
+  const int t_x0 = tile.x0, t_y0 = tile.y0, t_x1 = tile.x1, t_y1 = tile.y1, t_pitch = tile.pitch;
+  const double dxs[2] = {(double)(tx0 + lane), (double)(tx0 + lane + 32)};
+
+  for (int g = 0; g < GROUPS; ++g) {  // row groups of 16 output rows
+  const int tyg = ty0 + g * 16;
   float acc[4][3];
   int cover[4];
 #pragma unroll
@@ -268,12 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
     acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
     cover[q] = 0;
   }
-  const double dxs[2] = {(double)(tx0 + lane), (double)(tx0 + lane + 32)};
-  const double dys[2] = {(double)(ty0 + warp), (double)(ty0 + warp + NWARPS)};
-  const double x_hi = (double)(p.sw - 1), y_hi = (double)(p.sh - 1);
-  const bool t_on = tile.active;
-  const int t_x0 = tile.x0, t_y0 = tile.y0, t_x1 = tile.x1, t_y1 = tile.y1, t_pitch = tile.pitch;
-
+  const double dys[2] = {(double)(tyg + warp), (double)(tyg + warp + NWARPS)};
   for (int s = 0; s < S; ++s) {
     const double* m = s_minv + s * 9;
     const double m2 = m[2], m5 = m[5], m8 = m[8];
@@ -293,7 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int rr = q >> 1, cc = q & 1;
-      const int oy = ty0 + warp + rr * NWARPS, ox = tx0 + lane + cc * 32;
+      const int oy = tyg + warp + rr * NWARPS, ox = tx0 + lane + cc * 32;
       if (oy >= p.oh || ox >= p.ow) continue;
       const double X = __dadd_rn(__dadd_rn(ax[cc], bx[rr]), m2);
       const double Y = __dadd_rn(__dadd_rn(ay[cc], by[rr]), m5);
@@ -445,7 +531,7 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int rr = q >> 1, cc = q & 1;
-    const int oy = ty0 + warp + rr * NWARPS, ox = tx0 + lane + cc * 32;
+    const int oy = tyg + warp + rr * NWARPS, ox = tx0 + lane + cc * 32;
     if (oy < p.oh && ox < p.ow) {
       if (S > 1) {
         acc[q][0] = __fdiv_rn(acc[q][0], fS);
@@ -485,7 +571,7 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
     for (int q3 = 0; q3 < 3; ++q3) {
       const int q = lane + q3 * 32;
       const int rr = q / 48, qi = q - rr * 48;
-      const int oy = ty0 + warp + rr * NWARPS;
+      const int oy = tyg + warp + rr * NWARPS;
       if (oy < p.oh && qi * 4 < valid_floats) {
         const float4 v = *reinterpret_cast<const float4*>(scratch + rr * (TW * 3) + qi * 4);
         float* d = p.dst + (((size_t)frame_idx * p.oh + oy) * p.ow + tx0) * 3 + qi * 4;
@@ -493,6 +579,8 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
       }
     }
   }
+  if (p.vec_store) __syncwarp();
+  }  // row groups
 
   if (p.pad_count) {
     for (int o = 16; o > 0; o >>= 1) padded += __shfl_down_sync(0xffffffffu, padded, o);

@@ -26,6 +26,17 @@ from .pipeline import VideoContext, fused_warp
 
 MODE_NAMES = _native.MODE_NAMES
 
+# set to a list to collect (label, seconds) host-side phase timings of the last call (bench / debugging)
+PHASE_LOG = None
+
+
+def _mark(label, t0):
+    import time
+
+    if PHASE_LOG is not None:
+        PHASE_LOG.append((label, time.perf_counter() - t0))
+    return time.perf_counter()
+
 
 @dataclass
 class StabilizationResult:
@@ -198,10 +209,16 @@ def stabilize_frames(
     # ---- estimation: all candidate models of every pair -----------------------------------------
     work = hm.working_estimation_size(width, height)
     work_w, work_h = work if work is not None else (width, height)
+    import time
+
+    t0 = time.perf_counter()
     cands = estimator(context, work_w, work_h, transform_mode)
+    t0 = _mark("estimate (gray+flow/track+fit, waits for the GPU)", t0)
     if shard is not None:
         cands = shard.gather_candidates(cands)
+        t0 = _mark("all-gather candidates", t0)
     chosen, active_mode = replay_mode_ladder(cands, transform_mode, with_residual=is_flow)
+    t0 = _mark("ladder", t0)
     progress.advance(estimation_steps)
     check()
 
@@ -293,6 +310,7 @@ def stabilize_frames(
     # ---- warp + mask: one fused launch per chunk -------------------------------------------------
     lo, hi = (0, total_frames) if shard is None else shard.frame_range
     fwd = np.stack([np.asarray(m, dtype=np.float32).reshape(9) for m in final_matrices[lo:hi]], axis=0)[:, None, :]
+    t0 = _mark("host path/framing solve", t0)
     pending = fused_warp(
         context if shard is None else shard.owned_context(context), fwd, output_size, "bilinear",
         hm.border_value(padding_rgb), want_mask=True, want_pad_count=True, output=output, defer=True,
@@ -317,7 +335,9 @@ def stabilize_frames(
         pass
     path_list, target_list, effective_list = path.tolist(), target_path.tolist(), effective_target_path.tolist()
 
+    t0 = _mark("meta build (overlaps the warp)", t0)
     frames_out, masks_out, pad_counts = pending()
+    t0 = _mark("wait for warp + pad counts", t0)
     if shard is not None:
         pad_counts = shard.gather_pad_counts(pad_counts)
     pixels = int(output_size[0]) * int(output_size[1])

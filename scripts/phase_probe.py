@@ -37,6 +37,9 @@ out["full_step_ms"], res = t(lambda: flow.stabilize_frames(ctx, "crop_and_pad", 
 fwd = torch.eye(3, device=dev).reshape(1, 1, 9).repeat(N, 1, 1).contiguous()
 out["warp_only_ms"], _ = t(lambda: h.warp_fused(clip, fwd, (W, H), "bilinear", (0.5, 0.5, 0.5), want_pad_count=True))
 print(json.dumps(out, indent=1))
+core.PHASE_LOG = []
+flow.stabilize_frames(ctx, "crop_and_pad", "similarity", False, 0.7, 0.5, 0.6, (127, 127, 127), 16.0, output="device")
+print("PHASES", [(a, round(b * 1e3, 3)) for a, b in core.PHASE_LOG]); core.PHASE_LOG = None
 import cProfile, pstats, io
 dst = torch.empty((N, H, W, 3), device=dev); msk = torch.empty((N, H, W), device=dev)
 out2 = {}
