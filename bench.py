@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(k)
                 except Exception:
                     pass
-                self._stop_evt.wait(0.05)
+                self._stop_evt.wait(0.01)
         except Exception as exc:  # NVML missing: report that instead of inventing numbers
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
 

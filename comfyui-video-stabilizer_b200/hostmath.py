@@ -91,6 +91,67 @@ def params_to_matrix(params, base_mode: str) -> np.ndarray:
     return np.array(rows, dtype=np.float32)
 
 
+def matrices_to_params(matrices: np.ndarray, base_mode: str) -> np.ndarray:
+    """Stacked matrix_to_params: [P,3,3] float32 -> [P,K] float64, same bits as the per-matrix
+    version (float32 products for a*a + c*c, libm atan2 / log per element)."""
+    m = np.asarray(matrices)
+    n = m.shape[0]
+    if base_mode == "translation":
+        return np.stack([m[:, 0, 2], m[:, 1, 2]], axis=1).astype(np.float64)
+    if base_mode == "similarity":
+        a, c = m[:, 0, 0], m[:, 1, 0]
+        mag2 = a * a + c * c  # float32 arithmetic when the matrices are float32, like numpy scalars
+        out = np.empty((n, 4), dtype=np.float64)
+        out[:, 0] = m[:, 0, 2]
+        out[:, 1] = m[:, 1, 2]
+        out[:, 2] = [math.atan2(ci, ai) for ci, ai in zip(c.tolist() if c.dtype == np.float64 else c, a.tolist() if a.dtype == np.float64 else a)]
+        out[:, 3] = [math.log(math.sqrt(max(v, 1e-10))) for v in mag2]
+        return out
+    one = m.dtype.type(1.0)
+    return np.stack(
+        [m[:, 0, 0] - one, m[:, 0, 1], m[:, 0, 2], m[:, 1, 0], m[:, 1, 1] - one, m[:, 1, 2], m[:, 2, 0], m[:, 2, 1]], axis=1
+    ).astype(np.float64)
+
+
+def params_to_matrices(params: np.ndarray, base_mode: str) -> np.ndarray:
+    """Stacked params_to_matrix: [N,K] float64 -> [N,3,3] float32 (libm exp / cos / sin per element)."""
+    p = np.asarray(params, dtype=np.float64)
+    n = p.shape[0]
+    out = np.zeros((n, 3, 3), dtype=np.float64)
+    out[:, 2, 2] = 1.0
+    if base_mode == "translation":
+        out[:, 0, 0] = 1.0
+        out[:, 1, 1] = 1.0
+        out[:, 0, 2] = p[:, 0]
+        out[:, 1, 2] = p[:, 1]
+    elif base_mode == "similarity":
+        k = np.array([math.exp(v) for v in p[:, 3]])
+        cs = np.array([math.cos(v) for v in p[:, 2]])
+        sn = np.array([math.sin(v) for v in p[:, 2]])
+        out[:, 0, 0] = k * cs
+        out[:, 0, 1] = -k * sn
+        out[:, 1, 0] = k * sn
+        out[:, 1, 1] = k * cs
+        out[:, 0, 2] = p[:, 0]
+        out[:, 1, 2] = p[:, 1]
+    else:
+        out[:, 0, 0] = p[:, 0] + 1.0
+        out[:, 0, 1] = p[:, 1]
+        out[:, 0, 2] = p[:, 2]
+        out[:, 1, 0] = p[:, 3]
+        out[:, 1, 1] = p[:, 4] + 1.0
+        out[:, 1, 2] = p[:, 5]
+        out[:, 2, 0] = p[:, 6]
+        out[:, 2, 1] = p[:, 7]
+    return out.astype(np.float32)
+
+
+def left_multiply(shift: np.ndarray, matrices: np.ndarray) -> np.ndarray:
+    """[shift @ m for m in matrices] as one batched matmul (numpy runs the same 3x3 BLAS product per
+    matrix, so the result has the same bits as the reference's per-frame `translate_matrix @ mat`)."""
+    return np.matmul(np.asarray(shift)[None], np.asarray(matrices))
+
+
 def smoothing_window(smooth: float, fps: float) -> int:
     fps = float(max(1.0, fps))
     seconds = 3.0 / 16.0 + smooth * (13.0 / 16.0 - 3.0 / 16.0)
@@ -195,8 +256,8 @@ def build_stabilization_warp_meta(*, source_size, output_size, framing_mode, app
         "framing_mode": framing_mode,
         "matrix_convention": "source_to_stabilized",
         "per_frame": [
-            {"index": int(i), "applied_matrix": np.asarray(m, dtype=np.float32).tolist()}
-            for i, m in enumerate(applied_matrices)
+            {"index": i, "applied_matrix": m}
+            for i, m in enumerate(np.asarray(applied_matrices, dtype=np.float32).reshape(-1, 3, 3).tolist())
         ],
     }
 

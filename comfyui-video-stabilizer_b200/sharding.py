@@ -38,6 +38,11 @@ class FrameShard:
     total_frames: int
     group: Optional[dist.ProcessGroup] = None
     device: Optional[torch.device] = None  # device of the communication buffers (cuda for NCCL)
+    meta_rank: int = 0  # the rank that materialises the per-frame lists of `meta` (-1: every rank)
+
+    @property
+    def builds_meta(self) -> bool:
+        return self.meta_rank < 0 or self.meta_rank == self.rank
 
     @property
     def frame_range(self) -> Tuple[int, int]:

@@ -79,13 +79,44 @@ class PairCandidates:
 Estimator = Callable[[VideoContext, int, int, str], PairCandidates]
 
 
+def _accepts_requested(cands: PairCandidates, mode: str) -> np.ndarray:
+    """Per pair: would the ladder accept `mode` itself (no fallback)?  Vectorised."""
+    k = _native.MODE_INDEX[mode]
+    n_valid = cands.n_valid.max(axis=1)
+    ok = n_valid >= cands.min_points
+    if cands.detected is not None:
+        ok &= cands.detected >= 12
+    if mode == "translation":
+        return ok
+    conf = cands.n_inliers[:, k] / np.maximum(n_valid, 1).astype(np.float64)
+    need, thr = (4, 0.15) if mode == "perspective" else (3, 0.1)
+    return ok & (cands.ok[:, k] != 0) & (n_valid >= need) & (conf >= thr)
+
+
 def replay_mode_ladder(cands: PairCandidates, requested_mode: str, *, with_residual: bool):
     """The reference's per-pair fallback ladder with its clip-wide sticky downgrade
-    (flow.py:156-210 + :324-339; classic.py:104-158 + :264-272), replayed over the table."""
+    (flow.py:156-210 + :324-339; classic.py:104-158 + :264-272), replayed over the table.
+    Returns (list of (matrix f32, mode, confidence, residual), final active mode).  The common case
+    -- every pair accepts the requested model -- is answered from array operations; the per-pair
+    loop only starts at the first pair that falls back."""
     active = requested_mode
     out = []
     eye = np.eye(3, dtype=np.float32)
-    for p in range(cands.matrix.shape[0]):
+    total = cands.matrix.shape[0]
+    accepted = _accepts_requested(cands, requested_mode)
+    first_fallback = int(np.argmin(accepted)) if not accepted.all() else total
+    if first_fallback > 0:
+        k = _native.MODE_INDEX[requested_mode]
+        n_valid = cands.n_valid.max(axis=1)[:first_fallback]
+        mats32 = cands.matrix[:first_fallback, k].astype(np.float32)
+        if requested_mode == "translation":
+            denom = cands.detected[:first_fallback] if cands.detected is not None else cands.n_total[:first_fallback, k]
+            confs = (n_valid / denom.astype(np.float64)).tolist()
+        else:
+            confs = (cands.n_inliers[:first_fallback, k] / n_valid.astype(np.float64)).tolist()
+        resid = cands.residual[:first_fallback, k].tolist()
+        out = [(mats32[i], requested_mode, confs[i], resid[i] if with_residual else None) for i in range(first_fallback)]
+    for p in range(first_fallback, total):
         n_valid = int(cands.n_valid[p].max())
         chosen = None
         too_few = n_valid < cands.min_points
@@ -226,12 +257,11 @@ def stabilize_frames(
     stacked = np.stack([c[0] for c in chosen], axis=0)
     if work is not None:
         stacked = hm.rescale_transforms_to_full(stacked, (width, height), work)
-    matrices: List[np.ndarray] = [stacked[i] for i in range(stacked.shape[0])]
-    delta_params: List[np.ndarray] = [hm.matrix_to_params(m, base_mode) for m in matrices]
+    matrices = stacked  # [P,3,3] float32, full-resolution per-pair transforms
+    delta_params = hm.matrices_to_params(matrices, base_mode)
 
-    path = np.zeros((total_frames, delta_params[0].shape[0]), dtype=np.float64)
-    for i, delta in enumerate(delta_params, start=1):
-        path[i] = path[i - 1] + delta
+    path = np.zeros((total_frames, delta_params.shape[1]), dtype=np.float64)
+    np.cumsum(delta_params, axis=0, out=path[1:])  # sequential adds, same as path[i] = path[i-1] + delta
 
     strength = float(np.clip(strength, 0.0, 1.0))
     smooth = float(np.clip(smooth, 0.0, 1.0))
@@ -241,7 +271,7 @@ def stabilize_frames(
     else:
         target_path = path + strength * (hm.smooth_path(path, smooth, fps_effective) - path)
     diffs = target_path - path
-    delta_full = [d.copy() for d in diffs]
+    delta_full = diffs
 
     keep_fov_clamped = float(np.clip(keep_fov, 0.0, 1.0))
     keep_fov_applied = framing_mode == "crop" and keep_fov_clamped > 1e-6
@@ -260,7 +290,7 @@ def stabilize_frames(
         final_matrices, apply_matrices, crop_meta, stabilization_scale = crop
         output_size = (width, height)
     else:
-        apply_matrices = [hm.params_to_matrix(d, base_mode) for d in delta_full]
+        apply_matrices = hm.params_to_matrices(delta_full, base_mode)  # [N,3,3] float32
         final_matrices = apply_matrices
         output_size = (width, height)
         crop_meta = None
@@ -286,7 +316,7 @@ def stabilize_frames(
         off_x = width * 0.5 - (x0 + x1) * 0.5
         off_y = height * 0.5 - (y0 + y1) * 0.5
         shift = np.array([[1.0, 0.0, off_x], [0.0, 1.0, off_y], [0.0, 0.0, 1.0]], dtype=np.float32)
-        final_matrices = [shift @ m for m in apply_matrices]
+        final_matrices = hm.left_multiply(shift, apply_matrices)
         framing_meta.update(
             {
                 "safe_region_origin": [x0, y0],
@@ -297,43 +327,50 @@ def stabilize_frames(
         )
     else:
         shift, output_size = hm.prepare_expand_transform(mins, maxs)
-        final_matrices = [shift @ m for m in apply_matrices]
+        final_matrices = hm.left_multiply(shift, apply_matrices)
         framing_meta["expanded_size"] = list(output_size)
 
-    effective_diffs = (
-        np.array([hm.matrix_to_params(m, base_mode) for m in apply_matrices]) if framing_mode == "crop" else np.array(delta_full)
-    )
+    effective_diffs = hm.matrices_to_params(np.asarray(apply_matrices), base_mode) if framing_mode == "crop" else np.array(delta_full)
     stabilization_scale = float(np.clip(stabilization_scale, 0.0, 1.0))
     strength_effective = strength * stabilization_scale
     effective_target_path = path + effective_diffs
 
     # ---- warp + mask: one fused launch per chunk -------------------------------------------------
     lo, hi = (0, total_frames) if shard is None else shard.frame_range
-    fwd = np.stack([np.asarray(m, dtype=np.float32).reshape(9) for m in final_matrices[lo:hi]], axis=0)[:, None, :]
+    final_matrices = np.asarray(final_matrices, dtype=np.float32)
+    fwd = final_matrices[lo:hi].reshape(-1, 1, 9)
     t0 = _mark("host path/framing solve", t0)
     pending = fused_warp(
         context if shard is None else shard.owned_context(context), fwd, output_size, "bilinear",
         hm.border_value(padding_rgb), want_mask=True, want_pad_count=True, output=output, defer=True,
     )
 
-    # the kernels above are in flight: build the meta tree on the host meanwhile
+    # the kernels above are in flight: build the meta tree on the host meanwhile (when sharded only
+    # the meta rank materialises the per-frame lists; the others return the scalar part)
+    full_meta = shard is None or shard.builds_meta
     per_transition = []
-    for i, (_, mode, conf, resid) in enumerate(chosen):
-        entry = {"index": i, "mode": mode, "confidence": conf}
-        if is_flow:
-            entry["residual"] = resid
-        entry["matrix"] = matrices[i].astype(np.float32).tolist()
-        per_transition.append(entry)
+    if full_meta:
+        mat_lists = matrices.tolist()
+        for i, (_, mode, conf, resid) in enumerate(chosen):
+            entry = {"index": i, "mode": mode, "confidence": conf}
+            if is_flow:
+                entry["residual"] = resid
+            entry["matrix"] = mat_lists[i]
+            per_transition.append(entry)
 
     warp_meta = hm.build_stabilization_warp_meta(
-        source_size=(width, height), output_size=output_size, framing_mode=framing_mode, applied_matrices=final_matrices,
+        source_size=(width, height), output_size=output_size, framing_mode=framing_mode,
+        applied_matrices=final_matrices if full_meta else final_matrices[:0],
     )
     motion_block = None
-    try:
-        motion_block = applied_motion_meta_from_stabilization_warp(warp_meta, fps=fps_effective, source=source_tag)
-    except (KeyError, TypeError, ValueError, np.linalg.LinAlgError):
-        pass
-    path_list, target_list, effective_list = path.tolist(), target_path.tolist(), effective_target_path.tolist()
+    if full_meta:
+        try:
+            motion_block = applied_motion_meta_from_stabilization_warp(warp_meta, fps=fps_effective, source=source_tag)
+        except (KeyError, TypeError, ValueError, np.linalg.LinAlgError):
+            pass
+    path_list, target_list, effective_list = (
+        (path.tolist(), target_path.tolist(), effective_target_path.tolist()) if full_meta else ([], [], [])
+    )
 
     t0 = _mark("meta build (overlaps the warp)", t0)
     frames_out, masks_out, pad_counts = pending()
