@@ -76,6 +76,8 @@ def load_library() -> C.CDLL:
         lib.vstab_warp_fused.restype = i32
         lib.vstab_common_coverage.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
         lib.vstab_common_coverage.restype = i32
+        lib.vstab_coverage_bbox.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+        lib.vstab_coverage_bbox.restype = i32
         if hasattr(lib, "vstab_dis_flow"):
             lib.vstab_dis_flow.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp]
             lib.vstab_dis_flow.restype = i32
@@ -217,6 +219,16 @@ class Handle:
         ow, oh = int(out_size[0]), int(out_size[1])
         out = torch.empty((oh, ow), dtype=torch.uint8, device=fwd.device)
         self._check(self.lib.vstab_common_coverage(self._h, fwd.data_ptr(), n, sh, sw, oh, ow, int(mask_rule), out.data_ptr(), _stream_ptr(fwd.device)))
+        return out
+
+    def coverage_bbox(self, fwd: torch.Tensor, src_size, out_size, mask_rule: int = MASK_RULE_P) -> torch.Tensor:
+        """fwd [N,9] f32 -> int32 [N,4] (xmin, ymin, xmax, ymax) of the 3x3-closed coverage; xmax < 0 = empty."""
+        _check_cuda(fwd, torch.float32, "fwd")
+        n = int(fwd.shape[0])
+        sw, sh = int(src_size[0]), int(src_size[1])
+        ow, oh = int(out_size[0]), int(out_size[1])
+        out = torch.empty((n, 4), dtype=torch.int32, device=fwd.device)
+        self._check(self.lib.vstab_coverage_bbox(self._h, fwd.data_ptr(), n, sh, sw, oh, ow, int(mask_rule), out.data_ptr(), _stream_ptr(fwd.device)))
         return out
 
     # -- K3 + K4 ---------------------------------------------------------------------------------

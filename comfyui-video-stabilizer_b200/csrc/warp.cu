@@ -625,6 +625,73 @@ __global__ void __launch_bounds__(256) common_coverage_kernel(const float* __res
   if (ox < ow && oy < oh) common[(size_t)oy * ow + ox] = all_ok ? 1 : 0;
 }
 
+// Per-frame INTER_NEAREST coverage as bytes (crop solvers: the closing + bounding box below).
+__global__ void __launch_bounds__(256) coverage_u8_kernel(const float* __restrict__ fwd, int sh, int sw, int oh, int ow,
+                                                          int mask_rule, unsigned char* __restrict__ cov) {
+  __shared__ double s_m[9];
+  const int f = blockIdx.z;
+  if (threadIdx.x == 0) vstab_invert3(fwd + (size_t)f * 9, s_m);
+  __syncthreads();
+  const int ox = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (ox >= ow || oy >= oh) return;
+  const double dx = (double)ox, dy = (double)oy;
+  const double X = __dadd_rn(__dadd_rn(__dmul_rn(s_m[0], dx), __dmul_rn(s_m[1], dy)), s_m[2]);
+  const double Y = __dadd_rn(__dadd_rn(__dmul_rn(s_m[3], dx), __dmul_rn(s_m[4], dy)), s_m[5]);
+  const double W = __dadd_rn(__dadd_rn(__dmul_rn(s_m[6], dx), __dmul_rn(s_m[7], dy)), s_m[8]);
+  double cxs = __ddiv_rn(X, W), cys = __ddiv_rn(Y, W);
+  if (mask_rule == VSTAB_MASK_RULE_C) {
+    cxs = rint(cxs);
+    cys = rint(cys);
+  }
+  const bool ok = (cxs >= 0.0) && (cxs <= (double)(sw - 1)) && (cys >= 0.0) && (cys <= (double)(sh - 1));
+  cov[((size_t)f * oh + oy) * ow + ox] = ok ? 1 : 0;
+}
+
+// Bounding box of erode3x3(dilate3x3(coverage)) per frame (cv2 morphology ignores out-of-image
+// neighbours): bbox[f] = {xmin, ymin, xmax, ymax}, initialised to {INT_MAX, INT_MAX, -1, -1}.
+__global__ void __launch_bounds__(256) closed_bbox_kernel(const unsigned char* __restrict__ cov, int oh, int ow,
+                                                          int* __restrict__ bbox) {
+  const int f = blockIdx.z;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const unsigned char* c = cov + (size_t)f * oh * ow;
+  bool closed = false;
+  if (x < ow && y < oh) {
+    closed = true;
+    for (int qy = max(y - 1, 0); qy <= min(y + 1, oh - 1) && closed; ++qy)
+      for (int qx = max(x - 1, 0); qx <= min(x + 1, ow - 1) && closed; ++qx) {
+        bool any = false;
+        for (int ry = max(qy - 1, 0); ry <= min(qy + 1, oh - 1) && !any; ++ry)
+          for (int rx = max(qx - 1, 0); rx <= min(qx + 1, ow - 1) && !any; ++rx) any = c[(size_t)ry * ow + rx] != 0;
+        closed = any;
+      }
+  }
+  int xmin = closed ? x : INT_MAX, ymin = closed ? y : INT_MAX, xmax = closed ? x : -1, ymax = closed ? y : -1;
+  for (int o = 16; o > 0; o >>= 1) {
+    xmin = min(xmin, __shfl_down_sync(0xffffffffu, xmin, o));
+    ymin = min(ymin, __shfl_down_sync(0xffffffffu, ymin, o));
+    xmax = max(xmax, __shfl_down_sync(0xffffffffu, xmax, o));
+    ymax = max(ymax, __shfl_down_sync(0xffffffffu, ymax, o));
+  }
+  if ((threadIdx.x & 31) == 0 && xmax >= 0) {
+    atomicMin(bbox + f * 4 + 0, xmin);
+    atomicMin(bbox + f * 4 + 1, ymin);
+    atomicMax(bbox + f * 4 + 2, xmax);
+    atomicMax(bbox + f * 4 + 3, ymax);
+  }
+}
+
+__global__ void bbox_init_kernel(int* bbox, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    bbox[i * 4 + 0] = INT_MAX;
+    bbox[i * 4 + 1] = INT_MAX;
+    bbox[i * 4 + 2] = -1;
+    bbox[i * 4 + 3] = -1;
+  }
+}
+
 bool g_cubic_tab_ready[64] = {false};
 
 void build_cubic_tab(float tab[32][4]) {
@@ -754,5 +821,31 @@ extern "C" int vstab_common_coverage(vstab_handle* h, const float* fwd_dev, int 
   common_coverage_kernel<<<grid, 256, sizeof(double) * 64 * 9, st>>>(fwd_dev, n, src_h, src_w, out_h,
                                                                     out_w, mask_rule, common_dev);
   VSTAB_LAUNCH_CHECK(h, "common_coverage_kernel");
+  return VSTAB_OK;
+}
+
+extern "C" int vstab_coverage_bbox(vstab_handle* h, const float* fwd_dev, int n, int src_h, int src_w, int out_h, int out_w,
+                                   int mask_rule, int32_t* bbox_dev, void* stream) {
+  if (!h) return vstab_fail(nullptr, VSTAB_ERR_INVALID, "vstab_coverage_bbox: null handle");
+  if (!fwd_dev || !bbox_dev || n < 0 || src_h <= 0 || src_w <= 0 || out_h <= 0 || out_w <= 0)
+    return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_coverage_bbox: bad argument");
+  if (n == 0) return VSTAB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  VSTAB_CUDA(h, cudaSetDevice(h->device));
+  const int chunk = 64;
+  void* ws = nullptr;
+  int rc = vstab_workspace(h, (size_t)chunk * out_h * out_w, &ws);
+  if (rc != VSTAB_OK) return rc;
+  unsigned char* cov = (unsigned char*)ws;
+  bbox_init_kernel<<<vstab_ceil_div(n, 128), 128, 0, st>>>(bbox_dev, n);
+  VSTAB_LAUNCH_CHECK(h, "bbox_init_kernel");
+  for (int f0 = 0; f0 < n; f0 += chunk) {
+    const int F = (n - f0) < chunk ? (n - f0) : chunk;
+    dim3 grid(vstab_ceil_div(out_w, 32), vstab_ceil_div(out_h, 8), F);
+    coverage_u8_kernel<<<grid, 256, 0, st>>>(fwd_dev + (size_t)f0 * 9, src_h, src_w, out_h, out_w, mask_rule, cov);
+    VSTAB_LAUNCH_CHECK(h, "coverage_u8_kernel");
+    closed_bbox_kernel<<<grid, 256, 0, st>>>(cov, out_h, out_w, bbox_dev + (size_t)f0 * 4);
+    VSTAB_LAUNCH_CHECK(h, "closed_bbox_kernel");
+  }
   return VSTAB_OK;
 }

@@ -130,6 +130,14 @@ VSTAB_API int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, int
 VSTAB_API int vstab_common_coverage(vstab_handle* h, const float* fwd_dev, int n, int src_h, int src_w,
                           int out_h, int out_w, int mask_rule, uint8_t* common_dev, void* stream);
 
+/*
+ * Crop solver helper (nodes/stabilizer_utils.py:604-656 finalize_with_masks): for every matrix, the
+ * bounding box of erode3x3(dilate3x3(INTER_NEAREST coverage > 0.5)).
+ * bbox_dev [n][4] int32 = {xmin, ymin, xmax, ymax}; xmax < 0 when the closed coverage is empty.
+ */
+VSTAB_API int vstab_coverage_bbox(vstab_handle* h, const float* fwd_dev, int n, int src_h, int src_w,
+                                  int out_h, int out_w, int mask_rule, int32_t* bbox_dev, void* stream);
+
 /* ---- K3 + K4 : DIS dense optical flow, batched over frame pairs ------------------------- */
 
 /*

@@ -56,11 +56,13 @@ def gen_motion_apply(ref):
         print("apply", name, res.frames.shape, res.meta["motion_apply"])
 
 
-def gen_estimators(ref):
+def gen_estimators(ref, only_crop=False):
     """Flow / Classic stabilizers: per-pair matrices, paths and final matrices (+ small outputs)."""
     import cv2
 
-    for case in cases.STABILIZER_CASES:
+    for case in cases.STABILIZER_CASES + cases.CROP_CASES:
+        if only_crop and case not in cases.CROP_CASES:
+            continue
         frames = cases.make_frames(case)
         mod = ref.video_stabilizer_flow if case["node"] == "flow" else ref.video_stabilizer_classic
         ctx = ref.stabilizer_utils._normalize_video_input([f for f in frames])
@@ -101,9 +103,9 @@ def main():
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_import.load_reference()
-    gens = {"apply": gen_motion_apply, "stab": gen_estimators, "dis": gen_dis}
+    gens = {"apply": gen_motion_apply, "stab": gen_estimators, "dis": gen_dis, "crop": lambda r: gen_estimators(r, True)}
     for key, fn in gens.items():
-        if args.only in (None, key):
+        if args.only == key or (args.only is None and key != "crop"):
             fn(ref)
 
 

@@ -82,6 +82,25 @@ STABILIZER_CASES = [
 ]
 
 
+CROP_CASES = [
+    dict(name="flow_sim_crop06_480p", node="flow", n=8, w=832, h=480, seed=51, frames="texture", framing="crop",
+         mode="similarity", camera_lock=False, strength=1.0, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=24.0,
+         store="summary", patches=[(4, 100, 300, 48, 64)]),
+    dict(name="flow_trans_crop00_480p", node="flow", n=8, w=832, h=480, seed=52, frames="texture", amount=2.0, framing="crop",
+         mode="translation", camera_lock=False, strength=1.0, smooth=1.0, keep_fov=0.0, padding_rgb=PAD, fps=24.0,
+         store="summary", patches=[(4, 100, 300, 48, 64)]),
+    dict(name="flow_sim_crop095_480p", node="flow", n=8, w=832, h=480, seed=53, frames="texture", amount=3.0, framing="crop",
+         mode="similarity", camera_lock=True, strength=1.0, smooth=0.5, keep_fov=0.95, padding_rgb=PAD, fps=24.0,
+         store="summary", patches=[(4, 100, 300, 48, 64)]),
+    dict(name="flow_sim_crop1_480p", node="flow", n=5, w=832, h=480, seed=54, frames="texture", framing="crop",
+         mode="similarity", camera_lock=False, strength=1.0, smooth=0.5, keep_fov=1.0, padding_rgb=PAD, fps=24.0,
+         store="summary", patches=[(2, 100, 300, 48, 64)]),
+    dict(name="classic_sim_crop06_720p", node="classic", n=7, w=1280, h=720, seed=55, frames="texture", framing="crop",
+         mode="similarity", camera_lock=False, strength=1.0, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=24.0,
+         store="summary", patches=[(3, 300, 600, 48, 64)]),
+]
+
+
 def make_gray_pair(case):
     """Working-size uint8 pair for raw DIS parity: smooth texture + known similarity jitter."""
     import synth
