@@ -154,9 +154,11 @@ def normalize_video_input(value: Any, device=None) -> VideoContext:
         dev = _upload_batched(seq.contiguous(), device)
         origin_dtype = np.uint8 if seq.dtype == torch.uint8 else np.float32
         squeeze = dev.shape[3] == 1
+        # IEEE division by a TENSOR 255 (torch turns division by a Python scalar into a multiplication
+        # by the reciprocal on CUDA, which is 1 ulp off numpy's `arr /= 255.0` for some values)
+        div255 = torch.full((), 255.0, dtype=torch.float32, device=device)
         if dev.dtype == torch.uint8:
-            frames = dev.to(torch.float32)
-            frames /= 255.0
+            frames = torch.div(dev.to(torch.float32), div255)
             value_range = "0_255"
         else:
             frames = dev
@@ -166,7 +168,7 @@ def normalize_video_input(value: Any, device=None) -> VideoContext:
             if bool(big.any()):
                 if frames.data_ptr() == seq.data_ptr():
                     frames = frames.clone()
-                frames[big] = frames[big] / 255.0
+                frames[big] = torch.div(frames[big], div255)
         if frames.shape[3] == 1:
             frames = frames.expand(-1, -1, -1, 3)
         elif frames.shape[3] > 3:

@@ -1,0 +1,115 @@
+"""The reference's own script-level checks, re-run against the CUDA path:
+scripts/check_motion_meta.py:289-415 (identity apply, blur==0 baseline path, expand canvas, blur
+determinism, progress tick counts, crop -> crop_and_pad fallback),
+scripts/check_crop_aspect_ratio.py:123-161 (Motion Apply replay of a stabilizer's meta must equal the
+stabilizer's own frames and masks) and scripts/compare_refactor_behavior.py:289-324 (input adapters)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(n, w=32, h=24, seed=0):
+    return np.random.default_rng(seed).random((n, h, w, 3), dtype=np.float32)
+
+
+def _meta(mats, w=32, h=24):
+    from vstab_b200.motion_meta import build_motion_meta_v2
+
+    return {"motion_meta": build_motion_meta_v2(source="generated_shake", frame_count=len(mats), fps=16.0, input_size=(w, h),
+                                                output_size=(w, h), matrices=mats, generator={"node": "test"})}
+
+
+def _ctx(frames):
+    from vstab_b200 import pipeline
+
+    return pipeline.normalize_video_input(torch.from_numpy(np.ascontiguousarray(frames)))
+
+
+def test_identity_blur_zero_expand_determinism_and_ticks():
+    from vstab_b200.motion_apply import apply_motion
+
+    frames = _frames(3)
+    eye = [np.eye(3) for _ in range(3)]
+    base = apply_motion(_ctx(frames), _meta(eye), (127, 127, 127))
+    ident = apply_motion(_ctx(frames), _meta(eye), (127, 127, 127), motion_blur=0.0)
+    assert np.allclose(ident.frames, frames, atol=1e-6) and float(ident.masks.max()) == 0.0
+    assert np.array_equal(ident.frames, base.frames) and np.array_equal(ident.masks, base.masks)
+
+    shift = np.array([[1.0, 0.0, 6.0], [0.0, 1.0, -4.0], [0.0, 0.0, 1.0]])
+    exp = apply_motion(_ctx(frames), _meta([np.eye(3), shift, np.linalg.inv(shift)]), (127, 127, 127), framing_mode="expand")
+    assert exp.frames.shape[1] > 24 and exp.frames.shape[2] > 32 and exp.meta["motion_apply"]["framing_mode"] == "expand"
+
+    blur_m = np.array([[1.0, 0.0, 2.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+    bm = _meta([np.eye(3), blur_m, blur_m @ blur_m])
+    a = apply_motion(_ctx(frames), bm, (127, 127, 127), motion_blur=0.5, motion_blur_samples=7)
+    b = apply_motion(_ctx(frames), bm, (127, 127, 127), motion_blur=0.5, motion_blur_samples=7)
+    assert np.array_equal(a.frames, b.frames) and np.array_equal(a.masks, b.masks)
+    assert a.meta["motion_apply"]["motion_blur"] == 0.5 and a.meta["motion_apply"]["motion_blur_samples"] == 7
+
+    ticks = [0]
+
+    def tick():
+        ticks[0] += 1
+
+    apply_motion(_ctx(frames), bm, (127, 127, 127), motion_blur=0.5, motion_blur_samples=7, progress_callback=tick)
+    assert ticks[0] == 3 * 7
+    ticks[0] = 0
+    apply_motion(_ctx(frames), bm, (127, 127, 127), framing_mode="crop", motion_blur=0.5, motion_blur_samples=7, progress_callback=tick)
+    assert ticks[0] == 3 + 3 * 7
+
+    far = np.array([[1.0, 0.0, 60.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+    fb = apply_motion(_ctx(frames), _meta([np.eye(3), far, np.eye(3)]), (127, 127, 127), framing_mode="crop")
+    assert fb.meta.get("framing_fallback") == "crop_and_pad" and fb.meta["motion_apply"]["framing_mode"] == "crop_and_pad"
+
+
+def test_errors_match_the_reference_messages():
+    from vstab_b200.motion_apply import apply_motion
+
+    frames = _frames(3)
+    with pytest.raises(ValueError, match="Frame count mismatch"):
+        apply_motion(_ctx(frames), _meta([np.eye(3)] * 2), (0, 0, 0))
+    with pytest.raises(ValueError, match="Input frames must match motion_meta.input_size"):
+        apply_motion(_ctx(frames), _meta([np.eye(3)] * 3, w=40), (0, 0, 0))
+    with pytest.raises(ValueError, match="Unsupported interpolation"):
+        apply_motion(_ctx(frames), _meta([np.eye(3)] * 3), (0, 0, 0), interpolation="lanczos")
+    with pytest.raises(ValueError, match="Unsupported framing_mode"):
+        apply_motion(_ctx(frames), _meta([np.eye(3)] * 3), (0, 0, 0), framing_mode="stretch")
+
+
+@pytest.mark.parametrize("framing,mode", [("expand", "similarity"), ("crop_and_pad", "translation")])
+def test_motion_apply_replays_the_stabilizer_exactly(framing, mode):
+    """Replaying a stabilizer's emitted meta through Motion Apply must reproduce its frames and masks bit for bit."""
+    from vstab_b200 import flow
+    from vstab_b200.motion_apply import apply_motion
+
+    frames = cases.make_frames(dict(n=6, w=416, h=240, seed=61, frames="texture"))
+    direct = flow.stabilize_frames(_ctx(frames), framing, mode, False, 1.0, 0.5, 0.6, (127, 127, 127), 24.0)
+    replay = apply_motion(_ctx(frames), direct.meta, (127, 127, 127), framing_mode="crop_and_pad", interpolation="bilinear")
+    assert replay.frames.shape == direct.frames.shape
+    assert np.array_equal(replay.frames, direct.frames) and np.array_equal(replay.masks, direct.masks)
+
+
+def test_input_adapters_agree():
+    """list / batch tensor / dict / uint8 / 0..255 float / 1-channel inputs all reach the same clip in HBM."""
+    from vstab_b200 import pipeline
+
+    frames = _frames(4, 48, 32, seed=3)
+    want = pipeline.normalize_video_input(torch.from_numpy(frames)).frames.cpu().numpy()
+    as_list = pipeline.normalize_video_input([f for f in frames]).frames.cpu().numpy()
+    as_dict = pipeline.normalize_video_input({"frames": torch.from_numpy(frames), "fps": 24.0})
+    assert np.array_equal(want, as_list) and np.array_equal(want, as_dict.frames.cpu().numpy()) and as_dict.fps == 24.0
+    scaled = pipeline.normalize_video_input(torch.from_numpy(frames * np.float32(255.0))).frames.cpu().numpy()
+    assert np.allclose(scaled, want, atol=1e-6)
+    u8 = (frames * 255).astype(np.uint8)
+    got_u8 = pipeline.normalize_video_input(torch.from_numpy(u8)).frames.cpu().numpy()
+    assert np.array_equal(got_u8, u8.astype(np.float32) / np.float32(255.0))
+    chw = pipeline.normalize_video_input([np.moveaxis(f, -1, 0) for f in frames]).frames.cpu().numpy()
+    assert np.array_equal(chw, want)
+    gray = pipeline.normalize_video_input(torch.from_numpy(frames[..., :1].copy())).frames.cpu().numpy()
+    assert gray.shape[-1] == 3 and np.array_equal(gray[..., 0], gray[..., 2])
+    with pytest.raises(ValueError, match="empty"):
+        pipeline.normalize_video_input([])
