@@ -10,12 +10,15 @@
 // Replaces nodes/video_stabilizer_flow.py:560-588, nodes/video_stabilizer_classic.py:491-519,
 // nodes/motion_apply.py:75-122 and :137-202 of the reference.
 //
-// Tiling: a CTA of 256 threads owns a 64x16 output tile.  Warp w owns rows w and w+8, lane l
-// owns columns l and l+32 (stride-1 lanes => conflict-free shared-memory gathers, 3-word
-// stride).  The source footprint of the tile (bounding box of the four projected corners over
-// all samples, plus the tap margin) is staged once into shared memory with 16-byte cp.async
-// copies; taps that fall outside the staged box (degenerate maps) fall back to a global load,
-// so the staging is a pure optimisation and never changes results.
+// Tiling: a CTA of 256 threads owns a 64x32 output tile (two groups of 16 rows).  In a group warp w
+// owns rows w and w+8, lane l owns columns l and l+32 (stride-1 lanes => conflict-free
+// shared-memory gathers, 3-word stride).  The source footprint of the tile (bounding box of the
+// four projected corners over all samples, plus the tap margin) is staged once into shared memory
+// by the TMA engine: one cp.async.bulk per source row, all completing on one mbarrier, issued by
+// warp 0 while the other warps already compute their coordinates.  Taps that fall outside the
+// staged box (degenerate maps) fall back to a global load, so the staging is a pure optimisation
+// and never changes results.  Interior tiles (footprint >= 1 px inside the source, one sample,
+// bilinear) take a branch-free path without any per-tap or per-pixel tests.
 #include "common.cuh"
 
 namespace {
@@ -29,7 +32,7 @@ constexpr int TH = 16 * GROUPS;
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
 #ifndef VSTAB_WARP_MIN_CTAS
-#define VSTAB_WARP_MIN_CTAS 3
+#define VSTAB_WARP_MIN_CTAS 4
 #endif
 constexpr int MIN_CTAS = VSTAB_WARP_MIN_CTAS;
 constexpr int MAX_SAMPLES = 33;
@@ -89,6 +92,30 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
 }
+// ---- bulk asynchronous copies (TMA engine, 1-D form) completing on an mbarrier ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  unsigned done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(phase)
+                 : "memory");
+  } while (!done);
+}
+
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
@@ -100,7 +127,8 @@ template <bool AFFINE, bool VEC>
 __device__ __forceinline__ void interior_tile(const double* __restrict__ s_minv, const float* __restrict__ tile0, int pitch,
                                               int tx0, int ty0, int warp, int lane, int tid, int ow,
                                               float* __restrict__ scratch, float* __restrict__ dst_tile,
-                                              float* __restrict__ mask_tile, int vec_mask) {
+                                              float* __restrict__ mask_tile, int vec_mask, unsigned long long* bar,
+                                              bool bulk_pending) {
   const double m0 = s_minv[0], m1 = s_minv[1], m2 = s_minv[2], m3 = s_minv[3], m4 = s_minv[4], m5 = s_minv[5];
   const double m6 = s_minv[6], m7 = s_minv[7], m8 = s_minv[8];
   const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
@@ -148,8 +176,7 @@ __device__ __forceinline__ void interior_tile(const double* __restrict__ s_minv,
     }
   }
   // the source box has been streaming into shared memory meanwhile
-  cp_async_wait_all();
-  __syncthreads();
+  if (bulk_pending) mbar_wait(bar, 0); else __syncthreads();
 #pragma unroll
   for (int g = 0; g < GROUPS; ++g) {
 #pragma unroll
@@ -197,6 +224,7 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
   double* s_minv = reinterpret_cast<double*>(smem_raw);                       // [34][9], 16B multiple
   float* s_scratch = reinterpret_cast<float*>(s_minv + MINV_SLOTS * 9);       // [8][384]
   int* s_box = reinterpret_cast<int*>(s_scratch + NWARPS * SCRATCH_FLOATS_PER_WARP);  // 8 ints
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_box + 6);  // mbarrier of the bulk copies
   float* s_cubic = reinterpret_cast<float*>(s_box + 8);                       // [32][4] bicubic coefficients
   float* s_tile = s_cubic + 128;                                              // staged source box
 
@@ -210,6 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
   const float* __restrict__ frame = p.src + (size_t)frame_idx * p.sh * p.sw * 3;
 
   if (INTERP == VSTAB_INTERP_BICUBIC && tid < 128) s_cubic[tid] = c_cubic_tab[tid >> 2][tid & 3];
+  if (tid == NTHREADS - 1) mbar_init(s_bar, 1);  // made visible by the __syncthreads below
 
   // ---- inverse matrices + source footprint of the tile (4 corners x S samples) ---------------
   StagedTile tile;
@@ -219,6 +248,7 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
   tile.x1 = tile.y1 = -1;
   tile.pitch = 0;
   bool interior = false;
+  bool bulk_pending = false;  // CTA-uniform: the staged box arrives through bulk copies
   const int txe = min(tx0 + TW, p.ow) - 1;
   const int tye = min(ty0 + TH, p.oh) - 1;
   if (S == 1) {
@@ -301,12 +331,16 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
         tile.pitch = bw * 3;
         const int row_floats = bw * 3;
         if (p.vec_load) {
-          const int row_vec = row_floats >> 2;  // bw % 4 == 0 => exact
-          for (int r = warp; r < bh; r += NWARPS) {
-            const float* g = frame + ((size_t)(by0 + r) * p.sw + bx0) * 3;
-            float* s = s_tile + r * row_floats;
-            for (int v = lane; v < row_vec; v += 32) cp_async16(s + 4 * v, g + 4 * v);
+          // one bulk copy (TMA engine) per source row, issued by warp 0; bw % 4 == 0 keeps every row a
+          // 16-byte multiple at a 16-byte aligned address.  All of them complete on one mbarrier.
+          if (warp == 0) {
+            const unsigned row_bytes = (unsigned)row_floats * 4u;
+            if (lane == 0) mbar_expect_tx(s_bar, row_bytes * (unsigned)bh);
+            __syncwarp();
+            for (int r = lane; r < bh; r += 32)
+              bulk_copy_g2s(s_tile + r * row_floats, frame + ((size_t)(by0 + r) * p.sw + bx0) * 3, row_bytes, s_bar);
           }
+          bulk_pending = true;
         } else {
           for (int r = warp; r < bh; r += NWARPS) {
             const float* g = frame + ((size_t)(by0 + r) * p.sw + bx0) * 3;
@@ -328,16 +362,16 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
     float* mask_tile = p.mask ? p.mask + ((size_t)frame_idx * p.oh + ty0) * p.ow + tx0 : nullptr;
     const float* tile0 = s_tile - (tile.y0 * tile.pitch + tile.x0 * 3);  // so that tile0[sy*pitch + sx*3] is the texel
     if (p.vec_store) {
-      if (affine) interior_tile<true, true>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
-      else interior_tile<false, true>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
+      if (affine) interior_tile<true, true>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_bar, bulk_pending);
+      else interior_tile<false, true>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_bar, bulk_pending);
     } else {
-      if (affine) interior_tile<true, false>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
-      else interior_tile<false, false>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
+      if (affine) interior_tile<true, false>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_bar, bulk_pending);
+      else interior_tile<false, false>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_bar, bulk_pending);
     }
     return;
   }
-  cp_async_wait_all();
-  __syncthreads();
+  if (bulk_pending) mbar_wait(s_bar, 0);
+  __syncthreads();  // also orders the scalar staging path and the s_minv / s_cubic writes
 
   // ---- per-pixel resampling ------------------------------------------------------------------
   // Sample-outer loop: the per-sample row/column products of the inverse matrix are hoisted out of
