@@ -180,7 +180,8 @@ def compute_bounding_boxes(matrices: Sequence[np.ndarray], width: int, height: i
     )
     # one 3x3 @ 3x4 product per matrix, evaluated term by term in the order of a dot product so the
     # stacked form returns the same bits as the reference's per-matrix `matrix @ corners`
-    if any(np.asarray(x).dtype != np.float32 for x in matrices):
+    stacked_f32 = isinstance(matrices, np.ndarray) and matrices.ndim == 3 and matrices.dtype == np.float32
+    if not stacked_f32 and any(np.asarray(x).dtype != np.float32 for x in matrices):
         # float64 @ float64 goes through BLAS (fused multiply-adds): keep the per-matrix product
         lo, hi = [], []
         for mat in matrices:
@@ -190,7 +191,7 @@ def compute_bounding_boxes(matrices: Sequence[np.ndarray], width: int, height: i
             hi.append([q[0].max(), q[1].max()])
         return np.array(lo), np.array(hi)
     # float32 @ float64 promotes the float32 operand and multiplies without FMA (verified bit-equal)
-    m = np.stack([np.asarray(x) for x in matrices], axis=0).astype(np.float64)
+    m = (matrices if stacked_f32 else np.stack([np.asarray(x) for x in matrices], axis=0)).astype(np.float64)
     q = m[:, :, 0:1] * corners[0][None, None, :] + m[:, :, 1:2] * corners[1][None, None, :] + m[:, :, 2:3] * corners[2][None, None, :]
     q = q / q[:, 2:3, :]
     return np.stack([q[:, 0].min(axis=1), q[:, 1].min(axis=1)], axis=1), np.stack([q[:, 0].max(axis=1), q[:, 1].max(axis=1)], axis=1)

@@ -201,6 +201,40 @@ def applied_motion_meta_from_stabilization_warp(warp_meta, fps: float, source: s
     )
 
 
+def applied_motion_meta_from_matrices(matrices, *, source_size, output_size, fps: float, source: str) -> Dict[str, Any]:
+    """Same block as applied_motion_meta_from_stabilization_warp(build_stabilization_warp_meta(...)) for
+    matrices that are already a float32 numpy stack: the checks (finite, invertible) run once on the
+    stack instead of once per nested-list entry.  Raises the same ValueErrors."""
+    stack = np.asarray(matrices, dtype=np.float32).reshape(-1, 3, 3).astype(np.float64)
+    src = _size_pair("stabilization_warp", {"source_size": list(source_size)}, "source_size")
+    out = _size_pair("stabilization_warp", {"output_size": list(output_size)}, "output_size")
+    fps = float(fps)
+    if not np.isfinite(fps) or fps <= 0.0:
+        raise ValueError("motion_meta.fps must be a positive number.")
+    if not isinstance(source, str) or not source:
+        raise ValueError("motion_meta.source must be a non-empty string.")
+    for i in np.flatnonzero(~np.isfinite(stack).all(axis=(1, 2))):
+        raise ValueError(f"stabilization_warp.per_frame[{int(i)}].applied_matrix must contain finite numbers.")
+    try:
+        np.linalg.inv(stack)
+    except np.linalg.LinAlgError:
+        for i, m in enumerate(stack):
+            try:
+                np.linalg.inv(m)
+            except np.linalg.LinAlgError as exc:
+                raise ValueError(f"stabilization_warp.per_frame[{i}].applied_matrix is not invertible.") from exc
+    return {
+        "version": 2,
+        "source": source,
+        "frame_count": int(stack.shape[0]),
+        "fps": fps,
+        "input_size": [int(src[0]), int(src[1])],
+        "output_size": [int(out[0]), int(out[1])],
+        "matrix_convention": "input_to_output",
+        "per_frame": [{"index": i, "matrix": m} for i, m in enumerate(stack.tolist())],
+    }
+
+
 def resolve_motion_meta(meta: Dict[str, Any]) -> MotionMeta:
     if not isinstance(meta, dict):
         raise ValueError("meta must be a dictionary containing motion_meta or stabilization_warp.")

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _native, hostmath as hm
-from .motion_meta import applied_motion_meta_from_stabilization_warp
+from .motion_meta import applied_motion_meta_from_matrices, applied_motion_meta_from_stabilization_warp
 from .pipeline import VideoContext, fused_warp
 
 MODE_NAMES = _native.MODE_NAMES
@@ -116,6 +116,8 @@ def replay_mode_ladder(cands: PairCandidates, requested_mode: str, *, with_resid
             confs = (cands.n_inliers[:first_fallback, k] / n_valid.astype(np.float64)).tolist()
         resid = cands.residual[:first_fallback, k].tolist()
         out = [(mats32[i], requested_mode, confs[i], resid[i] if with_residual else None) for i in range(first_fallback)]
+        if first_fallback == total:
+            return out, active, mats32
     for p in range(first_fallback, total):
         n_valid = int(cands.n_valid[p].max())
         chosen = None
@@ -147,7 +149,7 @@ def replay_mode_ladder(cands: PairCandidates, requested_mode: str, *, with_resid
         if used != active:
             active = used
         out.append((matrix, used, conf, resid if with_residual else None))
-    return out, active
+    return out, active, np.stack([c[0] for c in out], axis=0) if out else np.zeros((0, 3, 3), np.float32)
 
 
 class _Progress:
@@ -248,13 +250,12 @@ def stabilize_frames(
     if shard is not None:
         cands = shard.gather_candidates(cands)
         t0 = _mark("all-gather candidates", t0)
-    chosen, active_mode = replay_mode_ladder(cands, transform_mode, with_residual=is_flow)
+    chosen, active_mode, stacked = replay_mode_ladder(cands, transform_mode, with_residual=is_flow)
     t0 = _mark("ladder", t0)
     progress.advance(estimation_steps)
     check()
 
     base_mode = transform_mode
-    stacked = np.stack([c[0] for c in chosen], axis=0)
     if work is not None:
         stacked = hm.rescale_transforms_to_full(stacked, (width, height), work)
     matrices = stacked  # [P,3,3] float32, full-resolution per-pair transforms
@@ -365,7 +366,9 @@ def stabilize_frames(
     motion_block = None
     if full_meta:
         try:
-            motion_block = applied_motion_meta_from_stabilization_warp(warp_meta, fps=fps_effective, source=source_tag)
+            motion_block = applied_motion_meta_from_matrices(
+                final_matrices, source_size=(width, height), output_size=output_size, fps=fps_effective, source=source_tag
+            )
         except (KeyError, TypeError, ValueError, np.linalg.LinAlgError):
             pass
     path_list, target_list, effective_list = (

@@ -31,7 +31,7 @@ out["decode_ms"], d = t(lambda: _native.decode_fit_results(raw))
 out["estimate_total_ms"], cands = t(lambda: flow.estimate_candidates(ctx, 960, 540, "similarity"))
 t0 = time.perf_counter()
 for _ in range(5):
-    chosen, active = core.replay_mode_ladder(cands, "similarity", with_residual=True)
+    chosen, active, _ = core.replay_mode_ladder(cands, "similarity", with_residual=True)
 out["ladder_ms"] = (time.perf_counter() - t0) / 5 * 1e3
 out["full_step_ms"], res = t(lambda: flow.stabilize_frames(ctx, "crop_and_pad", "similarity", False, 0.7, 0.5, 0.6, (127, 127, 127), 16.0, output="device"))
 fwd = torch.eye(3, device=dev).reshape(1, 1, 9).repeat(N, 1, 1).contiguous()

@@ -49,7 +49,7 @@ def _worker(rank, world, port, total, out):
     a, b = shard.pair_range
     local = PairCandidates.from_array(full.to_array()[a:b], 12)
     gathered = shard.gather_candidates(local)
-    chosen, active = replay_mode_ladder(gathered, "similarity", with_residual=True)
+    chosen, active, _ = replay_mode_ladder(gathered, "similarity", with_residual=True)
     pads = shard.gather_pad_counts(np.arange(*shard.frame_range) * 10)
     out[rank] = (gathered.to_array(), [c[1] for c in chosen], active, pads, shard.frame_range, shard.load_range)
     dist.destroy_process_group()
@@ -63,7 +63,7 @@ def test_two_rank_gather_equals_single_process():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), total, out), nprocs=world, join=True)
     full = _fake_candidates(total)
-    chosen, active = replay_mode_ladder(full, "similarity", with_residual=True)
+    chosen, active, _ = replay_mode_ladder(full, "similarity", with_residual=True)
     modes = [c[1] for c in chosen]
     assert modes[6] == "similarity" and modes[7] == "translation" and modes[-1] == "translation" and active == "translation"
     for r in range(world):
