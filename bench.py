@@ -235,13 +235,17 @@ def main():
         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
         "launches": len(warp_log), "avg_launch_ms": warp_ms / max(len(warp_log), 1),
         "algorithmic_bytes_per_frame": 12 * HEIGHT * WIDTH + 16 * HEIGHT * WIDTH,
+        "algorithmic_bytes_per_launch": warp_bytes / max(len(warp_log), 1),
         "share_of_step": warp_ms / total_ms,
     }
     traffic_file = os.path.join(ROOT, "profiles", "warp_traffic.json")
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as fh:
-                roofline["traffic"] = json.load(fh).get("dram_bytes_per_launch")
+                t = json.load(fh)
+                # ncu capture was a 32-frame launch; DRAM traffic scales per frame (no inter-frame reuse)
+                roofline["traffic"] = t["dram_bytes_per_frame"] * (sum(x[2] for x in warp_log) / max(len(warp_log), 1))
+                roofline["traffic_source"] = t.get("source")
         except Exception:
             pass
 

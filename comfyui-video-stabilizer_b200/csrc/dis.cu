@@ -161,25 +161,23 @@ __device__ __forceinline__ float quad_reduce(float v, unsigned mask) {
 
 // One 8x8 patch evaluation by a quad: lane l handles pixel columns l and l+4 of every row.
 // kind 0: mean-normalised SSD only; kind 1: SSD + gradient-weighted sums (processPatchMeanNorm).
+// The template patch (I0 and its gradients) is the same for every evaluation of a patch, so the
+// caller converts it to float once (z / gx / gy: [row][0] = column l, [row][1] = column l+4).
 template <int KIND>
-__device__ __forceinline__ float patch_eval(const unsigned char* __restrict__ I0p, const unsigned char* __restrict__ I1p,
-                                            const short* __restrict__ gxp, const short* __restrict__ gyp, int s0, int s1,
-                                            const Bil& b, int l, float xgs, float ygs, float& dUx, float& dUy,
-                                            unsigned mask) {
+__device__ __forceinline__ float patch_eval(const float (&z)[8][2], const float (&gxv)[8][2], const float (&gyv)[8][2],
+                                            const unsigned char* __restrict__ I1p, int s1, const Bil& b, int l, float xgs,
+                                            float ygs, float& dUx, float& dUy, unsigned mask) {
   float sd = 0.f, sq = 0.f, mx = 0.f, my = 0.f;
   float a0 = I1p[l], a1 = I1p[l + 1], a4 = I1p[l + 4], a5 = I1p[l + 5];
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     const unsigned char* nb = I1p + (r + 1) * s1;
     const float b0 = nb[l], b1 = nb[l + 1], b4 = nb[l + 4], b5 = nb[l + 5];
-    const float z0 = I0p[r * s0 + l], z4 = I0p[r * s0 + l + 4];
-    const float dl = b.w00 * a0 + b.w01 * a1 + b.w10 * b0 + b.w11 * b1 - z0;
-    const float dr = b.w00 * a4 + b.w01 * a5 + b.w10 * b4 + b.w11 * b5 - z4;
+    const float dl = b.w00 * a0 + b.w01 * a1 + b.w10 * b0 + b.w11 * b1 - z[r][0];
+    const float dr = b.w00 * a4 + b.w01 * a5 + b.w10 * b4 + b.w11 * b5 - z[r][1];
     if (KIND == 1) {
-      const float px0 = gxp[r * s0 + l], px4 = gxp[r * s0 + l + 4];
-      const float py0 = gyp[r * s0 + l], py4 = gyp[r * s0 + l + 4];
-      mx = mx + (dl * px0 + dr * px4);
-      my = my + (dl * py0 + dr * py4);
+      mx = mx + (dl * gxv[r][0] + dr * gxv[r][1]);
+      my = my + (dl * gyv[r][0] + dr * gyv[r][1]);
     }
     sq = sq + (dl * dl + dr * dr);
     sd = sd + (dl + dr);
@@ -242,20 +240,30 @@ __global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P) {
           sy = Sy[k];
         }
         const unsigned char* I0p = I0 + i * w + j;
+        float z[8][2], gxv[8][2], gyv[8][2];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          z[r][0] = I0p[r * w + l];
+          z[r][1] = I0p[r * w + l + 4];
+          gxv[r][0] = gx[(i + r) * w + j + l];
+          gxv[r][1] = gx[(i + r) * w + j + l + 4];
+          gyv[r][0] = gy[(i + r) * w + j + l];
+          gyv[r][1] = gy[(i + r) * w + j + l + 4];
+        }
         float dux, duy;
         // spatial propagation: own / previous column / previous row of this pass
         Bil b = bil_weights((float)i, (float)j, sx, sy, w, h, we);
-        float min_ssd = patch_eval<0>(I0p, I1e + b.off, nullptr, nullptr, w, we, b, l, 0.f, 0.f, dux, duy, qmask);
+        float min_ssd = patch_eval<0>(z, gxv, gyv, I1e + b.off, we, b, l, 0.f, 0.f, dux, duy, qmask);
         if (c > 0) {
           const float cx = Sx[k - dir], cy = Sy[k - dir];
           b = bil_weights((float)i, (float)j, cx, cy, w, h, we);
-          const float s = patch_eval<0>(I0p, I1e + b.off, nullptr, nullptr, w, we, b, l, 0.f, 0.f, dux, duy, qmask);
+          const float s = patch_eval<0>(z, gxv, gyv, I1e + b.off, we, b, l, 0.f, 0.f, dux, duy, qmask);
           if (s < min_ssd) { min_ssd = s; sx = cx; sy = cy; }
         }
         if (row_in_stripe > 0) {
           const float cx = Sx[k - dir * ws], cy = Sy[k - dir * ws];
           b = bil_weights((float)i, (float)j, cx, cy, w, h, we);
-          const float s = patch_eval<0>(I0p, I1e + b.off, nullptr, nullptr, w, we, b, l, 0.f, 0.f, dux, duy, qmask);
+          const float s = patch_eval<0>(z, gxv, gyv, I1e + b.off, we, b, l, 0.f, 0.f, dux, duy, qmask);
           if (s < min_ssd) { min_ssd = s; sx = cx; sy = cy; }
         }
         float cur_Ux = sx, cur_Uy = sy;
@@ -267,8 +275,7 @@ __global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P) {
         float prev_ssd = kInf;
         for (int t = 0; t < inner; t++) {
           b = bil_weights((float)i, (float)j, cur_Ux, cur_Uy, w, h, we);
-          const float ssd = patch_eval<1>(I0p, I1e + b.off, gx + i * w + j, gy + i * w + j, w, we, b, l, xgs, ygs, dux,
-                                          duy, qmask);
+          const float ssd = patch_eval<1>(z, gxv, gyv, I1e + b.off, we, b, l, xgs, ygs, dux, duy, qmask);
           const float dx = invH11 * dux + invH12 * duy;
           const float dy = invH12 * dux + invH22 * duy;
           cur_Ux -= dx;
