@@ -51,5 +51,41 @@ def main():
     print(json.dumps(out, indent=1))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def blur_probe():
+    """BASELINE config 4 shape: bicubic, 33 shutter samples, 1080p."""
+    import vstab_loader
+    from vstab_b200.motion_apply import sample_matrices
+    import synth
+
+    dev = torch.device("cuda", 0)
+    h = _native.get_handle(dev)
+    w, hh, n = 1920, 1080, 16
+    src = torch.rand((n, hh, w, 3), device=dev)
+    mats = synth.shake_matrices(n, 0, w, hh)
+    out = {}
+    for interp in ("bilinear", "bicubic"):
+        for s in (5, 33):
+            fwd = torch.from_numpy(sample_matrices(list(mats), 0.5, s)).to(dev)
+            dst = torch.empty((n, hh + 8, w + 10, 3), device=dev)
+            mask = torch.empty((n, hh + 8, w + 10), device=dev)
+            for _ in range(2):
+                h.warp_fused(src, fwd, (w + 10, hh + 8), interp, (0.5, 0.5, 0.5), out=dst, mask_out=mask)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                h.warp_fused(src, fwd, (w + 10, hh + 8), interp, (0.5, 0.5, 0.5), out=dst, mask_out=mask)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            taps = (4 if interp == "bilinear" else 16) * s
+            out[f"{interp}_S{s}"] = {"ms_per_frame": ms / n, "fps": n / ms * 1e3, "Gtaps_per_s": taps * (w + 10) * (hh + 8) * n / ms / 1e6}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "blur":
+    blur_probe()
