@@ -40,6 +40,7 @@ extern "C" void vstab_destroy(vstab_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->ws) cudaFree(h->ws);
+  if (h->plan) cudaFree(h->plan);
   for (int i = 0; i < h->n_area_cache; ++i)
     if (h->area_cache[i].dev) cudaFree(h->area_cache[i].dev);
   free(h);

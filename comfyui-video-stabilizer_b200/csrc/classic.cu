@@ -366,7 +366,7 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
     return vstab_fail(hnd, VSTAB_ERR_INVALID, "vstab_gftt_lk: bad argument");
   if (n_frames < 2) return VSTAB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  VSTAB_CUDA(hnd, cudaSetDevice(hnd->device));
+  VSTAB_ENTER(hnd);
   const int h = height, w = width;
   const int kChunk = 32;  // frames per pass of the corner detector (bounds the double row-sum buffer)
   int cap = 1024;  // per-frame candidate capacity: power of two >= h*w/4 (a 3x3 local maximum needs its own 2x2 block)

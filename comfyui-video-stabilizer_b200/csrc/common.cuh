@@ -26,6 +26,9 @@ struct vstab_handle {
   // grow-only device workspace (DIS pyramids, fit scratch)
   void* ws;
   size_t ws_bytes;
+  // grow-only tile plan of the streaming resampler
+  void* plan;
+  size_t plan_bytes;
   vstab_area_cache_entry area_cache[VSTAB_AREA_CACHE];
   int n_area_cache;
 };
@@ -54,6 +57,14 @@ static inline int vstab_fail(vstab_handle* h, int code, const char* fmt, const c
       return vstab_fail((h), VSTAB_ERR_CUDA, "launch of %s failed: %s", name,            \
                         cudaGetErrorString(_e));                                         \
     (h)->launches++;                                                                     \
+  } while (0)
+
+// Entry of every compute call: select the handle's device and drop any error another library left
+// sticky on this host thread, so that the launch checks below only ever report our own launches.
+#define VSTAB_ENTER(h)                            \
+  do {                                            \
+    VSTAB_CUDA((h), cudaSetDevice((h)->device));  \
+    (void)cudaGetLastError();                     \
   } while (0)
 
 // Returns a device workspace of at least `bytes` (grow-only; synchronises only when growing).

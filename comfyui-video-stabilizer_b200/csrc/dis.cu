@@ -792,7 +792,7 @@ extern "C" int vstab_dis_flow(vstab_handle* hnd, const uint8_t* gray_dev, int n_
   if (((height >> kFinest) - kPatch) / kStride + 1 > 8 * kStripes)
     return vstab_fail(hnd, VSTAB_ERR_UNSUPPORTED, "vstab_dis_flow: working image taller than 960 px is not supported");
   cudaStream_t st = (cudaStream_t)stream;
-  VSTAB_CUDA(hnd, cudaSetDevice(hnd->device));
+  VSTAB_ENTER(hnd);
 
   const int kChunk = 256;  // pairs per pass
   for (int p0 = 0; p0 < n_frames - 1; p0 += kChunk) {

@@ -840,7 +840,7 @@ extern "C" int vstab_fit_batch(vstab_handle* h, const float* prev_dev, const flo
   if (n_pairs == 0) return VSTAB_OK;
   static_assert(sizeof(FitOut) == sizeof(vstab_fit_result), "FitOut must mirror vstab_fit_result");
   cudaStream_t st = (cudaStream_t)stream;
-  VSTAB_CUDA(h, cudaSetDevice(h->device));
+  VSTAB_ENTER(h);
   // workspace: compacted correspondences, valid counts, consensus flags
   const size_t bytes_pts = sizeof(float2) * (size_t)n_pairs * n_pts;
   const size_t off_c = (bytes_pts + 255) & ~(size_t)255;

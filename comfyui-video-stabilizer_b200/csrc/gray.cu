@@ -226,7 +226,7 @@ extern "C" int vstab_gray_working(vstab_handle* h, const float* rgb_dev, int n, 
     return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_gray_working: bad argument");
   if (n == 0) return VSTAB_OK;
   if (n > 65535) return vstab_fail(h, VSTAB_ERR_UNSUPPORTED, "vstab_gray_working: n > 65535 frames per call");
-  VSTAB_CUDA(h, cudaSetDevice(h->device));
+  VSTAB_ENTER(h);
   RgbLuma s{rgb_dev, width};
   return launch_area(h, s, (size_t)height * width * 3, n, height, width, gray_dev, work_h, work_w,
                      (cudaStream_t)stream);

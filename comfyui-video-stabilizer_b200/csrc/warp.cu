@@ -10,15 +10,30 @@
 // Replaces nodes/video_stabilizer_flow.py:560-588, nodes/video_stabilizer_classic.py:491-519,
 // nodes/motion_apply.py:75-122 and :137-202 of the reference.
 //
-// Tiling: a CTA of 256 threads owns a 64x32 output tile (two groups of 16 rows).  In a group warp w
-// owns rows w and w+8, lane l owns columns l and l+32 (stride-1 lanes => conflict-free
-// shared-memory gathers, 3-word stride).  The source footprint of the tile (bounding box of the
-// four projected corners over all samples, plus the tap margin) is staged once into shared memory
-// by the TMA engine: one cp.async.bulk per source row, all completing on one mbarrier, issued by
-// warp 0 while the other warps already compute their coordinates.  Taps that fall outside the
-// staged box (degenerate maps) fall back to a global load, so the staging is a pure optimisation
-// and never changes results.  Interior tiles (footprint >= 1 px inside the source, one sample,
-// bilinear) take a branch-free path without any per-tap or per-pixel tests.
+// Two kernels share the arithmetic:
+//
+//  * warp_stream_kernel (single sample, 16-byte aligned source rows: every node path except motion blur).
+//    A plan pass computes per 64x16 output tile where its source box lies and what kind of tile it is.
+//    The resampling kernel is persistent (4 CTAs of 8 warps per SM); tiles are handed out by a global
+//    ticket so that the tiles in flight are neighbours in the frame and their halos hit in L2.  Each CTA
+//    runs a two-stage shared-memory pipeline fed by the TMA engine: one cp.async.bulk.tensor per tile
+//    (3-D descriptor over [frame][row][3*col], zero fill outside the frame, L2 evict_last) completing on an
+//    mbarrier; the warp that finishes a tile last issues the load that reuses its stage.  Interior tiles
+//    (footprint >= 1 px inside the source) run a branch-free bilinear path, edge tiles (footprint leaves
+//    the frame but fits the box) add per-tap border substitution and the coverage test, everything else
+//    (partial tiles, bicubic, oversized footprints) takes the general path.  Output leaves as streaming
+//    (evict-first) 16-byte stores through a per-warp shared-memory transpose.
+//
+//  * warp_fused_kernel (motion blur with up to 33 samples, unaligned sources, VSTAB_STAGE_GLOBAL): one CTA
+//    of 256 threads per 64x32 output tile; the bounding box of the four projected corners over all samples
+//    is staged by one cp.async.bulk per source row on one mbarrier.  Taps outside the staged box fall back
+//    to a global load, so staging is a pure optimisation and never changes results.
+//
+// In both, warp w owns rows w and w+8 of a 16-row group and lane l owns columns l and l+32 (stride-1
+// lanes => conflict-free shared-memory gathers with a 3-word stride).
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -88,10 +103,6 @@ __device__ __forceinline__ void fetch_rgb(const WarpParams& p, const float* __re
   b = __ldg(s + 2);
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
-}
 // ---- bulk asynchronous copies (TMA engine, 1-D form) completing on an mbarrier ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -106,7 +117,10 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+#ifndef VSTAB_WAIT_SLEEP
+#define VSTAB_WAIT_SLEEP 1
+#endif
+__device__ __forceinline__ void mbar_wait_spin(unsigned long long* bar, unsigned phase) {
   unsigned done;
   do {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
@@ -116,19 +130,35 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
   } while (!done);
 }
 
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// wait with a suspend-time hint: the warp sleeps in hardware instead of burning issue slots
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned phase) {
+  unsigned done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(phase), "r"(20000u)
+                 : "memory");
+  } while (!done);
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  if (VSTAB_WAIT_SLEEP) mbar_wait_sleep(bar, phase); else mbar_wait_spin(bar, phase);
+}
+
 
 // Interior tile, single sample, bilinear: every tap is inside the staged box and every pixel is
 // covered, so the loop body is coordinates -> 12 shared-memory loads -> blend, nothing else.
 // Column / row products of the inverse matrix are hoisted (2 columns x 2 rows per thread).
-template <bool AFFINE, bool VEC>
-__device__ __forceinline__ void interior_tile(const double* __restrict__ s_minv, const float* __restrict__ tile0, int pitch,
+template <bool AFFINE, bool VEC, bool WAIT, int G, int PITCH>
+__device__ __forceinline__ void interior_tile(const double* __restrict__ s_minv, const float* __restrict__ tile0, int pitch_rt,
                                               int tx0, int ty0, int warp, int lane, int tid, int ow,
                                               float* __restrict__ scratch, float* __restrict__ dst_tile,
                                               float* __restrict__ mask_tile, int vec_mask, unsigned long long* bar,
                                               bool bulk_pending) {
+  const int pitch = PITCH ? PITCH : pitch_rt;
   const double m0 = s_minv[0], m1 = s_minv[1], m2 = s_minv[2], m3 = s_minv[3], m4 = s_minv[4], m5 = s_minv[5];
   const double m6 = s_minv[6], m7 = s_minv[7], m8 = s_minv[8];
   const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
@@ -140,9 +170,9 @@ __device__ __forceinline__ void interior_tile(const double* __restrict__ s_minv,
     ay[k] = __dmul_rn(m3, dx);
     if (!AFFINE) aw[k] = __dmul_rn(m6, dx);
   }
-  int ixs[4 * GROUPS], iys[4 * GROUPS];
+  int ixs[4 * G], iys[4 * G];
 #pragma unroll
-  for (int g = 0; g < GROUPS; ++g) {
+  for (int g = 0; g < G; ++g) {
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       const double dy = (double)(ty0 + g * 16 + warp + NWARPS * rr);
@@ -166,7 +196,7 @@ __device__ __forceinline__ void interior_tile(const double* __restrict__ s_minv,
   }
   if (mask_tile) {  // fully covered tile: mask = 0; 64 x 16*GROUPS floats = GROUPS 16-byte stores per thread
 #pragma unroll
-    for (int g = 0; g < GROUPS; ++g) {
+    for (int g = 0; g < G; ++g) {
       float* mrow = mask_tile + (size_t)(g * 16 + (tid >> 4)) * ow + (tid & 15) * 4;
       if (vec_mask) {
         *reinterpret_cast<float4*>(mrow) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -176,9 +206,11 @@ __device__ __forceinline__ void interior_tile(const double* __restrict__ s_minv,
     }
   }
   // the source box has been streaming into shared memory meanwhile
-  if (bulk_pending) mbar_wait(bar, 0); else __syncthreads();
+  if (WAIT) {
+    if (bulk_pending) mbar_wait(bar, 0); else __syncthreads();
+  }
 #pragma unroll
-  for (int g = 0; g < GROUPS; ++g) {
+  for (int g = 0; g < G; ++g) {
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
 #pragma unroll
@@ -216,6 +248,278 @@ __device__ __forceinline__ void interior_tile(const double* __restrict__ s_minv,
       __syncwarp();
     }
   }
+}
+
+// General tile: any sample count, both interpolations, border handling, coverage mask and padded
+// count.  Uses the staged box where it can and global loads elsewhere; only warp-level
+// synchronisation inside, so it serves both the one-tile-per-CTA kernel and the streaming kernel.
+template <int INTERP, int G>
+__device__ __forceinline__ void general_tile_body(const WarpParams& p, const float* __restrict__ frame, int frame_idx, int tx0, int ty0,
+                                             const double* __restrict__ s_minv, const StagedTile& tile,
+                                             const float* __restrict__ s_cubic, float* __restrict__ scratch, int warp, int lane) {
+  const int S = p.samples;
+  const float* __restrict__ t_smem = tile.smem;
+  // ---- per-pixel resampling ------------------------------------------------------------------
+  // Sample-outer loop: the per-sample row/column products of the inverse matrix are hoisted out of
+  // the 4 pixels a thread owns; the float32 accumulation per pixel is still in sample order.
+  const float fS = (float)S;
+  unsigned int padded = 0;
+  const double x_hi = (double)(p.sw - 1), y_hi = (double)(p.sh - 1);
+  const bool t_on = tile.active;
+  const int t_x0 = tile.x0, t_y0 = tile.y0, t_x1 = tile.x1, t_y1 = tile.y1, t_pitch = tile.pitch;
+  const double dxs[2] = {(double)(tx0 + lane), (double)(tx0 + lane + 32)};
+
+  for (int g = 0; g < G; ++g) {  // row groups of 16 output rows
+  const int tyg = ty0 + g * 16;
+  float acc[4][3];
+  int cover[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
+    cover[q] = 0;
+  }
+  const double dys[2] = {(double)(tyg + warp), (double)(tyg + warp + NWARPS)};
+  for (int s = 0; s < S; ++s) {
+    const double* m = s_minv + s * 9;
+    const double m2 = m[2], m5 = m[5], m8 = m[8];
+    double ax[2], ay[2], aw[2], bx[2], by[2], bw[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      ax[k] = __dmul_rn(m[0], dxs[k]);
+      ay[k] = __dmul_rn(m[3], dxs[k]);
+      aw[k] = __dmul_rn(m[6], dxs[k]);
+      bx[k] = __dmul_rn(m[1], dys[k]);
+      by[k] = __dmul_rn(m[4], dys[k]);
+      bw[k] = __dmul_rn(m[7], dys[k]);
+    }
+    // affine maps (last row 0 0 w): W is the same double for every pixel => one division per CTA
+    const bool affine = (m[6] == 0.0) && (m[7] == 0.0);
+    const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int rr = q >> 1, cc = q & 1;
+      const int oy = tyg + warp + rr * NWARPS, ox = tx0 + lane + cc * 32;
+      if (oy >= p.oh || ox >= p.ow) continue;
+      const double X = __dadd_rn(__dadd_rn(ax[cc], bx[rr]), m2);
+      const double Y = __dadd_rn(__dadd_rn(ay[cc], by[rr]), m5);
+      double W, sc;
+      if (affine) {
+        W = m8;
+        sc = sc_affine;
+      } else {
+        W = __dadd_rn(__dadd_rn(aw[cc], bw[rr]), m8);
+        sc = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
+      }
+      // -- coverage (INTER_NEAREST ones warp): fl(X/W), fl(Y/W) inside the closed source rectangle.
+      //    X * fl(1/W) decides everything that is not within 1e-6 px of a boundary; only those
+      //    pixels pay for the exact divisions.
+      {
+        bool ok;
+        const double rw = sc * 0.03125;  // fl(32/W)/32 == fl(1/W): scaling by 2^-5 is exact
+        const double qx = X * rw, qy = Y * rw;
+        const double band = 1e-6;
+        if (p.mask_rule == VSTAB_MASK_RULE_P && qx > band && qx < x_hi - band && qy > band && qy < y_hi - band) {
+          ok = true;
+        } else if (p.mask_rule == VSTAB_MASK_RULE_P && (qx < -band || qx > x_hi + band || qy < -band || qy > y_hi + band)) {
+          ok = false;
+        } else {
+          double cxs = __ddiv_rn(X, W), cys = __ddiv_rn(Y, W);
+          if (p.mask_rule == VSTAB_MASK_RULE_C) {
+            cxs = rint(cxs);
+            cys = rint(cys);
+          }
+          ok = (cxs >= 0.0) && (cxs <= x_hi) && (cys >= 0.0) && (cys <= y_hi);
+        }
+        cover[q] += ok ? 1 : 0;
+      }
+      // -- 1/32-px fixed-point source coordinate
+      double fx = __dmul_rn(X, sc), fy = __dmul_rn(Y, sc);
+      fx = fmax(-2147483648.0, fmin(2147483647.0, fx));
+      fy = fmax(-2147483648.0, fmin(2147483647.0, fy));
+      const int ix = __double2int_rn(fx), iy = __double2int_rn(fy);
+      int sx = ix >> 5, sy = iy >> 5;
+      sx = max(-32768, min(32767, sx));
+      sy = max(-32768, min(32767, sy));
+      const int fxi = ix & 31, fyi = iy & 31;
+      float vr, vg, vb;
+      if (INTERP == VSTAB_INTERP_BILINEAR) {
+        const float fx1 = (float)fxi * 0.03125f, fy1 = (float)fyi * 0.03125f;
+        const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
+        const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
+        const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
+        float r0, g0, b0, r1, g1, b1, r2, g2, b2, r3, g3, b3;
+        bool have = true;
+        if (t_on && sx >= t_x0 && sx < t_x1 && sy >= t_y0 && sy < t_y1) {
+          // whole 2x2 footprint inside the staged (in-image) box: 12 conflict-free LDS
+          const float* s0 = t_smem + (sy - t_y0) * t_pitch + (sx - t_x0) * 3;
+          const float* s1 = s0 + t_pitch;
+          r0 = s0[0]; g0 = s0[1]; b0 = s0[2]; r1 = s0[3]; g1 = s0[4]; b1 = s0[5];
+          r2 = s1[0]; g2 = s1[1]; b2 = s1[2]; r3 = s1[3]; g3 = s1[4]; b3 = s1[5];
+        } else if (sx >= p.sw || sx + 1 < 0 || sy >= p.sh || sy + 1 < 0) {
+          // remapBilinear: footprint entirely outside the source => the border colour itself
+          have = false;
+          r0 = g0 = b0 = r1 = g1 = b1 = r2 = g2 = b2 = r3 = g3 = b3 = 0.f;
+        } else {
+          fetch_rgb(p, frame, tile, sy, sx, r0, g0, b0);
+          fetch_rgb(p, frame, tile, sy, sx + 1, r1, g1, b1);
+          fetch_rgb(p, frame, tile, sy + 1, sx, r2, g2, b2);
+          fetch_rgb(p, frame, tile, sy + 1, sx + 1, r3, g3, b3);
+        }
+        if (have) {
+          vr = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0, w00), __fmul_rn(r1, w01)), __fmul_rn(r2, w10)), __fmul_rn(r3, w11));
+          vg = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(g0, w00), __fmul_rn(g1, w01)), __fmul_rn(g2, w10)), __fmul_rn(g3, w11));
+          vb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b0, w00), __fmul_rn(b1, w01)), __fmul_rn(b2, w10)), __fmul_rn(b3, w11));
+        } else {
+          vr = p.border[0];
+          vg = p.border[1];
+          vb = p.border[2];
+        }
+      } else {
+        float wx[4], wy[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          wx[k] = s_cubic[fxi * 4 + k];
+          wy[k] = s_cubic[fyi * 4 + k];
+        }
+        const int bxs = sx - 1, bys = sy - 1;
+        if (bxs >= 0 && bxs < p.sw - 3 && bys >= 0 && bys < p.sh - 3) {
+          vr = vg = vb = 0.f;
+          if (t_on && bxs >= t_x0 && bxs + 3 <= t_x1 && bys >= t_y0 && bys + 3 <= t_y1) {
+            const float* s0 = t_smem + (bys - t_y0) * t_pitch + (bxs - t_x0) * 3;
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1) {
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const float w = __fmul_rn(wy[k1], wx[k2]);
+                const float* t = s0 + k1 * t_pitch + k2 * 3;
+                vr = __fadd_rn(vr, __fmul_rn(t[0], w));
+                vg = __fadd_rn(vg, __fmul_rn(t[1], w));
+                vb = __fadd_rn(vb, __fmul_rn(t[2], w));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1) {
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const float w = __fmul_rn(wy[k1], wx[k2]);
+                float r, g, b;
+                fetch_rgb(p, frame, tile, bys + k1, bxs + k2, r, g, b);
+                vr = __fadd_rn(vr, __fmul_rn(r, w));
+                vg = __fadd_rn(vg, __fmul_rn(g, w));
+                vb = __fadd_rn(vb, __fmul_rn(b, w));
+              }
+            }
+          }
+        } else {
+          // remapBicubic border branch: cv + sum over in-range taps of (S - cv) * w
+          vr = p.border[0];
+          vg = p.border[1];
+          vb = p.border[2];
+          if (!(bxs >= p.sw || bxs + 3 < 0 || bys >= p.sh || bys + 3 < 0)) {
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1) {
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const int yy = bys + k1, xx = bxs + k2;
+                if ((unsigned)xx < (unsigned)p.sw && (unsigned)yy < (unsigned)p.sh) {
+                  const float w = __fmul_rn(wy[k1], wx[k2]);
+                  float r, g, b;
+                  fetch_rgb(p, frame, tile, yy, xx, r, g, b);
+                  vr = __fadd_rn(vr, __fmul_rn(__fsub_rn(r, p.border[0]), w));
+                  vg = __fadd_rn(vg, __fmul_rn(__fsub_rn(g, p.border[1]), w));
+                  vb = __fadd_rn(vb, __fmul_rn(__fsub_rn(b, p.border[2]), w));
+                }
+              }
+            }
+          }
+        }
+      }
+      if (S == 1) {  // _warp_with_matrices copies the warp; only the blur path accumulates from zero
+        acc[q][0] = vr;
+        acc[q][1] = vg;
+        acc[q][2] = vb;
+      } else {
+        acc[q][0] = __fadd_rn(acc[q][0], vr);
+        acc[q][1] = __fadd_rn(acc[q][1], vg);
+        acc[q][2] = __fadd_rn(acc[q][2], vb);
+      }
+    }
+  }
+
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int rr = q >> 1, cc = q & 1;
+    const int oy = tyg + warp + rr * NWARPS, ox = tx0 + lane + cc * 32;
+    if (oy < p.oh && ox < p.ow) {
+      if (S > 1) {
+        acc[q][0] = __fdiv_rn(acc[q][0], fS);
+        acc[q][1] = __fdiv_rn(acc[q][1], fS);
+        acc[q][2] = __fdiv_rn(acc[q][2], fS);
+      }
+      // padding mask: 1 - (coverage > .5) for one sample, 1 - count/S for blur; <1e-3 -> 0
+      float mval;
+      if (S == 1) {
+        mval = cover[q] ? 0.0f : 1.0f;
+      } else {
+        mval = __fsub_rn(1.0f, __fdiv_rn((float)cover[q], fS));
+        if (mval < 1e-3f) mval = 0.0f;
+      }
+      if (mval > 1e-3f) ++padded;
+      if (p.mask) p.mask[((size_t)frame_idx * p.oh + oy) * p.ow + ox] = mval;
+      if (!p.vec_store) {
+        float* d = p.dst + (((size_t)frame_idx * p.oh + oy) * p.ow + ox) * 3;
+        d[0] = acc[q][0];
+        d[1] = acc[q][1];
+        d[2] = acc[q][2];
+      }
+    }
+    if (p.vec_store) {
+      float* sc = scratch + rr * (TW * 3) + (lane + cc * 32) * 3;
+      sc[0] = acc[q][0];
+      sc[1] = acc[q][1];
+      sc[2] = acc[q][2];
+    }
+  }
+
+  if (p.vec_store) {
+    __syncwarp();
+    // 2 rows x 192 floats = 96 float4 per warp, 3 per lane, fully coalesced 16-byte stores.
+    const int valid_floats = (min(tx0 + TW, p.ow) - tx0) * 3;  // multiple of 4 when ow % 4 == 0
+#pragma unroll
+    for (int q3 = 0; q3 < 3; ++q3) {
+      const int q = lane + q3 * 32;
+      const int rr = q / 48, qi = q - rr * 48;
+      const int oy = tyg + warp + rr * NWARPS;
+      if (oy < p.oh && qi * 4 < valid_floats) {
+        const float4 v = *reinterpret_cast<const float4*>(scratch + rr * (TW * 3) + qi * 4);
+        float* d = p.dst + (((size_t)frame_idx * p.oh + oy) * p.ow + tx0) * 3 + qi * 4;
+        *reinterpret_cast<float4*>(d) = v;
+      }
+    }
+  }
+  if (p.vec_store) __syncwarp();
+  }  // row groups
+
+  if (p.pad_count) {
+    for (int o = 16; o > 0; o >>= 1) padded += __shfl_down_sync(0xffffffffu, padded, o);
+    if (lane == 0 && padded) atomicAdd(p.pad_count + frame_idx, padded);
+  }
+}
+
+template <int INTERP, int G>
+__device__ __forceinline__ void general_tile(const WarpParams& p, const float* __restrict__ frame, int frame_idx, int tx0, int ty0,
+                                             const double* __restrict__ s_minv, const StagedTile& tile,
+                                             const float* __restrict__ s_cubic, float* __restrict__ scratch, int warp, int lane) {
+  general_tile_body<INTERP, G>(p, frame, frame_idx, tx0, ty0, s_minv, tile, s_cubic, scratch, warp, lane);
+}
+// out-of-line copy for the streaming kernel: border tiles are the minority there and must not
+// dictate the register allocation of the tile loop
+template <int INTERP, int G>
+__device__ __noinline__ void general_tile_call(const WarpParams& p, const float* __restrict__ frame, int frame_idx, int tx0, int ty0,
+                                               const double* __restrict__ s_minv, const StagedTile& tile,
+                                               const float* __restrict__ s_cubic, float* __restrict__ scratch, int warp, int lane) {
+  general_tile_body<INTERP, G>(p, frame, frame_idx, tx0, ty0, s_minv, tile, s_cubic, scratch, warp, lane);
 }
 
 template <int INTERP>
@@ -362,75 +666,264 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
     float* mask_tile = p.mask ? p.mask + ((size_t)frame_idx * p.oh + ty0) * p.ow + tx0 : nullptr;
     const float* tile0 = s_tile - (tile.y0 * tile.pitch + tile.x0 * 3);  // so that tile0[sy*pitch + sx*3] is the texel
     if (p.vec_store) {
-      if (affine) interior_tile<true, true>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_bar, bulk_pending);
-      else interior_tile<false, true>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_bar, bulk_pending);
+      if (affine) interior_tile<true, true, true, GROUPS, 0>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_bar, bulk_pending);
+      else interior_tile<false, true, true, GROUPS, 0>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_bar, bulk_pending);
     } else {
-      if (affine) interior_tile<true, false>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_bar, bulk_pending);
-      else interior_tile<false, false>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_bar, bulk_pending);
+      if (affine) interior_tile<true, false, true, GROUPS, 0>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_bar, bulk_pending);
+      else interior_tile<false, false, true, GROUPS, 0>(s_minv, tile0, tile.pitch, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_bar, bulk_pending);
     }
     return;
   }
   if (bulk_pending) mbar_wait(s_bar, 0);
   __syncthreads();  // also orders the scalar staging path and the s_minv / s_cubic writes
 
-  // ---- per-pixel resampling ------------------------------------------------------------------
-  // Sample-outer loop: the per-sample row/column products of the inverse matrix are hoisted out of
-  // the 4 pixels a thread owns; the float32 accumulation per pixel is still in sample order.
-  const float fS = (float)S;
-  float* scratch = s_scratch + warp * SCRATCH_FLOATS_PER_WARP;
-  unsigned int padded = 0;
-  const double x_hi = (double)(p.sw - 1), y_hi = (double)(p.sh - 1);
-  const bool t_on = tile.active;
-  const int t_x0 = tile.x0, t_y0 = tile.y0, t_x1 = tile.x1, t_y1 = tile.y1, t_pitch = tile.pitch;
-  const double dxs[2] = {(double)(tx0 + lane), (double)(tx0 + lane + 32)};
+  general_tile<INTERP, GROUPS>(p, frame, frame_idx, tx0, ty0, s_minv, tile, s_cubic, s_scratch + warp * SCRATCH_FLOATS_PER_WARP, warp, lane);
+}
 
-  for (int g = 0; g < GROUPS; ++g) {  // row groups of 16 output rows
-  const int tyg = ty0 + g * 16;
-  float acc[4][3];
-  int cover[4];
+// ---- streaming variant (single sample, 16-byte aligned source rows) ---------------------------------
+// Every node path except motion blur.  A plan kernel computes, per 64x16 output tile, where its source box
+// lies and whether the tile is interior; the resampling kernel is persistent (4 CTAs per SM) and walks its
+// tiles through a two-stage shared-memory pipeline: ONE cp.async.bulk.tensor (3-D TMA descriptor over
+// [frame][row][3*col], zero fill outside the frame) brings the 72x24 source box of tile i+2 while the
+// eight warps resample tiles i and i+1, so no warp waits for DRAM or for a per-tile prologue.  The warp
+// that finishes a tile last issues the next load for that stage.
+#ifndef VSTAB_TMA_HINT
+#define VSTAB_TMA_HINT 1
+#endif
+#ifndef VSTAB_STREAM_STORES
+#define VSTAB_STREAM_STORES 1
+#endif
+constexpr int S_G = 1;                 // row groups per streamed tile
+constexpr int S_TH = 16 * S_G;         // 64 x 16 output pixels
+constexpr int S_BW = 76;               // source box: tile + tap margin + alignment + rotation / zoom slack
+#ifndef VSTAB_S_BH_EXTRA
+#define VSTAB_S_BH_EXTRA 8
+#endif
+constexpr int S_BH = S_TH + VSTAB_S_BH_EXTRA;
+constexpr int S_PITCH = S_BW * 3;      // floats per staged row (228 <= 256, the TMA box limit)
+constexpr int S_BOX_BYTES = S_PITCH * S_BH * 4;
+constexpr int S_STAGE_BYTES = (S_BOX_BYTES + 127) / 128 * 128;  // stage buffers stay 128-byte aligned
+#ifndef VSTAB_S_STAGES
+#define VSTAB_S_STAGES 2
+#endif
+#ifndef VSTAB_S_CTAS
+#define VSTAB_S_CTAS 4
+#endif
+constexpr int S_STAGES = VSTAB_S_STAGES;
+constexpr int S_CTAS = VSTAB_S_CTAS;
+
+
+struct TilePlan {
+  int ox;        // source pixel of the box origin, multiple of 4 (may be negative: the TMA engine zero-fills)
+  int oy_flags;  // (oy << 4) | flags; flags bit 0: box loaded, bit 1: interior tile, bit 3: edge tile
+};
+
+struct StageMeta {
+  double minv[10];  // 80 bytes, written by a bulk copy
+  int tx0, ty0, frame, flags, ox, oy;
+  int pad[6];
+};
+static_assert(sizeof(StageMeta) == 128, "StageMeta layout");
+
+template <int INTERP>
+__global__ void __launch_bounds__(256) warp_plan_kernel(const float* __restrict__ fwd, unsigned ntiles, int gx, int gy, int ow, int oh,
+                                                        int sw, int sh, TilePlan* __restrict__ plan, double* __restrict__ minv) {
+  constexpr int LO = (INTERP == VSTAB_INTERP_BILINEAR) ? 1 : 2;
+  constexpr int HI = (INTERP == VSTAB_INTERP_BILINEAR) ? 2 : 3;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const unsigned per_frame = (unsigned)gx * (unsigned)gy;
+  const int frame = (int)(t / per_frame);
+  const unsigned rem = t - (unsigned)frame * per_frame;
+  const int tyi = (int)(rem / (unsigned)gx);
+  const int tx0 = (int)(rem - (unsigned)tyi * (unsigned)gx) * TW, ty0 = tyi * S_TH;
+  const int txe = min(tx0 + TW, ow) - 1, tye = min(ty0 + S_TH, oh) - 1;
+  double mi[9];
+  vstab_invert3(fwd + (size_t)frame * 9, mi);
+  if (rem == 0) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
-    cover[q] = 0;
+    for (int k = 0; k < 9; ++k) minv[(size_t)frame * 10 + k] = mi[k];
+    minv[(size_t)frame * 10 + 9] = 0.0;
   }
-  const double dys[2] = {(double)(tyg + warp), (double)(tyg + warp + NWARPS)};
-  for (int s = 0; s < S; ++s) {
-    const double* m = s_minv + s * 9;
-    const double m2 = m[2], m5 = m[5], m8 = m[8];
-    double ax[2], ay[2], aw[2], bx[2], by[2], bw[2];
+  int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+  bool bad = false;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      ax[k] = __dmul_rn(m[0], dxs[k]);
-      ay[k] = __dmul_rn(m[3], dxs[k]);
-      aw[k] = __dmul_rn(m[6], dxs[k]);
-      bx[k] = __dmul_rn(m[1], dys[k]);
-      by[k] = __dmul_rn(m[4], dys[k]);
-      bw[k] = __dmul_rn(m[7], dys[k]);
+  for (int c = 0; c < 4; ++c) {
+    const double cx = (c & 1) ? (double)txe : (double)tx0;
+    const double cy = (c & 2) ? (double)tye : (double)ty0;
+    const double X = mi[0] * cx + mi[1] * cy + mi[2];
+    const double Y = mi[3] * cx + mi[4] * cy + mi[5];
+    const double W = mi[6] * cx + mi[7] * cy + mi[8];
+    const double sx = X / W, sy = Y / W;
+    // convexity of the projected tile needs W to keep one sign; positive is the sane case
+    if (!(W > 1e-12) || !(fabs(sx) < 1e8) || !(fabs(sy) < 1e8)) {
+      bad = true;
+    } else {
+      const int fx = (int)floor(sx), fy = (int)floor(sy);
+      mnx = min(mnx, fx); mxx = max(mxx, fx);
+      mny = min(mny, fy); mxy = max(mxy, fy);
     }
-    // affine maps (last row 0 0 w): W is the same double for every pixel => one division per CTA
-    const bool affine = (m[6] == 0.0) && (m[7] == 0.0);
-    const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
+  }
+  int ox = 0, oy = 0, flags = 0;
+  if (!bad) {
+    // the TMA engine wants the innermost coordinate on a 16-byte boundary: ox is a multiple of 4 pixels
+    const int need_w = mxx - mnx + 1 + LO + HI, need_h = mxy - mny + 1 + LO + HI;
+    ox = (mnx - LO - (need_w + 3 <= S_BW ? (S_BW - need_w - 3) / 2 : 0)) & ~3;
+    oy = mny - LO - (need_h <= S_BH ? (S_BH - need_h) / 2 : 0);
+    flags = 1;
+    if ((INTERP == VSTAB_INTERP_BILINEAR) && (mxx + HI <= ox + S_BW - 1) && need_h <= S_BH && (tx0 + TW <= ow) && (ty0 + S_TH <= oh) &&
+        (mnx - LO >= 1) && (mny - LO >= 1) && (mxx + HI <= sw - 2) && (mxy + HI <= sh - 2))
+      flags |= 2;
+    else if ((INTERP == VSTAB_INTERP_BILINEAR) && (mxx + HI <= ox + S_BW - 1) && need_h <= S_BH && (tx0 + TW <= ow) && (ty0 + S_TH <= oh) &&
+             (mnx - LO >= -30000) && (mny - LO >= -30000) && (mxx + HI <= 30000) && (mxy + HI <= 30000))
+      flags |= 8;  // edge tile: the staged box holds every tap position, some of them outside the frame
+  }
+  TilePlan pl;
+  pl.ox = ox;
+  pl.oy_flags = oy * 16 + flags;
+  plan[t] = pl;
+}
+
+__device__ __forceinline__ void tma_load_box(void* smem_dst, const void* tmap, int c0, int c1, int c2, unsigned long long* bar) {
+#if VSTAB_TMA_HINT
+  // source rows are re-read by the neighbouring tiles (halo): keep them in L2 ahead of the write stream
+  unsigned long long policy;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(policy));
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+#else
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+#endif
+}
+
+// One thread: publish the stage's meta block and start the copies of tile t (box + inverse matrix).
+__device__ __forceinline__ void stream_issue(const void* tmap, int2 pl, const double* __restrict__ minv, unsigned t, unsigned per_frame,
+                                             int gx, StageMeta* meta, float* box, unsigned long long* full) {
+  const int frame = (int)(t / per_frame);
+  const unsigned rem = t - (unsigned)frame * per_frame;
+  const int tyi = (int)(rem / (unsigned)gx);
+  const int flags = pl.y & 15, oy = pl.y >> 4;
+  meta->tx0 = (int)(rem - (unsigned)tyi * (unsigned)gx) * TW;
+  meta->ty0 = tyi * S_TH;
+  meta->frame = frame;
+  meta->flags = flags;
+  meta->ox = pl.x;
+  meta->oy = oy;
+  // arrive.expect_tx has release semantics: the meta block is visible to whoever acquires the phase
+  const bool do_load = (flags & 1) != 0;
+  mbar_expect_tx(full, 80u + (do_load ? (unsigned)S_BOX_BYTES : 0u));
+  bulk_copy_g2s(meta->minv, minv + (size_t)frame * 10, 80u, full);
+  if (do_load) tma_load_box(box, tmap, pl.x * 3, oy, frame, full);
+}
+
+// Interior tile of the streaming kernel (64x16, box already in shared memory, compile-time pitch):
+// coordinates are computed pixel by pixel so that few values stay live across the tile loop.
+template <bool AFFINE, bool VEC>
+__device__ __forceinline__ void stream_interior(const double* __restrict__ s_minv, const float* __restrict__ tile0, int tx0, int ty0,
+                                                int warp, int lane, int tid, int ow, float* __restrict__ scratch,
+                                                float* __restrict__ dst_tile, float* __restrict__ mask_tile, int vec_mask) {
+  const double m0 = s_minv[0], m1 = s_minv[1], m2 = s_minv[2], m3 = s_minv[3], m4 = s_minv[4], m5 = s_minv[5];
+  const double m8 = s_minv[8];
+  const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
+  if (mask_tile) {  // fully covered tile: mask = 0; 64 x 16 floats = one 16-byte store per thread
+    float* mrow = mask_tile + (size_t)(tid >> 4) * ow + (tid & 15) * 4;
+    if (vec_mask) {
+      if (VSTAB_STREAM_STORES) __stcs(reinterpret_cast<float4*>(mrow), make_float4(0.f, 0.f, 0.f, 0.f));
+      else *reinterpret_cast<float4*>(mrow) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      mrow[0] = 0.f; mrow[1] = 0.f; mrow[2] = 0.f; mrow[3] = 0.f;
+    }
+  }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int rr = q >> 1, cc = q & 1;
-      const int oy = tyg + warp + rr * NWARPS, ox = tx0 + lane + cc * 32;
-      if (oy >= p.oh || ox >= p.ow) continue;
-      const double X = __dadd_rn(__dadd_rn(ax[cc], bx[rr]), m2);
-      const double Y = __dadd_rn(__dadd_rn(ay[cc], by[rr]), m5);
-      double W, sc;
-      if (affine) {
-        W = m8;
-        sc = sc_affine;
-      } else {
-        W = __dadd_rn(__dadd_rn(aw[cc], bw[rr]), m8);
+  for (int rr = 0; rr < 2; ++rr) {
+    const double dy = (double)(ty0 + warp + NWARPS * rr);
+    const double bx = __dmul_rn(m1, dy), by = __dmul_rn(m4, dy);
+    double bw = 0.0;
+    if (!AFFINE) bw = __dmul_rn(s_minv[7], dy);
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const double dx = (double)(tx0 + lane + 32 * cc);
+      const double X = __dadd_rn(__dadd_rn(__dmul_rn(m0, dx), bx), m2);
+      const double Y = __dadd_rn(__dadd_rn(__dmul_rn(m3, dx), by), m5);
+      double sc = sc_affine;
+      if (!AFFINE) {
+        const double W = __dadd_rn(__dadd_rn(__dmul_rn(s_minv[6], dx), bw), m8);
         sc = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
       }
-      // -- coverage (INTER_NEAREST ones warp): fl(X/W), fl(Y/W) inside the closed source rectangle.
-      //    X * fl(1/W) decides everything that is not within 1e-6 px of a boundary; only those
-      //    pixels pay for the exact divisions.
+      // |coordinates| < 2^15 here, so cv2's INT_MIN/INT_MAX and short saturation are no-ops
+      const int ix = __double2int_rn(__dmul_rn(X, sc)), iy = __double2int_rn(__dmul_rn(Y, sc));
+      const float fx1 = (float)(ix & 31) * 0.03125f, fy1 = (float)(iy & 31) * 0.03125f;
+      const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
+      const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
+      const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
+      const float* s0 = tile0 + (iy >> 5) * S_PITCH + (ix >> 5) * 3;
+      const float* s1 = s0 + S_PITCH;
+      float v[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch)
+        v[ch] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s0[ch], w00), __fmul_rn(s0[3 + ch], w01)), __fmul_rn(s1[ch], w10)),
+                          __fmul_rn(s1[3 + ch], w11));
+      float* o = VEC ? scratch + rr * (TW * 3) + (lane + cc * 32) * 3 : dst_tile + ((size_t)(warp + rr * NWARPS) * ow + lane + cc * 32) * 3;
+      o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+    }
+  }
+  if (VEC) {
+    __syncwarp();
+#pragma unroll
+    for (int q3 = 0; q3 < 3; ++q3) {
+      const int q = lane + q3 * 32;
+      const int rr = q >= 48 ? 1 : 0, qi = q - rr * 48;
+      const float4 val = *reinterpret_cast<const float4*>(scratch + rr * (TW * 3) + qi * 4);
+      float4* o4 = reinterpret_cast<float4*>(dst_tile + (size_t)(warp + rr * NWARPS) * ow * 3 + qi * 4);
+      if (VSTAB_STREAM_STORES) __stcs(o4, val); else *o4 = val;  // written once, never re-read by this launch
+    }
+    __syncwarp();
+  }
+}
+
+// Edge tile of the streaming kernel: a full 64x16 tile whose footprint leaves the source frame but still
+// fits the staged box.  Same arithmetic as stream_interior plus what the frame border needs: per-tap
+// BORDER_CONSTANT substitution (the TMA engine zero-filled those texels), remapBilinear's "footprint
+// entirely outside" rule, the coverage test of the padding mask and the padded-pixel count.
+template <bool AFFINE, bool VEC>
+__device__ __forceinline__ void stream_edge(const WarpParams& p, const double* __restrict__ s_minv, const float* __restrict__ tile0,
+                                            int tx0, int ty0, int frame_idx, int warp, int lane, float* __restrict__ scratch,
+                                            float* __restrict__ dst_tile, float* __restrict__ mask_tile) {
+  const double m0 = s_minv[0], m1 = s_minv[1], m2 = s_minv[2], m3 = s_minv[3], m4 = s_minv[4], m5 = s_minv[5];
+  const double m8 = s_minv[8];
+  const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
+  const double x_hi = (double)(p.sw - 1), y_hi = (double)(p.sh - 1);
+  const float br = p.border[0], bg = p.border[1], bb = p.border[2];
+  const int ow = p.ow;
+  unsigned padded = 0;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const double dy = (double)(ty0 + warp + NWARPS * rr);
+    const double bx = __dmul_rn(m1, dy), by = __dmul_rn(m4, dy);
+    double bw = 0.0;
+    if (!AFFINE) bw = __dmul_rn(s_minv[7], dy);
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const double dx = (double)(tx0 + lane + 32 * cc);
+      const double X = __dadd_rn(__dadd_rn(__dmul_rn(m0, dx), bx), m2);
+      const double Y = __dadd_rn(__dadd_rn(__dmul_rn(m3, dx), by), m5);
+      double W = m8, sc = sc_affine;
+      if (!AFFINE) {
+        W = __dadd_rn(__dadd_rn(__dmul_rn(s_minv[6], dx), bw), m8);
+        sc = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
+      }
+      // coverage (INTER_NEAREST ones warp, closed source rectangle): X * fl(1/W) decides everything that is
+      // not within 1e-6 px of a boundary; only those pixels pay for the exact divisions
+      bool ok;
       {
-        bool ok;
-        const double rw = sc * 0.03125;  // fl(32/W)/32 == fl(1/W): scaling by 2^-5 is exact
+        const double rw = sc * 0.03125;
         const double qx = X * rw, qy = Y * rw;
         const double band = 1e-6;
         if (p.mask_rule == VSTAB_MASK_RULE_P && qx > band && qx < x_hi - band && qy > band && qy < y_hi - band) {
@@ -445,180 +938,189 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
           }
           ok = (cxs >= 0.0) && (cxs <= x_hi) && (cys >= 0.0) && (cys <= y_hi);
         }
-        cover[q] += ok ? 1 : 0;
       }
-      // -- 1/32-px fixed-point source coordinate
-      double fx = __dmul_rn(X, sc), fy = __dmul_rn(Y, sc);
-      fx = fmax(-2147483648.0, fmin(2147483647.0, fx));
-      fy = fmax(-2147483648.0, fmin(2147483647.0, fy));
-      const int ix = __double2int_rn(fx), iy = __double2int_rn(fy);
-      int sx = ix >> 5, sy = iy >> 5;
-      sx = max(-32768, min(32767, sx));
-      sy = max(-32768, min(32767, sy));
-      const int fxi = ix & 31, fyi = iy & 31;
-      float vr, vg, vb;
-      if (INTERP == VSTAB_INTERP_BILINEAR) {
-        const float fx1 = (float)fxi * 0.03125f, fy1 = (float)fyi * 0.03125f;
-        const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
-        const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
-        const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
-        float r0, g0, b0, r1, g1, b1, r2, g2, b2, r3, g3, b3;
-        bool have = true;
-        if (t_on && sx >= t_x0 && sx < t_x1 && sy >= t_y0 && sy < t_y1) {
-          // whole 2x2 footprint inside the staged (in-image) box: 12 conflict-free LDS
-          const float* s0 = s_tile + (sy - t_y0) * t_pitch + (sx - t_x0) * 3;
-          const float* s1 = s0 + t_pitch;
-          r0 = s0[0]; g0 = s0[1]; b0 = s0[2]; r1 = s0[3]; g1 = s0[4]; b1 = s0[5];
-          r2 = s1[0]; g2 = s1[1]; b2 = s1[2]; r3 = s1[3]; g3 = s1[4]; b3 = s1[5];
-        } else if (sx >= p.sw || sx + 1 < 0 || sy >= p.sh || sy + 1 < 0) {
-          // remapBilinear: footprint entirely outside the source => the border colour itself
-          have = false;
-          r0 = g0 = b0 = r1 = g1 = b1 = r2 = g2 = b2 = r3 = g3 = b3 = 0.f;
-        } else {
-          fetch_rgb(p, frame, tile, sy, sx, r0, g0, b0);
-          fetch_rgb(p, frame, tile, sy, sx + 1, r1, g1, b1);
-          fetch_rgb(p, frame, tile, sy + 1, sx, r2, g2, b2);
-          fetch_rgb(p, frame, tile, sy + 1, sx + 1, r3, g3, b3);
-        }
-        if (have) {
-          vr = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0, w00), __fmul_rn(r1, w01)), __fmul_rn(r2, w10)), __fmul_rn(r3, w11));
-          vg = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(g0, w00), __fmul_rn(g1, w01)), __fmul_rn(g2, w10)), __fmul_rn(g3, w11));
-          vb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b0, w00), __fmul_rn(b1, w01)), __fmul_rn(b2, w10)), __fmul_rn(b3, w11));
-        } else {
-          vr = p.border[0];
-          vg = p.border[1];
-          vb = p.border[2];
-        }
-      } else {
-        float wx[4], wy[4];
+      const float mval = ok ? 0.0f : 1.0f;
+      padded += ok ? 0u : 1u;
+      if (mask_tile) __stcs(mask_tile + (size_t)(warp + rr * NWARPS) * ow + lane + cc * 32, mval);
+      // the plan keeps |coordinates| < 2^15 for edge tiles: cv2's saturations are no-ops
+      const int ix = __double2int_rn(__dmul_rn(X, sc)), iy = __double2int_rn(__dmul_rn(Y, sc));
+      const int sx = ix >> 5, sy = iy >> 5;
+      const float fx1 = (float)(ix & 31) * 0.03125f, fy1 = (float)(iy & 31) * 0.03125f;
+      const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
+      const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
+      const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
+      const bool x0in = (unsigned)sx < (unsigned)p.sw, x1in = (unsigned)(sx + 1) < (unsigned)p.sw;
+      const bool y0in = (unsigned)sy < (unsigned)p.sh, y1in = (unsigned)(sy + 1) < (unsigned)p.sh;
+      const bool in00 = x0in && y0in, in01 = x1in && y0in, in10 = x0in && y1in, in11 = x1in && y1in;
+      const bool any_in = (x0in || x1in) && (y0in || y1in);  // else: remapBilinear returns the border colour itself
+      const float* s0 = tile0 + sy * S_PITCH + sx * 3;
+      const float* s1 = s0 + S_PITCH;
+      float v[3];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          wx[k] = s_cubic[fxi * 4 + k];
-          wy[k] = s_cubic[fyi * 4 + k];
-        }
-        const int bxs = sx - 1, bys = sy - 1;
-        if (bxs >= 0 && bxs < p.sw - 3 && bys >= 0 && bys < p.sh - 3) {
-          vr = vg = vb = 0.f;
-          if (t_on && bxs >= t_x0 && bxs + 3 <= t_x1 && bys >= t_y0 && bys + 3 <= t_y1) {
-            const float* s0 = s_tile + (bys - t_y0) * t_pitch + (bxs - t_x0) * 3;
-#pragma unroll
-            for (int k1 = 0; k1 < 4; ++k1) {
-#pragma unroll
-              for (int k2 = 0; k2 < 4; ++k2) {
-                const float w = __fmul_rn(wy[k1], wx[k2]);
-                const float* t = s0 + k1 * t_pitch + k2 * 3;
-                vr = __fadd_rn(vr, __fmul_rn(t[0], w));
-                vg = __fadd_rn(vg, __fmul_rn(t[1], w));
-                vb = __fadd_rn(vb, __fmul_rn(t[2], w));
-              }
-            }
-          } else {
-#pragma unroll
-            for (int k1 = 0; k1 < 4; ++k1) {
-#pragma unroll
-              for (int k2 = 0; k2 < 4; ++k2) {
-                const float w = __fmul_rn(wy[k1], wx[k2]);
-                float r, g, b;
-                fetch_rgb(p, frame, tile, bys + k1, bxs + k2, r, g, b);
-                vr = __fadd_rn(vr, __fmul_rn(r, w));
-                vg = __fadd_rn(vg, __fmul_rn(g, w));
-                vb = __fadd_rn(vb, __fmul_rn(b, w));
-              }
-            }
-          }
-        } else {
-          // remapBicubic border branch: cv + sum over in-range taps of (S - cv) * w
-          vr = p.border[0];
-          vg = p.border[1];
-          vb = p.border[2];
-          if (!(bxs >= p.sw || bxs + 3 < 0 || bys >= p.sh || bys + 3 < 0)) {
-#pragma unroll
-            for (int k1 = 0; k1 < 4; ++k1) {
-#pragma unroll
-              for (int k2 = 0; k2 < 4; ++k2) {
-                const int yy = bys + k1, xx = bxs + k2;
-                if ((unsigned)xx < (unsigned)p.sw && (unsigned)yy < (unsigned)p.sh) {
-                  const float w = __fmul_rn(wy[k1], wx[k2]);
-                  float r, g, b;
-                  fetch_rgb(p, frame, tile, yy, xx, r, g, b);
-                  vr = __fadd_rn(vr, __fmul_rn(__fsub_rn(r, p.border[0]), w));
-                  vg = __fadd_rn(vg, __fmul_rn(__fsub_rn(g, p.border[1]), w));
-                  vb = __fadd_rn(vb, __fmul_rn(__fsub_rn(b, p.border[2]), w));
-                }
-              }
-            }
-          }
-        }
+      for (int ch = 0; ch < 3; ++ch) {
+        const float bc = ch == 0 ? br : (ch == 1 ? bg : bb);
+        const float t00 = in00 ? s0[ch] : bc, t01 = in01 ? s0[3 + ch] : bc;
+        const float t10 = in10 ? s1[ch] : bc, t11 = in11 ? s1[3 + ch] : bc;
+        const float r = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00, w00), __fmul_rn(t01, w01)), __fmul_rn(t10, w10)), __fmul_rn(t11, w11));
+        v[ch] = any_in ? r : bc;
       }
-      if (S == 1) {  // _warp_with_matrices copies the warp; only the blur path accumulates from zero
-        acc[q][0] = vr;
-        acc[q][1] = vg;
-        acc[q][2] = vb;
-      } else {
-        acc[q][0] = __fadd_rn(acc[q][0], vr);
-        acc[q][1] = __fadd_rn(acc[q][1], vg);
-        acc[q][2] = __fadd_rn(acc[q][2], vb);
-      }
+      float* o = VEC ? scratch + rr * (TW * 3) + (lane + cc * 32) * 3 : dst_tile + ((size_t)(warp + rr * NWARPS) * ow + lane + cc * 32) * 3;
+      o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
     }
   }
-
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int rr = q >> 1, cc = q & 1;
-    const int oy = tyg + warp + rr * NWARPS, ox = tx0 + lane + cc * 32;
-    if (oy < p.oh && ox < p.ow) {
-      if (S > 1) {
-        acc[q][0] = __fdiv_rn(acc[q][0], fS);
-        acc[q][1] = __fdiv_rn(acc[q][1], fS);
-        acc[q][2] = __fdiv_rn(acc[q][2], fS);
-      }
-      // padding mask: 1 - (coverage > .5) for one sample, 1 - count/S for blur; <1e-3 -> 0
-      float mval;
-      if (S == 1) {
-        mval = cover[q] ? 0.0f : 1.0f;
-      } else {
-        mval = __fsub_rn(1.0f, __fdiv_rn((float)cover[q], fS));
-        if (mval < 1e-3f) mval = 0.0f;
-      }
-      if (mval > 1e-3f) ++padded;
-      if (p.mask) p.mask[((size_t)frame_idx * p.oh + oy) * p.ow + ox] = mval;
-      if (!p.vec_store) {
-        float* d = p.dst + (((size_t)frame_idx * p.oh + oy) * p.ow + ox) * 3;
-        d[0] = acc[q][0];
-        d[1] = acc[q][1];
-        d[2] = acc[q][2];
-      }
-    }
-    if (p.vec_store) {
-      float* sc = scratch + rr * (TW * 3) + (lane + cc * 32) * 3;
-      sc[0] = acc[q][0];
-      sc[1] = acc[q][1];
-      sc[2] = acc[q][2];
-    }
-  }
-
-  if (p.vec_store) {
+  if (VEC) {
     __syncwarp();
-    // 2 rows x 192 floats = 96 float4 per warp, 3 per lane, fully coalesced 16-byte stores.
-    const int valid_floats = (min(tx0 + TW, p.ow) - tx0) * 3;  // multiple of 4 when ow % 4 == 0
 #pragma unroll
     for (int q3 = 0; q3 < 3; ++q3) {
       const int q = lane + q3 * 32;
-      const int rr = q / 48, qi = q - rr * 48;
-      const int oy = tyg + warp + rr * NWARPS;
-      if (oy < p.oh && qi * 4 < valid_floats) {
-        const float4 v = *reinterpret_cast<const float4*>(scratch + rr * (TW * 3) + qi * 4);
-        float* d = p.dst + (((size_t)frame_idx * p.oh + oy) * p.ow + tx0) * 3 + qi * 4;
-        *reinterpret_cast<float4*>(d) = v;
+      const int rr = q >= 48 ? 1 : 0, qi = q - rr * 48;
+      const float4 val = *reinterpret_cast<const float4*>(scratch + rr * (TW * 3) + qi * 4);
+      __stcs(reinterpret_cast<float4*>(dst_tile + (size_t)(warp + rr * NWARPS) * ow * 3 + qi * 4), val);
+    }
+    __syncwarp();
+  }
+  if (p.pad_count) {
+    padded = __reduce_add_sync(0xffffffffu, padded);
+    if (lane == 0 && padded) atomicAdd(p.pad_count + frame_idx, padded);
+  }
+}
+
+template <int INTERP>
+__global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __grid_constant__ CUtensorMap tmap, const WarpParams p,
+                                                                       const TilePlan* __restrict__ plan,
+                                                                       const double* __restrict__ minv, unsigned* __restrict__ ticket, unsigned ntiles, int gx, int gy) {
+  extern __shared__ __align__(128) unsigned char smem_stream[];
+  float* s_stage = reinterpret_cast<float*>(smem_stream);                                        // [STAGES][S_BOX_BYTES]
+  StageMeta* s_meta = reinterpret_cast<StageMeta*>(smem_stream + S_STAGES * S_STAGE_BYTES);      // [STAGES]
+  unsigned long long* s_full = reinterpret_cast<unsigned long long*>(s_meta + S_STAGES);         // [STAGES]
+  int* s_done = reinterpret_cast<int*>(s_full + S_STAGES);                                       // [STAGES] warps finished
+  int* s_ring = reinterpret_cast<int*>(smem_stream + S_STAGES * S_STAGE_BYTES + S_STAGES * 128 + 64);   // [8][4] ticket + plan entry per sequence slot
+  float* s_cubic = reinterpret_cast<float*>(smem_stream + S_STAGES * S_STAGE_BYTES + S_STAGES * 128 + 192);  // [32][4]
+  float* s_scratch = s_cubic + 128;                                                              // [8][384]
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const unsigned per_frame = (unsigned)gx * (unsigned)gy;
+  if (INTERP == VSTAB_INTERP_BICUBIC && tid < 128) s_cubic[tid] = c_cubic_tab[tid >> 2][tid & 3];
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < S_STAGES; ++k) {
+      mbar_init(s_full + k, 1);
+      s_done[k] = 0;
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  // Tiles are handed out through a global ticket so that the tiles in flight at any moment are neighbours
+  // in the frame (their halos hit in L2 whatever the relative speed of the CTAs).  Sequence slot q of this
+  // CTA owns ring entry q % 8: its ticket T and its plan entry P.  The warp that finishes tile j last issues
+  // the load of slot j+S (S = stages) from the ring, requests P[j+S+2] and T[j+S+3], and parks them in the
+  // ring after its next barrier wait: the two global round trips never sit on the resampling path.
+  // (An L2 prefetch of slot j+S+2 at that point was measured and did not pay.)
+  if (tid == 0) {
+    const unsigned base = atomicAdd(ticket, (unsigned)S_STAGES + 3u);
+#pragma unroll
+    for (int k = 0; k < S_STAGES + 3; ++k) s_ring[k * 4] = (int)(base + k);
+#pragma unroll
+    for (int k = 0; k < S_STAGES + 2; ++k) {
+      int2 pl = make_int2(0, 0);
+      if (base + k < ntiles) pl = __ldg(reinterpret_cast<const int2*>(plan) + base + k);
+      s_ring[k * 4 + 1] = pl.x;
+      s_ring[k * 4 + 2] = pl.y;
+    }
+#pragma unroll
+    for (int k = 0; k < S_STAGES; ++k) {
+      const unsigned t = base + k;
+      if (t < ntiles) {
+        stream_issue(&tmap, make_int2(s_ring[k * 4 + 1], s_ring[k * 4 + 2]), minv, t, per_frame, gx, s_meta + k,
+                     s_stage + k * (S_STAGE_BYTES / 4), s_full + k);
+      } else {
+        s_meta[k].flags = 4;  // nothing left: the tile loop stops at this stage
+        mbar_arrive(s_full + k);
       }
     }
   }
-  if (p.vec_store) __syncwarp();
-  }  // row groups
+  __syncthreads();
 
-  if (p.pad_count) {
-    for (int o = 16; o > 0; o >>= 1) padded += __shfl_down_sync(0xffffffffu, padded, o);
-    if (lane == 0 && padded) atomicAdd(p.pad_count + frame_idx, padded);
+  float* scratch = s_scratch + warp * SCRATCH_FLOATS_PER_WARP;
+  bool pending = false;       // lane 0: requests in flight for the ring
+  int2 pend_plan = make_int2(0, 0);
+  unsigned pend_ticket = 0;
+  for (unsigned it = 0;; ++it) {
+    const int stage = it % S_STAGES;
+    mbar_wait(s_full + stage, (it / S_STAGES) & 1);
+    if (pending) {  // requested at the end of tile it-1: P[it+S+1], T[it+S+2]
+      int* e3 = s_ring + ((it + S_STAGES + 1) & 7) * 4;
+      e3[1] = pend_plan.x;
+      e3[2] = pend_plan.y;
+      s_ring[((it + S_STAGES + 2) & 7) * 4] = (int)pend_ticket;
+      pending = false;
+    }
+    const StageMeta* meta = s_meta + stage;
+    const int flags = meta->flags;
+    if (flags & 4) break;
+    const float* box = s_stage + stage * (S_STAGE_BYTES / 4);
+    const int tx0 = meta->tx0, ty0 = meta->ty0, frame_idx = meta->frame;
+    const int ox = meta->ox, oy = meta->oy;
+    if (flags & 2) {
+      const bool affine = (meta->minv[6] == 0.0) && (meta->minv[7] == 0.0);
+      float* dst_tile = p.dst + (((size_t)frame_idx * p.oh + ty0) * p.ow + tx0) * 3;
+      float* mask_tile = p.mask ? p.mask + ((size_t)frame_idx * p.oh + ty0) * p.ow + tx0 : nullptr;
+      const float* tile0 = box - (oy * S_PITCH + ox * 3);
+      if (p.vec_store) {
+        if (affine) stream_interior<true, true>(meta->minv, tile0, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
+        else stream_interior<false, true>(meta->minv, tile0, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
+      } else {
+        if (affine) stream_interior<true, false>(meta->minv, tile0, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
+        else stream_interior<false, false>(meta->minv, tile0, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
+      }
+    } else if (flags & 8) {
+      const bool affine = (meta->minv[6] == 0.0) && (meta->minv[7] == 0.0);
+      float* dst_tile = p.dst + (((size_t)frame_idx * p.oh + ty0) * p.ow + tx0) * 3;
+      float* mask_tile = p.mask ? p.mask + ((size_t)frame_idx * p.oh + ty0) * p.ow + tx0 : nullptr;
+      const float* tile0 = box - (oy * S_PITCH + ox * 3);
+      if (p.vec_store) {
+        if (affine) stream_edge<true, true>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile);
+        else stream_edge<false, true>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile);
+      } else {
+        if (affine) stream_edge<true, false>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile);
+        else stream_edge<false, false>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile);
+      }
+    } else {
+      StagedTile tile;
+      tile.x0 = max(ox, 0);
+      tile.y0 = max(oy, 0);
+      tile.x1 = min(ox + S_BW - 1, p.sw - 1);
+      tile.y1 = min(oy + S_BH - 1, p.sh - 1);
+      tile.pitch = S_PITCH;
+      tile.active = (flags & 1) && tile.x1 >= tile.x0 && tile.y1 >= tile.y0;
+      tile.smem = box + ((tile.y0 - oy) * S_PITCH + (tile.x0 - ox) * 3);
+      const float* frame = p.src + (size_t)frame_idx * p.sh * p.sw * 3;
+      general_tile<INTERP, S_G>(p, frame, frame_idx, tx0, ty0, meta->minv, tile, s_cubic, scratch, warp, lane);
+    }
+    // the last warp to finish with this stage starts the load of the tile that reuses it
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      const int done = atomicAdd(s_done + stage, 1);
+      if (done == NWARPS - 1) {
+        s_done[stage] = 0;
+        __threadfence_block();
+        const int* e2 = s_ring + ((it + S_STAGES) & 7) * 4;
+        const unsigned nt = (unsigned)e2[0];
+        if (nt < ntiles) {
+          stream_issue(&tmap, make_int2(e2[1], e2[2]), minv, nt, per_frame, gx, s_meta + stage, s_stage + stage * (S_STAGE_BYTES / 4),
+                       s_full + stage);
+        } else {
+          s_meta[stage].flags = 4;
+          mbar_arrive(s_full + stage);
+        }
+        const unsigned t4 = (unsigned)s_ring[((it + S_STAGES + 2) & 7) * 4];
+        if (t4 < ntiles) pend_plan = __ldg(reinterpret_cast<const int2*>(plan) + t4);
+        pend_ticket = (nt < ntiles) ? atomicAdd(ticket, 1u) : 0xffffffffu;
+        pending = true;
+      }
+    }
   }
 }
 
@@ -728,6 +1230,21 @@ __global__ void bbox_init_kernel(int* bbox, int n) {
 
 bool g_cubic_tab_ready[64] = {false};
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (libcuda is not linked)
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+tensor_map_encode_fn tensor_map_encoder() {
+  static tensor_map_encode_fn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (tensor_map_encode_fn)f;
+  }();
+  return fn;
+}
+
 void build_cubic_tab(float tab[32][4]) {
   // cv::interpolateCubic with A = -0.75, float32 arithmetic in this exact order
   const volatile float A = -0.75f;
@@ -784,7 +1301,7 @@ extern "C" int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, in
   if (n == 0) return VSTAB_OK;
   if (n > 65535) return vstab_fail(h, VSTAB_ERR_UNSUPPORTED, "vstab_warp_fused: n > 65535 frames per call");
   cudaStream_t st = (cudaStream_t)stream;
-  VSTAB_CUDA(h, cudaSetDevice(h->device));
+  VSTAB_ENTER(h);
 
   if (!g_cubic_tab_ready[h->device & 63]) {
     float tab[32][4];
@@ -830,6 +1347,66 @@ extern "C" int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, in
 
   dim3 grid(vstab_ceil_div(out_w, TW), vstab_ceil_div(out_h, TH), n);
   if (grid.y > 65535) return vstab_fail(h, VSTAB_ERR_UNSUPPORTED, "vstab_warp_fused: output too tall");
+
+  // Single-sample launches with 16-byte aligned source rows (every node path except motion blur) go
+  // through the streaming kernel: plan pass + persistent CTAs fed by the TMA engine.
+  static const bool stream_off = [] {
+    const char* e = getenv("VSTAB_WARP_STREAM");
+    return e && e[0] == '0';
+  }();
+  const unsigned long long s_tiles = (unsigned long long)grid.x * vstab_ceil_div(out_h, S_TH) * n;
+  if (samples == 1 && p.vec_load && stage_mode == VSTAB_STAGE_AUTO && s_tiles < (1ull << 31) && src_w >= S_BW && src_h >= S_BH &&
+      !stream_off && tensor_map_encoder()) {
+    const int gx = (int)grid.x, gy = vstab_ceil_div(out_h, S_TH);
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {(cuuint64_t)src_w * 3, (cuuint64_t)src_h, (cuuint64_t)n};
+    const cuuint64_t gstride[2] = {(cuuint64_t)src_w * 12, (cuuint64_t)src_w * 12 * (cuuint64_t)src_h};
+    const cuuint32_t box[3] = {(cuuint32_t)S_PITCH, (cuuint32_t)S_BH, 1};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    static const CUtensorMapL2promotion promo = [] {
+      const char* e = getenv("VSTAB_TMA_PROMO");
+      const int v = e ? atoi(e) : 2;
+      return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }();
+    const CUresult cr = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)src_dev, gdim, gstride, box, estride,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr == CUDA_SUCCESS) {
+      const size_t plan_bytes = ((size_t)s_tiles * sizeof(TilePlan) + 15) & ~(size_t)15;
+      const size_t need = plan_bytes + (size_t)n * 80 + 16;
+      if (need > h->plan_bytes) {
+        VSTAB_CUDA(h, cudaDeviceSynchronize());  // the old block may still be read by enqueued work
+        if (h->plan) cudaFree(h->plan);
+        h->plan = nullptr;
+        h->plan_bytes = 0;
+        if (cudaMalloc(&h->plan, need + need / 4) != cudaSuccess) return vstab_fail(h, VSTAB_ERR_NOMEM, "vstab_warp_fused: plan allocation failed");
+        h->plan_bytes = need + need / 4;
+      }
+      TilePlan* plan = (TilePlan*)h->plan;
+      double* minv = (double*)((char*)h->plan + plan_bytes);
+      unsigned* ticket = (unsigned*)((char*)h->plan + plan_bytes + (size_t)n * 80);
+      VSTAB_CUDA(h, cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+      const size_t s_smem = (size_t)S_STAGES * S_STAGE_BYTES + S_STAGES * 128 + 192 + sizeof(float) * 128 +
+                            sizeof(float) * NWARPS * SCRATCH_FLOATS_PER_WARP;
+      unsigned ctas = (unsigned)h->sm_count * S_CTAS;
+      if ((unsigned long long)ctas > s_tiles) ctas = (unsigned)s_tiles;
+      const unsigned plan_blocks = (unsigned)((s_tiles + 255) / 256);
+      p.stage_capacity = S_BOX_BYTES / 4;
+      if (interp == VSTAB_INTERP_BILINEAR) {
+        warp_plan_kernel<VSTAB_INTERP_BILINEAR><<<plan_blocks, 256, 0, st>>>(fwd_dev, (unsigned)s_tiles, gx, gy, out_w, out_h, src_w, src_h, plan, minv);
+        VSTAB_LAUNCH_CHECK(h, "warp_plan_kernel");
+        VSTAB_CUDA(h, cudaFuncSetAttribute(warp_stream_kernel<VSTAB_INTERP_BILINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem));
+        warp_stream_kernel<VSTAB_INTERP_BILINEAR><<<ctas, NTHREADS, s_smem, st>>>(tmap, p, plan, minv, ticket, (unsigned)s_tiles, gx, gy);
+      } else {
+        warp_plan_kernel<VSTAB_INTERP_BICUBIC><<<plan_blocks, 256, 0, st>>>(fwd_dev, (unsigned)s_tiles, gx, gy, out_w, out_h, src_w, src_h, plan, minv);
+        VSTAB_LAUNCH_CHECK(h, "warp_plan_kernel");
+        VSTAB_CUDA(h, cudaFuncSetAttribute(warp_stream_kernel<VSTAB_INTERP_BICUBIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem));
+        warp_stream_kernel<VSTAB_INTERP_BICUBIC><<<ctas, NTHREADS, s_smem, st>>>(tmap, p, plan, minv, ticket, (unsigned)s_tiles, gx, gy);
+      }
+      VSTAB_LAUNCH_CHECK(h, "warp_stream_kernel");
+      return VSTAB_OK;
+    }
+  }
   if (interp == VSTAB_INTERP_BILINEAR) {
     VSTAB_CUDA(h, cudaFuncSetAttribute(warp_fused_kernel<VSTAB_INTERP_BILINEAR>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -850,7 +1427,7 @@ extern "C" int vstab_common_coverage(vstab_handle* h, const float* fwd_dev, int 
   if (!fwd_dev || !common_dev || n < 0 || src_h <= 0 || src_w <= 0 || out_h <= 0 || out_w <= 0)
     return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_common_coverage: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  VSTAB_CUDA(h, cudaSetDevice(h->device));
+  VSTAB_ENTER(h);
   dim3 grid(vstab_ceil_div(out_w, 32), vstab_ceil_div(out_h, 8));
   common_coverage_kernel<<<grid, 256, sizeof(double) * 64 * 9, st>>>(fwd_dev, n, src_h, src_w, out_h,
                                                                     out_w, mask_rule, common_dev);
@@ -865,7 +1442,7 @@ extern "C" int vstab_coverage_bbox(vstab_handle* h, const float* fwd_dev, int n,
     return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_coverage_bbox: bad argument");
   if (n == 0) return VSTAB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  VSTAB_CUDA(h, cudaSetDevice(h->device));
+  VSTAB_ENTER(h);
   const int chunk = 64;
   void* ws = nullptr;
   int rc = vstab_workspace(h, (size_t)chunk * out_h * out_w, &ws);
