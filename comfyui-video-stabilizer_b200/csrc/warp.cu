@@ -713,9 +713,11 @@ constexpr int S_STAGES = VSTAB_S_STAGES;
 constexpr int S_CTAS = VSTAB_S_CTAS;
 
 
-struct TilePlan {
+struct TilePlan {  // 16 bytes, read as one int4
   int ox;        // source pixel of the box origin, multiple of 4 (may be negative: the TMA engine zero-fills)
   int oy_flags;  // (oy << 4) | flags; flags bit 0: box loaded, bit 1: interior tile, bit 3: edge tile
+  int txy;       // output pixel of the tile origin: tx0 | ty0 << 16
+  int frame;
 };
 
 struct StageMeta {
@@ -724,6 +726,7 @@ struct StageMeta {
   int pad[6];
 };
 static_assert(sizeof(StageMeta) == 128, "StageMeta layout");
+static_assert(3 * S_STAGES + 1 <= 8 && S_STAGES * 12 <= 32, "ring of 8 slots, 32 bytes of barriers and counters");
 
 template <int INTERP>
 __global__ void __launch_bounds__(256) warp_plan_kernel(const float* __restrict__ fwd, unsigned ntiles, int gx, int gy, int ow, int oh,
@@ -781,6 +784,8 @@ __global__ void __launch_bounds__(256) warp_plan_kernel(const float* __restrict_
   TilePlan pl;
   pl.ox = ox;
   pl.oy_flags = oy * 16 + flags;
+  pl.txy = tx0 | (ty0 << 16);
+  pl.frame = frame;
   plan[t] = pl;
 }
 
@@ -804,14 +809,11 @@ __device__ __forceinline__ void tma_load_box(void* smem_dst, const void* tmap, i
 }
 
 // One thread: publish the stage's meta block and start the copies of tile t (box + inverse matrix).
-__device__ __forceinline__ void stream_issue(const void* tmap, int2 pl, const double* __restrict__ minv, unsigned t, unsigned per_frame,
-                                             int gx, StageMeta* meta, float* box, unsigned long long* full) {
-  const int frame = (int)(t / per_frame);
-  const unsigned rem = t - (unsigned)frame * per_frame;
-  const int tyi = (int)(rem / (unsigned)gx);
-  const int flags = pl.y & 15, oy = pl.y >> 4;
-  meta->tx0 = (int)(rem - (unsigned)tyi * (unsigned)gx) * TW;
-  meta->ty0 = tyi * S_TH;
+__device__ __forceinline__ void stream_issue(const void* tmap, int4 pl, const double* __restrict__ minv, StageMeta* meta, float* box,
+                                             unsigned long long* full) {
+  const int flags = pl.y & 15, oy = pl.y >> 4, frame = pl.w;
+  meta->tx0 = pl.z & 0xffff;
+  meta->ty0 = (int)((unsigned)pl.z >> 16);
   meta->frame = frame;
   meta->flags = flags;
   meta->ox = pl.x;
@@ -988,20 +990,20 @@ __device__ __forceinline__ void stream_edge(const WarpParams& p, const double* _
 template <int INTERP>
 __global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __grid_constant__ CUtensorMap tmap, const WarpParams p,
                                                                        const TilePlan* __restrict__ plan,
-                                                                       const double* __restrict__ minv, unsigned* __restrict__ ticket, unsigned ntiles, int gx, int gy) {
+                                                                       const double* __restrict__ minv, unsigned* __restrict__ ticket, unsigned ntiles) {
   extern __shared__ __align__(128) unsigned char smem_stream[];
   float* s_stage = reinterpret_cast<float*>(smem_stream);                                        // [STAGES][S_BOX_BYTES]
   StageMeta* s_meta = reinterpret_cast<StageMeta*>(smem_stream + S_STAGES * S_STAGE_BYTES);      // [STAGES]
   unsigned long long* s_full = reinterpret_cast<unsigned long long*>(s_meta + S_STAGES);         // [STAGES]
   int* s_done = reinterpret_cast<int*>(s_full + S_STAGES);                                       // [STAGES] warps finished
-  int* s_ring = reinterpret_cast<int*>(smem_stream + S_STAGES * S_STAGE_BYTES + S_STAGES * 128 + 64);   // [8][4] ticket + plan entry per sequence slot
+  unsigned* s_ring_t = reinterpret_cast<unsigned*>(smem_stream + S_STAGES * S_STAGE_BYTES + S_STAGES * 128 + 32);  // [8] ticket per sequence slot
+  int4* s_ring_p = reinterpret_cast<int4*>(smem_stream + S_STAGES * S_STAGE_BYTES + S_STAGES * 128 + 64);          // [8] plan entry per sequence slot
   float* s_cubic = reinterpret_cast<float*>(smem_stream + S_STAGES * S_STAGE_BYTES + S_STAGES * 128 + 192);  // [32][4]
   float* s_scratch = s_cubic + 128;                                                              // [8][384]
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const unsigned per_frame = (unsigned)gx * (unsigned)gy;
   if (INTERP == VSTAB_INTERP_BICUBIC && tid < 128) s_cubic[tid] = c_cubic_tab[tid >> 2][tid & 3];
   if (tid == 0) {
 #pragma unroll
@@ -1013,27 +1015,22 @@ __global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __g
   }
   // Tiles are handed out through a global ticket so that the tiles in flight at any moment are neighbours
   // in the frame (their halos hit in L2 whatever the relative speed of the CTAs).  Sequence slot q of this
-  // CTA owns ring entry q % 8: its ticket T and its plan entry P.  The warp that finishes tile j last issues
-  // the load of slot j+S (S = stages) from the ring, requests P[j+S+2] and T[j+S+3], and parks them in the
-  // ring after its next barrier wait: the two global round trips never sit on the resampling path.
-  // (An L2 prefetch of slot j+S+2 at that point was measured and did not pay.)
+  // CTA owns ring entry q % 8: its ticket T[q] and its plan entry P[q].  The warp that finishes tile j last
+  // issues the load of slot j+S (S = stages) straight from the ring.  Refilling the ring costs two global
+  // round trips (ticket, plan entry); warp j % 8 pays them at the end of tile j, for P[j+2S] and T[j+3S],
+  // before it reports the tile as finished -- so the entries are published by the stage's next
+  // arrive.expect_tx, S tiles before anybody reads them, and the issuing warp never waits on global memory.
   if (tid == 0) {
-    const unsigned base = atomicAdd(ticket, (unsigned)S_STAGES + 3u);
+    const unsigned base = atomicAdd(ticket, 3u * S_STAGES);
 #pragma unroll
-    for (int k = 0; k < S_STAGES + 3; ++k) s_ring[k * 4] = (int)(base + k);
+    for (int k = 0; k < 3 * S_STAGES; ++k) s_ring_t[k] = base + k;
 #pragma unroll
-    for (int k = 0; k < S_STAGES + 2; ++k) {
-      int2 pl = make_int2(0, 0);
-      if (base + k < ntiles) pl = __ldg(reinterpret_cast<const int2*>(plan) + base + k);
-      s_ring[k * 4 + 1] = pl.x;
-      s_ring[k * 4 + 2] = pl.y;
-    }
+    for (int k = 0; k < 2 * S_STAGES; ++k)
+      s_ring_p[k] = (base + k < ntiles) ? __ldg(reinterpret_cast<const int4*>(plan) + base + k) : make_int4(0, 0, 0, 0);
 #pragma unroll
     for (int k = 0; k < S_STAGES; ++k) {
-      const unsigned t = base + k;
-      if (t < ntiles) {
-        stream_issue(&tmap, make_int2(s_ring[k * 4 + 1], s_ring[k * 4 + 2]), minv, t, per_frame, gx, s_meta + k,
-                     s_stage + k * (S_STAGE_BYTES / 4), s_full + k);
+      if (base + k < ntiles) {
+        stream_issue(&tmap, s_ring_p[k], minv, s_meta + k, s_stage + k * (S_STAGE_BYTES / 4), s_full + k);
       } else {
         s_meta[k].flags = 4;  // nothing left: the tile loop stops at this stage
         mbar_arrive(s_full + k);
@@ -1043,19 +1040,9 @@ __global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __g
   __syncthreads();
 
   float* scratch = s_scratch + warp * SCRATCH_FLOATS_PER_WARP;
-  bool pending = false;       // lane 0: requests in flight for the ring
-  int2 pend_plan = make_int2(0, 0);
-  unsigned pend_ticket = 0;
   for (unsigned it = 0;; ++it) {
     const int stage = it % S_STAGES;
     mbar_wait(s_full + stage, (it / S_STAGES) & 1);
-    if (pending) {  // requested at the end of tile it-1: P[it+S+1], T[it+S+2]
-      int* e3 = s_ring + ((it + S_STAGES + 1) & 7) * 4;
-      e3[1] = pend_plan.x;
-      e3[2] = pend_plan.y;
-      s_ring[((it + S_STAGES + 2) & 7) * 4] = (int)pend_ticket;
-      pending = false;
-    }
     const StageMeta* meta = s_meta + stage;
     const int flags = meta->flags;
     if (flags & 4) break;
@@ -1098,27 +1085,34 @@ __global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __g
       const float* frame = p.src + (size_t)frame_idx * p.sh * p.sw * 3;
       general_tile<INTERP, S_G>(p, frame, frame_idx, tx0, ty0, meta->minv, tile, s_cubic, scratch, warp, lane);
     }
-    // the last warp to finish with this stage starts the load of the tile that reuses it
     __syncwarp();
     if (lane == 0) {
-      __threadfence_block();
+      if (warp == (int)(it & 7)) {  // this tile's ring refill (blocks this warp for one global round trip)
+        const unsigned tq = s_ring_t[(it + 2 * S_STAGES) & 7];
+        int4 pl = make_int4(0, 0, 0, 0);
+        unsigned tn = 0xffffffffu;
+        if (tq < ntiles) {
+          pl = __ldg(reinterpret_cast<const int4*>(plan) + tq);
+          tn = atomicAdd(ticket, 1u);
+        }
+        s_ring_p[(it + 2 * S_STAGES) & 7] = pl;
+        s_ring_t[(it + 3 * S_STAGES) & 7] = tn;
+      }
+      // The last warp to finish with this stage starts the load of the tile that reuses it.
+      // No memory fence here: a fence would also wait for this warp's global stores to drain (about a
+      // microsecond on the critical path of the next load).  Everything the counter orders lives in shared
+      // memory -- the stage (already read into registers) and the ring -- and the SM performs one warp's
+      // shared-memory operations in program order.
+      asm volatile("" ::: "memory");
       const int done = atomicAdd(s_done + stage, 1);
       if (done == NWARPS - 1) {
         s_done[stage] = 0;
-        __threadfence_block();
-        const int* e2 = s_ring + ((it + S_STAGES) & 7) * 4;
-        const unsigned nt = (unsigned)e2[0];
-        if (nt < ntiles) {
-          stream_issue(&tmap, make_int2(e2[1], e2[2]), minv, nt, per_frame, gx, s_meta + stage, s_stage + stage * (S_STAGE_BYTES / 4),
-                       s_full + stage);
+        if (s_ring_t[(it + S_STAGES) & 7] < ntiles) {
+          stream_issue(&tmap, s_ring_p[(it + S_STAGES) & 7], minv, s_meta + stage, s_stage + stage * (S_STAGE_BYTES / 4), s_full + stage);
         } else {
           s_meta[stage].flags = 4;
           mbar_arrive(s_full + stage);
         }
-        const unsigned t4 = (unsigned)s_ring[((it + S_STAGES + 2) & 7) * 4];
-        if (t4 < ntiles) pend_plan = __ldg(reinterpret_cast<const int2*>(plan) + t4);
-        pend_ticket = (nt < ntiles) ? atomicAdd(ticket, 1u) : 0xffffffffu;
-        pending = true;
       }
     }
   }
@@ -1355,7 +1349,7 @@ extern "C" int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, in
     return e && e[0] == '0';
   }();
   const unsigned long long s_tiles = (unsigned long long)grid.x * vstab_ceil_div(out_h, S_TH) * n;
-  if (samples == 1 && p.vec_load && stage_mode == VSTAB_STAGE_AUTO && s_tiles < (1ull << 31) && src_w >= S_BW && src_h >= S_BH &&
+  if (samples == 1 && p.vec_load && stage_mode == VSTAB_STAGE_AUTO && s_tiles < (1ull << 31) && src_w >= S_BW && src_h >= S_BH && out_w <= 65535 && out_h <= 65535 &&
       !stream_off && tensor_map_encoder()) {
     const int gx = (int)grid.x, gy = vstab_ceil_div(out_h, S_TH);
     CUtensorMap tmap;
@@ -1396,12 +1390,12 @@ extern "C" int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, in
         warp_plan_kernel<VSTAB_INTERP_BILINEAR><<<plan_blocks, 256, 0, st>>>(fwd_dev, (unsigned)s_tiles, gx, gy, out_w, out_h, src_w, src_h, plan, minv);
         VSTAB_LAUNCH_CHECK(h, "warp_plan_kernel");
         VSTAB_CUDA(h, cudaFuncSetAttribute(warp_stream_kernel<VSTAB_INTERP_BILINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem));
-        warp_stream_kernel<VSTAB_INTERP_BILINEAR><<<ctas, NTHREADS, s_smem, st>>>(tmap, p, plan, minv, ticket, (unsigned)s_tiles, gx, gy);
+        warp_stream_kernel<VSTAB_INTERP_BILINEAR><<<ctas, NTHREADS, s_smem, st>>>(tmap, p, plan, minv, ticket, (unsigned)s_tiles);
       } else {
         warp_plan_kernel<VSTAB_INTERP_BICUBIC><<<plan_blocks, 256, 0, st>>>(fwd_dev, (unsigned)s_tiles, gx, gy, out_w, out_h, src_w, src_h, plan, minv);
         VSTAB_LAUNCH_CHECK(h, "warp_plan_kernel");
         VSTAB_CUDA(h, cudaFuncSetAttribute(warp_stream_kernel<VSTAB_INTERP_BICUBIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem));
-        warp_stream_kernel<VSTAB_INTERP_BICUBIC><<<ctas, NTHREADS, s_smem, st>>>(tmap, p, plan, minv, ticket, (unsigned)s_tiles, gx, gy);
+        warp_stream_kernel<VSTAB_INTERP_BICUBIC><<<ctas, NTHREADS, s_smem, st>>>(tmap, p, plan, minv, ticket, (unsigned)s_tiles);
       }
       VSTAB_LAUNCH_CHECK(h, "warp_stream_kernel");
       return VSTAB_OK;
