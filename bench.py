@@ -231,7 +231,7 @@ def main():
     peak, peak_src = measured_peak_gbs()
     achieved = warp_bytes / (warp_ms * 1e-3) / 1e9 if warp_ms > 0 else 0.0
     roofline = {
-        "bound": "hbm", "kernel": "warp_fused_kernel<bilinear>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": "warp_stream_kernel<bilinear> (+ warp_plan_kernel, timed together)", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
         "launches": len(warp_log), "avg_launch_ms": warp_ms / max(len(warp_log), 1),
         "algorithmic_bytes_per_frame": 12 * HEIGHT * WIDTH + 16 * HEIGHT * WIDTH,
