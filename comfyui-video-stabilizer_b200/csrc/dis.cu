@@ -194,7 +194,13 @@ __device__ __forceinline__ float patch_eval(const float (&z)[8][2], const float 
 }
 
 // One warp per (pair, stripe): 8 patch rows x 4 lanes, anti-diagonal wavefront over the columns.
+// The search is a chain of dependent patch evaluations, so what it costs is the latency of one
+// evaluation: STAGED keeps everything the chain touches in shared memory (both images and the
+// sparse flow of the pair; the bordered I1 of a 240x135 level is 45 KB), which takes the global
+// load round trips out of every link of the chain.  Same arithmetic either way.
+template <bool STAGED>
 __global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P) {
+  extern __shared__ __align__(16) unsigned char ps_smem[];
   const int pair = blockIdx.x;
   const int stripe = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -204,19 +210,46 @@ __global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P) {
   const int stripe_sz = (hs + kStripes - 1) / kStripes;  // ceil(hs / 8)  (<= 8 for working sizes <= 960)
   const int lo = min(stripe * stripe_sz, hs), hi = min((stripe + 1) * stripe_sz, hs);
   const int rows = hi - lo;
-  if (rows <= 0) return;  // whole warp exits together
 
   const size_t npx = (size_t)h * w;
+  const size_t tp = (size_t)hs * ws;
   const unsigned char* I0 = L.I + (size_t)pair * npx;                                     // frame `pair`
   const unsigned char* I1e = L.Iext + (size_t)(pair + 1) * (h + 2 * kBorder) * we;        // frame `pair + 1`
+  volatile float* Sx = L.Sx + (size_t)pair * tp;
+  volatile float* Sy = L.Sy + (size_t)pair * tp;
+  if (STAGED) {
+    const int n1 = (h + 2 * kBorder) * we, n0 = h * w;
+    const int n1p = (n1 + 15) & ~15, n0p = (n0 + 15) & ~15;
+    unsigned char* s1 = ps_smem;
+    unsigned char* s0 = ps_smem + n1p;
+    float* ssx = reinterpret_cast<float*>(ps_smem + n1p + n0p);
+    float* ssy = ssx + tp;
+    // 16-byte copies where the frame's offset allows it, bytes otherwise
+    if ((reinterpret_cast<uintptr_t>(I1e) & 15) == 0) {
+      for (int v = threadIdx.x; v < n1 / 16; v += blockDim.x) reinterpret_cast<uint4*>(s1)[v] = reinterpret_cast<const uint4*>(I1e)[v];
+      for (int v = (n1 & ~15) + threadIdx.x; v < n1; v += blockDim.x) s1[v] = I1e[v];
+    } else {
+      for (int v = threadIdx.x; v < n1; v += blockDim.x) s1[v] = I1e[v];
+    }
+    if ((reinterpret_cast<uintptr_t>(I0) & 15) == 0) {
+      for (int v = threadIdx.x; v < n0 / 16; v += blockDim.x) reinterpret_cast<uint4*>(s0)[v] = reinterpret_cast<const uint4*>(I0)[v];
+      for (int v = (n0 & ~15) + threadIdx.x; v < n0; v += blockDim.x) s0[v] = I0[v];
+    } else {
+      for (int v = threadIdx.x; v < n0; v += blockDim.x) s0[v] = I0[v];
+    }
+    __syncthreads();
+    I1e = s1;
+    I0 = s0;
+    Sx = ssx;
+    Sy = ssy;
+  }
+  if (rows <= 0) return;  // whole warp exits together (after the only CTA-wide barrier)
+
   const short* gx = L.Ix + (size_t)pair * npx;
   const short* gy = L.Iy + (size_t)pair * npx;
   const float* T = L.T + (size_t)pair * 5 * hs * ws;
-  const size_t tp = (size_t)hs * ws;
   const float* Ux = L.Ux + (size_t)pair * npx;
   const float* Uy = L.Uy + (size_t)pair * npx;
-  volatile float* Sx = L.Sx + (size_t)pair * tp;
-  volatile float* Sy = L.Sy + (size_t)pair * tp;
   const int inner = kGdIter / 2;  // floor(25 / 2 passes) = 12
   const unsigned qmask = 0xFu << (lane & ~3);
 
@@ -289,6 +322,14 @@ __global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P) {
         if (l == 0) { Sx[k] = sx; Sy[k] = sy; }
       }
       __syncwarp();
+    }
+  }
+  if (STAGED) {  // the densification reads the sparse flow from global memory
+    float* gSx = L.Sx + (size_t)pair * tp;
+    float* gSy = L.Sy + (size_t)pair * tp;
+    for (int k = lo * ws + lane; k < hi * ws; k += 32) {
+      gSx[k] = Sx[k];
+      gSy[k] = Sy[k];
     }
   }
 }
@@ -872,7 +913,16 @@ extern "C" int vstab_dis_flow(vstab_handle* hnd, const uint8_t* gray_dev, int n_
     }
     for (int i = coarsest; i >= kFinest; i--) {
       dim3 gp(vstab_ceil_div(L[i].w, 32), vstab_ceil_div(L[i].h, 8), P);
-      patch_search_kernel<<<P, 256, 0, st>>>(L[i], P);
+      {
+        const size_t n1 = (size_t)(L[i].h + 2 * kBorder) * (L[i].w + 2 * kBorder), n0 = (size_t)L[i].h * L[i].w;
+        const size_t ps_bytes = ((n1 + 15) & ~(size_t)15) + ((n0 + 15) & ~(size_t)15) + 2 * sizeof(float) * L[i].hs * L[i].ws;
+        if (ps_bytes <= (size_t)hnd->max_smem_optin) {
+          VSTAB_CUDA(hnd, cudaFuncSetAttribute(patch_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_bytes));
+          patch_search_kernel<true><<<P, 256, ps_bytes, st>>>(L[i], P);
+        } else {
+          patch_search_kernel<false><<<P, 256, 0, st>>>(L[i], P);
+        }
+      }
       VSTAB_LAUNCH_CHECK(hnd, "patch_search_kernel");
       densify_kernel<<<gp, 256, 0, st>>>(L[i], P);
       VSTAB_LAUNCH_CHECK(hnd, "densify_kernel");

@@ -726,7 +726,7 @@ struct StageMeta {
   int pad[6];
 };
 static_assert(sizeof(StageMeta) == 128, "StageMeta layout");
-static_assert(3 * S_STAGES + 1 <= 8 && S_STAGES * 12 <= 32, "ring of 8 slots, 32 bytes of barriers and counters");
+static_assert(3 * S_STAGES + 1 <= 8 && S_STAGES * 12 + 4 <= 32, "ring of 8 slots, 32 bytes of barriers and counters");
 
 template <int INTERP>
 __global__ void __launch_bounds__(256) warp_plan_kernel(const float* __restrict__ fwd, unsigned ntiles, int gx, int gy, int ow, int oh,
@@ -1011,6 +1011,7 @@ __global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __g
       mbar_init(s_full + k, 1);
       s_done[k] = 0;
     }
+    s_done[S_STAGES] = 0;  // empty slots in a row
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
   // Tiles are handed out through a global ticket so that the tiles in flight at any moment are neighbours
@@ -1032,7 +1033,9 @@ __global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __g
       if (base + k < ntiles) {
         stream_issue(&tmap, s_ring_p[k], minv, s_meta + k, s_stage + k * (S_STAGE_BYTES / 4), s_full + k);
       } else {
-        s_meta[k].flags = 4;  // nothing left: the tile loop stops at this stage
+        const int run = s_done[S_STAGES] + 1;
+        s_done[S_STAGES] = run;
+        s_meta[k].flags = 4 | (run << 8);  // no tile for this slot
         mbar_arrive(s_full + k);
       }
     }
@@ -1042,14 +1045,19 @@ __global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __g
   float* scratch = s_scratch + warp * SCRATCH_FLOATS_PER_WARP;
   for (unsigned it = 0;; ++it) {
     const int stage = it % S_STAGES;
-    mbar_wait(s_full + stage, (it / S_STAGES) & 1);
+    mbar_wait_spin(s_full + stage, (it / S_STAGES) & 1);  // no suspend hint: a hinted wait sleeps its full 20 us when the phase is completed by a plain arrive
     const StageMeta* meta = s_meta + stage;
     const int flags = meta->flags;
-    if (flags & 4) break;
+    // The ring is refilled by different warps, so a CTA's tickets are not monotonic in slot order: an
+    // exhausted slot (flag 4) can be followed by a live one.  The issuing thread counts the empty slots
+    // in a row (bits 8.. of the flags); after 3S+1 of them every ticket this CTA ever drew has been served.
+    if ((flags & 4) && (flags >> 8) > 3 * S_STAGES) break;
     const float* box = s_stage + stage * (S_STAGE_BYTES / 4);
     const int tx0 = meta->tx0, ty0 = meta->ty0, frame_idx = meta->frame;
     const int ox = meta->ox, oy = meta->oy;
-    if (flags & 2) {
+    if (flags & 4) {
+      // empty slot: nothing to resample, the stage still goes through the hand-over below
+    } else if (flags & 2) {
       const bool affine = (meta->minv[6] == 0.0) && (meta->minv[7] == 0.0);
       float* dst_tile = p.dst + (((size_t)frame_idx * p.oh + ty0) * p.ow + tx0) * 3;
       float* mask_tile = p.mask ? p.mask + ((size_t)frame_idx * p.oh + ty0) * p.ow + tx0 : nullptr;
@@ -1108,9 +1116,12 @@ __global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __g
       if (done == NWARPS - 1) {
         s_done[stage] = 0;
         if (s_ring_t[(it + S_STAGES) & 7] < ntiles) {
+          s_done[S_STAGES] = 0;
           stream_issue(&tmap, s_ring_p[(it + S_STAGES) & 7], minv, s_meta + stage, s_stage + stage * (S_STAGE_BYTES / 4), s_full + stage);
         } else {
-          s_meta[stage].flags = 4;
+          const int run = s_done[S_STAGES] + 1;  // only the (serialised) issuing threads touch this counter
+          s_done[S_STAGES] = run;
+          s_meta[stage].flags = 4 | (run << 8);
           mbar_arrive(s_full + stage);
         }
       }
