@@ -12,7 +12,7 @@ from typing import Any, Callable, Optional, Tuple
 import numpy as np
 import torch
 
-from . import _native
+from . import _native, pipeline
 from .flow import mode_mask_for
 from .pipeline import VideoContext
 from .stabilizer_core import PairCandidates, StabilizationResult, stabilize_frames as _core
@@ -23,7 +23,7 @@ MAX_CORNERS = 400
 def estimate_candidates(context: VideoContext, work_w: int, work_h: int, requested_mode: str) -> PairCandidates:
     """K1/K2 -> K5 (corners of frame i) -> K6 (track into frame i+1) -> K7-K9 candidates per pair."""
     h = _native.get_handle(context.device)
-    gray = h.gray_working(context.frames, (work_w, work_h))
+    gray = pipeline.gray_working(context, (work_w, work_h))
     prev, curr, detected = h.gftt_lk(gray, MAX_CORNERS)  # [P,400,2] each, NaN rows = not found / lost
     raw = h.fit_points(prev, curr, mode_mask_for(requested_mode))
     d = _native.decode_fit_results(raw)

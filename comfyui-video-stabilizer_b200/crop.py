@@ -221,10 +221,7 @@ def solve_crop_framing(context, base_mode, delta_full, path, target_path, keep_f
             "padding_fraction_max": 0.0,
         }
         progress.finish()
-        frames = context.frames
-        masks = torch.zeros((n, height, width, 1), dtype=torch.float32, device=frames.device)
-        if output == "host":
-            return StabilizationResult(frames.cpu().numpy(), masks.cpu().numpy(), attach(meta))
+        frames, masks = context.untouched(output)
         return StabilizationResult(frames, masks, attach(meta))
 
     safety_margin_px = max(0.5, 0.02 * max(width, height))

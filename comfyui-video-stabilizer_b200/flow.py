@@ -13,7 +13,7 @@ from typing import Any, Callable, Optional, Tuple
 import numpy as np
 import torch
 
-from . import _native
+from . import _native, pipeline
 from .pipeline import VideoContext
 from .stabilizer_core import PairCandidates, StabilizationResult, stabilize_frames as _core
 
@@ -33,8 +33,7 @@ def estimate_candidates(context: VideoContext, work_w: int, work_h: int, request
     h = _native.get_handle(context.device)
     n = len(context)
     last_pair = n - 1 if last_pair is None else last_pair
-    frames = context.frames[first_pair : last_pair + 1]
-    gray = h.gray_working(frames, (work_w, work_h))
+    gray = pipeline.gray_working(context, (work_w, work_h), first_pair, last_pair + 1)
     _, grid = h.dis_flow(gray, want_flow=False, grid_step=SAMPLE_STEP)
     raw = h.fit_grid(grid, SAMPLE_STEP, mode_mask_for(requested_mode))
     d = _native.decode_fit_results(raw)

@@ -51,7 +51,11 @@ class FrameAdapter:
 
 @dataclass
 class VideoContext:
-    frames: torch.Tensor  # [N,H,W,3] float32, CUDA, values 0..1
+    """Clip resident in HBM (``frames``), or -- when it is too large for that -- a host tensor that is
+    streamed through the device twice (``host``: first pass for the gray working images, second pass
+    for the resampler).  Both kinds hand out normalised device chunks."""
+
+    frames: Optional[torch.Tensor]  # [N,H,W,3] float32, CUDA, values 0..1 (None when streamed)
     adapter: FrameAdapter
     width: int
     height: int
@@ -59,13 +63,66 @@ class VideoContext:
     fps: Optional[float]
     template_kind: Literal["dict", "sequence"]
     template_meta: Dict[str, Any] = field(default_factory=dict)
+    host: Optional[torch.Tensor] = None  # [N,H,W,C] float32 / uint8 CPU tensor (streamed clips only)
+    stream_device: Optional[torch.device] = None
 
     def __len__(self) -> int:
-        return int(self.frames.shape[0])
+        return int((self.frames if self.frames is not None else self.host).shape[0])
+
+    @property
+    def streamed(self) -> bool:
+        return self.frames is None
 
     @property
     def device(self) -> torch.device:
-        return self.frames.device
+        return self.frames.device if self.frames is not None else self.stream_device
+
+    def sliced(self, start: int) -> "VideoContext":
+        """The same clip without its first `start` frames (frame-range shards drop their halo frame)."""
+        import dataclasses
+
+        if self.frames is not None:
+            return dataclasses.replace(self, frames=self.frames[start:])
+        return dataclasses.replace(self, host=self.host[start:])
+
+    def chunk(self, a: int, b: int) -> torch.Tensor:
+        """Frames [a, b) as a normalised [b-a,H,W,3] float32 device tensor."""
+        if self.frames is not None:
+            return self.frames[a:b]
+        dev = self.host[a:b].to(self.stream_device, non_blocking=True)
+        return _normalize_device(dev)[0]
+
+    def chunk_frames(self) -> int:
+        return frames_per_chunk(self.height, self.width, 3)
+
+    def untouched(self, output: str) -> Tuple[Any, Any]:
+        """(frames, all-zero masks) for the paths that hand the input back unchanged
+        (keep_fov bypass, single frame): device tensors, or numpy arrays for output="host"."""
+        n = len(self)
+        if self.streamed:
+            if output != "host":
+                raise _native.VstabNativeError("a streamed clip can only be returned with output='host'")
+            out = torch.empty((n, self.height, self.width, 3), dtype=torch.float32)
+            step = self.chunk_frames()
+            for a in range(0, n, step):
+                out[a : a + step].copy_(self.chunk(a, min(a + step, n)))
+            return out.numpy(), np.zeros((n, self.height, self.width, 1), dtype=np.float32)
+        masks = torch.zeros((n, self.height, self.width, 1), dtype=torch.float32, device=self.frames.device)
+        if output == "host":
+            return self.frames.cpu().numpy(), masks.cpu().numpy()
+        return self.frames, masks
+
+
+def gray_working(context: VideoContext, size: Tuple[int, int], first: int = 0, last: Optional[int] = None) -> torch.Tensor:
+    """K1+K2 over frames [first, last) of the clip: [n,h,w] uint8 on the device.  A streamed clip is
+    uploaded chunk by chunk; only the working images (<= 960 px) stay resident."""
+    h = _native.get_handle(context.device)
+    last = len(context) if last is None else last
+    if not context.streamed:
+        return h.gray_working(context.frames[first:last], size)
+    step = context.chunk_frames()
+    parts = [h.gray_working(context.chunk(a, min(a + step, last)), size) for a in range(first, last, step)]
+    return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
 
 
 def _require_device(device) -> torch.device:
@@ -120,6 +177,47 @@ def _ensure_rgb_host(arr: np.ndarray) -> np.ndarray:
     return arr
 
 
+def _normalize_device(dev: torch.Tensor, source_ptr: Optional[int] = None) -> Tuple[torch.Tensor, str]:
+    """Adapter rules of _to_numpy_frame / _ensure_rgb (stabilizer_utils.py:96-147) on a device chunk
+    [n,H,W,C] (float32 or uint8): per-frame `max > 1.5 => /255`, 1 channel repeated, alpha dropped."""
+    device = dev.device
+    # IEEE division by a TENSOR 255 (torch turns division by a Python scalar into a multiplication
+    # by the reciprocal on CUDA, which is 1 ulp off numpy's `arr /= 255.0` for some values)
+    div255 = torch.full((), 255.0, dtype=torch.float32, device=device)
+    if dev.dtype == torch.uint8:
+        frames = torch.div(dev.to(torch.float32), div255)
+        value_range = "0_255"
+    else:
+        frames = dev
+        peaks = frames.reshape(frames.shape[0], -1).amax(dim=1)
+        big = peaks > 1.5
+        value_range = "0_255" if bool(big[0]) else "0_1"
+        if bool(big.any()):
+            if source_ptr is not None and frames.data_ptr() == source_ptr:
+                frames = frames.clone()
+            frames[big] = torch.div(frames[big], div255)
+    if frames.shape[3] == 1:
+        frames = frames.expand(-1, -1, -1, 3)
+    elif frames.shape[3] > 3:
+        frames = frames[..., :3]
+    elif frames.shape[3] == 2:
+        raise ValueError("2-channel frames are not supported.")
+    return frames.contiguous(), value_range
+
+
+def _must_stream(n: int, height: int, width: int, device: torch.device) -> bool:
+    """True when the float32 RGB clip should not be made resident: it would not leave room for the
+    staging buffers of a host-output run.  VSTAB_RESIDENT_LIMIT_MB overrides the budget (tests)."""
+    import os
+
+    need = n * height * width * 3 * 4
+    limit = os.environ.get("VSTAB_RESIDENT_LIMIT_MB")
+    if limit is not None:
+        return need > int(limit) << 20
+    free, _total = torch.cuda.mem_get_info(device)
+    return need > 0.7 * free - 4 * CHUNK_BYTES
+
+
 def normalize_video_input(value: Any, device=None) -> VideoContext:
     """ComfyUI IMAGE (or list / dict of frames) -> clip resident in HBM.
 
@@ -151,31 +249,19 @@ def normalize_video_input(value: Any, device=None) -> VideoContext:
         and not (seq.shape[1] in (1, 3, 4) and seq.shape[1] < seq.shape[3])
     )
     if fast:
-        dev = _upload_batched(seq.contiguous(), device)
         origin_dtype = np.uint8 if seq.dtype == torch.uint8 else np.float32
-        squeeze = dev.shape[3] == 1
-        # IEEE division by a TENSOR 255 (torch turns division by a Python scalar into a multiplication
-        # by the reciprocal on CUDA, which is 1 ulp off numpy's `arr /= 255.0` for some values)
-        div255 = torch.full((), 255.0, dtype=torch.float32, device=device)
-        if dev.dtype == torch.uint8:
-            frames = torch.div(dev.to(torch.float32), div255)
-            value_range = "0_255"
-        else:
-            frames = dev
-            peaks = frames.reshape(frames.shape[0], -1).amax(dim=1)
-            big = peaks > 1.5
-            value_range = "0_255" if bool(big[0]) else "0_1"
-            if bool(big.any()):
-                if frames.data_ptr() == seq.data_ptr():
-                    frames = frames.clone()
-                frames[big] = torch.div(frames[big], div255)
-        if frames.shape[3] == 1:
-            frames = frames.expand(-1, -1, -1, 3)
-        elif frames.shape[3] > 3:
-            frames = frames[..., :3]
-        elif frames.shape[3] == 2:
+        squeeze = seq.shape[3] == 1
+        if seq.shape[3] == 2:
             raise ValueError("2-channel frames are not supported.")
-        frames = frames.contiguous()
+        n, hh, ww = int(seq.shape[0]), int(seq.shape[1]), int(seq.shape[2])
+        if not seq.is_cuda and _must_stream(n, hh, ww, device):
+            # value range of the adapter = what the reference decides on the first frame
+            first = seq[0]
+            value_range = "0_255" if (first.dtype == torch.uint8 or float(first.max()) > 1.5) else "0_1"
+            adapter = FrameAdapter(origin_dtype, False, value_range, "torch", bool(squeeze))
+            return VideoContext(None, adapter, ww, hh, 3, fps, kind, extra, host=seq.contiguous(), stream_device=device)
+        dev = _upload_batched(seq.contiguous(), device)
+        frames, value_range = _normalize_device(dev, source_ptr=seq.data_ptr())
         adapter = FrameAdapter(origin_dtype, False, value_range, "torch", bool(squeeze))
     else:
         host: List[np.ndarray] = []
@@ -299,6 +385,10 @@ def fused_warp(
     fwd_t = torch.from_numpy(np.ascontiguousarray(fwd, dtype=np.float32)).to(dev, non_blocking=True)
     if fwd_t.dim() == 2:
         fwd_t = fwd_t.view(n, 1, 9)
+    if output == "device" and context.streamed:
+        raise _native.VstabNativeError(
+            "this clip is streamed through the device (it does not fit in HBM next to its results): ask for output='host'"
+        )
     if output == "device":
         dst_buf = _pooled((n, oh, ow, 3), dev, "warp_dst")
         mask_buf = _pooled((n, oh, ow), dev, "warp_mask") if want_mask else None
@@ -316,6 +406,8 @@ def fused_warp(
     masks_cpu = torch.empty((n, oh, ow), dtype=torch.float32, pin_memory=True) if want_mask else None
     pads: List[torch.Tensor] = []
     step = frames_per_chunk(oh, ow, 4)
+    if context.streamed:
+        step = min(step, context.chunk_frames())
     main = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(dev)
     bufs = [
@@ -331,8 +423,9 @@ def fused_warp(
         dbuf, mbuf = bufs[k % len(bufs)]
         if copied[k % len(bufs)] is not None:
             main.wait_event(copied[k % len(bufs)])  # buffer free again
+        # streamed clips: the upload of chunk k+1 (this stream) overlaps the download of chunk k (copy stream)
         dst, mask, pad = _timed_warp(
-            h, context.frames[a:b], fwd_t[a:b], (ow, oh), interpolation, border,
+            h, context.chunk(a, b), fwd_t[a:b], (ow, oh), interpolation, border,
             mask_rule=mask_rule, want_mask=want_mask, want_pad_count=want_pad_count,
             out=dbuf[: b - a], mask_out=(mbuf[: b - a] if mbuf is not None else None),
         )

@@ -101,13 +101,11 @@ class FrameShard:
 
     def owned_context(self, context):
         """Drop the halo frame so frame k of the result is global frame frame_range[0] + k."""
-        import dataclasses
-
         lo, _ = self.frame_range
         halo = lo - self.load_range[0]
         if halo == 0:
             return context
-        return dataclasses.replace(context, frames=context.frames[halo:])
+        return context.sliced(halo)
 
     def gather_pad_counts(self, local_counts) -> np.ndarray:
         counts = [split_range(self.total_frames, self.world, r) for r in range(self.world)]

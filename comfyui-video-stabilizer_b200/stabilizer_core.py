@@ -233,10 +233,7 @@ def stabilize_frames(
             "fps_effective": fps_effective,
         }
         progress.finish()
-        frames = context.frames
-        masks = torch.zeros((1, height, width, 1), dtype=torch.float32, device=frames.device)
-        if output == "host":
-            return StabilizationResult(frames.cpu().numpy(), masks.cpu().numpy(), attach(meta))
+        frames, masks = context.untouched(output)
         return StabilizationResult(frames, masks, attach(meta))
 
     # ---- estimation: all candidate models of every pair -----------------------------------------
