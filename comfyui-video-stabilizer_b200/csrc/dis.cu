@@ -647,10 +647,23 @@ __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
-__global__ void __launch_bounds__(256) vr_fused_kernel(Level L, VrBuf B, int cluster_size) {
+// ONCHIP: the level is small enough for all 19 planes of a pair to live in the shared memory of ONE CTA
+// (19 * h * w * 4 bytes: 39 KB at 30x17, 155 KB at 60x34): 1024 threads, __syncthreads between the
+// phases, and every plane access is a shared-memory access -- the phases of these levels are pure
+// latency, so that is what they cost.  The plane pointers are rebased so that the per-pixel code,
+// which indexes [pair][y][x], lands in the CTA's own copy.
+template <bool ONCHIP>
+__global__ void __launch_bounds__(ONCHIP ? 1024 : 256) vr_fused_kernel(Level L, VrBuf B, int cluster_size) {
+  extern __shared__ __align__(16) float vr_smem[];
   const int pair = blockIdx.x / cluster_size;
   const int crank = blockIdx.x % cluster_size;
   const int w = L.w, h = L.h;
+  if (ONCHIP) {
+    float** planes = reinterpret_cast<float**>(&B);
+    const size_t px = (size_t)h * w;
+#pragma unroll
+    for (int k = 0; k < 19; k++) planes[k] = vr_smem + k * px - (size_t)pair * px;
+  }
   const int rows_per = (h + cluster_size - 1) / cluster_size;
   const int r0 = min(crank * rows_per, h), r1 = min(r0 + rows_per, h);
   const int npx = (r1 - r0) * w;
@@ -662,13 +675,13 @@ __global__ void __launch_bounds__(256) vr_fused_kernel(Level L, VrBuf B, int clu
     __VA_ARGS__;                                                  \
   }
   FOR_PX(vr_px_warp(L, B, pair, x, y))
-  cluster_barrier();
+  if (ONCHIP) __syncthreads(); else cluster_barrier();
   FOR_PX(vr_px_deriv1(L, B, pair, x, y))
-  cluster_barrier();
+  if (ONCHIP) __syncthreads(); else cluster_barrier();
   FOR_PX(vr_px_deriv2(L, B, pair, x, y))
   for (int it = 0; it < kVrIter; it++) {
     FOR_PX(vr_px_weight(L, B, pair, x, y))
-    cluster_barrier();
+    if (ONCHIP) __syncthreads(); else cluster_barrier();
     FOR_PX(vr_px_system(L, B, pair, x, y))
     __syncthreads();  // the SOR sweeps map pixels to threads differently (checkerboard halves)
     for (int s = 0; s < kSorIter; s++)
@@ -678,7 +691,7 @@ __global__ void __launch_bounds__(256) vr_fused_kernel(Level L, VrBuf B, int clu
           const int x = 2 * (i - (i / half_w) * half_w) + ((y + colour) & 1);
           if (x < w) vr_px_sor(L, B, pair, x, y);
         }
-        cluster_barrier();
+        if (ONCHIP) __syncthreads(); else cluster_barrier();
       }
     {
       const int last = it == kVrIter - 1;
@@ -690,7 +703,7 @@ __global__ void __launch_bounds__(256) vr_fused_kernel(Level L, VrBuf B, int clu
         if (last) { L.Ux[k] = u; L.Uy[k] = v; }
       })
     }
-    cluster_barrier();
+    if (ONCHIP) __syncthreads(); else cluster_barrier();
   }
 #undef FOR_PX
 }
@@ -946,8 +959,15 @@ extern "C" int vstab_dis_flow(vstab_handle* hnd, const uint8_t* gray_dev, int n_
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        VSTAB_CUDA(hnd, cudaLaunchKernelEx(&cfg, vr_fused_kernel, L[i], B, cl));
-        hnd->launches++;
+        const size_t onchip_bytes = (size_t)19 * px * sizeof(float);
+        if (onchip_bytes <= (size_t)hnd->max_smem_optin) {
+          VSTAB_CUDA(hnd, cudaFuncSetAttribute(vr_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onchip_bytes));
+          vr_fused_kernel<true><<<P, 1024, onchip_bytes, st>>>(L[i], B, 1);
+          VSTAB_LAUNCH_CHECK(hnd, "vr_fused_kernel");
+        } else {
+          VSTAB_CUDA(hnd, cudaLaunchKernelEx(&cfg, vr_fused_kernel<false>, L[i], B, cl));
+          hnd->launches++;
+        }
       }
       if (i > kFinest) {
         dim3 gu(vstab_ceil_div(L[i - 1].w, 32), vstab_ceil_div(L[i - 1].h, 8), P);
