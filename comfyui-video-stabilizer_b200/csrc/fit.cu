@@ -147,11 +147,25 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const float* __restri
   if (threadIdx.x == 0) n_valid[pair] = s_base;
 }
 
-// ---- translation: per-axis median of float32 shifts (bitonic sort in shared memory) ----
+// ---- translation: per-axis median of float32 shifts ----
+// Exact selection instead of a sort: the shifts become order-preserving 32-bit keys and four 8-bit
+// histogram passes (both axes at once, warp 0 / warp 1 resolve the bins) pin down the element of rank
+// n/2; for even n the element of rank n/2 - 1 is that same value when it has duplicates below the
+// rank, else the largest smaller key.  Same result as np.median on the float32 shifts.
+__device__ __forceinline__ unsigned float_key(float v) {
+  const unsigned u = __float_as_uint(v + 0.0f);  // -0 -> +0
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 __global__ void __launch_bounds__(1024) translation_kernel(const float2* __restrict__ P, const float2* __restrict__ C,
                                                            const int* __restrict__ n_valid, int n_pts, int cap,
                                                            FitOut* __restrict__ out) {
-  extern __shared__ float s_val[];  // cap floats (power of two >= n_pts)
+  extern __shared__ unsigned s_key[];  // [2][cap]
+  __shared__ unsigned s_hist[2][256];
+  __shared__ unsigned s_prefix[2], s_rank[2], s_less[2], s_maxless[2];
   __shared__ float s_t[2];
   const int pair = blockIdx.x;
   const int n = n_valid[pair];
@@ -169,30 +183,87 @@ __global__ void __launch_bounds__(1024) translation_kernel(const float2* __restr
     }
     return;
   }
-  int m = 1;
-  while (m < n) m <<= 1;
-  for (int axis = 0; axis < 2; axis++) {
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
-      float v = INFINITY;
-      if (i < n) v = axis == 0 ? (c[i].x - p[i].x) : (c[i].y - p[i].y);
-      s_val[i] = v;
+  unsigned* kx = s_key;
+  unsigned* ky = s_key + cap;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    kx[i] = float_key(c[i].x - p[i].x);
+    ky[i] = float_key(c[i].y - p[i].y);
+  }
+  if (threadIdx.x < 2) {
+    s_prefix[threadIdx.x] = 0;
+    s_rank[threadIdx.x] = (unsigned)(n / 2);
+    s_less[threadIdx.x] = 0;
+    s_maxless[threadIdx.x] = 0;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pass = 3; pass >= 0; pass--) {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned mask = pass == 3 ? 0u : (0xffffffffu << (8 * (pass + 1)));
+    const unsigned px = s_prefix[0], py = s_prefix[1];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned a = kx[i], b2 = ky[i];
+      if ((a & mask) == px) atomicAdd(&s_hist[0][(a >> (8 * pass)) & 255u], 1u);
+      if ((b2 & mask) == py) atomicAdd(&s_hist[1][(b2 >> (8 * pass)) & 255u], 1u);
     }
     __syncthreads();
-    for (int k = 2; k <= m; k <<= 1)
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = threadIdx.x; i < m; i += blockDim.x) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const float a = s_val[i], b = s_val[ixj];
-            const bool up = (i & k) == 0;
-            if ((a > b) == up) { s_val[i] = b; s_val[ixj] = a; }
-          }
-        }
-        __syncthreads();
+    if (warp < 2) {  // warp `axis`: which bin holds the element of the wanted rank
+      const unsigned* hst = s_hist[warp];
+      unsigned loc = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) loc += hst[lane * 8 + q];
+      unsigned inc = loc;
+      for (int ofs = 1; ofs < 32; ofs <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, ofs);
+        if (lane >= ofs) inc += t;
       }
-    if (threadIdx.x == 0) {
-      // numpy: middle element, or the float32 mean of the two middle elements
-      s_t[axis] = (n & 1) ? s_val[n / 2] : (s_val[n / 2 - 1] + s_val[n / 2]) * 0.5f;
+      const unsigned rank = s_rank[warp];
+      const unsigned before = inc - loc;
+      if (rank >= before && rank < inc) {  // exactly one lane
+        unsigned cum = before;
+        int bin = lane * 8;
+        for (int q = 0; q < 8; q++) {
+          const unsigned hq = hst[lane * 8 + q];
+          if (rank < cum + hq) { bin = lane * 8 + q; break; }
+          cum += hq;
+        }
+        s_rank[warp] = rank - cum;
+        s_prefix[warp] |= (unsigned)bin << (8 * pass);
+      }
+    }
+    __syncthreads();
+  }
+  {
+    const unsigned hx = s_prefix[0], hy = s_prefix[1];
+    unsigned lx = 0, ly = 0, mx = 0, my = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned a = kx[i], b2 = ky[i];
+      if (a < hx) { lx++; mx = max(mx, a); }
+      if (b2 < hy) { ly++; my = max(my, b2); }
+    }
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+      lx += __shfl_down_sync(0xffffffffu, lx, ofs);
+      ly += __shfl_down_sync(0xffffffffu, ly, ofs);
+      mx = max(mx, __shfl_down_sync(0xffffffffu, mx, ofs));
+      my = max(my, __shfl_down_sync(0xffffffffu, my, ofs));
+    }
+    if (lane == 0) {
+      atomicAdd(&s_less[0], lx);
+      atomicAdd(&s_less[1], ly);
+      atomicMax(&s_maxless[0], mx);
+      atomicMax(&s_maxless[1], my);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      const int axis = threadIdx.x;
+      const float hi = key_float(s_prefix[axis]);
+      float med = hi;
+      if ((n & 1) == 0) {
+        // numpy: the float32 mean of the two middle elements
+        const float lo = (s_less[axis] < (unsigned)(n / 2)) ? hi : key_float(s_maxless[axis]);
+        med = (lo + hi) * 0.5f;
+      }
+      s_t[axis] = med;
     }
     __syncthreads();
   }
@@ -861,7 +932,7 @@ extern "C" int vstab_fit_batch(vstab_handle* h, const float* prev_dev, const flo
   if (mode_mask & (1 << VSTAB_MODE_TRANSLATION)) {
     int cap = 1;
     while (cap < n_pts) cap <<= 1;
-    const size_t smem = sizeof(float) * cap;
+    const size_t smem = sizeof(unsigned) * 2 * cap;
     VSTAB_CUDA(h, cudaFuncSetAttribute(translation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     translation_kernel<<<n_pairs, 1024, smem, st>>>(P, C, nvalid, n_pts, cap, out);
     VSTAB_LAUNCH_CHECK(h, "fit translation_kernel");
