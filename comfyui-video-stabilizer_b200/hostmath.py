@@ -17,7 +17,7 @@ Reference anchors (file:line in the reference repository):
 from __future__ import annotations
 
 import math
-from typing import Any, Dict, Sequence, Tuple
+from typing import Any, Dict, List, Sequence, Tuple
 
 import numpy as np
 
@@ -278,6 +278,11 @@ def resolve_fps_for_stabilizer(frame_rate, context_fps):
 def padded_fraction(pad_count: int, pixels: int) -> float:
     """float(mask.mean()) of a 0/1 float32 mask: numpy sums exactly (< 2^24), divides in f32."""
     return float(np.float32(pad_count) / np.float32(pixels))
+
+
+def padded_fractions(pad_counts, pixels: int) -> List[float]:
+    """padded_fraction for every frame of a clip in one array operation."""
+    return (np.asarray(pad_counts).astype(np.float32) / np.float32(pixels)).astype(np.float64).tolist()
 
 
 # reference-compatible private names (the reference's tests and scripts import these)

@@ -215,14 +215,19 @@ def applied_motion_meta_from_matrices(matrices, *, source_size, output_size, fps
         raise ValueError("motion_meta.source must be a non-empty string.")
     for i in np.flatnonzero(~np.isfinite(stack).all(axis=(1, 2))):
         raise ValueError(f"stabilization_warp.per_frame[{int(i)}].applied_matrix must contain finite numbers.")
-    try:
-        np.linalg.inv(stack)
-    except np.linalg.LinAlgError:
-        for i, m in enumerate(stack):
-            try:
-                np.linalg.inv(m)
-            except np.linalg.LinAlgError as exc:
-                raise ValueError(f"stabilization_warp.per_frame[{i}].applied_matrix is not invertible.") from exc
+    # np.linalg.inv fails on an exactly zero LU pivot; such a matrix has a determinant at rounding level.
+    # Only matrices whose cofactor determinant is tiny against their scale go through the LAPACK check
+    # (a per-matrix call costs microseconds, which adds up on long clips).
+    a, b, c = stack[:, 0, 0], stack[:, 0, 1], stack[:, 0, 2]
+    d, e, f = stack[:, 1, 0], stack[:, 1, 1], stack[:, 1, 2]
+    g, h2, k = stack[:, 2, 0], stack[:, 2, 1], stack[:, 2, 2]
+    det = a * (e * k - f * h2) - b * (d * k - f * g) + c * (d * h2 - e * g)
+    scale = np.abs(stack).reshape(-1, 9).max(axis=1)
+    for i in np.flatnonzero(~(np.abs(det) > 1e-9 * scale * scale * scale)):
+        try:
+            np.linalg.inv(stack[i])
+        except np.linalg.LinAlgError as exc:
+            raise ValueError(f"stabilization_warp.per_frame[{int(i)}].applied_matrix is not invertible.") from exc
     return {
         "version": 2,
         "source": source,

@@ -349,12 +349,12 @@ def stabilize_frames(
     per_transition = []
     if full_meta:
         mat_lists = matrices.tolist()
-        for i, (_, mode, conf, resid) in enumerate(chosen):
-            entry = {"index": i, "mode": mode, "confidence": conf}
-            if is_flow:
-                entry["residual"] = resid
-            entry["matrix"] = mat_lists[i]
-            per_transition.append(entry)
+        if is_flow:
+            per_transition = [{"index": i, "mode": c[1], "confidence": c[2], "residual": c[3], "matrix": m}
+                              for i, (c, m) in enumerate(zip(chosen, mat_lists))]
+        else:
+            per_transition = [{"index": i, "mode": c[1], "confidence": c[2], "matrix": m}
+                              for i, (c, m) in enumerate(zip(chosen, mat_lists))]
 
     warp_meta = hm.build_stabilization_warp_meta(
         source_size=(width, height), output_size=output_size, framing_mode=framing_mode,
@@ -378,7 +378,7 @@ def stabilize_frames(
     if shard is not None:
         pad_counts = shard.gather_pad_counts(pad_counts)
     pixels = int(output_size[0]) * int(output_size[1])
-    padded_ratios = [hm.padded_fraction(int(c), pixels) for c in pad_counts]
+    padded_ratios = hm.padded_fractions(pad_counts, pixels)
     framing_meta["padding_detected"] = bool(np.any(np.asarray(pad_counts) > 0))
     progress.advance(total_frames)
     check()
