@@ -368,7 +368,9 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
   cudaStream_t st = (cudaStream_t)stream;
   VSTAB_ENTER(hnd);
   const int h = height, w = width;
-  const int kChunk = 32;  // frames per pass of the corner detector (bounds the double row-sum buffer)
+  // frames per pass of the corner detector: every running-sum / selection kernel is a chain per row, column or
+  // frame, so a pass costs its chain latency whatever the frame count (20.7 MB of scratch per 960x540 frame)
+  const int kChunk = (n_frames - 1) < 256 ? (n_frames - 1) : 256;
   int cap = 1024;  // per-frame candidate capacity: power of two >= h*w/4 (a 3x3 local maximum needs its own 2x2 block)
   while (cap < (h * w) / 4) cap <<= 1;
   const int gw = (w + kCell - 1) / kCell, gh = (h + kCell - 1) / kCell;
