@@ -325,12 +325,27 @@ __global__ void __launch_bounds__(256) lk_track_kernel(LkPyr P, int n_pairs, int
       iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS)); iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
       iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS)); iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
       float b1 = 0, b2 = 0;
-      for (int k = lane; k < kWin * kWin; k += 32) {
-        const int y = k / kWin, x = k - y * kWin;
-        const int y0 = reflect101(iny + y, lh), y1 = reflect101(iny + y + 1, lh), x0 = reflect101(inx + x, lw), x1 = reflect101(inx + x + 1, lw);
-        const int diff = descale(J[y0 * lw + x0] * iw00 + J[y0 * lw + x1] * iw01 + J[y1 * lw + x0] * iw10 + J[y1 * lw + x1] * iw11, W_BITS - 5) - win[k * 3];
-        b1 += (float)(diff * win[k * 3 + 1]);
-        b2 += (float)(diff * win[k * 3 + 2]);
+      if (inx >= 0 && iny >= 0 && inx + kWin < lw && iny + kWin < lh) {
+        // window (with its +1 taps) inside the image: no border reflection, and (y, x) of pixel k = lane + 32 j
+        // advance by (+1, +1) with a wrap instead of a division -- same pixels, same order, same sums
+        const unsigned char* Jp = J + iny * lw + inx;
+        int y = lane >= kWin ? 1 : 0, x = lane >= kWin ? lane - kWin : lane;
+        for (int k = lane; k < kWin * kWin; k += 32) {
+          const unsigned char* q = Jp + y * lw + x;
+          const int diff = descale(q[0] * iw00 + q[1] * iw01 + q[lw] * iw10 + q[lw + 1] * iw11, W_BITS - 5) - win[k * 3];
+          b1 += (float)(diff * win[k * 3 + 1]);
+          b2 += (float)(diff * win[k * 3 + 2]);
+          x += 1; y += 1;
+          if (x >= kWin) { x -= kWin; y += 1; }
+        }
+      } else {
+        for (int k = lane; k < kWin * kWin; k += 32) {
+          const int y = k / kWin, x = k - y * kWin;
+          const int y0 = reflect101(iny + y, lh), y1 = reflect101(iny + y + 1, lh), x0 = reflect101(inx + x, lw), x1 = reflect101(inx + x + 1, lw);
+          const int diff = descale(J[y0 * lw + x0] * iw00 + J[y0 * lw + x1] * iw01 + J[y1 * lw + x0] * iw10 + J[y1 * lw + x1] * iw11, W_BITS - 5) - win[k * 3];
+          b1 += (float)(diff * win[k * 3 + 1]);
+          b2 += (float)(diff * win[k * 3 + 2]);
+        }
       }
       b1 = warp_sum(b1) * FLT_SCALE; b2 = warp_sum(b2) * FLT_SCALE;
       const float ddx = (A12 * b2 - A22 * b1) * Dd, ddy = (A12 * b1 - A11 * b2) * Dd;
