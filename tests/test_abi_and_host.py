@@ -175,3 +175,32 @@ def test_node_schema_matches_reference_contract():
     defaults = {s.args[0]: s.kwargs.get("default") for s in nodes.VideoStabilizerFlow.define_schema().inputs}
     assert defaults["frame_rate"] == 16.0 and defaults["framing_mode"] == "crop_and_pad" and defaults["transform_mode"] == "similarity"
     assert defaults["strength"] == 0.7 and defaults["smooth"] == 0.5 and defaults["keep_fov"] == 0.6 and defaults["padding_color"] == "#7F7F7F"
+
+
+def test_meta_helpers_for_long_clips_keep_the_reference_results(monkeypatch):
+    """The O(frames) host pieces were vectorised for long / sharded clips: same values, same errors."""
+    from vstab_b200 import hostmath as hm, motion_meta as mm, pipeline
+
+    counts = [0, 1, 10, 12345, 2073599, 2073600]
+    assert hm.padded_fractions(counts, 1920 * 1080) == [hm.padded_fraction(c, 1920 * 1080) for c in counts]
+
+    rng = np.random.default_rng(3)
+    mats = np.tile(np.eye(3, dtype=np.float32), (50, 1, 1))
+    mats[:, :2, 2] = rng.normal(0, 20, (50, 2))
+    mats[7] *= np.float32(1e-6)  # tiny but invertible: must pass like np.linalg.inv does
+    block = mm.applied_motion_meta_from_matrices(mats, source_size=(64, 48), output_size=(64, 48), fps=16.0, source="t")
+    assert block["frame_count"] == 50 and block["per_frame"][7]["matrix"] == mats[7].astype(np.float64).tolist()
+    for bad in (np.zeros((3, 3), np.float32), np.array([[1, 2, 3], [2, 4, 6], [0, 0, 1]], np.float32)):
+        broken = mats.copy()
+        broken[11] = bad
+        with pytest.raises(ValueError, match=r"per_frame\[11\]\.applied_matrix is not invertible"):
+            mm.applied_motion_meta_from_matrices(broken, source_size=(64, 48), output_size=(64, 48), fps=16.0, source="t")
+    broken = mats.copy()
+    broken[3, 0, 0] = np.nan
+    with pytest.raises(ValueError, match=r"per_frame\[3\]\.applied_matrix must contain finite numbers"):
+        mm.applied_motion_meta_from_matrices(broken, source_size=(64, 48), output_size=(64, 48), fps=16.0, source="t")
+
+    # streaming decision: explicit budget in MiB of the float32 RGB clip
+    monkeypatch.setenv("VSTAB_RESIDENT_LIMIT_MB", "10")
+    assert pipeline._must_stream(10, 480, 832, None)       # 47.9 MB
+    assert not pipeline._must_stream(2, 480, 832, None)    # 9.6 MB
