@@ -36,48 +36,117 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 
 // ---- GFTT ---------------------------------------------------------------------------------------
 
+// Covariance of the Sobel derivatives, written TRANSPOSED: covT[f][x][y][3].  The horizontal box-filter
+// pass below is a chain along x per row, so its parallelism is across rows; with x-major storage the 32 rows
+// of a warp sit next to each other at every step of the chain.  (A 32x32 tile goes through shared memory:
+// image reads coalesced along x, covariance writes coalesced along y.)
 __global__ void __launch_bounds__(256) gftt_cov_kernel(const unsigned char* __restrict__ gray, int h, int w, float s, float s2,
-                                                       float* __restrict__ cov /* [F][h][w][3] */) {
+                                                       float* __restrict__ covT /* [F][w][h][3] */) {
+  __shared__ float tile[32][32 * 3 + 3];  // [x][3 y + c]; 99-float rows: both access patterns are conflict-free
   const int f = blockIdx.z;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= w || y >= h) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
   const unsigned char* img = gray + (size_t)f * h * w;
-  const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
-  const int ym = reflect101(y - 1, h), yp = reflect101(y + 1, h);
-  auto smooth_row = [&](int yy) {  // row filter [s 2s s], fused chain like cv2's AVX2 row filter
-    const float a = img[yy * w + xm], b = img[yy * w + x], c = img[yy * w + xp];
-    return fmaf(s, c, fmaf(s2, b, s * a));
-  };
-  auto diff_row = [&](int yy) { return (float)((int)img[yy * w + xp] - (int)img[yy * w + xm]); };
-  const float dy = smooth_row(yp) - smooth_row(ym);
-  const float dx = fmaf(diff_row(ym) + diff_row(yp), s, diff_row(y) * s2);
-  float* o = cov + (((size_t)f * h + y) * w + x) * 3;
-  o[0] = dx * dx;
-  o[1] = dx * dy;
-  o[2] = dy * dy;
+  const int x = x0 + lane;
+#pragma unroll
+  for (int rr = 0; rr < 4; rr++) {
+    const int yl = warp * 4 + rr, y = y0 + yl;
+    if (x < w && y < h) {
+      const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+      const int ym = reflect101(y - 1, h), yp = reflect101(y + 1, h);
+      auto smooth_row = [&](int yy) {  // row filter [s 2s s], fused chain like cv2's AVX2 row filter
+        const float a = img[yy * w + xm], b = img[yy * w + x], c = img[yy * w + xp];
+        return fmaf(s, c, fmaf(s2, b, s * a));
+      };
+      auto diff_row = [&](int yy) { return (float)((int)img[yy * w + xp] - (int)img[yy * w + xm]); };
+      const float dy = smooth_row(yp) - smooth_row(ym);
+      const float dx = fmaf(diff_row(ym) + diff_row(yp), s, diff_row(y) * s2);
+      tile[lane][yl * 3] = dx * dx;
+      tile[lane][yl * 3 + 1] = dx * dy;
+      tile[lane][yl * 3 + 2] = dy * dy;
+    }
+  }
+  __syncthreads();
+  const int nvalid = min(32, h - y0) * 3;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int xl = warp * 4 + k;
+    if (x0 + xl < w) {
+      float* dst = covT + (((size_t)f * w + x0 + xl) * h + y0) * 3;
+      for (int e = lane; e < nvalid; e += 32) dst[e] = tile[xl][e];
+    }
+  }
 }
 
-// horizontal running sums in double: one thread per (frame, row)
-__global__ void gftt_box_rows_kernel(const float* __restrict__ cov, int F, int h, int w, double* __restrict__ rows /* [F][h][w][3] */) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= F * h) return;
-  const float* c = cov + (size_t)idx * w * 3;
-  double* o = rows + (size_t)idx * w * 3;
+// horizontal running sums in double (cv::boxFilter's sliding sum, add for add): one lane per (frame, row),
+// one warp per 32 consecutive rows.  Loads from covT are coalesced across the rows at every step; the sums
+// of 32 steps are collected in a shared-memory tile and leave row-major (rows[f][y][x][3]) as coalesced
+// 768-byte row segments, which is the layout the vertical pass streams.
+constexpr int kRowTileStride = 32 * 3 + 1;  // doubles per x-slot of the output tile
+__global__ void __launch_bounds__(128) gftt_box_rows_kernel(const float* __restrict__ covT, int F, int h, int w,
+                                                            double* __restrict__ rows /* [F][h][w][3] */) {
+  extern __shared__ double s_rows[];  // [4 warps][32 x-slots][kRowTileStride]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ytiles = (h + 31) / 32;
+  const int t = blockIdx.x * 4 + warp;
+  if (t >= F * ytiles) return;  // whole warp
+  const int f = t / ytiles, y0 = (t - f * ytiles) * 32;
+  const int y = min(y0 + lane, h - 1);  // lanes past the last row repeat it and are never written out
+  const size_t stride = (size_t)h * 3;
+  const float* c = covT + (size_t)f * w * stride + (size_t)y * 3;
+  double* tile = s_rows + (size_t)warp * 32 * kRowTileStride;
   double a0 = 0, a1 = 0, a2 = 0;
   for (int i = 0; i < kBlock; i++) {
-    const int x = reflect101(i - kRadius, w);
-    a0 += (double)c[x * 3];
-    a1 += (double)c[x * 3 + 1];
-    a2 += (double)c[x * 3 + 2];
+    const float* q = c + (size_t)reflect101(i - kRadius, w) * stride;
+    a0 += (double)q[0];
+    a1 += (double)q[1];
+    a2 += (double)q[2];
   }
-  o[0] = a0; o[1] = a1; o[2] = a2;
-  for (int x = 1; x < w; x++) {
-    const int xn = reflect101(x + kBlock - 1 - kRadius, w), xo = reflect101(x - 1 - kRadius, w);
-    a0 += (double)c[xn * 3] - (double)c[xo * 3];
-    a1 += (double)c[xn * 3 + 1] - (double)c[xo * 3 + 1];
-    a2 += (double)c[xn * 3 + 2] - (double)c[xo * 3 + 2];
-    o[x * 3] = a0; o[x * 3 + 1] = a1; o[x * 3 + 2] = a2;
+  for (int x0 = 0; x0 < w; x0 += 32) {
+    const int cnt = min(32, w - x0);
+    if (x0 - 1 - kRadius >= 0 && x0 + 31 + kRadius < w) {
+      // no reflection in this chunk: the loads of four steps are issued before the chain consumes them
+#pragma unroll 2
+      for (int xs = 0; xs < 32; xs += 4) {
+        float in[4][3], out[4][3];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const float* qn = c + (size_t)(x0 + xs + q + kRadius) * stride;
+          const float* qo = c + (size_t)(x0 + xs + q - 1 - kRadius) * stride;
+          in[q][0] = qn[0]; in[q][1] = qn[1]; in[q][2] = qn[2];
+          out[q][0] = qo[0]; out[q][1] = qo[1]; out[q][2] = qo[2];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          a0 += (double)in[q][0] - (double)out[q][0];
+          a1 += (double)in[q][1] - (double)out[q][1];
+          a2 += (double)in[q][2] - (double)out[q][2];
+          double* o = tile + (xs + q) * kRowTileStride + lane * 3;
+          o[0] = a0; o[1] = a1; o[2] = a2;
+        }
+      }
+    } else {
+      for (int xs = 0; xs < cnt; xs++) {
+        const int x = x0 + xs;
+        if (x > 0) {
+          const float* qn = c + (size_t)reflect101(x + kBlock - 1 - kRadius, w) * stride;
+          const float* qo = c + (size_t)reflect101(x - 1 - kRadius, w) * stride;
+          a0 += (double)qn[0] - (double)qo[0];
+          a1 += (double)qn[1] - (double)qo[1];
+          a2 += (double)qn[2] - (double)qo[2];
+        }
+        double* o = tile + xs * kRowTileStride + lane * 3;
+        o[0] = a0; o[1] = a1; o[2] = a2;
+      }
+    }
+    __syncwarp();
+    const int n = cnt * 3;
+    const int rmax = min(32, h - y0);
+    for (int r = 0; r < rmax; r++) {
+      double* dst = rows + (((size_t)f * h + y0 + r) * w + x0) * 3;
+      for (int e = lane; e < n; e += 32) dst[e] = tile[(e / 3) * kRowTileStride + r * 3 + (e % 3)];
+    }
+    __syncwarp();
   }
 }
 
@@ -438,10 +507,14 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
   for (int f0 = 0; f0 < P; f0 += kChunk) {
     const int F = (P - f0) < kChunk ? (P - f0) : kChunk;
     const unsigned char* g = gray_dev + (size_t)f0 * h * w;
-    dim3 gp(vstab_ceil_div(w, 32), vstab_ceil_div(h, 8), F);
+    dim3 gp(vstab_ceil_div(w, 32), vstab_ceil_div(h, 32), F);
     gftt_cov_kernel<<<gp, 256, 0, st>>>(g, h, w, s, s2, cov);
     VSTAB_LAUNCH_CHECK(hnd, "gftt_cov_kernel");
-    gftt_box_rows_kernel<<<vstab_ceil_div(F * h, 128), 128, 0, st>>>(cov, F, h, w, rows);
+    {
+      const size_t rows_smem = sizeof(double) * 4 * 32 * kRowTileStride;  // 99 KB: the tiles of 4 warps
+      VSTAB_CUDA(hnd, cudaFuncSetAttribute(gftt_box_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
+      gftt_box_rows_kernel<<<vstab_ceil_div(F * vstab_ceil_div(h, 32), 4), 128, rows_smem, st>>>(cov, F, h, w, rows);
+    }
     VSTAB_LAUNCH_CHECK(hnd, "gftt_box_rows_kernel");
     VSTAB_CUDA(hnd, cudaMemsetAsync(maxb, 0, sizeof(unsigned) * kChunk, st));
     VSTAB_CUDA(hnd, cudaMemsetAsync(cnt, 0, sizeof(int) * kChunk, st));
