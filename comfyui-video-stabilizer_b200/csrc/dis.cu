@@ -377,160 +377,20 @@ struct VrBuf {  // all [P][h][w] float
   float *A11, *A12, *A22, *b1, *b2, *wgt, *tu, *tv, *du, *dv;
 };
 
-#define PIXEL_INDEX()                                         \
-  const int pair = blockIdx.z;                                \
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);         \
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);          \
-  const int w = L.w, h = L.h;                                 \
-  if (x >= w || y >= h) return;                               \
-  const size_t base = (size_t)pair * h * w;                   \
-  const size_t k = base + (size_t)y * w + x;
-
-// warp I1 by the current flow (cv::remap INTER_LINEAR, BORDER_REPLICATE, 1/32 px), average, Iz
-__global__ void __launch_bounds__(256) vr_warp_kernel(Level L, VrBuf B) {
-  PIXEL_INDEX();
-  const unsigned char* I0 = L.I + (size_t)pair * h * w;
-  const unsigned char* I1 = L.I + (size_t)(pair + 1) * h * w;
-  const float mx = x + L.Ux[k], my = y + L.Uy[k];
-  const int ix = __float2int_rn(mx * 32.f), iy = __float2int_rn(my * 32.f);
-  int sx = ix >> 5, sy = iy >> 5;
-  const int ax = ix & 31, ay = iy & 31;
-  sx = min(max(sx, -32768), 32767);
-  sy = min(max(sy, -32768), 32767);
-  const float fx1 = ax * (1.f / 32.f), fy1 = ay * (1.f / 32.f), fx0 = 1.f - fx1, fy0 = 1.f - fy1;
-  const float w00 = fy0 * fx0, w01 = fy0 * fx1, w10 = fy1 * fx0, w11 = fy1 * fx1;
-  const int x0 = min(max(sx, 0), w - 1), x1 = min(max(sx + 1, 0), w - 1);
-  const int y0 = min(max(sy, 0), h - 1), y1 = min(max(sy + 1, 0), h - 1);
-  const float warped = (float)I1[y0 * w + x0] * w00 + (float)I1[y0 * w + x1] * w01 + (float)I1[y1 * w + x0] * w10 +
-                       (float)I1[y1 * w + x1] * w11;
-  const float i0 = (float)I0[y * w + x];
-  B.avg[k] = 0.5f * (i0 + warped);
-  B.Iz[k] = warped - i0;
-  B.tu[k] = L.Ux[k];
-  B.tv[k] = L.Uy[k];
-  B.du[k] = 0.f;
-  B.dv[k] = 0.f;
-}
-
 __device__ __forceinline__ float at_clamped(const float* p, size_t base, int y, int x, int h, int w) {
   return p[base + (size_t)min(max(y, 0), h - 1) * w + min(max(x, 0), w - 1)];
 }
 
-// first derivatives of avg and of Iz (central differences without the 1/2, replicate border)
-__global__ void __launch_bounds__(256) vr_deriv1_kernel(Level L, VrBuf B) {
-  PIXEL_INDEX();
-  B.Ix[k] = at_clamped(B.avg, base, y, x + 1, h, w) - at_clamped(B.avg, base, y, x - 1, h, w);
-  B.Iy[k] = at_clamped(B.avg, base, y + 1, x, h, w) - at_clamped(B.avg, base, y - 1, x, h, w);
-  B.Ixz[k] = at_clamped(B.Iz, base, y, x + 1, h, w) - at_clamped(B.Iz, base, y, x - 1, h, w);
-  B.Iyz[k] = at_clamped(B.Iz, base, y + 1, x, h, w) - at_clamped(B.Iz, base, y - 1, x, h, w);
-}
-
-__global__ void __launch_bounds__(256) vr_deriv2_kernel(Level L, VrBuf B) {
-  PIXEL_INDEX();
-  B.Ixx[k] = at_clamped(B.Ix, base, y, x + 1, h, w) - at_clamped(B.Ix, base, y, x - 1, h, w);
-  B.Ixy[k] = at_clamped(B.Ix, base, y + 1, x, h, w) - at_clamped(B.Ix, base, y - 1, x, h, w);
-  B.Iyy[k] = at_clamped(B.Iy, base, y + 1, x, h, w) - at_clamped(B.Iy, base, y - 1, x, h, w);
-}
-
-// smoothness weight of the current flow (forward differences, replicate border)
-__global__ void __launch_bounds__(256) vr_weight_kernel(Level L, VrBuf B) {
-  PIXEL_INDEX();
-  const size_t kr = base + (size_t)y * w + min(x + 1, w - 1), kd = base + (size_t)min(y + 1, h - 1) * w + x;
-  const float ux = B.tu[kr] - B.tu[k], vx = B.tv[kr] - B.tv[k], uy = B.tu[kd] - B.tu[k], vy = B.tv[kd] - B.tv[k];
-  const float eps2 = kEpsilon * kEpsilon;
-  B.wgt[k] = (kAlpha / 2) / sqrtf(ux * ux + vx * vx + uy * uy + vy * vy + eps2);
-}
-
-// data term + smoothness term of the linear system, accumulated per pixel in the order OpenCV's
-// red/black scatter passes touch it (see oracle/dis_ref.c: red = (x + y) even goes first).
-__global__ void __launch_bounds__(256) vr_system_kernel(Level L, VrBuf B) {
-  PIXEL_INDEX();
-  const float zeta2 = 0.1f * 0.1f, eps2 = kEpsilon * kEpsilon, gamma2 = kGamma / 2, delta2 = kDelta / 2;
-  const float ix = B.Ix[k], iy = B.Iy[k], iz = B.Iz[k], ixx = B.Ixx[k], ixy = B.Ixy[k], iyy = B.Iyy[k];
-  const float ixz = B.Ixz[k], iyz = B.Iyz[k], dU = B.du[k], dV = B.dv[k];
-  float derivNorm = ix * ix + iy * iy + zeta2;
-  const float Ik1z = iz + ix * dU + iy * dV;
-  float weight = (delta2 / sqrtf(Ik1z * Ik1z / derivNorm + eps2)) / derivNorm;
-  float a11 = weight * (ix * ix) + zeta2;
-  float a12 = weight * (ix * iy);
-  float a22 = weight * (iy * iy) + zeta2;
-  float bb1 = -weight * (iz * ix);
-  float bb2 = -weight * (iz * iy);
-  derivNorm = ixx * ixx + ixy * ixy + zeta2;
-  const float derivNorm2 = iyy * iyy + ixy * ixy + zeta2;
-  const float Ik1zx = ixz + ixx * dU + ixy * dV;
-  const float Ik1zy = iyz + ixy * dU + iyy * dV;
-  weight = gamma2 / sqrtf(Ik1zx * Ik1zx / derivNorm + Ik1zy * Ik1zy / derivNorm2 + eps2);
-  a11 += weight * (ixx * ixx / derivNorm + ixy * ixy / derivNorm2);
-  a12 += weight * (ixx * ixy / derivNorm + ixy * iyy / derivNorm2);
-  a22 += weight * (ixy * ixy / derivNorm + iyy * iyy / derivNorm2);
-  bb1 += -weight * (ixx * ixz / derivNorm + ixy * iyz / derivNorm2);
-  bb2 += -weight * (ixy * ixz / derivNorm + iyy * iyz / derivNorm2);
-
-  const float* u0 = L.Ux;
-  const float* v0 = L.Uy;
-  const bool red = ((x + y) & 1) == 0;
-  const float wc = B.wgt[k];
-  // horizontal: own forward term (x < w-1) and the left neighbour's forward term (x > 0)
-  const bool own_h = x < w - 1, left_h = x > 0;
-  float own_ux = 0.f, own_vx = 0.f, left_ux = 0.f, left_vx = 0.f, wl = 0.f;
-  if (own_h) { own_ux = wc * (u0[k + 1] - u0[k]); own_vx = wc * (v0[k + 1] - v0[k]); }
-  if (left_h) { wl = B.wgt[k - 1]; left_ux = wl * (u0[k] - u0[k - 1]); left_vx = wl * (v0[k] - v0[k - 1]); }
 #define ADD_OWN_H() if (own_h) { bb1 += own_ux; a11 += wc; bb2 += own_vx; a22 += wc; }
 #define ADD_LEFT_H() if (left_h) { bb1 -= left_ux; a11 += wl; bb2 -= left_vx; a22 += wl; }
-  if (red) { ADD_OWN_H(); ADD_LEFT_H(); } else { ADD_LEFT_H(); ADD_OWN_H(); }
-  // vertical: own forward term (y < h-1) and the upper neighbour's forward term (y > 0)
-  const bool own_v = y < h - 1, up_v = y > 0;
-  float own_uy = 0.f, own_vy = 0.f, up_uy = 0.f, up_vy = 0.f, wu = 0.f;
-  if (own_v) { own_uy = wc * (u0[k + w] - u0[k]); own_vy = wc * (v0[k + w] - v0[k]); }
-  if (up_v) { wu = B.wgt[k - w]; up_uy = wu * (u0[k] - u0[k - w]); up_vy = wu * (v0[k] - v0[k - w]); }
 #define ADD_OWN_V() if (own_v) { bb1 += own_uy; a11 += wc; bb2 += own_vy; a22 += wc; }
 #define ADD_UP_V() if (up_v) { bb1 -= up_uy; a11 += wu; bb2 -= up_vy; a22 += wu; }
-  if (red) { ADD_OWN_V(); ADD_UP_V(); } else { ADD_UP_V(); ADD_OWN_V(); }
-  B.A11[k] = a11; B.A12[k] = a12; B.A22[k] = a22; B.b1[k] = bb1; B.b2[k] = bb2;
-}
 
-// one colour of one red-black SOR sweep on the flow increment (zero outside the image)
-__global__ void __launch_bounds__(256) vr_sor_kernel(Level L, VrBuf B, int colour) {
-  const int pair = blockIdx.z;
-  const int xh = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  const int w = L.w, h = L.h;
-  if (y >= h) return;
-  const int x = 2 * xh + ((y + colour) & 1);
-  if (x >= w) return;
-  const size_t k = (size_t)pair * h * w + (size_t)y * w + x;
-  const float wl = x > 0 ? B.wgt[k - 1] : 0.f, dul = x > 0 ? B.du[k - 1] : 0.f, dvl = x > 0 ? B.dv[k - 1] : 0.f;
-  const float dur = x + 1 < w ? B.du[k + 1] : 0.f, dvr = x + 1 < w ? B.dv[k + 1] : 0.f;
-  const float wu = y > 0 ? B.wgt[k - w] : 0.f, duu = y > 0 ? B.du[k - w] : 0.f, dvu = y > 0 ? B.dv[k - w] : 0.f;
-  const float dud = y + 1 < h ? B.du[k + w] : 0.f, dvd = y + 1 < h ? B.dv[k + w] : 0.f;
-  const float wc = B.wgt[k];
-  const float sigmaU = wl * dul + wc * dur + wu * duu + wc * dud;
-  const float sigmaV = wl * dvl + wc * dvr + wu * dvu + wc * dvd;
-  float du = B.du[k], dv = B.dv[k];
-  du += kOmega * ((sigmaU + B.b1[k] - dv * B.A12[k]) / B.A11[k] - du);
-  dv += kOmega * ((sigmaV + B.b2[k] - du * B.A12[k]) / B.A22[k] - dv);
-  B.du[k] = du;
-  B.dv[k] = dv;
-}
-
-// tempW = W + dW ; last == 1 also writes the refined flow back into the level
-__global__ void __launch_bounds__(256) vr_update_kernel(Level L, VrBuf B, int last) {
-  PIXEL_INDEX();
-  const float u = L.Ux[k] + B.du[k], v = L.Uy[k] + B.dv[k];
-  B.tu[k] = u;
-  B.tv[k] = v;
-  if (last) { L.Ux[k] = u; L.Uy[k] = v; }
-}
-
-// ---- fused variational refinement: one launch per pyramid level ---------------------------------
-//
 // All 5 fixed-point iterations x (weights, linear system, 5 red + 5 black SOR half-sweeps, update)
 // plus the warp / derivative prologue run in ONE kernel.  A frame pair is owned by one thread-block
 // cluster (1, 2, 4 or 8 CTAs depending on the level size, each CTA a band of rows); the phases are
 // separated by cluster barriers (barrier.cluster release/acquire orders the global-memory traffic
 // between the CTAs of the cluster), so the ~70 dependent launches per level collapse into one.
-// The per-pixel arithmetic is the same device code as the stand-alone kernels above (bit-identical).
 
 __device__ __forceinline__ void vr_px_warp(const Level& L, const VrBuf& B, int pair, int x, int y) {
   const int w = L.w, h = L.h;
