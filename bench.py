@@ -100,6 +100,16 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def settle_gc():
+    """After warm-up, both arms: collect once and move every surviving object (torch, numpy, cv2 module
+    state) to the permanent generation, the way a long-running serving process does after start-up, so a
+    full collection inside the timed steps only walks the objects of the steps themselves."""
+    import gc
+
+    gc.collect()
+    gc.freeze()
+
+
 def run_reference_arm(args):
     """The reference's own CPU implementation of the path on the host cores (oracle/cv_path.py:
     the Python reference cannot travel to the GPU box; this restates its cv2 call sequence and is
@@ -128,6 +138,7 @@ def run_reference_arm(args):
 
     for _ in range(args.warmup):
         step()
+    settle_gc()
     times = [step() for _ in range(args.steps)]
     sec = float(np.mean(times))
     fps = n / sec
@@ -200,6 +211,7 @@ def main():
     def timed(step_fn, steps, warmup, collect_warp=False):
         for _ in range(warmup):
             step_fn()
+        settle_gc()
         barrier()
         if collect_warp:
             pipeline.WARP_LAUNCH_LOG = []

@@ -16,6 +16,8 @@ Reference anchors (file:line in the reference repository):
 """
 from __future__ import annotations
 
+import contextlib
+import gc
 import math
 from typing import Any, Dict, List, Sequence, Tuple
 
@@ -30,6 +32,22 @@ MODE_LADDER = {
     "similarity": ("similarity", "translation"),
     "translation": ("translation",),
 }
+
+
+@contextlib.contextmanager
+def gc_paused():
+    """Cyclic GC off while a call builds its result.  `meta` is tens of thousands of acyclic lists and
+    dicts per clip; allocating them with the collector on triggers a generation-0 pass every 700
+    containers, promotes the survivors and soon a full collection over every object of the process
+    (tens of ms with torch loaded) -- measured 8 ms median / 125 ms worst per call for a 968-frame meta
+    against 4 ms with the collector paused.  Reference counting still frees everything as usual."""
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 def working_estimation_size(width: int, height: int, max_side: int = ESTIMATION_MAX_SIDE):
@@ -104,8 +122,13 @@ def matrices_to_params(matrices: np.ndarray, base_mode: str) -> np.ndarray:
         out = np.empty((n, 4), dtype=np.float64)
         out[:, 0] = m[:, 0, 2]
         out[:, 1] = m[:, 1, 2]
-        out[:, 2] = [math.atan2(ci, ai) for ci, ai in zip(c.tolist() if c.dtype == np.float64 else c, a.tolist() if a.dtype == np.float64 else a)]
-        out[:, 3] = [math.log(math.sqrt(max(v, 1e-10))) for v in mag2]
+        # libm per element through map(): no interpreter frame per item.  float32 -> Python float is exact,
+        # so atan2 sees the same doubles as math.atan2(np.float32, np.float32) does in the reference.
+        out[:, 2] = np.fromiter(map(math.atan2, c.tolist(), a.tolist()), dtype=np.float64, count=n)
+        # max(v, 1e-10) keeps v when v > 1e-10 compared in v's own dtype (NEP 50: the Python float is weak)
+        floor = mag2.dtype.type(1e-10)
+        clamped = np.where(mag2 > floor, mag2.astype(np.float64), 1e-10)
+        out[:, 3] = np.fromiter(map(math.log, np.sqrt(clamped).tolist()), dtype=np.float64, count=n)  # sqrt is IEEE-exact
         return out
     one = m.dtype.type(1.0)
     return np.stack(
@@ -125,9 +148,10 @@ def params_to_matrices(params: np.ndarray, base_mode: str) -> np.ndarray:
         out[:, 0, 2] = p[:, 0]
         out[:, 1, 2] = p[:, 1]
     elif base_mode == "similarity":
-        k = np.array([math.exp(v) for v in p[:, 3]])
-        cs = np.array([math.cos(v) for v in p[:, 2]])
-        sn = np.array([math.sin(v) for v in p[:, 2]])
+        ang = p[:, 2].tolist()
+        k = np.fromiter(map(math.exp, p[:, 3].tolist()), dtype=np.float64, count=n)
+        cs = np.fromiter(map(math.cos, ang), dtype=np.float64, count=n)
+        sn = np.fromiter(map(math.sin, ang), dtype=np.float64, count=n)
         out[:, 0, 0] = k * cs
         out[:, 0, 1] = -k * sn
         out[:, 1, 0] = k * sn

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _native
-from .hostmath import border_value, compute_bounding_boxes, prepare_expand_transform
+from .hostmath import border_value, compute_bounding_boxes, gc_paused, prepare_expand_transform
 from .motion_meta import MotionMeta, motion_meta_from_stabilization_warp, resolve_motion_meta
 from .pipeline import VideoContext, fused_warp
 
@@ -186,6 +186,13 @@ def apply_motion(
     progress_callback: Optional[ProgressCallback] = None,
     output: Literal["host", "device"] = "host",
 ) -> MotionApplyResult:
+    with gc_paused():  # per-frame matrices and meta are acyclic; see hostmath.gc_paused
+        return _apply_motion(context, meta, padding_rgb, framing_mode, interpolation, motion_blur, motion_blur_samples,
+                             progress_callback, output)
+
+
+def _apply_motion(context, meta, padding_rgb, framing_mode, interpolation, motion_blur, motion_blur_samples, progress_callback,
+                  output) -> MotionApplyResult:
     motion = _resolve_motion_for_context(meta, context)
     _validate_context(context, motion)
 

@@ -67,11 +67,11 @@ class PairCandidates:
     @staticmethod
     def from_array(arr: np.ndarray, min_points: int) -> "PairCandidates":
         p = arr.shape[0]
-        ints = lambda a: np.rint(a).astype(np.int64)
-        det = ints(arr[:, 42])
+        ints = np.rint(arr[:, 30:43]).astype(np.int64)  # the five integer blocks in one pass
+        det = ints[:, 12]
         return PairCandidates(
-            matrix=arr[:, :27].reshape(p, 3, 3, 3).copy(), residual=arr[:, 27:30].copy(), n_inliers=ints(arr[:, 30:33]),
-            n_valid=ints(arr[:, 33:36]), n_total=ints(arr[:, 36:39]), ok=ints(arr[:, 39:42]), min_points=min_points,
+            matrix=arr[:, :27].reshape(p, 3, 3, 3).copy(), residual=arr[:, 27:30].copy(), n_inliers=ints[:, 0:3],
+            n_valid=ints[:, 3:6], n_total=ints[:, 6:9], ok=ints[:, 9:12], min_points=min_points,
             detected=None if (det < 0).all() else det,
         )
 
@@ -93,18 +93,42 @@ def _accepts_requested(cands: PairCandidates, mode: str) -> np.ndarray:
     return ok & (cands.ok[:, k] != 0) & (n_valid >= need) & (conf >= thr)
 
 
+class LadderEntries:
+    """Per-pair outcome of the ladder as parallel columns (mode, confidence, residual) next to the
+    float32 matrix stack.  Indexing / iterating yields the reference's per-pair tuples
+    (matrix, mode, confidence, residual); the columns are what the meta builder consumes, so long
+    clips do not pay for a tuple and a matrix view per pair on every rank."""
+
+    __slots__ = ("matrices", "modes", "confidences", "residuals")
+
+    def __init__(self, matrices, modes, confidences, residuals):
+        self.matrices, self.modes, self.confidences, self.residuals = matrices, modes, confidences, residuals
+
+    def __len__(self):
+        return len(self.modes)
+
+    def __getitem__(self, i):
+        return (self.matrices[i], self.modes[i], self.confidences[i], self.residuals[i])
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 def replay_mode_ladder(cands: PairCandidates, requested_mode: str, *, with_residual: bool):
     """The reference's per-pair fallback ladder with its clip-wide sticky downgrade
     (flow.py:156-210 + :324-339; classic.py:104-158 + :264-272), replayed over the table.
-    Returns (list of (matrix f32, mode, confidence, residual), final active mode).  The common case
-    -- every pair accepts the requested model -- is answered from array operations; the per-pair
-    loop only starts at the first pair that falls back."""
+    Returns (LadderEntries of (matrix f32, mode, confidence, residual), final active mode, matrix
+    stack).  The common case -- every pair accepts the requested model -- is answered from array
+    operations; the per-pair loop only starts at the first pair that falls back."""
     active = requested_mode
-    out = []
     eye = np.eye(3, dtype=np.float32)
     total = cands.matrix.shape[0]
     accepted = _accepts_requested(cands, requested_mode)
     first_fallback = int(np.argmin(accepted)) if not accepted.all() else total
+    modes: List[str] = []
+    confs: List[float] = []
+    resid: List[Optional[float]] = []
+    mats32 = np.zeros((0, 3, 3), np.float32)
     if first_fallback > 0:
         k = _native.MODE_INDEX[requested_mode]
         n_valid = cands.n_valid.max(axis=1)[:first_fallback]
@@ -114,10 +138,11 @@ def replay_mode_ladder(cands: PairCandidates, requested_mode: str, *, with_resid
             confs = (n_valid / denom.astype(np.float64)).tolist()
         else:
             confs = (cands.n_inliers[:first_fallback, k] / n_valid.astype(np.float64)).tolist()
-        resid = cands.residual[:first_fallback, k].tolist()
-        out = [(mats32[i], requested_mode, confs[i], resid[i] if with_residual else None) for i in range(first_fallback)]
+        resid = cands.residual[:first_fallback, k].tolist() if with_residual else [None] * first_fallback
+        modes = [requested_mode] * first_fallback
         if first_fallback == total:
-            return out, active, mats32
+            return LadderEntries(mats32, modes, confs, resid), active, mats32
+    tail = []
     for p in range(first_fallback, total):
         n_valid = int(cands.n_valid[p].max())
         chosen = None
@@ -145,11 +170,15 @@ def replay_mode_ladder(cands: PairCandidates, requested_mode: str, *, with_resid
                     break
         if chosen is None:
             chosen = (eye.copy(), "translation", 0.0, 0.0)
-        matrix, used, conf, resid = chosen
+        matrix, used, conf, res = chosen
         if used != active:
             active = used
-        out.append((matrix, used, conf, resid if with_residual else None))
-    return out, active, np.stack([c[0] for c in out], axis=0) if out else np.zeros((0, 3, 3), np.float32)
+        tail.append(matrix)
+        modes.append(used)
+        confs.append(conf)
+        resid.append(res if with_residual else None)
+    stacked = np.concatenate([mats32, np.stack(tail, axis=0)], axis=0) if tail else mats32
+    return LadderEntries(stacked, modes, confs, resid), active, stacked
 
 
 class _Progress:
@@ -192,6 +221,14 @@ def stabilize_frames(
     output: str = "host",
     shard=None,
 ) -> StabilizationResult:
+    with hm.gc_paused():
+        return _stabilize_frames(context, framing_mode, transform_mode, camera_lock, strength, smooth, keep_fov, padding_rgb,
+                                 frame_rate, estimator=estimator, flavour=flavour, progress_bar=progress_bar,
+                                 interrupt_check=interrupt_check, output=output, shard=shard)
+
+
+def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, strength, smooth, keep_fov, padding_rgb, frame_rate, *,
+                      estimator, flavour, progress_bar, interrupt_check, output, shard) -> StabilizationResult:
     is_flow = flavour == "flow"
     total_frames = len(context)
     width, height = context.width, context.height
@@ -349,12 +386,13 @@ def stabilize_frames(
     per_transition = []
     if full_meta:
         mat_lists = matrices.tolist()
+        columns = zip(chosen.modes, chosen.confidences, chosen.residuals, mat_lists)
         if is_flow:
-            per_transition = [{"index": i, "mode": c[1], "confidence": c[2], "residual": c[3], "matrix": m}
-                              for i, (c, m) in enumerate(zip(chosen, mat_lists))]
+            per_transition = [{"index": i, "mode": mode, "confidence": conf, "residual": res, "matrix": m}
+                              for i, (mode, conf, res, m) in enumerate(columns)]
         else:
-            per_transition = [{"index": i, "mode": c[1], "confidence": c[2], "matrix": m}
-                              for i, (c, m) in enumerate(zip(chosen, mat_lists))]
+            per_transition = [{"index": i, "mode": mode, "confidence": conf, "matrix": m}
+                              for i, (mode, conf, _, m) in enumerate(columns)]
 
     warp_meta = hm.build_stabilization_warp_meta(
         source_size=(width, height), output_size=output_size, framing_mode=framing_mode,

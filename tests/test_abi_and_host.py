@@ -204,3 +204,59 @@ def test_meta_helpers_for_long_clips_keep_the_reference_results(monkeypatch):
     monkeypatch.setenv("VSTAB_RESIDENT_LIMIT_MB", "10")
     assert pipeline._must_stream(10, 480, 832, None)       # 47.9 MB
     assert not pipeline._must_stream(2, 480, 832, None)    # 9.6 MB
+
+
+def test_stacked_conversions_ladder_columns_and_gc_pause():
+    """Stacked matrix<->params equal the per-matrix helpers (themselves pinned to the reference above)
+    on both dtypes incl. degenerate scales; ladder entries behave like the reference's tuples with and
+    without a fallback; gc_paused restores the collector state."""
+    import gc
+
+    from vstab_b200 import hostmath as hm
+    from vstab_b200.stabilizer_core import PairCandidates, replay_mode_ladder
+
+    rng = np.random.default_rng(11)
+    for dt in (np.float32, np.float64):
+        m = np.tile(np.eye(3), (400, 1, 1)) + rng.normal(size=(400, 3, 3)) * 0.05
+        m[:5, 0, 0] = 0
+        m[:5, 1, 0] = 0            # a^2 + c^2 below the 1e-10 floor
+        m[5:9, 0, 0] = 1e-5
+        m[5:9, 1, 0] = 0           # exactly at the floor in float32
+        m = m.astype(dt)
+        for mode in hm.TRANSFORM_MODES:
+            stacked = hm.matrices_to_params(m, mode)
+            assert np.array_equal(stacked, np.stack([hm.matrix_to_params(x, mode) for x in m]))
+            back = hm.params_to_matrices(stacked * 0.7, mode)
+            assert np.array_equal(back, np.stack([hm.params_to_matrix(x, mode) for x in stacked * 0.7]))
+
+    pairs = 9
+    mats = np.tile(np.eye(3), (pairs, 3, 1, 1)) + rng.normal(size=(pairs, 3, 3, 3)) * 1e-3
+    full = dict(residual=rng.random((pairs, 3)), n_inliers=np.full((pairs, 3), 900), n_valid=np.full((pairs, 3), 1000),
+                n_total=np.full((pairs, 3), 1000), ok=np.ones((pairs, 3), int))
+    entries, active, stack = replay_mode_ladder(PairCandidates(mats, **full), "similarity", with_residual=True)
+    assert active == "similarity" and len(entries) == pairs and stack.dtype == np.float32
+    matrix, mode, conf, resid = entries[4]
+    assert mode == "similarity" and conf == 0.9 and resid == full["residual"][4, 1]
+    assert np.array_equal(matrix, mats[4, 1].astype(np.float32)) and [e[1] for e in entries] == ["similarity"] * pairs
+    # pair 3 loses the similarity model: it and every later pair fall back to translation (sticky)
+    full["ok"][3, 1] = 0
+    entries, active, stack = replay_mode_ladder(PairCandidates(mats, **full), "similarity", with_residual=False)
+    assert active == "translation" and entries.modes == ["similarity"] * 3 + ["translation"] * 6
+    assert entries.residuals == [None] * pairs and entries.confidences[3:] == [1.0] * 6
+    assert np.array_equal(stack[2], mats[2, 1].astype(np.float32)) and np.array_equal(stack[5], mats[5, 0].astype(np.float32))
+    table = PairCandidates(mats, **full).to_array()
+    again = PairCandidates.from_array(table, 12)
+    assert np.array_equal(again.ok, full["ok"]) and np.array_equal(again.n_valid, full["n_valid"]) and again.detected is None
+
+    for state in (True, False):
+        (gc.enable if state else gc.disable)()
+        try:
+            with hm.gc_paused():
+                assert not gc.isenabled()
+            assert gc.isenabled() == state
+            with pytest.raises(KeyError):
+                with hm.gc_paused():
+                    raise KeyError("x")
+            assert gc.isenabled() == state
+        finally:
+            gc.enable()
