@@ -522,11 +522,132 @@ __device__ __noinline__ void general_tile_call(const WarpParams& p, const float*
   general_tile_body<INTERP, G>(p, frame, frame_idx, tx0, ty0, s_minv, tile, s_cubic, scratch, warp, lane);
 }
 
-template <int INTERP>
-__global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const WarpParams p) {
+// Motion-blur tile (2..33 shutter samples) whose footprint, over every sample, lies >= 1 px inside the
+// source and inside the staged box: every tap is in shared memory and every sample covers the pixel.
+// Consecutive shutter samples of a pixel land a fraction of a pixel apart, so the 2x2 / 4x4 texel
+// footprint stays in registers across samples and is re-read from shared memory only when its integer
+// origin moves: pixel-outer, sample-inner.  What is left per sample is the coordinate (double), the
+// weights and the blend -- the same operations in the same order as general_tile_body, so the same bits.
+template <int INTERP, bool AFFINE, int G>
+__device__ __forceinline__ void blur_interior_tile(const WarpParams& p, int frame_idx, int tx0, int ty0,
+                                                   const double* __restrict__ s_minv, const double* __restrict__ s_pk,
+                                                   const float* __restrict__ tile0, int pitch, const float* __restrict__ s_cubic,
+                                                   float* __restrict__ scratch, int warp, int lane, int tid) {
+  constexpr int NT = (INTERP == VSTAB_INTERP_BILINEAR) ? 2 : 4;   // taps per axis
+  constexpr int OFF = (INTERP == VSTAB_INTERP_BILINEAR) ? 0 : 1;  // footprint origin relative to (sx, sy)
+  const int S = p.samples;
+  const float fS = (float)S;
+  float* dst_tile = p.dst + (((size_t)frame_idx * p.oh + ty0) * p.ow + tx0) * 3;
+  if (p.mask) {  // every sample covers every pixel: mask = 1 - S/S = 0
+    float* mask_tile = p.mask + ((size_t)frame_idx * p.oh + ty0) * p.ow + tx0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float* mrow = mask_tile + (size_t)(g * 16 + (tid >> 4)) * p.ow + (tid & 15) * 4;
+      if (p.vec_mask) {
+        *reinterpret_cast<float4*>(mrow) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        mrow[0] = 0.f; mrow[1] = 0.f; mrow[2] = 0.f; mrow[3] = 0.f;
+      }
+    }
+  }
+#pragma unroll 1
+  for (int g = 0; g < G; ++g) {
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      const int rr = q >> 1, cc = q & 1;
+      const double dx = (double)(tx0 + lane + cc * 32), dy = (double)(ty0 + g * 16 + warp + rr * NWARPS);
+      float t[NT * NT * 3];
+      int csx = INT_MIN, csy = INT_MIN;
+      float ar = 0.f, ag = 0.f, ab = 0.f;
+#pragma unroll 1
+      for (int s = 0; s < S; ++s) {
+        double X, Y, sc;
+        if (AFFINE) {
+          const double2* pk = reinterpret_cast<const double2*>(s_pk + s * 8);  // m0 m1 | m2 m3 | m4 m5 | 32/m8 -
+          const double2 a = pk[0], b = pk[1], c = pk[2], d = pk[3];
+          X = __dadd_rn(__dadd_rn(__dmul_rn(a.x, dx), __dmul_rn(a.y, dy)), b.x);
+          Y = __dadd_rn(__dadd_rn(__dmul_rn(b.y, dx), __dmul_rn(c.x, dy)), c.y);
+          sc = d.x;
+        } else {
+          const double* m = s_minv + s * 9;
+          X = __dadd_rn(__dadd_rn(__dmul_rn(m[0], dx), __dmul_rn(m[1], dy)), m[2]);
+          Y = __dadd_rn(__dadd_rn(__dmul_rn(m[3], dx), __dmul_rn(m[4], dy)), m[5]);
+          const double W = __dadd_rn(__dadd_rn(__dmul_rn(m[6], dx), __dmul_rn(m[7], dy)), m[8]);
+          sc = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
+        }
+        // |coordinates| < 2^15 here, so cv2's INT_MIN/INT_MAX and short saturation are no-ops
+        const int ix = __double2int_rn(__dmul_rn(X, sc)), iy = __double2int_rn(__dmul_rn(Y, sc));
+        const int sx = ix >> 5, sy = iy >> 5;
+        if (sx != csx || sy != csy) {
+          const float* s0 = tile0 + (sy - OFF) * pitch + (sx - OFF) * 3;
+#pragma unroll
+          for (int k1 = 0; k1 < NT; ++k1) {
+#pragma unroll
+            for (int j = 0; j < NT * 3; ++j) t[k1 * NT * 3 + j] = s0[k1 * pitch + j];
+          }
+          csx = sx;
+          csy = sy;
+        }
+        float vr, vg, vb;
+        if (INTERP == VSTAB_INTERP_BILINEAR) {
+          const float fx1 = (float)(ix & 31) * 0.03125f, fy1 = (float)(iy & 31) * 0.03125f;
+          const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
+          const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
+          const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
+          vr = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[0], w00), __fmul_rn(t[3], w01)), __fmul_rn(t[6], w10)), __fmul_rn(t[9], w11));
+          vg = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[1], w00), __fmul_rn(t[4], w01)), __fmul_rn(t[7], w10)), __fmul_rn(t[10], w11));
+          vb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[2], w00), __fmul_rn(t[5], w01)), __fmul_rn(t[8], w10)), __fmul_rn(t[11], w11));
+        } else {
+          const float4 wx4 = *reinterpret_cast<const float4*>(s_cubic + (ix & 31) * 4);
+          const float4 wy4 = *reinterpret_cast<const float4*>(s_cubic + (iy & 31) * 4);
+          const float wx[4] = {wx4.x, wx4.y, wx4.z, wx4.w}, wy[4] = {wy4.x, wy4.y, wy4.z, wy4.w};
+          vr = vg = vb = 0.f;
+#pragma unroll
+          for (int k1 = 0; k1 < 4; ++k1) {
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const float w = __fmul_rn(wy[k1], wx[k2]);
+              vr = __fadd_rn(vr, __fmul_rn(t[(k1 * 4 + k2) * 3 + 0], w));
+              vg = __fadd_rn(vg, __fmul_rn(t[(k1 * 4 + k2) * 3 + 1], w));
+              vb = __fadd_rn(vb, __fmul_rn(t[(k1 * 4 + k2) * 3 + 2], w));
+            }
+          }
+        }
+        ar = __fadd_rn(ar, vr);
+        ag = __fadd_rn(ag, vg);
+        ab = __fadd_rn(ab, vb);
+      }
+      ar = __fdiv_rn(ar, fS);
+      ag = __fdiv_rn(ag, fS);
+      ab = __fdiv_rn(ab, fS);
+      float* o = p.vec_store ? scratch + rr * (TW * 3) + (lane + cc * 32) * 3
+                             : dst_tile + ((size_t)(g * 16 + warp + rr * NWARPS) * p.ow + lane + cc * 32) * 3;
+      o[0] = ar;
+      o[1] = ag;
+      o[2] = ab;
+    }
+    if (p.vec_store) {
+      __syncwarp();
+#pragma unroll
+      for (int q3 = 0; q3 < 3; ++q3) {
+        const int q = lane + q3 * 32;
+        const int rr = q >= 48 ? 1 : 0, qi = q - rr * 48;
+        const float4 val = *reinterpret_cast<const float4*>(scratch + rr * (TW * 3) + qi * 4);
+        *reinterpret_cast<float4*>(dst_tile + (size_t)(g * 16 + warp + rr * NWARPS) * p.ow * 3 + qi * 4) = val;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// BLUR = launches with 2..33 shutter samples: their staged box leaves room for 2 CTAs per SM anyway, so that
+// instantiation trades occupancy for the registers of blur_interior_tile's texel cache.
+template <int INTERP, bool BLUR>
+__global__ void __launch_bounds__(NTHREADS, BLUR ? 2 : MIN_CTAS) warp_fused_kernel(const WarpParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_minv = reinterpret_cast<double*>(smem_raw);                       // [34][9], 16B multiple
-  float* s_scratch = reinterpret_cast<float*>(s_minv + MINV_SLOTS * 9);       // [8][384]
+  double* s_pk = s_minv + MINV_SLOTS * 9;                                     // [34][8] affine samples, packed for 16-byte loads
+  float* s_scratch = reinterpret_cast<float*>(s_pk + MINV_SLOTS * 8);         // [8][384]
   int* s_box = reinterpret_cast<int*>(s_scratch + NWARPS * SCRATCH_FLOATS_PER_WARP);  // 8 ints
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_box + 6);  // mbarrier of the bulk copies
   float* s_cubic = reinterpret_cast<float*>(s_box + 8);                       // [32][4] bicubic coefficients
@@ -552,7 +673,8 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
   tile.x1 = tile.y1 = -1;
   tile.pitch = 0;
   bool interior = false;
-  bool bulk_pending = false;  // CTA-uniform: the staged box arrives through bulk copies
+  bool blur_interior = false;  // BLUR: every sample's footprint inside the source and the staged box
+  bool bulk_pending = false;   // CTA-uniform: the staged box arrives through bulk copies
   const int txe = min(tx0 + TW, p.ow) - 1;
   const int tye = min(ty0 + TH, p.oh) - 1;
   if (S == 1) {
@@ -579,18 +701,29 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
       }
     }
   } else {
-    if (tid < S) vstab_invert3(p.fwd + ((size_t)frame_idx * S + tid) * 9, s_minv + tid * 9);
+    if (tid < S) {
+      double* m = s_minv + tid * 9;
+      vstab_invert3(p.fwd + ((size_t)frame_idx * S + tid) * 9, m);
+      if (BLUR) {
+        double* pk = s_pk + tid * 8;
+        pk[0] = m[0]; pk[1] = m[1]; pk[2] = m[2]; pk[3] = m[3]; pk[4] = m[4]; pk[5] = m[5];
+        pk[6] = (m[8] != 0.0) ? __ddiv_rn(32.0, m[8]) : 0.0;  // general_tile_body's sc_affine
+        pk[7] = 0.0;
+      }
+    }
     if (tid == 0) {
       s_box[0] = INT_MAX;  // min x
       s_box[1] = INT_MAX;  // min y
       s_box[2] = INT_MIN;  // max x
       s_box[3] = INT_MIN;  // max y
       s_box[4] = 0;        // degenerate flag
+      s_box[5] = 0;        // some sample has a projective last row
     }
     __syncthreads();
     if (p.stage_mode == VSTAB_STAGE_AUTO) {
       for (int k = tid; k < 4 * S; k += NTHREADS) {
         const double* m = s_minv + (k >> 2) * 9;
+        if (BLUR && (k & 3) == 0 && !((m[6] == 0.0) && (m[7] == 0.0))) atomicOr(&s_box[5], 1);
         const double cx = (k & 1) ? (double)txe : (double)tx0;
         const double cy = (k & 2) ? (double)tye : (double)ty0;
         const double X = m[0] * cx + m[1] * cy + m[2];
@@ -625,9 +758,10 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
         tile.active = true;
         // Interior tile: the whole (unclipped) footprint lies >= 1 px inside the source, so every
         // tap is in the staged box and every pixel is covered: no per-tap or per-pixel tests.
-        interior = (S == 1) && (INTERP == VSTAB_INTERP_BILINEAR) && (tx0 + TW <= p.ow) && (ty0 + TH <= p.oh) &&
-                   (s_box[0] - LO >= 1) && (s_box[1] - LO >= 1) && (s_box[2] + HI <= p.sw - 2) &&
-                   (s_box[3] + HI <= p.sh - 2);
+        const bool inside = (tx0 + TW <= p.ow) && (ty0 + TH <= p.oh) && (s_box[0] - LO >= 1) && (s_box[1] - LO >= 1) &&
+                            (s_box[2] + HI <= p.sw - 2) && (s_box[3] + HI <= p.sh - 2);
+        interior = inside && (S == 1) && (INTERP == VSTAB_INTERP_BILINEAR);
+        blur_interior = inside && BLUR && (S > 1);
         tile.x0 = bx0;
         tile.y0 = by0;
         tile.x1 = bx1;
@@ -677,6 +811,13 @@ __global__ void __launch_bounds__(NTHREADS, MIN_CTAS) warp_fused_kernel(const Wa
   if (bulk_pending) mbar_wait(s_bar, 0);
   __syncthreads();  // also orders the scalar staging path and the s_minv / s_cubic writes
 
+  if (BLUR && blur_interior) {
+    const float* tile0 = s_tile - (tile.y0 * tile.pitch + tile.x0 * 3);  // tile0[sy*pitch + sx*3] is the texel
+    float* scratch = s_scratch + warp * SCRATCH_FLOATS_PER_WARP;
+    if (s_box[5] == 0) blur_interior_tile<INTERP, true, GROUPS>(p, frame_idx, tx0, ty0, s_minv, s_pk, tile0, tile.pitch, s_cubic, scratch, warp, lane, tid);
+    else blur_interior_tile<INTERP, false, GROUPS>(p, frame_idx, tx0, ty0, s_minv, s_pk, tile0, tile.pitch, s_cubic, scratch, warp, lane, tid);
+    return;
+  }
   general_tile<INTERP, GROUPS>(p, frame, frame_idx, tx0, ty0, s_minv, tile, s_cubic, s_scratch + warp * SCRATCH_FLOATS_PER_WARP, warp, lane);
 }
 
@@ -1337,7 +1478,7 @@ extern "C" int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, in
   p.border[1] = border_host[1];
   p.border[2] = border_host[2];
 
-  const size_t fixed = sizeof(double) * MINV_SLOTS * 9 + sizeof(float) * NWARPS * SCRATCH_FLOATS_PER_WARP + sizeof(int) * 8 + sizeof(float) * 128;
+  const size_t fixed = sizeof(double) * MINV_SLOTS * (9 + 8) + sizeof(float) * NWARPS * SCRATCH_FLOATS_PER_WARP + sizeof(int) * 8 + sizeof(float) * 128;
   // Staged source box: (TW + margin) x (TH + margin) pixels for near-identity maps; blur and
   // bicubic get a larger box.  Degenerate footprints gather from global memory instead.
   int box_w = TW + 8, box_h = TH + 8;
@@ -1412,15 +1553,20 @@ extern "C" int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, in
       return VSTAB_OK;
     }
   }
+#define VSTAB_LAUNCH_FUSED(INTERP_, BLUR_)                                                                              \
+  do {                                                                                                                 \
+    VSTAB_CUDA(h, cudaFuncSetAttribute(warp_fused_kernel<INTERP_, BLUR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                                    \
+    warp_fused_kernel<INTERP_, BLUR_><<<grid, NTHREADS, smem, st>>>(p);                                                \
+  } while (0)
   if (interp == VSTAB_INTERP_BILINEAR) {
-    VSTAB_CUDA(h, cudaFuncSetAttribute(warp_fused_kernel<VSTAB_INTERP_BILINEAR>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    warp_fused_kernel<VSTAB_INTERP_BILINEAR><<<grid, NTHREADS, smem, st>>>(p);
+    if (samples > 1) VSTAB_LAUNCH_FUSED(VSTAB_INTERP_BILINEAR, true);
+    else VSTAB_LAUNCH_FUSED(VSTAB_INTERP_BILINEAR, false);
   } else {
-    VSTAB_CUDA(h, cudaFuncSetAttribute(warp_fused_kernel<VSTAB_INTERP_BICUBIC>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    warp_fused_kernel<VSTAB_INTERP_BICUBIC><<<grid, NTHREADS, smem, st>>>(p);
+    if (samples > 1) VSTAB_LAUNCH_FUSED(VSTAB_INTERP_BICUBIC, true);
+    else VSTAB_LAUNCH_FUSED(VSTAB_INTERP_BICUBIC, false);
   }
+#undef VSTAB_LAUNCH_FUSED
   VSTAB_LAUNCH_CHECK(h, "warp_fused_kernel");
   return VSTAB_OK;
 }
