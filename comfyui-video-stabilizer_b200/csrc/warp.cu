@@ -522,23 +522,70 @@ __device__ __noinline__ void general_tile_call(const WarpParams& p, const float*
   general_tile_body<INTERP, G>(p, frame, frame_idx, tx0, ty0, s_minv, tile, s_cubic, scratch, warp, lane);
 }
 
-// Motion-blur tile (2..33 shutter samples) whose footprint, over every sample, lies >= 1 px inside the
-// source and inside the staged box: every tap is in shared memory and every sample covers the pixel.
-// Consecutive shutter samples of a pixel land a fraction of a pixel apart, so the 2x2 / 4x4 texel
-// footprint stays in registers across samples and is re-read from shared memory only when its integer
-// origin moves: pixel-outer, sample-inner.  What is left per sample is the coordinate (double), the
-// weights and the blend -- the same operations in the same order as general_tile_body, so the same bits.
-template <int INTERP, bool AFFINE, int G>
-__device__ __forceinline__ void blur_interior_tile(const WarpParams& p, int frame_idx, int tx0, int ty0,
-                                                   const double* __restrict__ s_minv, const double* __restrict__ s_pk,
-                                                   const float* __restrict__ tile0, int pitch, const float* __restrict__ s_cubic,
-                                                   float* __restrict__ scratch, int warp, int lane, int tid) {
+// Motion-blur tiles (2..33 shutter samples).  Consecutive shutter samples of a pixel land a fraction of a
+// pixel apart, so the 2x2 / 4x4 texel footprint stays in registers across samples and is re-read only when
+// its integer origin moves: pixel-outer, sample-inner.  What is left per sample is the coordinate (double),
+// the weights and the blend -- the same operations in the same order as general_tile_body, so the same bits.
+//   EDGE = false: the footprint of every sample lies >= 1 px inside the source and inside the staged box:
+//                 every tap is in shared memory, every sample covers the pixel (mask 0, nothing padded).
+//   EDGE = true:  everything else (frame border, partial tiles, unstaged footprints).  The reload applies
+//                 cv2's border rules once per footprint: bilinear substitutes the border colour per tap and
+//                 returns it outright when the footprint is outside; bicubic near the border is
+//                 cv + sum over in-range taps of (S - cv) * w, cached as (S - cv) with zeros for the taps
+//                 that are skipped (x + 0*w == x for the sums that occur: they start at +0 or cv).
+template <int INTERP, bool EDGE>
+__device__ __forceinline__ int blur_reload(const WarpParams& p, const float* __restrict__ frame, const StagedTile& tile, int sx, int sy,
+                                           float* __restrict__ t) {
+  constexpr int NT = (INTERP == VSTAB_INTERP_BILINEAR) ? 2 : 4;
+  constexpr int OFF = (INTERP == VSTAB_INTERP_BILINEAR) ? 0 : 1;
+  const int bx = sx - OFF, by = sy - OFF;
+  const bool staged = tile.active && bx >= tile.x0 && bx + NT - 1 <= tile.x1 && by >= tile.y0 && by + NT - 1 <= tile.y1;
+  if (!EDGE || staged) {  // the staged box is clipped to the source, so these taps are all in the image
+    const float* s0 = tile.smem + (by - tile.y0) * tile.pitch + (bx - tile.x0) * 3;
+#pragma unroll
+    for (int k1 = 0; k1 < NT; ++k1) {
+#pragma unroll
+      for (int j = 0; j < NT * 3; ++j) t[k1 * NT * 3 + j] = s0[k1 * tile.pitch + j];
+    }
+    return 0;
+  }
+  if (INTERP == VSTAB_INTERP_BILINEAR) {
+    if (sx >= p.sw || sx + 1 < 0 || sy >= p.sh || sy + 1 < 0) return 2;  // remapBilinear: the border colour itself
+#pragma unroll
+    for (int k = 0; k < 4; ++k) fetch_rgb(p, frame, tile, sy + (k >> 1), sx + (k & 1), t[k * 3], t[k * 3 + 1], t[k * 3 + 2]);
+    return 0;
+  }
+  const bool in_image = bx >= 0 && bx < p.sw - 3 && by >= 0 && by < p.sh - 3;
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+      const int yy = by + k1, xx = bx + k2;
+      float r = 0.f, g = 0.f, b = 0.f;
+      if (in_image) {
+        fetch_rgb(p, frame, tile, yy, xx, r, g, b);
+      } else if ((unsigned)xx < (unsigned)p.sw && (unsigned)yy < (unsigned)p.sh) {
+        fetch_rgb(p, frame, tile, yy, xx, r, g, b);
+        r = __fsub_rn(r, p.border[0]);
+        g = __fsub_rn(g, p.border[1]);
+        b = __fsub_rn(b, p.border[2]);
+      }
+      t[(k1 * 4 + k2) * 3 + 0] = r;
+      t[(k1 * 4 + k2) * 3 + 1] = g;
+      t[(k1 * 4 + k2) * 3 + 2] = b;
+    }
+  }
+  return in_image ? 0 : 1;  // 1: remapBicubic's border branch, the sum starts at the border colour
+}
+
+template <int INTERP, bool AFFINE, bool EDGE, int G>
+__device__ __forceinline__ void blur_tile(const WarpParams& p, const float* __restrict__ frame, int frame_idx, int tx0, int ty0,
+                                          const double* __restrict__ s_minv, const double* __restrict__ s_pk, const StagedTile& tile,
+                                          const float* __restrict__ s_cubic, float* __restrict__ scratch, int warp, int lane, int tid) {
   constexpr int NT = (INTERP == VSTAB_INTERP_BILINEAR) ? 2 : 4;   // taps per axis
-  constexpr int OFF = (INTERP == VSTAB_INTERP_BILINEAR) ? 0 : 1;  // footprint origin relative to (sx, sy)
   const int S = p.samples;
   const float fS = (float)S;
-  float* dst_tile = p.dst + (((size_t)frame_idx * p.oh + ty0) * p.ow + tx0) * 3;
-  if (p.mask) {  // every sample covers every pixel: mask = 1 - S/S = 0
+  if (!EDGE && p.mask) {  // every sample covers every pixel: mask = 1 - S/S = 0
     float* mask_tile = p.mask + ((size_t)frame_idx * p.oh + ty0) * p.ow + tx0;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -550,93 +597,153 @@ __device__ __forceinline__ void blur_interior_tile(const WarpParams& p, int fram
       }
     }
   }
+  unsigned int padded = 0;
+  const double x_hi = (double)(p.sw - 1), y_hi = (double)(p.sh - 1);
 #pragma unroll 1
   for (int g = 0; g < G; ++g) {
+    const int tyg = ty0 + g * 16;
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
       const int rr = q >> 1, cc = q & 1;
-      const double dx = (double)(tx0 + lane + cc * 32), dy = (double)(ty0 + g * 16 + warp + rr * NWARPS);
-      float t[NT * NT * 3];
-      int csx = INT_MIN, csy = INT_MIN;
+      const int oy = tyg + warp + rr * NWARPS, ox = tx0 + lane + cc * 32;
+      const bool live = !EDGE || (oy < p.oh && ox < p.ow);
       float ar = 0.f, ag = 0.f, ab = 0.f;
+      if (live) {
+        const double dx = (double)ox, dy = (double)oy;
+        float t[NT * NT * 3];
+        int csx = INT_MIN, csy = INT_MIN, mode = 0, cover = 0;
 #pragma unroll 1
-      for (int s = 0; s < S; ++s) {
-        double X, Y, sc;
-        if (AFFINE) {
-          const double2* pk = reinterpret_cast<const double2*>(s_pk + s * 8);  // m0 m1 | m2 m3 | m4 m5 | 32/m8 -
-          const double2 a = pk[0], b = pk[1], c = pk[2], d = pk[3];
-          X = __dadd_rn(__dadd_rn(__dmul_rn(a.x, dx), __dmul_rn(a.y, dy)), b.x);
-          Y = __dadd_rn(__dadd_rn(__dmul_rn(b.y, dx), __dmul_rn(c.x, dy)), c.y);
-          sc = d.x;
-        } else {
-          const double* m = s_minv + s * 9;
-          X = __dadd_rn(__dadd_rn(__dmul_rn(m[0], dx), __dmul_rn(m[1], dy)), m[2]);
-          Y = __dadd_rn(__dadd_rn(__dmul_rn(m[3], dx), __dmul_rn(m[4], dy)), m[5]);
-          const double W = __dadd_rn(__dadd_rn(__dmul_rn(m[6], dx), __dmul_rn(m[7], dy)), m[8]);
-          sc = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
-        }
-        // |coordinates| < 2^15 here, so cv2's INT_MIN/INT_MAX and short saturation are no-ops
-        const int ix = __double2int_rn(__dmul_rn(X, sc)), iy = __double2int_rn(__dmul_rn(Y, sc));
-        const int sx = ix >> 5, sy = iy >> 5;
-        if (sx != csx || sy != csy) {
-          const float* s0 = tile0 + (sy - OFF) * pitch + (sx - OFF) * 3;
-#pragma unroll
-          for (int k1 = 0; k1 < NT; ++k1) {
-#pragma unroll
-            for (int j = 0; j < NT * 3; ++j) t[k1 * NT * 3 + j] = s0[k1 * pitch + j];
+        for (int s = 0; s < S; ++s) {
+          double X, Y, W, sc;
+          if (AFFINE) {
+            const double2* pk = reinterpret_cast<const double2*>(s_pk + s * 8);  // m0 m1 | m2 m3 | m4 m5 | 32/m8 m8
+            const double2 a = pk[0], b = pk[1], c = pk[2], d = pk[3];
+            X = __dadd_rn(__dadd_rn(__dmul_rn(a.x, dx), __dmul_rn(a.y, dy)), b.x);
+            Y = __dadd_rn(__dadd_rn(__dmul_rn(b.y, dx), __dmul_rn(c.x, dy)), c.y);
+            sc = d.x;
+            W = d.y;
+          } else {
+            const double* m = s_minv + s * 9;
+            X = __dadd_rn(__dadd_rn(__dmul_rn(m[0], dx), __dmul_rn(m[1], dy)), m[2]);
+            Y = __dadd_rn(__dadd_rn(__dmul_rn(m[3], dx), __dmul_rn(m[4], dy)), m[5]);
+            W = __dadd_rn(__dadd_rn(__dmul_rn(m[6], dx), __dmul_rn(m[7], dy)), m[8]);
+            sc = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
           }
-          csx = sx;
-          csy = sy;
-        }
-        float vr, vg, vb;
-        if (INTERP == VSTAB_INTERP_BILINEAR) {
-          const float fx1 = (float)(ix & 31) * 0.03125f, fy1 = (float)(iy & 31) * 0.03125f;
-          const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
-          const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
-          const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
-          vr = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[0], w00), __fmul_rn(t[3], w01)), __fmul_rn(t[6], w10)), __fmul_rn(t[9], w11));
-          vg = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[1], w00), __fmul_rn(t[4], w01)), __fmul_rn(t[7], w10)), __fmul_rn(t[10], w11));
-          vb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[2], w00), __fmul_rn(t[5], w01)), __fmul_rn(t[8], w10)), __fmul_rn(t[11], w11));
-        } else {
-          const float4 wx4 = *reinterpret_cast<const float4*>(s_cubic + (ix & 31) * 4);
-          const float4 wy4 = *reinterpret_cast<const float4*>(s_cubic + (iy & 31) * 4);
-          const float wx[4] = {wx4.x, wx4.y, wx4.z, wx4.w}, wy[4] = {wy4.x, wy4.y, wy4.z, wy4.w};
-          vr = vg = vb = 0.f;
+          double fx = __dmul_rn(X, sc), fy = __dmul_rn(Y, sc);
+          if (EDGE) {
+            // coverage (INTER_NEAREST ones warp), as in general_tile_body: X * fl(1/W) decides everything
+            // that is not within 1e-6 px of a boundary; only those pixels pay for the exact divisions
+            bool ok;
+            const double rw = sc * 0.03125;
+            const double qx = X * rw, qy = Y * rw;
+            const double band = 1e-6;
+            if (p.mask_rule == VSTAB_MASK_RULE_P && qx > band && qx < x_hi - band && qy > band && qy < y_hi - band) {
+              ok = true;
+            } else if (p.mask_rule == VSTAB_MASK_RULE_P && (qx < -band || qx > x_hi + band || qy < -band || qy > y_hi + band)) {
+              ok = false;
+            } else {
+              double cxs = __ddiv_rn(X, W), cys = __ddiv_rn(Y, W);
+              if (p.mask_rule == VSTAB_MASK_RULE_C) {
+                cxs = rint(cxs);
+                cys = rint(cys);
+              }
+              ok = (cxs >= 0.0) && (cxs <= x_hi) && (cys >= 0.0) && (cys <= y_hi);
+            }
+            cover += ok ? 1 : 0;
+            fx = fmax(-2147483648.0, fmin(2147483647.0, fx));
+            fy = fmax(-2147483648.0, fmin(2147483647.0, fy));
+          }
+          // interior tiles: |coordinates| < 2^15, cv2's INT_MIN/INT_MAX and short saturation are no-ops
+          const int ix = __double2int_rn(fx), iy = __double2int_rn(fy);
+          int sx = ix >> 5, sy = iy >> 5;
+          if (EDGE) {
+            sx = max(-32768, min(32767, sx));
+            sy = max(-32768, min(32767, sy));
+          }
+          if (sx != csx || sy != csy) {
+            mode = blur_reload<INTERP, EDGE>(p, frame, tile, sx, sy, t);
+            csx = sx;
+            csy = sy;
+          }
+          float vr, vg, vb;
+          if (INTERP == VSTAB_INTERP_BILINEAR) {
+            const float fx1 = (float)(ix & 31) * 0.03125f, fy1 = (float)(iy & 31) * 0.03125f;
+            const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
+            const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
+            const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
+            vr = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[0], w00), __fmul_rn(t[3], w01)), __fmul_rn(t[6], w10)), __fmul_rn(t[9], w11));
+            vg = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[1], w00), __fmul_rn(t[4], w01)), __fmul_rn(t[7], w10)), __fmul_rn(t[10], w11));
+            vb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[2], w00), __fmul_rn(t[5], w01)), __fmul_rn(t[8], w10)), __fmul_rn(t[11], w11));
+            if (EDGE && mode == 2) {
+              vr = p.border[0];
+              vg = p.border[1];
+              vb = p.border[2];
+            }
+          } else {
+            const float4 wx4 = *reinterpret_cast<const float4*>(s_cubic + (ix & 31) * 4);
+            const float4 wy4 = *reinterpret_cast<const float4*>(s_cubic + (iy & 31) * 4);
+            const float wx[4] = {wx4.x, wx4.y, wx4.z, wx4.w}, wy[4] = {wy4.x, wy4.y, wy4.z, wy4.w};
+            vr = (EDGE && mode) ? p.border[0] : 0.f;
+            vg = (EDGE && mode) ? p.border[1] : 0.f;
+            vb = (EDGE && mode) ? p.border[2] : 0.f;
 #pragma unroll
-          for (int k1 = 0; k1 < 4; ++k1) {
+            for (int k1 = 0; k1 < 4; ++k1) {
 #pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              const float w = __fmul_rn(wy[k1], wx[k2]);
-              vr = __fadd_rn(vr, __fmul_rn(t[(k1 * 4 + k2) * 3 + 0], w));
-              vg = __fadd_rn(vg, __fmul_rn(t[(k1 * 4 + k2) * 3 + 1], w));
-              vb = __fadd_rn(vb, __fmul_rn(t[(k1 * 4 + k2) * 3 + 2], w));
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const float w = __fmul_rn(wy[k1], wx[k2]);
+                vr = __fadd_rn(vr, __fmul_rn(t[(k1 * 4 + k2) * 3 + 0], w));
+                vg = __fadd_rn(vg, __fmul_rn(t[(k1 * 4 + k2) * 3 + 1], w));
+                vb = __fadd_rn(vb, __fmul_rn(t[(k1 * 4 + k2) * 3 + 2], w));
+              }
             }
           }
+          ar = __fadd_rn(ar, vr);
+          ag = __fadd_rn(ag, vg);
+          ab = __fadd_rn(ab, vb);
         }
-        ar = __fadd_rn(ar, vr);
-        ag = __fadd_rn(ag, vg);
-        ab = __fadd_rn(ab, vb);
+        ar = __fdiv_rn(ar, fS);
+        ag = __fdiv_rn(ag, fS);
+        ab = __fdiv_rn(ab, fS);
+        if (EDGE) {  // padding mask: 1 - count/S, < 1e-3 -> 0
+          float mval = __fsub_rn(1.0f, __fdiv_rn((float)cover, fS));
+          if (mval < 1e-3f) mval = 0.0f;
+          if (mval > 1e-3f) ++padded;
+          if (p.mask) p.mask[((size_t)frame_idx * p.oh + oy) * p.ow + ox] = mval;
+        }
+        if (!p.vec_store) {
+          float* d = p.dst + (((size_t)frame_idx * p.oh + oy) * p.ow + ox) * 3;
+          d[0] = ar;
+          d[1] = ag;
+          d[2] = ab;
+        }
       }
-      ar = __fdiv_rn(ar, fS);
-      ag = __fdiv_rn(ag, fS);
-      ab = __fdiv_rn(ab, fS);
-      float* o = p.vec_store ? scratch + rr * (TW * 3) + (lane + cc * 32) * 3
-                             : dst_tile + ((size_t)(g * 16 + warp + rr * NWARPS) * p.ow + lane + cc * 32) * 3;
-      o[0] = ar;
-      o[1] = ag;
-      o[2] = ab;
+      if (p.vec_store) {
+        float* o = scratch + rr * (TW * 3) + (lane + cc * 32) * 3;
+        o[0] = ar;
+        o[1] = ag;
+        o[2] = ab;
+      }
     }
     if (p.vec_store) {
       __syncwarp();
+      // 2 rows x 192 floats = 96 float4 per warp, 3 per lane, fully coalesced 16-byte stores
+      const int valid_floats = (min(tx0 + TW, p.ow) - tx0) * 3;  // multiple of 4 when ow % 4 == 0
 #pragma unroll
       for (int q3 = 0; q3 < 3; ++q3) {
         const int q = lane + q3 * 32;
         const int rr = q >= 48 ? 1 : 0, qi = q - rr * 48;
-        const float4 val = *reinterpret_cast<const float4*>(scratch + rr * (TW * 3) + qi * 4);
-        *reinterpret_cast<float4*>(dst_tile + (size_t)(g * 16 + warp + rr * NWARPS) * p.ow * 3 + qi * 4) = val;
+        const int oy = tyg + warp + rr * NWARPS;
+        if (oy < p.oh && qi * 4 < valid_floats) {
+          const float4 val = *reinterpret_cast<const float4*>(scratch + rr * (TW * 3) + qi * 4);
+          *reinterpret_cast<float4*>(p.dst + (((size_t)frame_idx * p.oh + oy) * p.ow + tx0) * 3 + qi * 4) = val;
+        }
       }
       __syncwarp();
     }
+  }
+  if (EDGE && p.pad_count) {
+    for (int o = 16; o > 0; o >>= 1) padded += __shfl_down_sync(0xffffffffu, padded, o);
+    if (lane == 0 && padded) atomicAdd(p.pad_count + frame_idx, padded);
   }
 }
 
@@ -674,6 +781,7 @@ __global__ void __launch_bounds__(NTHREADS, BLUR ? 2 : MIN_CTAS) warp_fused_kern
   tile.pitch = 0;
   bool interior = false;
   bool blur_interior = false;  // BLUR: every sample's footprint inside the source and the staged box
+  bool projective = false, any_projective = false;  // BLUR: some shutter sample has a projective last row
   bool bulk_pending = false;   // CTA-uniform: the staged box arrives through bulk copies
   const int txe = min(tx0 + TW, p.ow) - 1;
   const int tye = min(ty0 + TH, p.oh) - 1;
@@ -708,7 +816,8 @@ __global__ void __launch_bounds__(NTHREADS, BLUR ? 2 : MIN_CTAS) warp_fused_kern
         double* pk = s_pk + tid * 8;
         pk[0] = m[0]; pk[1] = m[1]; pk[2] = m[2]; pk[3] = m[3]; pk[4] = m[4]; pk[5] = m[5];
         pk[6] = (m[8] != 0.0) ? __ddiv_rn(32.0, m[8]) : 0.0;  // general_tile_body's sc_affine
-        pk[7] = 0.0;
+        pk[7] = m[8];
+        projective = !((m[6] == 0.0) && (m[7] == 0.0));
       }
     }
     if (tid == 0) {
@@ -717,13 +826,11 @@ __global__ void __launch_bounds__(NTHREADS, BLUR ? 2 : MIN_CTAS) warp_fused_kern
       s_box[2] = INT_MIN;  // max x
       s_box[3] = INT_MIN;  // max y
       s_box[4] = 0;        // degenerate flag
-      s_box[5] = 0;        // some sample has a projective last row
     }
-    __syncthreads();
+    any_projective = __syncthreads_or(projective) != 0;
     if (p.stage_mode == VSTAB_STAGE_AUTO) {
       for (int k = tid; k < 4 * S; k += NTHREADS) {
         const double* m = s_minv + (k >> 2) * 9;
-        if (BLUR && (k & 3) == 0 && !((m[6] == 0.0) && (m[7] == 0.0))) atomicOr(&s_box[5], 1);
         const double cx = (k & 1) ? (double)txe : (double)tx0;
         const double cy = (k & 2) ? (double)tye : (double)ty0;
         const double X = m[0] * cx + m[1] * cy + m[2];
@@ -811,11 +918,16 @@ __global__ void __launch_bounds__(NTHREADS, BLUR ? 2 : MIN_CTAS) warp_fused_kern
   if (bulk_pending) mbar_wait(s_bar, 0);
   __syncthreads();  // also orders the scalar staging path and the s_minv / s_cubic writes
 
-  if (BLUR && blur_interior) {
-    const float* tile0 = s_tile - (tile.y0 * tile.pitch + tile.x0 * 3);  // tile0[sy*pitch + sx*3] is the texel
+  // VSTAB_STAGE_GLOBAL keeps every tile on general_tile_body: the reference the cached paths are tested against
+  if (BLUR && p.stage_mode == VSTAB_STAGE_AUTO) {
     float* scratch = s_scratch + warp * SCRATCH_FLOATS_PER_WARP;
-    if (s_box[5] == 0) blur_interior_tile<INTERP, true, GROUPS>(p, frame_idx, tx0, ty0, s_minv, s_pk, tile0, tile.pitch, s_cubic, scratch, warp, lane, tid);
-    else blur_interior_tile<INTERP, false, GROUPS>(p, frame_idx, tx0, ty0, s_minv, s_pk, tile0, tile.pitch, s_cubic, scratch, warp, lane, tid);
+    if (blur_interior) {
+      if (!any_projective) blur_tile<INTERP, true, false, GROUPS>(p, frame, frame_idx, tx0, ty0, s_minv, s_pk, tile, s_cubic, scratch, warp, lane, tid);
+      else blur_tile<INTERP, false, false, GROUPS>(p, frame, frame_idx, tx0, ty0, s_minv, s_pk, tile, s_cubic, scratch, warp, lane, tid);
+    } else {
+      if (!any_projective) blur_tile<INTERP, true, true, GROUPS>(p, frame, frame_idx, tx0, ty0, s_minv, s_pk, tile, s_cubic, scratch, warp, lane, tid);
+      else blur_tile<INTERP, false, true, GROUPS>(p, frame, frame_idx, tx0, ty0, s_minv, s_pk, tile, s_cubic, scratch, warp, lane, tid);
+    }
     return;
   }
   general_tile<INTERP, GROUPS>(p, frame, frame_idx, tx0, ty0, s_minv, tile, s_cubic, s_scratch + warp * SCRATCH_FLOATS_PER_WARP, warp, lane);
