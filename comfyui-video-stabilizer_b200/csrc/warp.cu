@@ -1027,9 +1027,9 @@ __global__ void __launch_bounds__(256) warp_plan_kernel(const float* __restrict_
     ox = (mnx - LO - (need_w + 3 <= S_BW ? (S_BW - need_w - 3) / 2 : 0)) & ~3;
     oy = mny - LO - (need_h <= S_BH ? (S_BH - need_h) / 2 : 0);
     flags = 1;
-    if ((INTERP == VSTAB_INTERP_BILINEAR) && (mxx + HI <= ox + S_BW - 1) && need_h <= S_BH && (tx0 + TW <= ow) && (ty0 + S_TH <= oh) &&
+    if ((mxx + HI <= ox + S_BW - 1) && need_h <= S_BH && (tx0 + TW <= ow) && (ty0 + S_TH <= oh) &&
         (mnx - LO >= 1) && (mny - LO >= 1) && (mxx + HI <= sw - 2) && (mxy + HI <= sh - 2))
-      flags |= 2;
+      flags |= 2;  // interior tile (either interpolation): every tap in the box and in the frame, every pixel covered
     else if ((INTERP == VSTAB_INTERP_BILINEAR) && (mxx + HI <= ox + S_BW - 1) && need_h <= S_BH && (tx0 + TW <= ow) && (ty0 + S_TH <= oh) &&
              (mnx - LO >= -30000) && (mny - LO >= -30000) && (mxx + HI <= 30000) && (mxy + HI <= 30000))
       flags |= 8;  // edge tile: the staged box holds every tap position, some of them outside the frame
@@ -1080,10 +1080,11 @@ __device__ __forceinline__ void stream_issue(const void* tmap, int4 pl, const do
 
 // Interior tile of the streaming kernel (64x16, box already in shared memory, compile-time pitch):
 // coordinates are computed pixel by pixel so that few values stay live across the tile loop.
-template <bool AFFINE, bool VEC>
+template <int INTERP, bool AFFINE, bool VEC>
 __device__ __forceinline__ void stream_interior(const double* __restrict__ s_minv, const float* __restrict__ tile0, int tx0, int ty0,
                                                 int warp, int lane, int tid, int ow, float* __restrict__ scratch,
-                                                float* __restrict__ dst_tile, float* __restrict__ mask_tile, int vec_mask) {
+                                                float* __restrict__ dst_tile, float* __restrict__ mask_tile, int vec_mask,
+                                                const float* __restrict__ s_cubic) {
   const double m0 = s_minv[0], m1 = s_minv[1], m2 = s_minv[2], m3 = s_minv[3], m4 = s_minv[4], m5 = s_minv[5];
   const double m8 = s_minv[8];
   const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
@@ -1114,17 +1115,35 @@ __device__ __forceinline__ void stream_interior(const double* __restrict__ s_min
       }
       // |coordinates| < 2^15 here, so cv2's INT_MIN/INT_MAX and short saturation are no-ops
       const int ix = __double2int_rn(__dmul_rn(X, sc)), iy = __double2int_rn(__dmul_rn(Y, sc));
-      const float fx1 = (float)(ix & 31) * 0.03125f, fy1 = (float)(iy & 31) * 0.03125f;
-      const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
-      const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
-      const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
-      const float* s0 = tile0 + (iy >> 5) * S_PITCH + (ix >> 5) * 3;
-      const float* s1 = s0 + S_PITCH;
       float v[3];
+      if (INTERP == VSTAB_INTERP_BILINEAR) {
+        const float fx1 = (float)(ix & 31) * 0.03125f, fy1 = (float)(iy & 31) * 0.03125f;
+        const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
+        const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
+        const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
+        const float* s0 = tile0 + (iy >> 5) * S_PITCH + (ix >> 5) * 3;
+        const float* s1 = s0 + S_PITCH;
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch)
-        v[ch] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s0[ch], w00), __fmul_rn(s0[3 + ch], w01)), __fmul_rn(s1[ch], w10)),
-                          __fmul_rn(s1[3 + ch], w11));
+        for (int ch = 0; ch < 3; ++ch)
+          v[ch] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s0[ch], w00), __fmul_rn(s0[3 + ch], w01)), __fmul_rn(s1[ch], w10)),
+                            __fmul_rn(s1[3 + ch], w11));
+      } else {
+        // remapBicubic away from the border: sum over the 4x4 taps of S * (wy * wx), rows outer (general_tile_body's order)
+        const float4 wx4 = *reinterpret_cast<const float4*>(s_cubic + (ix & 31) * 4);
+        const float4 wy4 = *reinterpret_cast<const float4*>(s_cubic + (iy & 31) * 4);
+        const float wx[4] = {wx4.x, wx4.y, wx4.z, wx4.w}, wy[4] = {wy4.x, wy4.y, wy4.z, wy4.w};
+        const float* s0 = tile0 + ((iy >> 5) - 1) * S_PITCH + ((ix >> 5) - 1) * 3;
+        v[0] = v[1] = v[2] = 0.f;
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) {
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            const float w = __fmul_rn(wy[k1], wx[k2]);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) v[ch] = __fadd_rn(v[ch], __fmul_rn(s0[k1 * S_PITCH + k2 * 3 + ch], w));
+          }
+        }
+      }
       float* o = VEC ? scratch + rr * (TW * 3) + (lane + cc * 32) * 3 : dst_tile + ((size_t)(warp + rr * NWARPS) * ow + lane + cc * 32) * 3;
       o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
     }
@@ -1316,11 +1335,11 @@ __global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __g
       float* mask_tile = p.mask ? p.mask + ((size_t)frame_idx * p.oh + ty0) * p.ow + tx0 : nullptr;
       const float* tile0 = box - (oy * S_PITCH + ox * 3);
       if (p.vec_store) {
-        if (affine) stream_interior<true, true>(meta->minv, tile0, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
-        else stream_interior<false, true>(meta->minv, tile0, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
+        if (affine) stream_interior<INTERP, true, true>(meta->minv, tile0, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_cubic);
+        else stream_interior<INTERP, false, true>(meta->minv, tile0, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_cubic);
       } else {
-        if (affine) stream_interior<true, false>(meta->minv, tile0, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
-        else stream_interior<false, false>(meta->minv, tile0, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask);
+        if (affine) stream_interior<INTERP, true, false>(meta->minv, tile0, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_cubic);
+        else stream_interior<INTERP, false, false>(meta->minv, tile0, tx0, ty0, warp, lane, tid, p.ow, scratch, dst_tile, mask_tile, p.vec_mask, s_cubic);
       }
     } else if (flags & 8) {
       const bool affine = (meta->minv[6] == 0.0) && (meta->minv[7] == 0.0);
