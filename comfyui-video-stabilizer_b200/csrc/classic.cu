@@ -83,9 +83,13 @@ __global__ void __launch_bounds__(256) gftt_cov_kernel(const unsigned char* __re
 // of 32 steps are collected in a shared-memory tile and leave row-major (rows[f][y][x][3]) as coalesced
 // 768-byte row segments, which is the layout the vertical pass streams.
 constexpr int kRowTileStride = 32 * 3 + 1;  // doubles per x-slot of the output tile
+#ifndef VSTAB_BOX_XS
+#define VSTAB_BOX_XS 8
+#endif
+constexpr int kRowXs = VSTAB_BOX_XS;  // x-slots per tile.  Measured on 241 x 960x540: 32 slots (99 KB per CTA, 8 warps/SM) 3.09 ms, 16: 2.43 ms, 8 (25 KB): 1.44 ms, 4: 2.05 ms
 __global__ void __launch_bounds__(128) gftt_box_rows_kernel(const float* __restrict__ covT, int F, int h, int w,
                                                             double* __restrict__ rows /* [F][h][w][3] */) {
-  extern __shared__ double s_rows[];  // [4 warps][32 x-slots][kRowTileStride]
+  extern __shared__ double s_rows[];  // [4 warps][kRowXs x-slots][kRowTileStride]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ytiles = (h + 31) / 32;
   const int t = blockIdx.x * 4 + warp;
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(128) gftt_box_rows_kernel(const float* __restr
   const int y = min(y0 + lane, h - 1);  // lanes past the last row repeat it and are never written out
   const size_t stride = (size_t)h * 3;
   const float* c = covT + (size_t)f * w * stride + (size_t)y * 3;
-  double* tile = s_rows + (size_t)warp * 32 * kRowTileStride;
+  double* tile = s_rows + (size_t)warp * kRowXs * kRowTileStride;
   double a0 = 0, a1 = 0, a2 = 0;
   for (int i = 0; i < kBlock; i++) {
     const float* q = c + (size_t)reflect101(i - kRadius, w) * stride;
@@ -102,12 +106,12 @@ __global__ void __launch_bounds__(128) gftt_box_rows_kernel(const float* __restr
     a1 += (double)q[1];
     a2 += (double)q[2];
   }
-  for (int x0 = 0; x0 < w; x0 += 32) {
-    const int cnt = min(32, w - x0);
-    if (x0 - 1 - kRadius >= 0 && x0 + 31 + kRadius < w) {
+  for (int x0 = 0; x0 < w; x0 += kRowXs) {
+    const int cnt = min(kRowXs, w - x0);
+    if (x0 - 1 - kRadius >= 0 && x0 + kRowXs - 1 + kRadius < w) {
       // no reflection in this chunk: the loads of four steps are issued before the chain consumes them
 #pragma unroll 2
-      for (int xs = 0; xs < 32; xs += 4) {
+      for (int xs = 0; xs < kRowXs; xs += 4) {
         float in[4][3], out[4][3];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -511,7 +515,7 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
     gftt_cov_kernel<<<gp, 256, 0, st>>>(g, h, w, s, s2, cov);
     VSTAB_LAUNCH_CHECK(hnd, "gftt_cov_kernel");
     {
-      const size_t rows_smem = sizeof(double) * 4 * 32 * kRowTileStride;  // 99 KB: the tiles of 4 warps
+      const size_t rows_smem = sizeof(double) * 4 * kRowXs * kRowTileStride;  // the tiles of 4 warps
       VSTAB_CUDA(hnd, cudaFuncSetAttribute(gftt_box_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
       gftt_box_rows_kernel<<<vstab_ceil_div(F * vstab_ceil_div(h, 32), 4), 128, rows_smem, st>>>(cov, F, h, w, rows);
     }
