@@ -1030,7 +1030,7 @@ __global__ void __launch_bounds__(256) warp_plan_kernel(const float* __restrict_
     if ((mxx + HI <= ox + S_BW - 1) && need_h <= S_BH && (tx0 + TW <= ow) && (ty0 + S_TH <= oh) &&
         (mnx - LO >= 1) && (mny - LO >= 1) && (mxx + HI <= sw - 2) && (mxy + HI <= sh - 2))
       flags |= 2;  // interior tile (either interpolation): every tap in the box and in the frame, every pixel covered
-    else if ((INTERP == VSTAB_INTERP_BILINEAR) && (mxx + HI <= ox + S_BW - 1) && need_h <= S_BH && (tx0 + TW <= ow) && (ty0 + S_TH <= oh) &&
+    else if ((mxx + HI <= ox + S_BW - 1) && need_h <= S_BH && (tx0 + TW <= ow) && (ty0 + S_TH <= oh) &&
              (mnx - LO >= -30000) && (mny - LO >= -30000) && (mxx + HI <= 30000) && (mxy + HI <= 30000))
       flags |= 8;  // edge tile: the staged box holds every tap position, some of them outside the frame
   }
@@ -1166,10 +1166,10 @@ __device__ __forceinline__ void stream_interior(const double* __restrict__ s_min
 // fits the staged box.  Same arithmetic as stream_interior plus what the frame border needs: per-tap
 // BORDER_CONSTANT substitution (the TMA engine zero-filled those texels), remapBilinear's "footprint
 // entirely outside" rule, the coverage test of the padding mask and the padded-pixel count.
-template <bool AFFINE, bool VEC>
+template <int INTERP, bool AFFINE, bool VEC>
 __device__ __forceinline__ void stream_edge(const WarpParams& p, const double* __restrict__ s_minv, const float* __restrict__ tile0,
                                             int tx0, int ty0, int frame_idx, int warp, int lane, float* __restrict__ scratch,
-                                            float* __restrict__ dst_tile, float* __restrict__ mask_tile) {
+                                            float* __restrict__ dst_tile, float* __restrict__ mask_tile, const float* __restrict__ s_cubic) {
   const double m0 = s_minv[0], m1 = s_minv[1], m2 = s_minv[2], m3 = s_minv[3], m4 = s_minv[4], m5 = s_minv[5];
   const double m8 = s_minv[8];
   const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
@@ -1219,24 +1219,61 @@ __device__ __forceinline__ void stream_edge(const WarpParams& p, const double* _
       // the plan keeps |coordinates| < 2^15 for edge tiles: cv2's saturations are no-ops
       const int ix = __double2int_rn(__dmul_rn(X, sc)), iy = __double2int_rn(__dmul_rn(Y, sc));
       const int sx = ix >> 5, sy = iy >> 5;
-      const float fx1 = (float)(ix & 31) * 0.03125f, fy1 = (float)(iy & 31) * 0.03125f;
-      const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
-      const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
-      const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
-      const bool x0in = (unsigned)sx < (unsigned)p.sw, x1in = (unsigned)(sx + 1) < (unsigned)p.sw;
-      const bool y0in = (unsigned)sy < (unsigned)p.sh, y1in = (unsigned)(sy + 1) < (unsigned)p.sh;
-      const bool in00 = x0in && y0in, in01 = x1in && y0in, in10 = x0in && y1in, in11 = x1in && y1in;
-      const bool any_in = (x0in || x1in) && (y0in || y1in);  // else: remapBilinear returns the border colour itself
-      const float* s0 = tile0 + sy * S_PITCH + sx * 3;
-      const float* s1 = s0 + S_PITCH;
       float v[3];
+      if (INTERP == VSTAB_INTERP_BILINEAR) {
+        const float fx1 = (float)(ix & 31) * 0.03125f, fy1 = (float)(iy & 31) * 0.03125f;
+        const float fx0 = 1.0f - fx1, fy0 = 1.0f - fy1;
+        const float w00 = __fmul_rn(fy0, fx0), w01 = __fmul_rn(fy0, fx1);
+        const float w10 = __fmul_rn(fy1, fx0), w11 = __fmul_rn(fy1, fx1);
+        const bool x0in = (unsigned)sx < (unsigned)p.sw, x1in = (unsigned)(sx + 1) < (unsigned)p.sw;
+        const bool y0in = (unsigned)sy < (unsigned)p.sh, y1in = (unsigned)(sy + 1) < (unsigned)p.sh;
+        const bool in00 = x0in && y0in, in01 = x1in && y0in, in10 = x0in && y1in, in11 = x1in && y1in;
+        const bool any_in = (x0in || x1in) && (y0in || y1in);  // else: remapBilinear returns the border colour itself
+        const float* s0 = tile0 + sy * S_PITCH + sx * 3;
+        const float* s1 = s0 + S_PITCH;
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        const float bc = ch == 0 ? br : (ch == 1 ? bg : bb);
-        const float t00 = in00 ? s0[ch] : bc, t01 = in01 ? s0[3 + ch] : bc;
-        const float t10 = in10 ? s1[ch] : bc, t11 = in11 ? s1[3 + ch] : bc;
-        const float r = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00, w00), __fmul_rn(t01, w01)), __fmul_rn(t10, w10)), __fmul_rn(t11, w11));
-        v[ch] = any_in ? r : bc;
+        for (int ch = 0; ch < 3; ++ch) {
+          const float bc = ch == 0 ? br : (ch == 1 ? bg : bb);
+          const float t00 = in00 ? s0[ch] : bc, t01 = in01 ? s0[3 + ch] : bc;
+          const float t10 = in10 ? s1[ch] : bc, t11 = in11 ? s1[3 + ch] : bc;
+          const float r = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00, w00), __fmul_rn(t01, w01)), __fmul_rn(t10, w10)), __fmul_rn(t11, w11));
+          v[ch] = any_in ? r : bc;
+        }
+      } else {
+        // remapBicubic: all 16 taps inside the frame -> plain sum from 0; otherwise the border branch,
+        // cv + sum over the in-range taps of (S - cv) * w (nothing in range leaves cv itself)
+        const float4 wx4 = *reinterpret_cast<const float4*>(s_cubic + (ix & 31) * 4);
+        const float4 wy4 = *reinterpret_cast<const float4*>(s_cubic + (iy & 31) * 4);
+        const float wx[4] = {wx4.x, wx4.y, wx4.z, wx4.w}, wy[4] = {wy4.x, wy4.y, wy4.z, wy4.w};
+        const int bxs = sx - 1, bys = sy - 1;
+        const float* s0 = tile0 + bys * S_PITCH + bxs * 3;
+        if (bxs >= 0 && bxs < p.sw - 3 && bys >= 0 && bys < p.sh - 3) {
+          v[0] = v[1] = v[2] = 0.f;
+#pragma unroll
+          for (int k1 = 0; k1 < 4; ++k1) {
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const float w = __fmul_rn(wy[k1], wx[k2]);
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) v[ch] = __fadd_rn(v[ch], __fmul_rn(s0[k1 * S_PITCH + k2 * 3 + ch], w));
+            }
+          }
+        } else {
+          v[0] = br; v[1] = bg; v[2] = bb;
+#pragma unroll
+          for (int k1 = 0; k1 < 4; ++k1) {
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              if ((unsigned)(bxs + k2) < (unsigned)p.sw && (unsigned)(bys + k1) < (unsigned)p.sh) {
+                const float w = __fmul_rn(wy[k1], wx[k2]);
+                const float* t = s0 + k1 * S_PITCH + k2 * 3;
+                v[0] = __fadd_rn(v[0], __fmul_rn(__fsub_rn(t[0], br), w));
+                v[1] = __fadd_rn(v[1], __fmul_rn(__fsub_rn(t[1], bg), w));
+                v[2] = __fadd_rn(v[2], __fmul_rn(__fsub_rn(t[2], bb), w));
+              }
+            }
+          }
+        }
       }
       float* o = VEC ? scratch + rr * (TW * 3) + (lane + cc * 32) * 3 : dst_tile + ((size_t)(warp + rr * NWARPS) * ow + lane + cc * 32) * 3;
       o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
@@ -1347,11 +1384,11 @@ __global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __g
       float* mask_tile = p.mask ? p.mask + ((size_t)frame_idx * p.oh + ty0) * p.ow + tx0 : nullptr;
       const float* tile0 = box - (oy * S_PITCH + ox * 3);
       if (p.vec_store) {
-        if (affine) stream_edge<true, true>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile);
-        else stream_edge<false, true>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile);
+        if (affine) stream_edge<INTERP, true, true>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile, s_cubic);
+        else stream_edge<INTERP, false, true>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile, s_cubic);
       } else {
-        if (affine) stream_edge<true, false>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile);
-        else stream_edge<false, false>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile);
+        if (affine) stream_edge<INTERP, true, false>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile, s_cubic);
+        else stream_edge<INTERP, false, false>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile, s_cubic);
       }
     } else {
       StagedTile tile;
