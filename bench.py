@@ -234,6 +234,18 @@ def main():
     sampler.start()
     total_ms, launches, warp_log = timed(device_step, args.steps, args.warmup, collect_warp=True)
     clocks = sampler.stop()
+    if os.environ.get("VSTAB_BENCH_PHASES"):  # diagnostics: host-side phase times of three more steps, every rank, to stderr
+        from vstab_b200 import stabilizer_core as core
+
+        for _ in range(3):
+            core.PHASE_LOG = []
+            barrier()
+            t0 = time.perf_counter()
+            device_step()
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3
+            print(f"[phases rank {rank}] step {wall:.2f} ms " + ", ".join(f"{a[:18]} {b * 1e3:.2f}" for a, b in core.PHASE_LOG), file=sys.stderr, flush=True)
+        core.PHASE_LOG = None
     ms_per_step = total_ms / args.steps
     value = total_frames / (ms_per_step * 1e-3)
 

@@ -274,7 +274,7 @@ def border_value(padding_rgb) -> Tuple[float, float, float]:
     return tuple(float(x) for x in v)
 
 
-def build_stabilization_warp_meta(*, source_size, output_size, framing_mode, applied_matrices) -> Dict[str, Any]:
+def build_stabilization_warp_meta(*, source_size, output_size, framing_mode, applied_matrices, first_index: int = 0) -> Dict[str, Any]:
     return {
         "source_size": [int(source_size[0]), int(source_size[1])],
         "output_size": [int(output_size[0]), int(output_size[1])],
@@ -282,7 +282,7 @@ def build_stabilization_warp_meta(*, source_size, output_size, framing_mode, app
         "matrix_convention": "source_to_stabilized",
         "per_frame": [
             {"index": i, "applied_matrix": m}
-            for i, m in enumerate(np.asarray(applied_matrices, dtype=np.float32).reshape(-1, 3, 3).tolist())
+            for i, m in enumerate(np.asarray(applied_matrices, dtype=np.float32).reshape(-1, 3, 3).tolist(), first_index)
         ],
     }
 

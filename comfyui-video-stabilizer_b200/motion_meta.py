@@ -201,7 +201,7 @@ def applied_motion_meta_from_stabilization_warp(warp_meta, fps: float, source: s
     )
 
 
-def applied_motion_meta_from_matrices(matrices, *, source_size, output_size, fps: float, source: str) -> Dict[str, Any]:
+def applied_motion_meta_from_matrices(matrices, *, source_size, output_size, fps: float, source: str, first_index: int = 0) -> Dict[str, Any]:
     """Same block as applied_motion_meta_from_stabilization_warp(build_stabilization_warp_meta(...)) for
     matrices that are already a float32 numpy stack: the checks (finite, invertible) run once on the
     stack instead of once per nested-list entry.  Raises the same ValueErrors."""
@@ -214,7 +214,7 @@ def applied_motion_meta_from_matrices(matrices, *, source_size, output_size, fps
     if not isinstance(source, str) or not source:
         raise ValueError("motion_meta.source must be a non-empty string.")
     for i in np.flatnonzero(~np.isfinite(stack).all(axis=(1, 2))):
-        raise ValueError(f"stabilization_warp.per_frame[{int(i)}].applied_matrix must contain finite numbers.")
+        raise ValueError(f"stabilization_warp.per_frame[{int(i) + first_index}].applied_matrix must contain finite numbers.")
     # np.linalg.inv fails on an exactly zero LU pivot; such a matrix has a determinant at rounding level.
     # Only matrices whose cofactor determinant is tiny against their scale go through the LAPACK check
     # (a per-matrix call costs microseconds, which adds up on long clips).
@@ -227,7 +227,7 @@ def applied_motion_meta_from_matrices(matrices, *, source_size, output_size, fps
         try:
             np.linalg.inv(stack[i])
         except np.linalg.LinAlgError as exc:
-            raise ValueError(f"stabilization_warp.per_frame[{int(i)}].applied_matrix is not invertible.") from exc
+            raise ValueError(f"stabilization_warp.per_frame[{int(i) + first_index}].applied_matrix is not invertible.") from exc
     return {
         "version": 2,
         "source": source,
@@ -236,7 +236,7 @@ def applied_motion_meta_from_matrices(matrices, *, source_size, output_size, fps
         "input_size": [int(src[0]), int(src[1])],
         "output_size": [int(out[0]), int(out[1])],
         "matrix_convention": "input_to_output",
-        "per_frame": [{"index": i, "matrix": m} for i, m in enumerate(stack.tolist())],
+        "per_frame": [{"index": i, "matrix": m} for i, m in enumerate(stack.tolist(), first_index)],
     }
 
 

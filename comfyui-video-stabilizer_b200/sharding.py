@@ -22,6 +22,7 @@ import torch.distributed as dist
 from .stabilizer_core import PairCandidates
 
 TABLE_COLS = 43
+META_OWN_RANGE, META_EVERY_RANK = -2, -1
 
 
 def split_range(total: int, world: int, rank: int) -> Tuple[int, int]:
@@ -38,11 +39,26 @@ class FrameShard:
     total_frames: int
     group: Optional[dist.ProcessGroup] = None
     device: Optional[torch.device] = None  # device of the communication buffers (cuda for NCCL)
-    meta_rank: int = 0  # the rank that materialises the per-frame lists of `meta` (-1: every rank)
+    # Who materialises the per-frame lists of `meta` (tens of thousands of Python objects on long clips):
+    #   META_OWN_RANGE  every rank the entries of its own frames -- the per-frame meta is sharded like the
+    #                   frames it describes; merge_sharded_meta() concatenates the ranks' metas when the
+    #                   whole tree is wanted (default: no rank carries O(total frames) of list building)
+    #   META_EVERY_RANK every rank the whole clip
+    #   r >= 0          rank r the whole clip, the others only the scalar part
+    meta_rank: int = -2
 
     @property
     def builds_meta(self) -> bool:
-        return self.meta_rank < 0 or self.meta_rank == self.rank
+        return self.meta_rank == META_EVERY_RANK or self.meta_rank == self.rank
+
+    @property
+    def meta_frame_range(self) -> Tuple[int, int]:
+        """Frames whose per-frame meta entries this rank materialises (empty range: scalars only)."""
+        if self.builds_meta:
+            return 0, self.total_frames
+        if self.meta_rank == META_OWN_RANGE:
+            return self.frame_range
+        return 0, 0
 
     @property
     def frame_range(self) -> Tuple[int, int]:
@@ -112,6 +128,27 @@ class FrameShard:
         sizes = [hi - lo for lo, hi in counts]
         rows = np.asarray(local_counts, dtype=np.float64).reshape(-1, 1)
         return np.rint(self._all_gather_rows(rows, sizes)[:, 0]).astype(np.int64)
+
+
+def merge_sharded_meta(metas: List[dict]) -> dict:
+    """The single-process `meta` from the metas of all ranks (rank order) of a META_OWN_RANGE run:
+    scalars from rank 0, per-frame / per-transition lists concatenated, motion_meta.frame_count restored."""
+    import copy
+
+    out = copy.deepcopy(metas[0])
+    out.pop("shard", None)
+    for m in metas[1:]:
+        out["stabilization_warp"]["per_frame"].extend(copy.deepcopy(m["stabilization_warp"]["per_frame"]))
+        est, src = out["estimated_motion"], m["estimated_motion"]
+        for key in ("per_transition", "path", "target_path", "target_path_effective"):
+            est[key].extend(copy.deepcopy(src[key]))
+        if "motion_meta" in out and "motion_meta" in m:
+            out["motion_meta"]["per_frame"].extend(copy.deepcopy(m["motion_meta"]["per_frame"]))
+        elif "motion_meta" in out:
+            del out["motion_meta"]  # a rank could not build its block: the merged tree has none either
+    if "motion_meta" in out:
+        out["motion_meta"]["frame_count"] = len(out["motion_meta"]["per_frame"])
+    return out
 
 
 def init_from_env(total_frames: int, backend: Optional[str] = None) -> FrameShard:

@@ -380,34 +380,38 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
         hm.border_value(padding_rgb), want_mask=True, want_pad_count=True, output=output, defer=True,
     )
 
-    # the kernels above are in flight: build the meta tree on the host meanwhile (when sharded only
-    # the meta rank materialises the per-frame lists; the others return the scalar part)
-    full_meta = shard is None or shard.builds_meta
+    # the kernels above are in flight: build the meta tree on the host meanwhile.  Sharded runs materialise
+    # the per-frame lists only for shard.meta_frame_range (by default the rank's own frames: the per-frame
+    # meta is sharded like the frames it describes, sharding.merge_sharded_meta() reassembles it); entries
+    # keep their clip-wide indices.  Transitions go with the frame they end in.
+    m_lo, m_hi = (0, total_frames) if shard is None else shard.meta_frame_range
+    t_lo, t_hi = max(m_lo, 1) - 1, max(m_hi - 1, max(m_lo, 1) - 1)
     per_transition = []
-    if full_meta:
-        mat_lists = matrices.tolist()
-        columns = zip(chosen.modes, chosen.confidences, chosen.residuals, mat_lists)
+    if t_hi > t_lo:
+        mat_lists = matrices[t_lo:t_hi].tolist()
+        columns = zip(chosen.modes[t_lo:t_hi], chosen.confidences[t_lo:t_hi], chosen.residuals[t_lo:t_hi], mat_lists)
         if is_flow:
             per_transition = [{"index": i, "mode": mode, "confidence": conf, "residual": res, "matrix": m}
-                              for i, (mode, conf, res, m) in enumerate(columns)]
+                              for i, (mode, conf, res, m) in enumerate(columns, t_lo)]
         else:
             per_transition = [{"index": i, "mode": mode, "confidence": conf, "matrix": m}
-                              for i, (mode, conf, _, m) in enumerate(columns)]
+                              for i, (mode, conf, _, m) in enumerate(columns, t_lo)]
 
     warp_meta = hm.build_stabilization_warp_meta(
         source_size=(width, height), output_size=output_size, framing_mode=framing_mode,
-        applied_matrices=final_matrices if full_meta else final_matrices[:0],
+        applied_matrices=final_matrices[m_lo:m_hi], first_index=m_lo,
     )
     motion_block = None
-    if full_meta:
+    if m_hi > m_lo:
         try:
             motion_block = applied_motion_meta_from_matrices(
-                final_matrices, source_size=(width, height), output_size=output_size, fps=fps_effective, source=source_tag
+                final_matrices[m_lo:m_hi], source_size=(width, height), output_size=output_size, fps=fps_effective,
+                source=source_tag, first_index=m_lo,
             )
         except (KeyError, TypeError, ValueError, np.linalg.LinAlgError):
             pass
     path_list, target_list, effective_list = (
-        (path.tolist(), target_path.tolist(), effective_target_path.tolist()) if full_meta else ([], [], [])
+        path[m_lo:m_hi].tolist(), target_path[m_lo:m_hi].tolist(), effective_target_path[m_lo:m_hi].tolist()
     )
 
     t0 = _mark("meta build (overlaps the warp)", t0)
@@ -415,6 +419,7 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
     t0 = _mark("wait for warp + pad counts", t0)
     if shard is not None:
         pad_counts = shard.gather_pad_counts(pad_counts)
+        t0 = _mark("all-gather pad counts", t0)
     pixels = int(output_size[0]) * int(output_size[1])
     padded_ratios = hm.padded_fractions(pad_counts, pixels)
     framing_meta["padding_detected"] = bool(np.any(np.asarray(pad_counts) > 0))
@@ -447,6 +452,9 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
     }
     if motion_block is not None:
         meta["motion_meta"] = motion_block
+    if shard is not None and (m_lo, m_hi) != (0, total_frames):
+        meta["shard"] = {"rank": shard.rank, "world": shard.world, "frame_range": list(shard.frame_range),
+                         "meta_frame_range": [m_lo, m_hi]}
     if output == "host":
         return StabilizationResult(frames_out.numpy(), masks_out.numpy()[..., None], meta)
     return StabilizationResult(frames_out, masks_out[..., None], meta)

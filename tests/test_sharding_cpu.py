@@ -87,3 +87,66 @@ def test_split_covers_everything():
                 a, b = FrameShard(r, world, total).pair_range
                 pairs += list(range(a, b))
             assert pairs == list(range(max(total - 1, 0)))
+
+
+def test_own_range_meta_merges_to_the_single_process_meta(monkeypatch):
+    """META_OWN_RANGE: every rank materialises only the per-frame meta of its own frames (clip-wide indices);
+    merge_sharded_meta() of the ranks' metas is the single-process meta, key for key and value for value.
+    Host logic only: the estimator, the collectives and the resampler are stand-ins."""
+    from vstab_b200 import stabilizer_core as core
+    from vstab_b200.sharding import META_EVERY_RANK, FrameShard, merge_sharded_meta
+
+    total, world, W, H = 23, 3, 640, 360
+    full = _fake_candidates(total)
+    pads_all = (np.arange(total) * 7) % 50
+
+    class Ctx:
+        def __init__(self, n):
+            self.n, self.width, self.height, self.fps = n, W, H, None
+
+        def __len__(self):
+            return self.n
+
+        def sliced(self, k):
+            return self
+
+    class Shard(FrameShard):
+        def gather_candidates(self, local):
+            return core.PairCandidates.from_array(full.to_array(), 12)
+
+        def gather_pad_counts(self, local_counts):
+            return pads_all.astype(np.int64)
+
+    def fake_warp(context, fwd, *a, **k):
+        return lambda: (np.zeros(1, np.float32), np.zeros(1, np.float32), np.zeros(len(fwd), np.int64))
+
+    monkeypatch.setattr(core, "fused_warp", fake_warp)
+    monkeypatch.setattr(core, "StabilizationResult", lambda frames, masks, meta: meta)
+
+    def run(shard):
+        n = total if shard is None else shard.load_range[1] - shard.load_range[0]
+
+        def est(ctx, w, h, mode):
+            return full if shard is None else full  # the shard's gather stand-in supplies the table anyway
+
+        meta = core.stabilize_frames(Ctx(n), "crop_and_pad", "similarity", False, 0.7, 0.5, 0.6, (127, 127, 127), 16.0,
+                                     estimator=est, flavour="flow", output="device", shard=shard)
+        return meta
+
+    # single process: pad counts come from the warp stand-in (zeros); give it the same counts through a 1-rank shard
+    single = run(Shard(0, 1, total, None, torch.device("cpu"), meta_rank=META_EVERY_RANK))
+    assert "shard" not in single and len(single["stabilization_warp"]["per_frame"]) == total
+    metas = [run(Shard(r, world, total, None, torch.device("cpu"))) for r in range(world)]
+    for r, m in enumerate(metas):
+        lo, hi = FrameShard(r, world, total).frame_range
+        assert m["shard"]["frame_range"] == [lo, hi] and m["frames"] == total
+        assert [e["index"] for e in m["stabilization_warp"]["per_frame"]] == list(range(lo, hi))
+        assert [e["index"] for e in m["motion_meta"]["per_frame"]] == list(range(lo, hi))
+        assert [e["index"] for e in m["estimated_motion"]["per_transition"]] == list(range(max(lo, 1) - 1, hi - 1))
+        assert len(m["estimated_motion"]["path"]) == hi - lo and m["motion_meta"]["frame_count"] == hi - lo
+    assert merge_sharded_meta(metas) == single
+    # a designated meta rank still builds the whole tree, the others only the scalar part
+    whole = run(Shard(1, world, total, None, torch.device("cpu"), meta_rank=1))
+    bare = run(Shard(0, world, total, None, torch.device("cpu"), meta_rank=1))
+    assert whole == single and bare["estimated_motion"]["per_transition"] == [] and "motion_meta" not in bare
+    assert bare["padding_fraction_max"] == single["padding_fraction_max"]
