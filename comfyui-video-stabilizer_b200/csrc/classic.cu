@@ -313,11 +313,35 @@ __global__ void __launch_bounds__(256) scharr_kernel(const unsigned char* __rest
   d[((size_t)f * h + y) * w + x] = make_short2((short)(t0p - t0m), (short)((t1p + t1m) * 3 + t1c * 10));
 }
 
+constexpr int kLkPad = 32;  // >= kWin + 1: every tap of a window the tracker accepts lies inside the padded copy
 struct LkLevel {
   const unsigned char* img;  // [F][h][w]
+  const unsigned char* ext;  // [F][h + 2 kLkPad][w + 2 kLkPad]: img with its reflect-101 border written out
   const short2* deriv;       // [F][h][w]
   int h, w;
 };
+
+// ext[y][x] = img[reflect101(y - kLkPad)][reflect101(x - kLkPad)]: the search windows of the tracker hang over the
+// frame border for most features of the coarse levels (a 31x31 window in a 120x67 image); with the border written
+// out once, every Gauss-Newton iteration walks its window without reflecting coordinates.
+__global__ void __launch_bounds__(256) lk_pad_kernel(const unsigned char* __restrict__ img, int h, int w, unsigned char* __restrict__ ext) {
+  // four consecutive bytes per thread: one 32-bit load + store wherever the four source bytes are consecutive and aligned
+  const int f = blockIdx.z;
+  const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int pw = w + 2 * kLkPad, ph = h + 2 * kLkPad;
+  if (x >= pw || y >= ph) return;
+  const unsigned char* row = img + ((size_t)f * h + reflect101(y - kLkPad, h)) * w;
+  unsigned char* dst = ext + ((size_t)f * ph + y) * pw + x;
+  const int sx = x - kLkPad;
+  if (((w | pw) & 3) == 0 && sx >= 0 && sx + 3 < w && ((((size_t)f * h) * w) & 3) == 0) {
+    *reinterpret_cast<unsigned int*>(dst) = *reinterpret_cast<const unsigned int*>(row + sx);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (x + k < pw) dst[k] = row[reflect101(sx + k, w)];
+  }
+}
 struct LkPyr {
   LkLevel lv[kMaxLevel + 1];
   int levels;  // highest level index
@@ -354,8 +378,8 @@ __global__ void __launch_bounds__(256) lk_track_kernel(LkPyr P, int n_pairs, int
   float nx = 0.f, ny = 0.f;
   for (int level = P.levels; level >= 0; level--) {
     const LkLevel L = P.lv[level];
-    const unsigned char* I = L.img + (size_t)pair * L.h * L.w;
-    const unsigned char* J = L.img + (size_t)(pair + 1) * L.h * L.w;
+    const int pw = L.w + 2 * kLkPad;
+    const unsigned char* Jext = L.ext + (size_t)(pair + 1) * (L.h + 2 * kLkPad) * pw;
     const short2* D = L.deriv + (size_t)pair * L.h * L.w;
     const int lh = L.h, lw = L.w;
     float px = fx * (float)(1. / (1 << level)), py = fy * (float)(1. / (1 << level));
@@ -368,20 +392,36 @@ __global__ void __launch_bounds__(256) lk_track_kernel(LkPyr P, int n_pairs, int
     int iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS)), iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
     float A11 = 0, A12 = 0, A22 = 0;
     __syncwarp();
-    for (int k = lane; k < kWin * kWin; k += 32) {
-      const int y = k / kWin, x = k - y * kWin;
-      const int sy = ipy + y, sx = ipx + x;
-      const int y0 = reflect101(sy, lh), y1 = reflect101(sy + 1, lh), x0 = reflect101(sx, lw), x1 = reflect101(sx + 1, lw);
-      const int ival = descale(I[y0 * lw + x0] * iw00 + I[y0 * lw + x1] * iw01 + I[y1 * lw + x0] * iw10 + I[y1 * lw + x1] * iw11, W_BITS - 5);
-      const bool in00 = sx >= 0 && sy >= 0 && sx < lw && sy < lh, in01 = sx + 1 >= 0 && sy >= 0 && sx + 1 < lw && sy < lh;
-      const bool in10 = sx >= 0 && sy + 1 >= 0 && sx < lw && sy + 1 < lh, in11 = sx + 1 >= 0 && sy + 1 >= 0 && sx + 1 < lw && sy + 1 < lh;
-      const short2 zero = make_short2(0, 0);
-      const short2 d00 = in00 ? D[sy * lw + sx] : zero, d01 = in01 ? D[sy * lw + sx + 1] : zero;
-      const short2 d10 = in10 ? D[(sy + 1) * lw + sx] : zero, d11 = in11 ? D[(sy + 1) * lw + sx + 1] : zero;
-      const int ixval = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, W_BITS);
-      const int iyval = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, W_BITS);
-      win[k * 3] = (short)ival; win[k * 3 + 1] = (short)ixval; win[k * 3 + 2] = (short)iyval;
-      A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval);
+    {
+      // template window: intensities from the padded copy (no reflection), derivatives zero outside the frame;
+      // (y, x) of pixel k = lane + 32 j advance by (+1, +1) with a wrap, like the iteration loop below
+      const unsigned char* Ip = L.ext + (size_t)pair * (lh + 2 * kLkPad) * pw + (ipy + kLkPad) * pw + (ipx + kLkPad);
+      const bool inside = ipx >= 0 && ipy >= 0 && ipx + kWin < lw && ipy + kWin < lh;  // with the +1 taps
+      int x = lane >= kWin ? lane - kWin : lane, y = lane >= kWin ? 1 : 0;
+      short* wq = win + lane * 3;
+      for (int k = lane; k < kWin * kWin; k += 32) {
+        const unsigned char* q = Ip + y * pw + x;
+        const int ival = descale(q[0] * iw00 + q[1] * iw01 + q[pw] * iw10 + q[pw + 1] * iw11, W_BITS - 5);
+        const int sy = ipy + y, sx = ipx + x;
+        short2 d00, d01, d10, d11;
+        if (inside) {
+          const short2* dq = D + sy * lw + sx;
+          d00 = dq[0]; d01 = dq[1]; d10 = dq[lw]; d11 = dq[lw + 1];
+        } else {
+          const bool in00 = sx >= 0 && sy >= 0 && sx < lw && sy < lh, in01 = sx + 1 >= 0 && sy >= 0 && sx + 1 < lw && sy < lh;
+          const bool in10 = sx >= 0 && sy + 1 >= 0 && sx < lw && sy + 1 < lh, in11 = sx + 1 >= 0 && sy + 1 >= 0 && sx + 1 < lw && sy + 1 < lh;
+          const short2 zero = make_short2(0, 0);
+          d00 = in00 ? D[sy * lw + sx] : zero; d01 = in01 ? D[sy * lw + sx + 1] : zero;
+          d10 = in10 ? D[(sy + 1) * lw + sx] : zero; d11 = in11 ? D[(sy + 1) * lw + sx + 1] : zero;
+        }
+        const int ixval = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, W_BITS);
+        const int iyval = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, W_BITS);
+        wq[0] = (short)ival; wq[1] = (short)ixval; wq[2] = (short)iyval;
+        wq += 32 * 3;
+        A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval);
+        x += 1; y += 1;
+        if (x >= kWin) { x -= kWin; y += 1; }
+      }
     }
     A11 = warp_sum(A11) * FLT_SCALE; A12 = warp_sum(A12) * FLT_SCALE; A22 = warp_sum(A22) * FLT_SCALE;
     __syncwarp();
@@ -398,26 +438,24 @@ __global__ void __launch_bounds__(256) lk_track_kernel(LkPyr P, int n_pairs, int
       iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS)); iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
       iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS)); iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
       float b1 = 0, b2 = 0;
-      if (inx >= 0 && iny >= 0 && inx + kWin < lw && iny + kWin < lh) {
-        // window (with its +1 taps) inside the image: no border reflection, and (y, x) of pixel k = lane + 32 j
-        // advance by (+1, +1) with a wrap instead of a division -- same pixels, same order, same sums
-        const unsigned char* Jp = J + iny * lw + inx;
-        int y = lane >= kWin ? 1 : 0, x = lane >= kWin ? lane - kWin : lane;
+      {
+        // (y, x) of pixel k = lane + 32 j advance by (+1, +1) with a wrap instead of a division -- same pixels,
+        // same order, same sums.  The tracker is issue-bound on integer work, so the walk keeps one running byte
+        // offset into the padded frame and one running window pointer instead of recomputing them per pixel.
+        const unsigned char* Jp = Jext + (iny + kLkPad) * pw + (inx + kLkPad);
+        int x = lane >= kWin ? lane - kWin : lane;
+        unsigned off = (lane >= kWin ? (unsigned)pw : 0u) + (unsigned)x;
+        const unsigned step_off = (unsigned)pw + 1u, wrap_off = (unsigned)(pw - kWin);
+        const short* wp = win + lane * 3;
         for (int k = lane; k < kWin * kWin; k += 32) {
-          const unsigned char* q = Jp + y * lw + x;
-          const int diff = descale(q[0] * iw00 + q[1] * iw01 + q[lw] * iw10 + q[lw + 1] * iw11, W_BITS - 5) - win[k * 3];
-          b1 += (float)(diff * win[k * 3 + 1]);
-          b2 += (float)(diff * win[k * 3 + 2]);
-          x += 1; y += 1;
-          if (x >= kWin) { x -= kWin; y += 1; }
-        }
-      } else {
-        for (int k = lane; k < kWin * kWin; k += 32) {
-          const int y = k / kWin, x = k - y * kWin;
-          const int y0 = reflect101(iny + y, lh), y1 = reflect101(iny + y + 1, lh), x0 = reflect101(inx + x, lw), x1 = reflect101(inx + x + 1, lw);
-          const int diff = descale(J[y0 * lw + x0] * iw00 + J[y0 * lw + x1] * iw01 + J[y1 * lw + x0] * iw10 + J[y1 * lw + x1] * iw11, W_BITS - 5) - win[k * 3];
-          b1 += (float)(diff * win[k * 3 + 1]);
-          b2 += (float)(diff * win[k * 3 + 2]);
+          const unsigned char* q = Jp + off;
+          const int diff = descale(q[0] * iw00 + q[1] * iw01 + q[pw] * iw10 + q[pw + 1] * iw11, W_BITS - 5) - wp[0];
+          b1 += (float)(diff * wp[1]);
+          b2 += (float)(diff * wp[2]);
+          wp += 32 * 3;
+          x += 1;
+          off += step_off;
+          if (x >= kWin) { x -= kWin; off += wrap_off; }
         }
       }
       b1 = warp_sum(b1) * FLT_SCALE; b2 = warp_sum(b2) * FLT_SCALE;
@@ -477,7 +515,7 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
   const size_t o_ccnt = take((size_t)kChunk * gw * gh);
   const size_t o_feats = take(sizeof(float) * 2 * (size_t)P * max_corners);
   LkPyr pyr;
-  size_t o_img[kMaxLevel + 1], o_der[kMaxLevel + 1];
+  size_t o_img[kMaxLevel + 1], o_der[kMaxLevel + 1], o_ext[kMaxLevel + 1];
   int lh = h, lw = w;
   pyr.levels = 0;
   for (int l = 0; l <= kMaxLevel; l++) {
@@ -490,6 +528,7 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
     }
     pyr.lv[l].h = lh; pyr.lv[l].w = lw;
     o_der[l] = take(sizeof(short2) * (size_t)n_frames * lh * lw);
+    o_ext[l] = take((size_t)n_frames * (lh + 2 * kLkPad) * (lw + 2 * kLkPad));
   }
   void* wsp = nullptr;
   int rc = vstab_workspace(hnd, off, &wsp);
@@ -549,6 +588,11 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
     scharr_kernel<<<gs, 256, 0, st>>>(pyr.lv[l].img, pyr.lv[l].h, pyr.lv[l].w, der);
     VSTAB_LAUNCH_CHECK(hnd, "scharr_kernel");
     pyr.lv[l].deriv = der;
+    unsigned char* ext = base + o_ext[l];
+    dim3 ge(vstab_ceil_div(pyr.lv[l].w + 2 * kLkPad, 128), vstab_ceil_div(pyr.lv[l].h + 2 * kLkPad, 8), n_frames);
+    lk_pad_kernel<<<ge, 256, 0, st>>>(pyr.lv[l].img, pyr.lv[l].h, pyr.lv[l].w, ext);
+    VSTAB_LAUNCH_CHECK(hnd, "lk_pad_kernel");
+    pyr.lv[l].ext = ext;
   }
   // ---- track ----
   const size_t smem = sizeof(short) * 8 * kWin * kWin * 3;
