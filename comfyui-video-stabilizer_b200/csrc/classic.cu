@@ -187,20 +187,39 @@ __global__ void __launch_bounds__(256) gftt_candidates_kernel(const float* __res
                                                               int* __restrict__ counts) {
   const int f = blockIdx.z;
   const int x = 1 + blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = 1 + blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= w - 1 || y >= h - 1) return;
+  const int y0 = 1 + (blockIdx.y * 8 + (threadIdx.x >> 5)) * 8;  // 8 rows per thread: the grid was bound by block launches
+  if (y0 >= h - 1) return;  // whole warp (a warp is one row of the block)
+  const bool live = x < w - 1;
   const float* e = eig + (size_t)f * h * w;
   const float thr = (float)((double)__uint_as_float(max_bits[f]) * quality);
-  const float v = e[y * w + x];
-  if (!(v > thr)) return;
-  float m = v;
-#pragma unroll
-  for (int j = -1; j <= 1; j++)
-#pragma unroll
-    for (int i = -1; i <= 1; i++) m = fmaxf(m, e[(y + j) * w + x + i]);
-  if (v != m) return;
-  const int slot = atomicAdd(counts + f, 1);
-  if (slot < cap) keys[(size_t)f * cap + slot] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
+  // All candidates of a frame bump ONE counter: a warp reserves its slots with a single atomic (the keys are
+  // sorted afterwards, so the slot order does not matter).  Lanes past the right edge stay in the loop for the ballot.
+  // 3x3 dilation as a rolling maximum of per-row maxima: 3 loads per row instead of 9 per pixel (max is exact).
+  const float* ex = e + (live ? x : 1);
+  auto row_max = [&](int y, float& centre) {
+    const float* q = ex + (size_t)y * w;
+    centre = q[0];
+    return fmaxf(fmaxf(q[-1], q[0]), q[1]);
+  };
+  float c_cur, c_next = 0.f, unused;
+  float hm_prev = row_max(y0 - 1, unused), hm_cur = row_max(y0, c_cur), hm_next = 0.f;
+  for (int r = 0; r < 8; r++) {
+    const int y = y0 + r;
+    const bool row_ok = y < h - 1;  // warp-uniform
+    if (row_ok) hm_next = row_max(y + 1, c_next);
+    const float v = c_cur;
+    const bool cand = live && row_ok && (v > thr) && (v == fmaxf(fmaxf(hm_prev, hm_cur), hm_next));
+    hm_prev = hm_cur; hm_cur = hm_next; c_cur = c_next;
+    const unsigned votes = __ballot_sync(0xffffffffu, cand);
+    if (votes) {
+      const int lane = threadIdx.x & 31, leader = __ffs(votes) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(counts + f, __popc(votes));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      const int slot = base + __popc(votes & ((1u << lane) - 1u));
+      if (cand && slot < cap) keys[(size_t)f * cap + slot] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
+    }
+  }
 }
 
 // descending bitonic sort of each frame's keys in global memory (one CTA per frame)
@@ -280,37 +299,43 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const unsigned char* __re
                                                        unsigned char* __restrict__ dst, int dh, int dw) {
   const int f = blockIdx.z;
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= dw || y >= dh) return;
+  const int y0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 8;  // 8 rows per thread (kRowsPerThread, declared below)
+  if (x >= dw || y0 >= dh) return;
   const unsigned char* s = src + (size_t)f * sh * sw;
-  int cx[5], cy[5];
+  int cx[5];
 #pragma unroll
-  for (int k = 0; k < 5; k++) { cx[k] = reflect101(2 * x + k - 2, sw); cy[k] = reflect101(2 * y + k - 2, sh); }
+  for (int k = 0; k < 5; k++) cx[k] = reflect101(2 * x + k - 2, sw);
   const int wk[5] = {1, 4, 6, 4, 1};
-  int sum = 0;
+  for (int y = y0; y < min(y0 + 8, dh); y++) {
+    int sum = 0;
 #pragma unroll
-  for (int j = 0; j < 5; j++) {
-    const unsigned char* r = s + (size_t)cy[j] * sw;
-    const int row = r[cx[0]] + 4 * r[cx[1]] + 6 * r[cx[2]] + 4 * r[cx[3]] + r[cx[4]];
-    sum += wk[j] * row;
+    for (int j = 0; j < 5; j++) {
+      const unsigned char* r = s + (size_t)reflect101(2 * y + j - 2, sh) * sw;
+      const int row = r[cx[0]] + 4 * r[cx[1]] + 6 * r[cx[2]] + 4 * r[cx[3]] + r[cx[4]];
+      sum += wk[j] * row;
+    }
+    dst[((size_t)f * dh + y) * dw + x] = (unsigned char)((sum + 128) >> 8);
   }
-  dst[((size_t)f * dh + y) * dw + x] = (unsigned char)((sum + 128) >> 8);
 }
 
 // Scharr derivatives (dx, dy) interleaved int16, reflect-101 inside the image
+constexpr int kRowsPerThread = 8;  // one-pixel-per-thread grids of these small kernels were bound by block launches, not by work
+
 __global__ void __launch_bounds__(256) scharr_kernel(const unsigned char* __restrict__ img, int h, int w, short2* __restrict__ d) {
   const int f = blockIdx.z;
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= w || y >= h) return;
+  const int y0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kRowsPerThread;
+  if (x >= w || y0 >= h) return;
   const unsigned char* I = img + (size_t)f * h * w;
-  const unsigned char* r0 = I + (size_t)reflect101(y - 1, h) * w;
-  const unsigned char* r1 = I + (size_t)y * w;
-  const unsigned char* r2 = I + (size_t)reflect101(y + 1, h) * w;
   const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
-  const int t0p = (r0[xp] + r2[xp]) * 3 + r1[xp] * 10, t0m = (r0[xm] + r2[xm]) * 3 + r1[xm] * 10;
-  const int t1m = r2[xm] - r0[xm], t1c = r2[x] - r0[x], t1p = r2[xp] - r0[xp];
-  d[((size_t)f * h + y) * w + x] = make_short2((short)(t0p - t0m), (short)((t1p + t1m) * 3 + t1c * 10));
+  for (int y = y0; y < min(y0 + kRowsPerThread, h); y++) {
+    const unsigned char* r0 = I + (size_t)reflect101(y - 1, h) * w;
+    const unsigned char* r1 = I + (size_t)y * w;
+    const unsigned char* r2 = I + (size_t)reflect101(y + 1, h) * w;
+    const int t0p = (r0[xp] + r2[xp]) * 3 + r1[xp] * 10, t0m = (r0[xm] + r2[xm]) * 3 + r1[xm] * 10;
+    const int t1m = r2[xm] - r0[xm], t1c = r2[x] - r0[x], t1p = r2[xp] - r0[xp];
+    d[((size_t)f * h + y) * w + x] = make_short2((short)(t0p - t0m), (short)((t1p + t1m) * 3 + t1c * 10));
+  }
 }
 
 constexpr int kLkPad = 32;  // >= kWin + 1: every tap of a window the tracker accepts lies inside the padded copy
@@ -564,7 +589,7 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
     VSTAB_CUDA(hnd, cudaMemsetAsync(ccnt, 0, (size_t)kChunk * gw * gh, st));
     gftt_box_cols_kernel<<<vstab_ceil_div(F * w, 128), 128, 0, st>>>(rows, F, h, w, eig, maxb);
     VSTAB_LAUNCH_CHECK(hnd, "gftt_box_cols_kernel");
-    dim3 gc(vstab_ceil_div(w - 2, 32), vstab_ceil_div(h - 2, 8), F);
+    dim3 gc(vstab_ceil_div(w - 2, 32), vstab_ceil_div(h - 2, 64), F);
     gftt_candidates_kernel<<<gc, 256, 0, st>>>(eig, h, w, maxb, 0.01, keys, cap, cnt);
     VSTAB_LAUNCH_CHECK(hnd, "gftt_candidates_kernel");
     gftt_sort_kernel<<<F, 1024, 0, st>>>(keys, cap, cnt);
@@ -578,13 +603,13 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
   for (int l = 0; l <= pyr.levels; l++) {
     if (l > 0) {
       unsigned char* dst = base + o_img[l];
-      dim3 gd(vstab_ceil_div(pyr.lv[l].w, 32), vstab_ceil_div(pyr.lv[l].h, 8), n_frames);
+      dim3 gd(vstab_ceil_div(pyr.lv[l].w, 32), vstab_ceil_div(pyr.lv[l].h, 64), n_frames);
       pyr_down_kernel<<<gd, 256, 0, st>>>(pyr.lv[l - 1].img, pyr.lv[l - 1].h, pyr.lv[l - 1].w, dst, pyr.lv[l].h, pyr.lv[l].w);
       VSTAB_LAUNCH_CHECK(hnd, "pyr_down_kernel");
       pyr.lv[l].img = dst;
     }
     short2* der = (short2*)(base + o_der[l]);
-    dim3 gs(vstab_ceil_div(pyr.lv[l].w, 32), vstab_ceil_div(pyr.lv[l].h, 8), n_frames);
+    dim3 gs(vstab_ceil_div(pyr.lv[l].w, 32), vstab_ceil_div(pyr.lv[l].h, kRowsPerThread * 8), n_frames);
     scharr_kernel<<<gs, 256, 0, st>>>(pyr.lv[l].img, pyr.lv[l].h, pyr.lv[l].w, der);
     VSTAB_LAUNCH_CHECK(hnd, "scharr_kernel");
     pyr.lv[l].deriv = der;
