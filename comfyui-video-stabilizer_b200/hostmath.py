@@ -192,8 +192,13 @@ def smooth_path(path: np.ndarray, smooth: float, fps: float) -> np.ndarray:
     half = window // 2
     taps = np.ones(window, dtype=np.float64) / float(window)
     out = np.zeros_like(path)
+    n = path.shape[0]
+    padded = np.empty(n + 2 * half, dtype=path.dtype)  # np.pad(mode="edge") written out: it costs 35 us per call
     for col in range(path.shape[1]):
-        out[:, col] = np.convolve(np.pad(path[:, col], (half, half), mode="edge"), taps, mode="valid")
+        padded[:half] = path[0, col]
+        padded[half : half + n] = path[:, col]
+        padded[half + n :] = path[n - 1, col]
+        out[:, col] = np.convolve(padded, taps, mode="valid")
     return out
 
 
@@ -217,8 +222,8 @@ def compute_bounding_boxes(matrices: Sequence[np.ndarray], width: int, height: i
     # float32 @ float64 promotes the float32 operand and multiplies without FMA (verified bit-equal)
     m = (matrices if stacked_f32 else np.stack([np.asarray(x) for x in matrices], axis=0)).astype(np.float64)
     q = m[:, :, 0:1] * corners[0][None, None, :] + m[:, :, 1:2] * corners[1][None, None, :] + m[:, :, 2:3] * corners[2][None, None, :]
-    q = q / q[:, 2:3, :]
-    return np.stack([q[:, 0].min(axis=1), q[:, 1].min(axis=1)], axis=1), np.stack([q[:, 0].max(axis=1), q[:, 1].max(axis=1)], axis=1)
+    xy = q[:, :2] / q[:, 2:3]  # the reference divides all three rows; the third one (w / w) is never read
+    return xy.min(axis=2), xy.max(axis=2)
 
 
 def min_content_ratio(mins, maxs, width: int, height: int) -> float:
