@@ -77,9 +77,10 @@ def rescale_transforms_to_full(matrices: np.ndarray, source_size, working_size) 
     diagonal products have a single non-zero term per element, so this is bit-identical."""
     kx = working_size[0] / float(source_size[0])
     ky = working_size[1] / float(source_size[1])
-    down = np.diag([kx, ky, 1.0]).astype(np.float64)
-    up = np.diag([1.0 / kx, 1.0 / ky, 1.0]).astype(np.float64)
-    return (up @ np.asarray(matrices).astype(np.float64) @ down).astype(np.float32)
+    down = np.array([kx, ky, 1.0], dtype=np.float64)
+    up = np.array([1.0 / kx, 1.0 / ky, 1.0], dtype=np.float64)
+    # (up @ M) @ down with diagonal factors: element (i, j) is (up_i * M_ij) * down_j plus exact zeros
+    return ((np.asarray(matrices).astype(np.float64) * up[None, :, None]) * down[None, None, :]).astype(np.float32)
 
 
 def matrix_to_params(matrix, base_mode: str) -> np.ndarray:
@@ -223,12 +224,21 @@ def compute_bounding_boxes(matrices: Sequence[np.ndarray], width: int, height: i
     m = (matrices if stacked_f32 else np.stack([np.asarray(x) for x in matrices], axis=0)).astype(np.float64)
     q = m[:, :, 0:1] * corners[0][None, None, :] + m[:, :, 1:2] * corners[1][None, None, :] + m[:, :, 2:3] * corners[2][None, None, :]
     xy = q[:, :2] / q[:, 2:3]  # the reference divides all three rows; the third one (w / w) is never read
-    return xy.min(axis=2), xy.max(axis=2)
+    # min / max over the four corners as three element-wise operations (a reduction over an axis of 4 costs more)
+    a, b, c, d = xy[:, :, 0], xy[:, :, 1], xy[:, :, 2], xy[:, :, 3]
+    return np.minimum(np.minimum(a, b), np.minimum(c, d)), np.maximum(np.maximum(a, b), np.maximum(c, d))
 
 
-def min_content_ratio(mins, maxs, width: int, height: int) -> float:
-    iw = max(0.0, np.min(maxs[:, 0]) - np.max(mins[:, 0]))
-    ih = max(0.0, np.min(maxs[:, 1]) - np.max(mins[:, 1]))
+def inner_rectangle(mins, maxs):
+    """(x0, y0, x1, y1) common to all bounding boxes: max of the minima, min of the maxima (two reductions)."""
+    lo, hi = np.max(mins, axis=0), np.min(maxs, axis=0)
+    return lo[0], lo[1], hi[0], hi[1]
+
+
+def min_content_ratio(mins, maxs, width: int, height: int, inner=None) -> float:
+    x0, y0, x1, y1 = inner if inner is not None else inner_rectangle(mins, maxs)
+    iw = max(0.0, x1 - x0)
+    ih = max(0.0, y1 - y0)
     if iw <= 0.0 or ih <= 0.0:
         return 1e-6
     return max(1e-6, min(iw / width, ih / height))

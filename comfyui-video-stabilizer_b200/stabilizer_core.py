@@ -331,11 +331,12 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
         crop_meta = None
 
     mins, maxs = hm.compute_bounding_boxes(apply_matrices, width, height)
+    inner = hm.inner_rectangle(mins, maxs)
     framing_meta: Dict[str, Any] = {
         "mode": framing_mode,
         "input_size": [width, height],
         "padding_color_rgb": [int(c) for c in padding_rgb],
-        "min_content_ratio": hm.min_content_ratio(mins, maxs, width, height),
+        "min_content_ratio": hm.min_content_ratio(mins, maxs, width, height, inner),
     }
     if framing_mode == "crop":
         framing_meta.update(crop_meta)
@@ -345,8 +346,7 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
         if note:
             framing_meta["keep_fov_note"] = note
     elif framing_mode == "crop_and_pad":
-        x0, y0 = float(np.max(mins[:, 0])), float(np.max(mins[:, 1]))
-        x1, y1 = float(np.min(maxs[:, 0])), float(np.min(maxs[:, 1]))
+        x0, y0, x1, y1 = (float(v) for v in inner)
         iw, ih = max(1.0, x1 - x0), max(1.0, y1 - y0)
         off_x = width * 0.5 - (x0 + x1) * 0.5
         off_y = height * 0.5 - (y0 + y1) * 0.5
