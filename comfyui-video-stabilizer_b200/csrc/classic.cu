@@ -48,22 +48,30 @@ __global__ void __launch_bounds__(256) gftt_cov_kernel(const unsigned char* __re
   const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
   const unsigned char* img = gray + (size_t)f * h * w;
   const int x = x0 + lane;
+  // A warp owns four consecutive rows: the six source rows they touch are read once (3 bytes each), their row
+  // filters evaluated once, and the four pixels combine them -- the same operations per pixel as before.
+  if (x < w && y0 + warp * 4 < h) {
+    const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+    float sm[6], df[6];  // row filter [s 2s s] (fused chain like cv2's AVX2 row filter) and the central difference, rows y-1 .. y+4
 #pragma unroll
-  for (int rr = 0; rr < 4; rr++) {
-    const int yl = warp * 4 + rr, y = y0 + yl;
-    if (x < w && y < h) {
-      const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
-      const int ym = reflect101(y - 1, h), yp = reflect101(y + 1, h);
-      auto smooth_row = [&](int yy) {  // row filter [s 2s s], fused chain like cv2's AVX2 row filter
-        const float a = img[yy * w + xm], b = img[yy * w + x], c = img[yy * w + xp];
-        return fmaf(s, c, fmaf(s2, b, s * a));
-      };
-      auto diff_row = [&](int yy) { return (float)((int)img[yy * w + xp] - (int)img[yy * w + xm]); };
-      const float dy = smooth_row(yp) - smooth_row(ym);
-      const float dx = fmaf(diff_row(ym) + diff_row(yp), s, diff_row(y) * s2);
-      tile[lane][yl * 3] = dx * dx;
-      tile[lane][yl * 3 + 1] = dx * dy;
-      tile[lane][yl * 3 + 2] = dy * dy;
+    for (int r = 0; r < 6; r++) {
+      const int yy = reflect101(min(y0 + warp * 4 - 1 + r, h), h);  // rows past y+1 of the last valid pixel are never used
+      const unsigned char* row = img + yy * w;
+      const int ia = row[xm], ib = row[x], ic = row[xp];
+      const float a = (float)ia, b = (float)ib, c = (float)ic;
+      sm[r] = fmaf(s, c, fmaf(s2, b, s * a));
+      df[r] = (float)(ic - ia);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+      const int yl = warp * 4 + rr;
+      if (y0 + yl < h) {
+        const float dy = sm[rr + 2] - sm[rr];
+        const float dx = fmaf(df[rr] + df[rr + 2], s, df[rr + 1] * s2);
+        tile[lane][yl * 3] = dx * dx;
+        tile[lane][yl * 3 + 1] = dx * dy;
+        tile[lane][yl * 3 + 2] = dy * dy;
+      }
     }
   }
   __syncthreads();
