@@ -19,15 +19,18 @@
 //    runs a two-stage shared-memory pipeline fed by the TMA engine: one cp.async.bulk.tensor per tile
 //    (3-D descriptor over [frame][row][3*col], zero fill outside the frame, L2 evict_last) completing on an
 //    mbarrier; the warp that finishes a tile last issues the load that reuses its stage.  Interior tiles
-//    (footprint >= 1 px inside the source) run a branch-free bilinear path, edge tiles (footprint leaves
-//    the frame but fits the box) add per-tap border substitution and the coverage test, everything else
-//    (partial tiles, bicubic, oversized footprints) takes the general path.  Output leaves as streaming
+//    (footprint >= 1 px inside the source) run a branch-free bilinear or bicubic path, edge tiles (footprint
+//    leaves the frame but fits the box) add cv2's border rules and the coverage test, everything else
+//    (partial tiles, oversized footprints) takes the general path.  Output leaves as streaming
 //    (evict-first) 16-byte stores through a per-warp shared-memory transpose.
 //
-//  * warp_fused_kernel (motion blur with up to 33 samples, unaligned sources, VSTAB_STAGE_GLOBAL): one CTA
-//    of 256 threads per 64x32 output tile; the bounding box of the four projected corners over all samples
-//    is staged by one cp.async.bulk per source row on one mbarrier.  Taps outside the staged box fall back
-//    to a global load, so staging is a pure optimisation and never changes results.
+//  * warp_fused_kernel<interp, blur> (motion blur with up to 33 samples, unaligned sources, VSTAB_STAGE_GLOBAL):
+//    one CTA of 256 threads per 64x32 output tile; the bounding box of the four projected corners over all
+//    samples is staged by one cp.async.bulk per source row on one mbarrier.  Taps outside the staged box fall
+//    back to a global load, so staging is a pure optimisation and never changes results.  The blur
+//    instantiation (2..33 samples) walks pixel-outer / sample-inner and keeps the 2x2 / 4x4 texel footprint in
+//    registers across shutter samples (blur_tile); VSTAB_STAGE_GLOBAL keeps every tile on general_tile_body,
+//    the reference those paths are tested against.
 //
 // In both, warp w owns rows w and w+8 of a 16-row group and lane l owns columns l and l+32 (stride-1
 // lanes => conflict-free shared-memory gathers with a 3-word stride).
