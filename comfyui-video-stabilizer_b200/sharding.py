@@ -135,6 +135,11 @@ def merge_sharded_meta(metas: List[dict]) -> dict:
     scalars from rank 0, per-frame / per-transition lists concatenated, motion_meta.frame_count restored."""
     import copy
 
+    def covers_frames(m):
+        lo, hi = m.get("shard", {}).get("meta_frame_range", (0, 1))
+        return hi > lo
+
+    metas = [m for m in metas if covers_frames(m)] or metas[:1]  # ranks without frames contribute nothing
     out = copy.deepcopy(metas[0])
     out.pop("shard", None)
     for m in metas[1:]:

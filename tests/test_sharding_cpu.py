@@ -145,6 +145,10 @@ def test_own_range_meta_merges_to_the_single_process_meta(monkeypatch):
         assert [e["index"] for e in m["estimated_motion"]["per_transition"]] == list(range(max(lo, 1) - 1, hi - 1))
         assert len(m["estimated_motion"]["path"]) == hi - lo and m["motion_meta"]["frame_count"] == hi - lo
     assert merge_sharded_meta(metas) == single
+    # a rank that owns no frames (more ranks than frames) has nothing to contribute and must not break the merge
+    empty = {k: v for k, v in metas[0].items() if k != "motion_meta"}
+    empty["shard"] = dict(metas[0]["shard"], meta_frame_range=[5, 5])
+    assert merge_sharded_meta(metas + [empty]) == single
     # a designated meta rank still builds the whole tree, the others only the scalar part
     whole = run(Shard(1, world, total, None, torch.device("cpu"), meta_rank=1))
     bare = run(Shard(0, world, total, None, torch.device("cpu"), meta_rank=1))
