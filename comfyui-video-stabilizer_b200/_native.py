@@ -81,6 +81,8 @@ def load_library() -> C.CDLL:
         if hasattr(lib, "vstab_dis_flow"):
             lib.vstab_dis_flow.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp]
             lib.vstab_dis_flow.restype = i32
+            lib.vstab_dis_flow_at.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]
+            lib.vstab_dis_flow_at.restype = i32
         if hasattr(lib, "vstab_gftt_lk"):
             lib.vstab_gftt_lk.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
             lib.vstab_gftt_lk.restype = i32
@@ -232,8 +234,10 @@ class Handle:
         return out
 
     # -- K3 + K4 ---------------------------------------------------------------------------------
-    def dis_flow(self, gray: torch.Tensor, *, want_flow: bool = False, grid_step: int = 8):
-        """gray [N,h,w] u8 -> (flow [N-1,h,w,2] | None, grid [N-1,gh,gw,2] | None)."""
+    def dis_flow(self, gray: torch.Tensor, *, want_flow: bool = False, grid_step: int = 8, first_pair: int = 0):
+        """gray [N,h,w] u8 -> (flow [N-1,h,w,2] | None, grid [N-1,gh,gw,2] | None).
+        first_pair: clip-wide index of the pair (gray[0], gray[1]); only pair 0 of a clip meets the backend
+        object in its configured state (include/vstab.h, vstab_dis_flow_at)."""
         _check_cuda(gray, torch.uint8, "gray")
         if not hasattr(self.lib, "vstab_dis_flow"):
             raise VstabNativeError("libvstab.so was built without vstab_dis_flow")
@@ -244,7 +248,8 @@ class Handle:
         if grid_step > 0:
             gh, gw = (h + grid_step - 1) // grid_step, (w + grid_step - 1) // grid_step
             grid = torch.empty((npairs, gh, gw, 2), dtype=torch.float32, device=gray.device)
-        self._check(self.lib.vstab_dis_flow(self._h, gray.data_ptr(), n, h, w, _ptr(flow), _ptr(grid), int(max(grid_step, 0)), _stream_ptr(gray.device)))
+        self._check(self.lib.vstab_dis_flow_at(self._h, gray.data_ptr(), n, h, w, int(first_pair), _ptr(flow), _ptr(grid),
+                                               int(max(grid_step, 0)), _stream_ptr(gray.device)))
         return flow, grid
 
     # -- K5 + K6 ---------------------------------------------------------------------------------

@@ -31,6 +31,7 @@ struct vstab_handle {
   size_t plan_bytes;
   vstab_area_cache_entry area_cache[VSTAB_AREA_CACHE];
   int n_area_cache;
+  int area_evict;  // next slot to recycle once the cache is full
 };
 
 extern char g_vstab_err[512];

@@ -685,28 +685,83 @@ size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 int coarsest_scale(int h, int w) {
   const int mx = w > h ? w : h, mn = w < h ? w : h;
   const int a = (int)(log(mx / (4.0 * kPatch)) / log(2.0) + 0.5);
-  const int b = (int)(log((double)(mn / kPatch)) / log(2.0));
+  const int b = mn / kPatch > 0 ? (int)(log((double)(mn / kPatch)) / log(2.0)) : -1;
   return a < b ? a : b;
 }
 
+// The pyramid levels cv2.DISOpticalFlow::calc works on, given the finest scale the backend object
+// currently holds.  calc() derives the coarsest scale from the frame size; when that falls below the
+// finest scale (with the reference's finest scale 2: frames under ~91 px on the long or 32 px on the
+// short side) autoSelectPatchSizeAndScales() replaces both -- coarsest = max(0, floor(log2(2 w / (5 *
+// patch)))) in float, finest = max(coarsest - 2, 0) -- and LEAVES the new finest scale on the object,
+// so the later pairs of a clip (same object, nodes/video_stabilizer_flow.py:312) see another state than
+// the first one and may use fewer levels (90x50: levels 2..0 for pair 0, 1..0 afterwards).
+struct Scales { int finest, coarsest; };
+
+bool select_scales(int h, int w, int finest_state, Scales* out) {
+  int c = coarsest_scale(h, w), f = finest_state;
+  if (c < 0) return false;  // cv2: "The input image must have either width or height >= 12"
+  if (c < f) {
+    c = (int)floorf(log2f((2.0f * (float)w) / (5.0f * (float)kPatch)));
+    if (c < 0) c = 0;
+    f = c - 2 > 0 ? c - 2 : 0;
+  }
+  out->finest = f;
+  out->coarsest = c;
+  return true;
+}
+
+const char* check_scales(int h, int w, Scales s) {
+  if (s.coarsest >= kMaxLevels) return "vstab_dis_flow: too many pyramid levels";
+  int lh = h >> s.finest, lw = w >> s.finest;
+  if ((lh - kPatch) / kStride + 1 > 8 * kStripes) return "vstab_dis_flow: more than 64 patch rows at the finest level (working image taller than 960 px, or a narrow portrait frame that cv2 computes at full resolution)";
+  for (int i = s.finest; i < s.coarsest; i++) { lh /= 2; lw /= 2; }
+  // cv2 itself reads outside the level (and usually crashes) when its coarsest level is smaller than a patch
+  if (lh < kPatch || lw < kPatch) return "vstab_dis_flow: the coarsest pyramid level is smaller than one 8x8 patch (cv2 crashes on this size)";
+  return nullptr;
+}
+
+int dis_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width, Scales sc,
+            float* flow_dev, float* grid_dev, int grid_step, cudaStream_t st);
+
 }  // namespace
 
-// Pairs are processed in chunks so the workspace stays bounded (about 6.5 MB per pair at 960x540).
-extern "C" int vstab_dis_flow(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width,
-                              float* flow_dev, float* grid_dev, int grid_step, void* stream) {
+extern "C" int vstab_dis_flow_at(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width,
+                                 int first_pair_index, float* flow_dev, float* grid_dev, int grid_step, void* stream) {
   if (!hnd) return vstab_fail(nullptr, VSTAB_ERR_INVALID, "vstab_dis_flow: null handle");
-  if (!gray_dev || n_frames < 0 || height <= 0 || width <= 0)
+  if (!gray_dev || n_frames < 0 || height <= 0 || width <= 0 || first_pair_index < 0)
     return vstab_fail(hnd, VSTAB_ERR_INVALID, "vstab_dis_flow: bad argument");
   if (grid_dev && grid_step <= 0) return vstab_fail(hnd, VSTAB_ERR_INVALID, "vstab_dis_flow: grid_step must be > 0");
   if (n_frames < 2) return VSTAB_OK;
-  const int coarsest = coarsest_scale(height, width);
-  if (coarsest < kFinest || coarsest >= kMaxLevels)
-    return vstab_fail(hnd, VSTAB_ERR_UNSUPPORTED,
-                      "vstab_dis_flow: frame too small for finest scale 2 (OpenCV's automatic scale selection is not implemented)");
-  if (((height >> kFinest) - kPatch) / kStride + 1 > 8 * kStripes)
-    return vstab_fail(hnd, VSTAB_ERR_UNSUPPORTED, "vstab_dis_flow: working image taller than 960 px is not supported");
+  Scales first, later;
+  if (!select_scales(height, width, kFinest, &first) || !select_scales(height, width, first.finest, &later))
+    return vstab_fail(hnd, VSTAB_ERR_UNSUPPORTED, "vstab_dis_flow: frame smaller than 12 px (cv2 raises on this size)");
+  if (const char* why = check_scales(height, width, first)) return vstab_fail(hnd, VSTAB_ERR_UNSUPPORTED, why);
+  if (const char* why = check_scales(height, width, later)) return vstab_fail(hnd, VSTAB_ERR_UNSUPPORTED, why);
   cudaStream_t st = (cudaStream_t)stream;
   VSTAB_ENTER(hnd);
+  const bool split = first_pair_index == 0 && (first.finest != later.finest || first.coarsest != later.coarsest);
+  if (!split) return dis_run(hnd, gray_dev, n_frames, height, width, first_pair_index == 0 ? first : later, flow_dev, grid_dev, grid_step, st);
+  // pair 0 is the call that found the backend object in its configured state
+  int rc = dis_run(hnd, gray_dev, 2, height, width, first, flow_dev, grid_dev, grid_step, st);
+  if (rc != VSTAB_OK || n_frames == 2) return rc;
+  const size_t npx = (size_t)height * width;
+  const size_t gpx = grid_dev ? (size_t)vstab_ceil_div(width, grid_step) * vstab_ceil_div(height, grid_step) : 0;
+  return dis_run(hnd, gray_dev + npx, n_frames - 1, height, width, later, flow_dev ? flow_dev + npx * 2 : nullptr,
+                 grid_dev ? grid_dev + gpx * 2 : nullptr, grid_step, st);
+}
+
+extern "C" int vstab_dis_flow(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width,
+                              float* flow_dev, float* grid_dev, int grid_step, void* stream) {
+  return vstab_dis_flow_at(hnd, gray_dev, n_frames, height, width, 0, flow_dev, grid_dev, grid_step, stream);
+}
+
+namespace {
+
+// Pairs are processed in chunks so the workspace stays bounded (about 6.5 MB per pair at 960x540).
+int dis_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width, Scales sc,
+            float* flow_dev, float* grid_dev, int grid_step, cudaStream_t st) {
+  const int finest = sc.finest, coarsest = sc.coarsest;
 
   const int kChunk = 256;  // pairs per pass
   for (int p0 = 0; p0 < n_frames - 1; p0 += kChunk) {
@@ -720,9 +775,9 @@ extern "C" int vstab_dis_flow(vstab_handle* hnd, const uint8_t* gray_dev, int n_
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
     size_t o_I[kMaxLevels], o_E[kMaxLevels], o_gx[kMaxLevels], o_gy[kMaxLevels], o_T[kMaxLevels], o_Ux[kMaxLevels],
         o_Uy[kMaxLevels], o_Sx[kMaxLevels], o_Sy[kMaxLevels];
-    int fraction = 1 << kFinest;
-    for (int i = kFinest; i <= coarsest; i++) {
-      if (i == kFinest) { L[i].h = height / fraction; L[i].w = width / fraction; }
+    int fraction = 1 << finest;
+    for (int i = finest; i <= coarsest; i++) {
+      if (i == finest) { L[i].h = height / fraction; L[i].w = width / fraction; }
       else { L[i].h = L[i - 1].h / 2; L[i].w = L[i - 1].w / 2; }
       L[i].ws = 1 + (L[i].w - kPatch) / kStride;
       L[i].hs = 1 + (L[i].h - kPatch) / kStride;
@@ -737,15 +792,15 @@ extern "C" int vstab_dis_flow(vstab_handle* hnd, const uint8_t* gray_dev, int n_
       o_Sx[i] = take(t * 4 * P);
       o_Sy[i] = take(t * 4 * P);
     }
-    const size_t nf = (size_t)L[kFinest].h * L[kFinest].w;
-    const size_t o_aux = take((size_t)L[kFinest].h * L[kFinest].ws * 5 * 4 * F);
+    const size_t nf = (size_t)L[finest].h * L[finest].w;
+    const size_t o_aux = take((size_t)L[finest].h * L[finest].ws * 5 * 4 * F);
     size_t o_vr[19];
     for (int k = 0; k < 19; k++) o_vr[k] = take(nf * 4 * P);
     void* wsp = nullptr;
     int rc = vstab_workspace(hnd, off, &wsp);
     if (rc != VSTAB_OK) return rc;
     unsigned char* base = (unsigned char*)wsp;
-    for (int i = kFinest; i <= coarsest; i++) {
+    for (int i = finest; i <= coarsest; i++) {
       L[i].I = base + o_I[i];
       L[i].Iext = base + o_E[i];
       L[i].Ix = (short*)(base + o_gx[i]);
@@ -764,8 +819,8 @@ extern "C" int vstab_dis_flow(vstab_handle* hnd, const uint8_t* gray_dev, int n_
     }
 
     // ---- per-frame pyramid, gradients, bordered copies, structure tensors ----
-    for (int i = kFinest; i <= coarsest; i++) {
-      if (i == kFinest) rc = vstab_area_u8(hnd, gray, F, height, width, L[i].I, L[i].h, L[i].w, st);
+    for (int i = finest; i <= coarsest; i++) {
+      if (i == finest) rc = vstab_area_u8(hnd, gray, F, height, width, L[i].I, L[i].h, L[i].w, st);
       else rc = vstab_area_u8(hnd, L[i - 1].I, F, L[i - 1].h, L[i - 1].w, L[i].I, L[i].h, L[i].w, st);
       if (rc != VSTAB_OK) return rc;
       dim3 ge(vstab_ceil_div(L[i].w + 2 * kBorder, 32), vstab_ceil_div(L[i].h + 2 * kBorder, 8), F);
@@ -784,7 +839,7 @@ extern "C" int vstab_dis_flow(vstab_handle* hnd, const uint8_t* gray_dev, int n_
       zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L[coarsest].Uy, n);
       hnd->launches += 2;
     }
-    for (int i = coarsest; i >= kFinest; i--) {
+    for (int i = coarsest; i >= finest; i--) {
       dim3 gp(vstab_ceil_div(L[i].w, 32), vstab_ceil_div(L[i].h, 8), P);
       {
         const size_t n1 = (size_t)(L[i].h + 2 * kBorder) * (L[i].w + 2 * kBorder), n0 = (size_t)L[i].h * L[i].w;
@@ -829,25 +884,27 @@ extern "C" int vstab_dis_flow(vstab_handle* hnd, const uint8_t* gray_dev, int n_
           hnd->launches++;
         }
       }
-      if (i > kFinest) {
+      if (i > finest) {
         dim3 gu(vstab_ceil_div(L[i - 1].w, 32), vstab_ceil_div(L[i - 1].h, 8), P);
         upsample_kernel<<<gu, 256, 0, st>>>(L[i], L[i - 1]);
         VSTAB_LAUNCH_CHECK(hnd, "upsample_kernel");
       }
     }
-    const float mul = (float)(1 << kFinest);
+    const float mul = (float)(1 << finest);
     if (flow_dev) {
       dim3 gf(vstab_ceil_div(width, 32), vstab_ceil_div(height, 8), P);
-      final_flow_kernel<<<gf, 256, 0, st>>>(L[kFinest], width, height, mul, flow_dev + (size_t)p0 * height * width * 2);
+      final_flow_kernel<<<gf, 256, 0, st>>>(L[finest], width, height, mul, flow_dev + (size_t)p0 * height * width * 2);
       VSTAB_LAUNCH_CHECK(hnd, "final_flow_kernel");
     }
     if (grid_dev) {
       const int gw = vstab_ceil_div(width, grid_step), gh = vstab_ceil_div(height, grid_step);
       dim3 gg(vstab_ceil_div(gw, 32), vstab_ceil_div(gh, 8), P);
-      final_grid_kernel<<<gg, 256, 0, st>>>(L[kFinest], width, height, mul, grid_step, gw, gh,
+      final_grid_kernel<<<gg, 256, 0, st>>>(L[finest], width, height, mul, grid_step, gw, gh,
                                             grid_dev + (size_t)p0 * gh * gw * 2);
       VSTAB_LAUNCH_CHECK(hnd, "final_grid_kernel");
     }
   }
   return VSTAB_OK;
 }
+
+}  // namespace

@@ -130,8 +130,17 @@ int vstab_area_tab_get(vstab_handle* h, int ssize, int dsize, vstab_area_tab* ou
       *out = h->area_cache[i].tab;
       return VSTAB_OK;
     }
-  if (h->n_area_cache >= VSTAB_AREA_CACHE)
-    return vstab_fail(h, VSTAB_ERR_NOMEM, "INTER_AREA table cache is full");
+  int slot = h->n_area_cache;
+  if (slot >= VSTAB_AREA_CACHE) {
+    // full (a long-lived process that has seen many frame sizes): recycle the slots round robin.
+    // Launches that still read the old table may be in flight on any stream, hence the drain.
+    slot = h->area_evict;
+    h->area_evict = (h->area_evict + 1) % VSTAB_AREA_CACHE;
+    VSTAB_CUDA(h, cudaDeviceSynchronize());
+    VSTAB_CUDA(h, cudaFree(h->area_cache[slot].dev));
+    h->area_cache[slot].dev = nullptr;
+    h->area_cache[slot].ssize = h->area_cache[slot].dsize = -1;
+  }
   std::vector<int> start, si;
   std::vector<float> alpha;
   const double inv_scale = (double)dsize / ssize;
@@ -147,7 +156,8 @@ int vstab_area_tab_get(vstab_handle* h, int ssize, int dsize, vstab_area_tab* ou
   VSTAB_CUDA(h, cudaMalloc(&dev, host.size()));
   VSTAB_CUDA(h, cudaMemcpy(dev, host.data(), host.size(), cudaMemcpyHostToDevice));
   unsigned char* d = (unsigned char*)dev;
-  vstab_area_cache_entry& e = h->area_cache[h->n_area_cache++];
+  vstab_area_cache_entry& e = h->area_cache[slot];
+  if (slot == h->n_area_cache) h->n_area_cache++;
   e.ssize = ssize;
   e.dsize = dsize;
   e.dev = dev;
@@ -186,6 +196,8 @@ int launch_area(vstab_handle* h, Src src, size_t src_frame_stride, int n, int sh
   int rc = vstab_area_tab_get(h, sw, dw, &xt);
   if (rc != VSTAB_OK) return rc;
   rc = vstab_area_tab_get(h, sh, dh, &yt);
+  if (rc != VSTAB_OK) return rc;
+  rc = vstab_area_tab_get(h, sw, dw, &xt);  // a full cache may just have recycled xt's slot for yt
   if (rc != VSTAB_OK) return rc;
   area_general_kernel<Src><<<grid, 256, 0, st>>>(src, src_frame_stride, xt, yt, dh, dw, dst);
   VSTAB_LAUNCH_CHECK(h, "area_general_kernel");

@@ -8,6 +8,7 @@ it pins (no cv2.optflow) and are not provided: this path has exactly one backend
 """
 from __future__ import annotations
 
+import functools
 from typing import Any, Callable, Optional, Tuple
 
 import numpy as np
@@ -27,14 +28,16 @@ def mode_mask_for(requested: str) -> int:
 
 
 def estimate_candidates(context: VideoContext, work_w: int, work_h: int, requested_mode: str,
-                        first_pair: int = 0, last_pair: Optional[int] = None) -> PairCandidates:
+                        first_pair: int = 0, last_pair: Optional[int] = None, clip_pair_offset: int = 0) -> PairCandidates:
     """K1/K2 -> K3 -> K4/K7-K9 for pairs [first_pair, last_pair) of the clip held by `context`
-    (pair i = frames i, i+1).  Everything stays on the device until the [P,3] result table."""
+    (pair i = frames i, i+1).  Everything stays on the device until the [P,3] result table.
+    clip_pair_offset: clip-wide index of the context's pair 0 (a frame-range shard holds a slice of the
+    clip; on small frames cv2's DIS treats the first pair of a clip differently, see vstab_dis_flow_at)."""
     h = _native.get_handle(context.device)
     n = len(context)
     last_pair = n - 1 if last_pair is None else last_pair
     gray = pipeline.gray_working(context, (work_w, work_h), first_pair, last_pair + 1)
-    _, grid = h.dis_flow(gray, want_flow=False, grid_step=SAMPLE_STEP)
+    _, grid = h.dis_flow(gray, want_flow=False, grid_step=SAMPLE_STEP, first_pair=clip_pair_offset + first_pair)
     raw = h.fit_grid(grid, SAMPLE_STEP, mode_mask_for(requested_mode))
     d = _native.decode_fit_results(raw)
     return PairCandidates(d["matrix"], d["residual"], d["n_inliers"], d["n_valid"], d["n_total"], d["ok"], min_points=12)
@@ -57,7 +60,7 @@ def stabilize_frames(
     shard=None,
 ) -> StabilizationResult:
     if shard is not None:
-        estimator = shard.wrap_estimator(estimate_candidates)
+        estimator = shard.wrap_estimator(functools.partial(estimate_candidates, clip_pair_offset=shard.pair_range[0]))
     else:
         estimator = estimate_candidates
     return _core(

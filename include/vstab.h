@@ -154,6 +154,21 @@ VSTAB_API int vstab_coverage_bbox(vstab_handle* h, const float* fwd_dev, int n, 
 VSTAB_API int vstab_dis_flow(vstab_handle* h, const uint8_t* gray_dev, int n_frames, int height, int width,
                    float* flow_dev, float* grid_dev, int grid_step, void* stream);
 
+/*
+ * The same for a run of pairs that does not start at the head of the clip (frame-range shards, streamed
+ * chunks): first_pair_index is the clip-wide index of the pair (gray_dev[0], gray_dev[1]).
+ * It matters on small frames only.  The reference keeps ONE backend object per clip
+ * (nodes/video_stabilizer_flow.py:312) and cv2's calc() rewrites that object's finest scale when the frame
+ * is too small for the configured one (longest side < ~91 px or shortest < 32 px: automatic scale selection,
+ * the flow is then computed down to full resolution).  Pair 0 therefore runs with the automatically selected
+ * levels and every later pair with the levels calc() derives from the rewritten state, which can be fewer
+ * (90x50: levels 2..0, then 1..0).  vstab_dis_flow(...) == vstab_dis_flow_at(..., first_pair_index = 0, ...).
+ * Sizes on which cv2 itself raises (< 12 px) or reads outside its coarsest level (that level smaller than one
+ * 8x8 patch, e.g. 100x30) return VSTAB_ERR_UNSUPPORTED.
+ */
+VSTAB_API int vstab_dis_flow_at(vstab_handle* h, const uint8_t* gray_dev, int n_frames, int height, int width,
+                                int first_pair_index, float* flow_dev, float* grid_dev, int grid_step, void* stream);
+
 /* ---- K5 + K6 : Shi-Tomasi corners + pyramidal Lucas-Kanade, batched over frame pairs ---- */
 
 /*

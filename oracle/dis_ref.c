@@ -624,7 +624,7 @@ void disref_variational_refinement(const float* I0f, const float* I1f, int h, in
 int disref_coarsest_scale(int h, int w, int psz) {
   int mx = w > h ? w : h, mn = w < h ? w : h;
   int a = (int)(log(mx / (4.0 * psz)) / log(2.0) + 0.5);
-  int b = (int)(log((double)(mn / psz)) / log(2.0));
+  int b = mn / psz > 0 ? (int)(log((double)(mn / psz)) / log(2.0)) : -1; /* log(0): cv2 ends up below zero too */
   return a < b ? a : b;
 }
 
@@ -651,11 +651,8 @@ static void run_level(dis_level* L, const dis_params* P) {
 
 /* flow: [h][w][2] float32.  stage_stop: 0 = full algorithm; k > 0 = return after processing
  * only the coarsest k levels' worth of work is not supported -- use dis_params knobs instead. */
-int disref_calc(const uint8_t* I0, const uint8_t* I1, int h, int w, const dis_params* P, float* flow) {
-  const int psz = P->patch_size;
-  int coarsest = disref_coarsest_scale(h, w, psz);
-  const int finest = P->finest_scale;
-  if (coarsest < 0 || coarsest < finest) return -1; /* autoSelectPatchSizeAndScales: not restated */
+static int calc_scales(const uint8_t* I0, const uint8_t* I1, int h, int w, const dis_params* P, int finest, int coarsest,
+                       float* flow) {
   dis_level* Ls = (dis_level*)calloc(coarsest + 1, sizeof(dis_level));
   int fraction = 1;
   for (int i = 0; i <= coarsest; i++) {
@@ -705,4 +702,44 @@ int disref_calc(const uint8_t* I0, const uint8_t* I1, int h, int w, const dis_pa
   }
   free(Ls);
   return 0;
+}
+
+/* Which pyramid levels calc() works on.  dis_flow.cpp computes the coarsest scale from the frame size; when it
+ * falls below the configured finest scale (frames under ~91 px on the long or 32 px on the short side with the
+ * reference's finest_scale 2) autoSelectPatchSizeAndScales() replaces both: coarsest = max(0, floor(log2(2 w /
+ * (5 * patch)))) in float, finest = max(coarsest - 2, 0), patch size 8.  Returns -1 where cv2 raises
+ * ("The input image must have either width or height >= 12"). */
+int disref_select_scales(int h, int w, const dis_params* P, int* finest, int* coarsest) {
+  int c = disref_coarsest_scale(h, w, P->patch_size);
+  int f = P->finest_scale;
+  if (c < 0) return -1;
+  if (c < f) {
+    c = (int)floorf(log2f((2.0f * (float)w) / (5.0f * 8.0f)));
+    if (c < 0) c = 0;
+    f = c - 2 > 0 ? c - 2 : 0;
+  }
+  *finest = f; *coarsest = c;
+  return 0;
+}
+
+/* cv2 reads outside its coarsest level (and usually crashes) when that level is smaller than one patch. */
+static int levels_fit(int h, int w, int psz, int finest, int coarsest) {
+  int lh = h >> finest, lw = w >> finest;
+  for (int i = finest; i < coarsest; i++) { lh /= 2; lw /= 2; }
+  return lh >= psz && lw >= psz;
+}
+
+/* Explicit levels (probing aid for the selection rule above). */
+int disref_calc_scales(const uint8_t* I0, const uint8_t* I1, int h, int w, const dis_params* P, int finest, int coarsest,
+                       float* flow) {
+  if (finest < 0 || coarsest < finest) return -1;
+  if (!levels_fit(h, w, P->patch_size, finest, coarsest)) return -2;
+  return calc_scales(I0, I1, h, w, P, finest, coarsest, flow);
+}
+
+int disref_calc(const uint8_t* I0, const uint8_t* I1, int h, int w, const dis_params* P, float* flow) {
+  int finest, coarsest;
+  if (disref_select_scales(h, w, P, &finest, &coarsest)) return -1;
+  if (!levels_fit(h, w, P->patch_size, finest, coarsest)) return -2;
+  return calc_scales(I0, I1, h, w, P, finest, coarsest, flow);
 }

@@ -46,17 +46,43 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def select_scales(h: int, w: int, finest_state: int = 2):
+    """(finest, coarsest) pyramid levels cv2's calc() works on for an h x w frame when the backend object
+    holds `finest_state` (autoSelectPatchSizeAndScales for small frames); None where cv2 raises."""
+    fi, co = C.c_int(), C.c_int()
+    rc = lib().disref_select_scales(C.c_int(h), C.c_int(w), C.byref(default_params(finest_scale=finest_state)), C.byref(fi), C.byref(co))
+    return None if rc else (fi.value, co.value)
+
+
 def calc(i0: np.ndarray, i1: np.ndarray, params: DisParams | None = None) -> np.ndarray:
-    """uint8 [h,w] pair -> float32 [h,w,2] flow, the reference's DIS configuration by default."""
+    """uint8 [h,w] pair -> float32 [h,w,2] flow, the reference's DIS configuration by default: what the
+    FIRST calc() of a freshly configured backend object returns (see Backend for the later ones)."""
     i0 = np.ascontiguousarray(i0, dtype=np.uint8)
     i1 = np.ascontiguousarray(i1, dtype=np.uint8)
     h, w = i0.shape
     params = params or default_params()
     flow = np.zeros((h, w, 2), np.float32)
     rc = lib().disref_calc(_p(i0), _p(i1), C.c_int(h), C.c_int(w), C.byref(params), _p(flow))
+    if rc == -1:
+        raise ValueError("cv2 raises on this size: the input image must have either width or height >= 12")
     if rc != 0:
-        raise ValueError("image too small for the configured finest scale (auto scale selection not restated)")
+        raise ValueError("coarsest pyramid level smaller than one patch: cv2 reads out of bounds on this size")
     return flow
+
+
+class Backend:
+    """The stateful object of nodes/video_stabilizer_flow.py:76-87 / :312: one per clip, calc() per pair.
+    On frames too small for finest scale 2 cv2 rewrites the object's finest scale during the first calc(),
+    so later pairs may run on other levels than the first one (90x50: 2..0, then 1..0)."""
+
+    def __init__(self, **over):
+        self.params = default_params(**over)
+
+    def calc(self, i0: np.ndarray, i1: np.ndarray) -> np.ndarray:
+        flow = calc(i0, i1, self.params)
+        sel = select_scales(i0.shape[0], i0.shape[1], self.params.finest_scale)
+        self.params.finest_scale = sel[0]
+        return flow
 
 
 def resize_area_u8(src: np.ndarray, dsize) -> np.ndarray:

@@ -56,11 +56,12 @@ def gen_motion_apply(ref):
         print("apply", name, res.frames.shape, res.meta["motion_apply"])
 
 
-def gen_estimators(ref, only_crop=False):
+def gen_estimators(ref, only_crop=False, only_small=False):
     """Flow / Classic stabilizers: per-pair matrices, paths and final matrices (+ small outputs)."""
     import cv2
 
-    for case in cases.STABILIZER_CASES + cases.CROP_CASES:
+    todo = cases.SMALL_STABILIZER_CASES if only_small else cases.STABILIZER_CASES + cases.CROP_CASES
+    for case in todo:
         if only_crop and case not in cases.CROP_CASES:
             continue
         frames = cases.make_frames(case)
@@ -103,9 +104,10 @@ def main():
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_import.load_reference()
-    gens = {"apply": gen_motion_apply, "stab": gen_estimators, "dis": gen_dis, "crop": lambda r: gen_estimators(r, True)}
+    gens = {"apply": gen_motion_apply, "stab": gen_estimators, "dis": gen_dis, "crop": lambda r: gen_estimators(r, True),
+            "small": lambda r: gen_estimators(r, only_small=True)}
     for key, fn in gens.items():
-        if args.only == key or (args.only is None and key != "crop"):
+        if args.only == key or (args.only is None and key not in ("crop", "small")):
             fn(ref)
 
 

@@ -81,6 +81,24 @@ STABILIZER_CASES = [
          store="summary", patches=[(3, 300, 600, 48, 64)]),
 ]
 
+# Frame sizes of the reference's own script-level checks (scripts/compare_refactor_behavior.py:220: 73x45,
+# scripts/check_crop_aspect_ratio.py:165: 121x73) and one size where cv2's DIS object changes state after the
+# first pair (90x50).  Below ~91 px cv2 selects the pyramid levels itself and computes down to full resolution.
+SMALL_STABILIZER_CASES = [
+    dict(name="flow_sim_pad_73x45", node="flow", n=8, w=73, h=45, seed=71, frames="texture", framing="crop_and_pad",
+         mode="similarity", camera_lock=False, strength=0.7, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=16.0,
+         store="full", patches=[(4, 8, 8, 24, 32)]),
+    dict(name="flow_sim_pad_90x50", node="flow", n=6, w=90, h=50, seed=72, frames="texture", amount=2.0, framing="crop_and_pad",
+         mode="similarity", camera_lock=False, strength=1.0, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=24.0,
+         store="full", patches=[(3, 8, 8, 24, 32)]),
+    dict(name="flow_trans_crop_121x73", node="flow", n=6, w=121, h=73, seed=73, frames="texture", framing="crop",
+         mode="translation", camera_lock=False, strength=1.0, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=24.0,
+         store="full", patches=[(3, 8, 8, 24, 32)]),
+    dict(name="classic_sim_pad_73x45", node="classic", n=8, w=73, h=45, seed=74, frames="texture", framing="crop_and_pad",
+         mode="similarity", camera_lock=False, strength=0.7, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=16.0,
+         store="full", patches=[(4, 8, 8, 24, 32)]),
+]
+
 
 CROP_CASES = [
     dict(name="flow_sim_crop06_480p", node="flow", n=8, w=832, h=480, seed=51, frames="texture", framing="crop",

@@ -59,11 +59,3 @@ def test_dis_white_noise(handle):
     want = dis_ref.calc(i0, i1)
     assert float(np.abs(flow[0] - want).max()) <= 1e-3
     assert np.array_equal(flow[0], want)
-
-
-def test_dis_rejects_tiny_frames(handle):
-    from vstab_b200._native import VstabNativeError
-
-    g = torch.zeros((2, 45, 73), dtype=torch.uint8, device="cuda")
-    with pytest.raises(VstabNativeError):
-        handle.dis_flow(g)

@@ -75,3 +75,31 @@ def test_flow_upsampling_paths(shape):
     assert np.array_equal(cv2.resize(a, (dw, dh)), dis_ref.resize_linear_f32(a, (dw, dh), mode=2))
     a2 = rng.normal(0, 3, (sh, sw, 2)).astype(np.float32)
     assert np.array_equal(cv2.resize(a2, (dw * 2, dh * 2)), dis_ref.resize_linear_f32(a2, (dw * 2, dh * 2), mode=0))
+
+
+SMALL_SIZES = [(73, 45), (121, 73), (90, 50), (40, 24), (30, 100), (64, 48), (20, 9), (12, 12), (89, 33)]
+
+
+@pytest.mark.parametrize("size", SMALL_SIZES, ids=[f"{w}x{h}" for w, h in SMALL_SIZES])
+def test_dis_oracle_small_frames_follow_the_backend_state(size):
+    """Frames too small for finest scale 2 (the reference's own checks run Flow on 73x45 and 121x73:
+    scripts/compare_refactor_behavior.py:220, scripts/check_crop_aspect_ratio.py:165): cv2 selects the levels
+    itself, computes down to full resolution and leaves the new finest scale on the object, so the second
+    pair of a clip can run on fewer levels than the first (90x50, 40x24, 30x100).  One object, three calls."""
+    cv2 = pytest.importorskip("cv2")
+    w, h = size
+    prev, curr = cases.make_gray_pair(dict(w=w, h=h, seed=w + h, amount=2.0))
+    ref, mine = _cv2_dis(cv2), dis_ref.Backend()
+    for a, b in ((prev, curr), (curr, prev), (prev, curr)):
+        assert np.array_equal(ref.calc(a, b, None), mine.calc(a, b))
+    assert ref.getFinestScale() == mine.params.finest_scale
+
+
+def test_dis_oracle_scale_selection_table():
+    assert dis_ref.select_scales(540, 960) == (2, 5) and dis_ref.select_scales(73, 121) == (2, 2)
+    assert dis_ref.select_scales(45, 73) == (0, 1) and dis_ref.select_scales(45, 73, 0) == (0, 1)
+    assert dis_ref.select_scales(50, 90) == (0, 2) and dis_ref.select_scales(50, 90, 0) == (0, 1)
+    assert dis_ref.select_scales(100, 30) == (0, 0) and dis_ref.select_scales(100, 30, 0) == (0, 1)
+    assert dis_ref.select_scales(10, 10) is None and dis_ref.select_scales(7, 200) is None
+    with pytest.raises(ValueError, match="smaller than one patch"):  # 100x30 -> levels 2..0, level 2 is 25x7
+        dis_ref.calc(np.zeros((30, 100), np.uint8), np.zeros((30, 100), np.uint8))
