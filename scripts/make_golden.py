@@ -98,6 +98,45 @@ def gen_dis(ref):
         print("dis", case["name"], flow.shape, flow.reshape(-1, 2).mean(axis=0))
 
 
+def gen_ab(ref):
+    """The reference's A/B gate (scripts/compare_refactor_behavior.py:220-243, :352-366): its synthetic
+    73x45 clip through both stabilizers in its three scenarios; the input frames are stored too."""
+    import cv2
+
+    width, height, count = 73, 45, 8
+    yy, xx = np.mgrid[0:height, 0:width]
+    base = np.zeros((height, width, 3), dtype=np.float32)
+    base[..., 0] = xx / max(width - 1, 1)
+    base[..., 1] = yy / max(height - 1, 1)
+    base[..., 2] = (((xx // 5) + (yy // 7)) % 2).astype(np.float32)
+    cv2.rectangle(base, (9, 8), (31, 24), (1.0, 0.2, 0.1), -1)
+    cv2.circle(base, (width - 20, height - 14), 7, (0.1, 1.0, 0.3), -1)
+    frames = []
+    center = (width * 0.5, height * 0.5)
+    for idx in range(count):
+        matrix = cv2.getRotationMatrix2D(center, idx * 0.6, 1.0 + idx * 0.002)
+        matrix[0, 2] += idx * 0.7
+        matrix[1, 2] += idx * 0.35
+        frames.append(cv2.warpAffine(base, matrix, (width, height), flags=cv2.INTER_LINEAR,
+                                     borderMode=cv2.BORDER_REFLECT).astype(np.float32))
+    payload = {"input": np.stack(frames)}
+    metas = {}
+    a = cases.AB_ARGS
+    for node in ("classic", "flow"):
+        mod = ref.video_stabilizer_flow if node == "flow" else ref.video_stabilizer_classic
+        for name, framing, mode, keep_fov in cases.AB_SCENARIOS:
+            ctx = ref.stabilizer_utils._normalize_video_input(frames)
+            res = mod._stabilize_frames(ctx, framing, mode, a["camera_lock"], a["strength"], a["smooth"], keep_fov,
+                                        a["padding_rgb"], a["fps"])
+            payload[f"{node}.{name}.frames"] = np.asarray(res.frames, dtype=np.float32)
+            payload[f"{node}.{name}.masks"] = np.asarray(res.masks, dtype=np.float32)
+            metas[f"{node}.{name}"] = res.meta
+            print("ab", node, name, payload[f"{node}.{name}.frames"].shape, res.meta.get("transform_mode_applied"))
+    np.savez_compressed(os.path.join(GOLDEN, "ab_73x45.npz"), **payload)
+    with open(os.path.join(GOLDEN, "ab_73x45_meta.json"), "w") as fh:
+        json.dump(metas, fh)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -105,9 +144,9 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_import.load_reference()
     gens = {"apply": gen_motion_apply, "stab": gen_estimators, "dis": gen_dis, "crop": lambda r: gen_estimators(r, True),
-            "small": lambda r: gen_estimators(r, only_small=True)}
+            "small": lambda r: gen_estimators(r, only_small=True), "ab": gen_ab}
     for key, fn in gens.items():
-        if args.only == key or (args.only is None and key not in ("crop", "small")):
+        if args.only == key or (args.only is None and key not in ("crop", "small", "ab")):
             fn(ref)
 
 

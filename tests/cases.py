@@ -136,3 +136,13 @@ DIS_CASES = [
     dict(name="pair_832x480", w=832, h=480, seed=32, store="grid"),
     dict(name="pair_320x180", w=320, h=180, seed=33, store="full"),
 ]
+
+
+# scripts/compare_refactor_behavior.py:352-366 compare_stabilizers: the reference's own A/B gate between two
+# revisions of itself ("base" = the unmodified reference, "head" = here the CUDA path), 8 frames of 73x45.
+AB_SCENARIOS = [
+    ("crop_and_pad_similarity", "crop_and_pad", "similarity", 0.6),
+    ("expand_translation", "expand", "translation", 0.6),
+    ("crop_keep_fov_bypass", "crop", "translation", 1.0),
+]
+AB_ARGS = dict(camera_lock=False, strength=0.7, smooth=0.5, padding_rgb=PAD, fps=24.0)

@@ -113,3 +113,102 @@ def test_input_adapters_agree():
     assert gray.shape[-1] == 3 and np.array_equal(gray[..., 0], gray[..., 2])
     with pytest.raises(ValueError, match="empty"):
         pipeline.normalize_video_input([])
+
+
+def _check_script_frames(width=121, height=73, count=6):
+    """scripts/check_crop_aspect_ratio.py:58-79 make_synthetic_frames (cv2 only draws the test card)."""
+    cv2 = pytest.importorskip("cv2")
+    yy, xx = np.mgrid[0:height, 0:width]
+    base = np.zeros((height, width, 3), dtype=np.float32)
+    base[..., 0] = xx / max(width - 1, 1)
+    base[..., 1] = yy / max(height - 1, 1)
+    base[..., 2] = ((xx // 9 + yy // 7) % 2).astype(np.float32)
+    cv2.rectangle(base, (12, 10), (44, 34), (1.0, 0.2, 0.1), -1)
+    cv2.circle(base, (width - 22, height - 16), 9, (0.1, 0.9, 0.3), -1)
+    out = []
+    for index in range(count):
+        matrix = np.array([[1.0, 0.0, index * 1.1], [0.0, 1.0, -index * 0.35]], dtype=np.float32)
+        out.append(cv2.warpAffine(base, matrix, (width, height), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT))
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("node", ["classic", "flow"])
+@pytest.mark.parametrize("mode", ["translation", "similarity"])
+@pytest.mark.parametrize("keep_fov", [0.0, 0.6])
+def test_check_crop_aspect_ratio_grid(node, mode, keep_fov):
+    """scripts/check_crop_aspect_ratio.py:82-120 + :236-241, the reference's own grid on its own 121x73 frames:
+    crop never pads, the crop keeps the frame's aspect ratio, the applied scale is uniform."""
+    from vstab_b200 import classic, flow
+
+    frames = _check_script_frames()
+    driver = flow if node == "flow" else classic
+    res = driver.stabilize_frames(_ctx(frames), "crop", mode, False, 1.0, 0.5, keep_fov, (127, 127, 127), 24.0)
+    assert len(res.frames) == len(frames) and len(res.masks) == len(frames)
+    for mask in res.masks:
+        assert tuple(mask.shape) == (73, 121, 1) and float(np.max(mask)) == 0.0
+    cw, ch = res.meta["framing"]["crop_size"]
+    assert abs(cw / ch - 121 / 73) <= 1e-6
+    for entry in res.meta["stabilization_warp"]["per_frame"]:
+        m = np.asarray(entry["applied_matrix"], dtype=np.float64)
+        assert abs(m[0, 0] - m[1, 1]) <= 1e-6
+
+
+@pytest.mark.parametrize("node", ["classic", "flow"])
+@pytest.mark.parametrize("framing", ["expand", "crop_and_pad"])
+def test_check_script_replay(node, framing):
+    """scripts/check_crop_aspect_ratio.py:123-161 + :242-243 on the same frames: Motion Apply replays the
+    stabilizer's meta to the stabilizer's own frames and masks, bit for bit."""
+    from vstab_b200 import classic, flow
+    from vstab_b200.motion_apply import apply_motion
+
+    frames = _check_script_frames()
+    driver = flow if node == "flow" else classic
+    direct = driver.stabilize_frames(_ctx(frames), framing, "similarity", False, 1.0, 0.5, 0.6, (127, 127, 127), 24.0)
+    replay = apply_motion(_ctx(frames), direct.meta, (127, 127, 127), framing_mode="crop_and_pad", interpolation="bilinear")
+    assert replay.frames.shape == direct.frames.shape
+    assert np.array_equal(replay.frames, direct.frames) and np.array_equal(replay.masks, direct.masks)
+
+
+@pytest.mark.parametrize("node", ["classic", "flow"])
+@pytest.mark.parametrize("scenario", cases.AB_SCENARIOS, ids=[s[0] for s in cases.AB_SCENARIOS])
+def test_reference_ab_gate(node, scenario):
+    """scripts/compare_refactor_behavior.py:352-377, the reference's own gate between two revisions of itself, with
+    the unmodified reference as "base" (tests/golden/ab_73x45*, scripts/make_golden.py --only ab) and the CUDA path
+    as "head", on the script's own 8 x 73x45 clip.  The script's tolerance is 2e-5 on pixels, masks and meta.
+    Flow meets it (DIS is bit-exact; what remains is float32 rounding of the fitted matrices, which can move a
+    pixel across one of cv2's 1/32-px quantisation steps: at most 0.1 % of the pixels may differ, by one step on
+    an edge).  Classic tracks features to ~1e-3 px of cv2 (float accumulation order inside LK), so its matrices get
+    the north_star tolerance and its pixels a mean-error bound."""
+    import json
+    import os
+
+    from tests import parity
+    from tests.conftest import GOLDEN_DIR
+    from vstab_b200 import classic, flow
+
+    name, framing, mode, keep_fov = scenario
+    gold = np.load(os.path.join(GOLDEN_DIR, "ab_73x45.npz"))
+    with open(os.path.join(GOLDEN_DIR, "ab_73x45_meta.json")) as fh:
+        gmeta = json.load(fh)[f"{node}.{name}"]
+    a = cases.AB_ARGS
+    driver = flow if node == "flow" else classic
+    res = driver.stabilize_frames(_ctx(gold["input"]), framing, mode, a["camera_lock"], a["strength"], a["smooth"], keep_fov,
+                                  a["padding_rgb"], a["fps"])
+    want_f, want_m = gold[f"{node}.{name}.frames"], gold[f"{node}.{name}.masks"]
+    got_f, got_m = np.asarray(res.frames), np.asarray(res.masks)
+    assert got_f.shape == want_f.shape and got_m.shape == want_m.shape
+    assert 0.0 <= float(got_m.min()) <= float(got_m.max()) <= 1.0
+    meta = json.loads(json.dumps(res.meta))
+    assert meta["transform_mode_applied"] == gmeta["transform_mode_applied"]
+    err = np.abs(got_f - want_f)
+    if node == "flow" or name == "crop_keep_fov_bypass":
+        parity.compare_nested(gmeta, meta, "meta", atol=2e-5, rtol=2e-5)
+        assert float((err > 2e-5).mean()) <= 1e-3 and float(err.max()) <= 0.04, (float((err > 2e-5).mean()), float(err.max()))
+        assert float((got_m != want_m).mean()) <= 1e-3
+    else:
+        for mine, ref in zip(meta["estimated_motion"]["per_transition"], gmeta["estimated_motion"]["per_transition"]):
+            assert mine["mode"] == ref["mode"]
+            parity.assert_transform_close(mine["matrix"], ref["matrix"], f"pair {ref['index']}")
+        parity.compare_nested(gmeta, meta, "meta", atol=5e-3, rtol=5e-3)
+        assert float(err.mean()) <= 1e-3 and float(err.max()) <= 0.05, (float(err.mean()), float(err.max()))
+        assert float((got_m != want_m).mean()) <= 5e-3
