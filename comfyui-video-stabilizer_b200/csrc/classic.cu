@@ -52,14 +52,18 @@ __global__ void __launch_bounds__(256) gftt_cov_kernel(const unsigned char* __re
   // filters evaluated once, and the four pixels combine them -- the same operations per pixel as before.
   if (x < w && y0 + warp * 4 < h) {
     const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
-    float sm[6], df[6];  // row filter [s 2s s] (fused chain like cv2's AVX2 row filter) and the central difference, rows y-1 .. y+4
+    // row filter [s 2s s] and the central difference, rows y-1 .. y+4.  cv2's row filter fuses the chain in its
+    // 32-pixel vector blocks; the last w % 32 pixels of a row go through its scalar loop, which does not
+    // (found black-box: the eigenvalue map differed from the wheel by an ulp right of column (w / 32) * 32).
+    const bool scalar_tail = x0 >= (w / 32) * 32;  // block-uniform: tiles are 32 columns wide
+    float sm[6], df[6];
 #pragma unroll
     for (int r = 0; r < 6; r++) {
       const int yy = reflect101(min(y0 + warp * 4 - 1 + r, h), h);  // rows past y+1 of the last valid pixel are never used
       const unsigned char* row = img + yy * w;
       const int ia = row[xm], ib = row[x], ic = row[xp];
       const float a = (float)ia, b = (float)ib, c = (float)ic;
-      sm[r] = fmaf(s, c, fmaf(s2, b, s * a));
+      sm[r] = scalar_tail ? (s * a + s2 * b) + s * c : fmaf(s, c, fmaf(s2, b, s * a));
       df[r] = (float)(ic - ia);
     }
 #pragma unroll

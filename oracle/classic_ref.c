@@ -10,7 +10,8 @@
  * The arithmetic lives in opencv-python-headless (4.13.0.92 here); this restates the published
  * algorithms (Shi-Tomasi minimum-eigenvalue corners; Bouguet's pyramidal Lucas-Kanade as in
  * modules/video/src/lkpyramid.cpp) with the operation order identified black-box against the wheel:
- *   Sobel 3x3 scaled by 1/(4*21*255):  Dx = fma(r0 + r2, s, r1 * 2s),  rows of Dy = fma(s,c,fma(2s,b,s*a))
+ *   Sobel 3x3 scaled by 1/(4*21*255):  Dx = fma(r0 + r2, s, r1 * 2s),  rows of Dy = fma(s,c,fma(2s,b,s*a)) in the
+ *   32-pixel blocks of a row and (s*a + 2s*b) + s*c, unfused, in the last w % 32 pixels
  *   unnormalised 21x21 box filter with DOUBLE running sums (row sums, then column sums)
  *   minEig = (a/2 + c/2) - sqrt((a/2 - c/2)^2 + b^2), threshold-to-zero at 0.01*max, 3x3 local maxima,
  *   descending sort (ties: higher address first), greedy 7-px minimum distance on a 7-px grid
@@ -38,11 +39,13 @@ void classicref_min_eigen(const uint8_t* img, int h, int w, int block, float* ei
   float* dx = (float*)malloc(n * sizeof(float));
   float* dy = (float*)malloc(n * sizeof(float));
   float* rowsm = (float*)malloc(n * sizeof(float));
-  /* Dy: row filter [s 2s s] (fused chain), then rows y+1 minus y-1 */
+  /* Dy: row filter [s 2s s], then rows y+1 minus y-1.  The wheel's row filter works on blocks of 32 pixels with a
+   * fused chain; the last w % 32 pixels of a row go through its scalar loop, which does not fuse. */
+  const int vec_end = (w / 32) * 32;
   for (int y = 0; y < h; y++)
     for (int x = 0; x < w; x++) {
       float a = img[y * w + reflect101(x - 1, w)], b = img[y * w + x], c = img[y * w + reflect101(x + 1, w)];
-      rowsm[y * w + x] = fmaf(s, c, fmaf(s2, b, s * a));
+      rowsm[y * w + x] = x < vec_end ? fmaf(s, c, fmaf(s2, b, s * a)) : (s * a + s2 * b) + s * c;
     }
   for (int y = 0; y < h; y++)
     for (int x = 0; x < w; x++)

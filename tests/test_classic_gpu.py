@@ -13,7 +13,7 @@ from tests.conftest import GOLDEN_DIR
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("size", [(960, 540), (832, 480), (640, 360)])
+@pytest.mark.parametrize("size", [(960, 540), (832, 480), (640, 360), (540, 960), (333, 187), (121, 73)])
 def test_gftt_lk_matches_oracle(handle, size):
     w, h = size
     import synth
