@@ -154,3 +154,44 @@ def test_own_range_meta_merges_to_the_single_process_meta(monkeypatch):
     bare = run(Shard(0, world, total, None, torch.device("cpu"), meta_rank=1))
     assert whole == single and bare["estimated_motion"]["per_transition"] == [] and "motion_meta" not in bare
     assert bare["padding_fraction_max"] == single["padding_fraction_max"]
+
+
+def test_shards_tell_dis_where_their_pairs_sit_in_the_clip(monkeypatch):
+    """On small frames cv2's DIS treats the first pair of a CLIP differently (vstab_dis_flow_at): a frame-range shard
+    must pass the clip-wide index of its first pair, a single-process run passes 0."""
+    from vstab_b200 import _native, flow, pipeline
+    from vstab_b200.sharding import FrameShard
+    from vstab_b200.stabilizer_core import PairCandidates
+
+    seen = []
+
+    class FakeHandle:
+        def dis_flow(self, gray, *, want_flow, grid_step, first_pair=0):
+            seen.append(first_pair)
+            return None, "grid"
+
+        def fit_grid(self, grid, step, mask):
+            return "raw"
+
+    z = np.zeros
+    monkeypatch.setattr(_native, "get_handle", lambda device: FakeHandle())
+    monkeypatch.setattr(_native, "decode_fit_results", lambda raw: dict(matrix=z((0, 3, 3, 3)), residual=z((0, 3)), n_inliers=z((0, 3), int),
+                                                                       n_valid=z((0, 3), int), n_total=z((0, 3), int), ok=z((0, 3), int)))
+    monkeypatch.setattr(pipeline, "gray_working", lambda context, size, a, b: "gray")
+
+    class Ctx:
+        device = torch.device("cpu")
+
+        def __len__(self):
+            return 9
+
+    captured = {}
+    monkeypatch.setattr(flow, "_core", lambda *a, estimator, **k: captured.setdefault("est", estimator))
+    args = ("crop_and_pad", "similarity", False, 0.7, 0.5, 0.6, (127, 127, 127), 16.0)
+    for shard, want in ((None, 0), (FrameShard(0, 3, 24), 0), (FrameShard(1, 3, 24), 7), (FrameShard(2, 3, 24), 15)):
+        captured.clear()
+        flow.stabilize_frames(Ctx(), *args, shard=shard)
+        assert isinstance(captured["est"](Ctx(), 73, 45, "similarity"), PairCandidates)
+        assert seen[-1] == want, (shard, seen[-1])
+        if shard is not None:
+            assert shard.pair_range[0] == want
