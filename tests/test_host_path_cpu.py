@@ -1,0 +1,131 @@
+"""The product's host path (stabilizer_core: candidate table -> sticky ladder -> rescale -> params -> cumsum ->
+box smoothing -> framing -> meta) end to end on the CPU, with the oracle standing in for the two GPU stages
+(estimation: dis_ref + fit_np; resampler: resample_np), against outputs of the UNMODIFIED reference
+(tests/golden, scripts/make_golden.py).  What the `-m gpu` node tests check with the CUDA kernels in place,
+checked here without a GPU: if this passes and the kernel parity tests pass, the nodes are the reference's."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dis_ref, fit_np, gray_np, resample_np
+from tests import cases, parity
+from tests.conftest import GOLDEN_DIR
+
+
+class _Clip:
+    """What stabilizer_core needs from a VideoContext."""
+
+    def __init__(self, frames, fps=None):
+        self.frames, self.fps = frames, fps
+        self.height, self.width = frames.shape[1:3]
+        self.device = None
+
+    def __len__(self):
+        return len(self.frames)
+
+
+def _oracle_estimator(context, work_w, work_h, requested):
+    """flow.estimate_candidates with the oracle in place of K1-K4 / K7-K9: all candidate models of every pair."""
+    from vstab_b200.stabilizer_core import PairCandidates
+
+    work = None if (work_w, work_h) == (context.width, context.height) else (work_w, work_h)
+    gray = [gray_np.gray_for_estimation(f, work) for f in context.frames]
+    backend = dis_ref.Backend()  # one object per clip, like the reference (flow.py:312)
+    P = len(gray) - 1
+    m = np.tile(np.eye(3), (P, 3, 1, 1))
+    res, inl, valid, total, ok = (np.zeros((P, 3)) for _ in range(5))
+    for p in range(P):
+        prev, curr, n_total = fit_np.grid_correspondences(backend.calc(gray[p], gray[p + 1]))
+        valid[p], total[p] = len(prev), n_total
+        t = fit_np.median_shift(prev, curr)
+        m[p, 0, :2, 2] = t
+        res[p, 0] = float(np.abs((prev + t) - curr).mean())
+        inl[p, 0], ok[p, 0] = len(prev), 1
+        if requested in ("similarity", "perspective") and len(prev) >= 3:
+            A, mask = fit_np.estimate_affine_partial_2d(prev, curr)
+            if A is not None:
+                m[p, 1, :2] = A
+                res[p, 1] = float(np.abs((prev @ A[:, :2].T + A[:, 2]) - curr).mean())
+                inl[p, 1], ok[p, 1] = int(mask.sum()), 1
+        if requested == "perspective" and len(prev) >= 4:
+            H, mask = fit_np.find_homography(prev, curr)
+            if H is not None:
+                m[p, 2] = H
+                res[p, 2] = float(np.abs((prev @ H[:2, :2].T + H[:2, 2]) - curr).mean())
+                inl[p, 2], ok[p, 2] = int(mask.sum()), 1
+    return PairCandidates(m, res, inl.astype(int), valid.astype(int), total.astype(int), ok.astype(int), min_points=12)
+
+
+def _oracle_warp(context, fwd, out_size, interpolation, border, **kw):
+    """pipeline.fused_warp(defer=True) with the numpy resampler: frames, masks, padded-pixel counts."""
+    def run():
+        frames, masks = [], []
+        for f, m in zip(context.frames, np.asarray(fwd, np.float32).reshape(-1, 3, 3)):
+            frames.append(resample_np.warp_np(f, m, out_size, interpolation, border))
+            masks.append(resample_np.mask_np(m, (context.width, context.height), out_size))
+        masks = np.stack(masks)
+        return np.stack(frames), masks, (masks > 0).reshape(len(masks), -1).sum(axis=1)
+
+    return run
+
+
+def _run(monkeypatch, frames, framing, mode, camera_lock, strength, smooth, keep_fov, padding_rgb, fps):
+    from vstab_b200 import stabilizer_core as core
+
+    monkeypatch.setattr(core, "fused_warp", _oracle_warp)
+    return core.stabilize_frames(_Clip(frames), framing, mode, camera_lock, strength, smooth, keep_fov, padding_rgb, fps,
+                                 estimator=_oracle_estimator, flavour="flow", output="device")
+
+
+def _check(res, gmeta, want_frames=None, want_masks=None, gold=None):
+    meta = json.loads(json.dumps(res.meta))
+    for mine, ref in zip(meta["estimated_motion"]["per_transition"], gmeta["estimated_motion"]["per_transition"]):
+        assert mine["mode"] == ref["mode"]
+        parity.assert_transform_close(mine["matrix"], ref["matrix"], f"pair {ref['index']}")
+    parity.compare_nested(gmeta, meta, "meta", atol=2e-5, rtol=2e-5)  # the reference's own A/B tolerance
+    if want_frames is not None:
+        err = np.abs(np.asarray(res.frames) - want_frames)
+        assert float((err > 2e-5).mean()) <= 1e-3 and float(err.max()) <= 0.04
+        assert float((np.asarray(res.masks) != want_masks).mean()) <= 1e-3
+    if gold is not None:
+        assert tuple(np.asarray(res.frames).shape) == tuple(gold["shape"])
+        f, y, x, hh, ww = gold["patch0_at"]
+        assert float(np.abs(np.asarray(res.frames)[f, y:y + hh, x:x + ww] - gold["patch0"]).max()) <= parity.TOL_PIXEL["bilinear"]
+        assert float(np.abs(np.asarray(res.masks)[f, y:y + hh, x:x + ww, 0] - gold["mpatch0"]).max()) == 0.0
+
+
+SMALL_FLOW = [c for c in cases.SMALL_STABILIZER_CASES if c["node"] == "flow" and c["framing"] != "crop"]
+
+
+@pytest.mark.parametrize("case", SMALL_FLOW, ids=[c["name"] for c in SMALL_FLOW])
+def test_host_path_on_small_clips(monkeypatch, case):
+    gold = np.load(os.path.join(GOLDEN_DIR, f"stab_{case['name']}.npz"))
+    with open(os.path.join(GOLDEN_DIR, f"stab_{case['name']}_meta.json")) as fh:
+        gmeta = json.load(fh)
+    res = _run(monkeypatch, cases.make_frames(case), case["framing"], case["mode"], case["camera_lock"], case["strength"],
+               case["smooth"], case["keep_fov"], case["padding_rgb"], case["fps"])
+    _check(res, gmeta, gold["frames"], gold["masks"])
+
+
+@pytest.mark.parametrize("scenario", cases.AB_SCENARIOS[:2], ids=[s[0] for s in cases.AB_SCENARIOS[:2]])
+def test_host_path_on_the_reference_ab_clip(monkeypatch, scenario):
+    name, framing, mode, keep_fov = scenario
+    gold = np.load(os.path.join(GOLDEN_DIR, "ab_73x45.npz"))
+    with open(os.path.join(GOLDEN_DIR, "ab_73x45_meta.json")) as fh:
+        gmeta = json.load(fh)[f"flow.{name}"]
+    a = cases.AB_ARGS
+    res = _run(monkeypatch, gold["input"], framing, mode, a["camera_lock"], a["strength"], a["smooth"], keep_fov, a["padding_rgb"], a["fps"])
+    _check(res, gmeta, gold[f"flow.{name}.frames"], gold[f"flow.{name}.masks"])
+
+
+def test_host_path_with_a_working_size(monkeypatch):
+    """1080p clip: estimation at 960x540, transforms rescaled to full resolution (stabilizer_utils.py:279-297)."""
+    case = next(c for c in cases.STABILIZER_CASES if c["name"] == "flow_sim_pad_1080p")
+    gold = np.load(os.path.join(GOLDEN_DIR, f"stab_{case['name']}.npz"))
+    with open(os.path.join(GOLDEN_DIR, f"stab_{case['name']}_meta.json")) as fh:
+        gmeta = json.load(fh)
+    res = _run(monkeypatch, cases.make_frames(case), case["framing"], case["mode"], case["camera_lock"], case["strength"],
+               case["smooth"], case["keep_fov"], case["padding_rgb"], case["fps"])
+    _check(res, gmeta, gold=gold)
