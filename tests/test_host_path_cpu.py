@@ -129,3 +129,60 @@ def test_host_path_with_a_working_size(monkeypatch):
     res = _run(monkeypatch, cases.make_frames(case), case["framing"], case["mode"], case["camera_lock"], case["strength"],
                case["smooth"], case["keep_fov"], case["padding_rgb"], case["fps"])
     _check(res, gmeta, gold=gold)
+
+
+# ---- Motion Apply: the product's engine (meta resolution, framing, shutter samples) with the numpy resampler -------
+
+def _oracle_sample_warp(context, fwd, out_size, interpolation, border, *, want_mask=True, **kw):
+    """pipeline.fused_warp for [N,S,9] shutter samples: f32 accumulate in sample order, / S, soft mask."""
+    import torch
+
+    fwd = np.asarray(fwd, np.float32)
+    n, s = fwd.shape[0], fwd.shape[1]
+    ow, oh = int(out_size[0]), int(out_size[1])
+    frames = np.zeros((n, oh, ow, 3), np.float32)
+    masks = np.zeros((n, oh, ow), np.float32)
+    for i in range(n):
+        acc = np.zeros((oh, ow, 3), np.float32)
+        cov = np.zeros((oh, ow), np.float32)
+        for k in range(s):
+            m = fwd[i, k].reshape(3, 3)
+            acc += resample_np.warp_np(context.frames[i], m, out_size, interpolation, border)
+            cov += resample_np.coverage_np(m, (context.width, context.height), out_size).astype(np.float32)
+        frames[i] = acc / np.float32(s) if s > 1 else acc
+        mk = np.float32(1.0) - cov / np.float32(s)
+        mk[mk < 1e-3] = 0.0
+        masks[i] = mk
+    return torch.from_numpy(frames), (torch.from_numpy(masks) if want_mask else None), None
+
+
+SMALL_APPLY = [c for c in cases.MOTION_APPLY_CASES if c["store"] == "full"]
+
+
+@pytest.mark.parametrize("case", SMALL_APPLY, ids=[c["name"] for c in SMALL_APPLY])
+def test_motion_apply_engine_on_the_cpu(monkeypatch, case):
+    from vstab_b200 import motion_apply as ma
+
+    def common(context, input_size, output_size, matrices, progress_callback=None):
+        out = np.ones((output_size[1], output_size[0]), dtype=bool)
+        for m in matrices:
+            out &= resample_np.coverage_np(np.asarray(m, np.float32), input_size, output_size)
+        ma._tick(progress_callback, len(matrices))
+        return out
+
+    monkeypatch.setattr(ma, "fused_warp", _oracle_sample_warp)
+    monkeypatch.setattr(ma, "common_valid_mask", common)
+    gold = np.load(os.path.join(GOLDEN_DIR, f"apply_{case['name']}.npz"))
+    with open(os.path.join(GOLDEN_DIR, f"apply_{case['name']}_meta.json")) as fh:
+        meta = json.load(fh)
+    ticks = [0]
+    res = ma.apply_motion(_Clip(cases.make_frames(case)), meta, case["padding_rgb"], framing_mode=case["framing"],
+                          interpolation=case["interp"], motion_blur=case["blur"], motion_blur_samples=case["samples"],
+                          progress_callback=lambda: ticks.__setitem__(0, ticks[0] + 1))
+    assert res.frames.shape == gold["frames"].shape and res.masks.shape == gold["masks"].shape
+    exact = case["interp"] == "bilinear" and case["blur"] == 0.0
+    assert float(np.abs(res.frames - gold["frames"]).max()) <= (0.0 if exact else 2e-6)
+    assert float(np.abs(res.masks - gold["masks"]).max()) <= (0.0 if case["blur"] == 0.0 else 1e-6)
+    n, s = case["n"], (int(np.clip(case["samples"], 3, 33)) if case["blur"] > 0 else 1)
+    assert ticks[0] == n * s + (n if case["framing"] == "crop" else 0)  # scripts/check_motion_meta.py:366-394
+    assert res.meta["motion_apply"]["framing_mode"] == ("crop_and_pad" if case["framing"] == "pad" else case["framing"])
