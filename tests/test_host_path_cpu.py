@@ -186,3 +186,63 @@ def test_motion_apply_engine_on_the_cpu(monkeypatch, case):
     n, s = case["n"], (int(np.clip(case["samples"], 3, 33)) if case["blur"] > 0 else 1)
     assert ticks[0] == n * s + (n if case["framing"] == "crop" else 0)  # scripts/check_motion_meta.py:366-394
     assert res.meta["motion_apply"]["framing_mode"] == ("crop_and_pad" if case["framing"] == "pad" else case["framing"])
+
+
+# ---- Classic: corners + tracks from the C oracle, same host path ------------------------------------------------
+
+def _oracle_classic_estimator(context, work_w, work_h, requested):
+    """classic.estimate_candidates with oracle/classic_ref.c in place of K5/K6 and fit_np in place of K7-K9."""
+    from oracle import classic_ref as CR
+    from vstab_b200.stabilizer_core import PairCandidates
+
+    work = None if (work_w, work_h) == (context.width, context.height) else (work_w, work_h)
+    gray = [gray_np.gray_for_estimation(f, work) for f in context.frames]
+    P = len(gray) - 1
+    m = np.tile(np.eye(3), (P, 3, 1, 1))
+    res, inl, valid, total, ok = (np.zeros((P, 3)) for _ in range(5))
+    detected = np.zeros(P, np.int64)
+    for p in range(P):
+        feats = CR.good_features(gray[p])
+        detected[p] = len(feats)
+        if len(feats) == 0:
+            continue
+        nxt, st = CR.pyr_lk(gray[p], gray[p + 1], feats)
+        prev, curr = feats[st == 1], nxt[st == 1].astype(np.float32)
+        valid[p], total[p] = len(prev), 400
+        if len(prev) == 0:
+            continue
+        m[p, 0, :2, 2] = fit_np.median_shift(prev, curr)
+        inl[p, 0], ok[p, 0] = len(prev), 1
+        if requested in ("similarity", "perspective") and len(prev) >= 3:
+            A, mask = fit_np.estimate_affine_partial_2d(prev, curr)
+            if A is not None:
+                m[p, 1, :2] = A
+                inl[p, 1], ok[p, 1] = int(mask.sum()), 1
+    return PairCandidates(m, res, inl.astype(int), valid.astype(int), total.astype(int), ok.astype(int), min_points=8, detected=detected)
+
+
+CLASSIC_AB = [s for s in cases.AB_SCENARIOS[:2]]
+
+
+@pytest.mark.parametrize("scenario", CLASSIC_AB, ids=[s[0] for s in CLASSIC_AB])
+def test_classic_host_path_on_the_reference_ab_clip(monkeypatch, scenario):
+    """Tracks from the C oracle sit within ~1e-4 px of cv2's (float accumulation order inside LK), so the matrices
+    get the north_star tolerance and the meta 2e-3 instead of the 2e-5 of the bit-exact Flow chain."""
+    from vstab_b200 import stabilizer_core as core
+
+    name, framing, mode, keep_fov = scenario
+    gold = np.load(os.path.join(GOLDEN_DIR, "ab_73x45.npz"))
+    with open(os.path.join(GOLDEN_DIR, "ab_73x45_meta.json")) as fh:
+        gmeta = json.load(fh)[f"classic.{name}"]
+    a = cases.AB_ARGS
+    monkeypatch.setattr(core, "fused_warp", _oracle_warp)
+    res = core.stabilize_frames(_Clip(gold["input"]), framing, mode, a["camera_lock"], a["strength"], a["smooth"], keep_fov,
+                                a["padding_rgb"], a["fps"], estimator=_oracle_classic_estimator, flavour="classic", output="device")
+    meta = json.loads(json.dumps(res.meta))
+    assert meta["transform_mode_applied"] == gmeta["transform_mode_applied"]
+    for mine, ref in zip(meta["estimated_motion"]["per_transition"], gmeta["estimated_motion"]["per_transition"]):
+        assert mine["mode"] == ref["mode"] and "residual" not in mine
+        parity.assert_transform_close(mine["matrix"], ref["matrix"], f"pair {ref['index']}")
+    parity.compare_nested(gmeta, meta, "meta", atol=2e-3, rtol=2e-3)
+    err = np.abs(np.asarray(res.frames) - gold[f"classic.{name}.frames"])
+    assert float(err.mean()) <= 1e-3 and float(err.max()) <= 0.05
