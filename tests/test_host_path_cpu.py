@@ -246,3 +246,68 @@ def test_classic_host_path_on_the_reference_ab_clip(monkeypatch, scenario):
     parity.compare_nested(gmeta, meta, "meta", atol=2e-3, rtol=2e-3)
     err = np.abs(np.asarray(res.frames) - gold[f"classic.{name}.frames"])
     assert float(err.mean()) <= 1e-3 and float(err.max()) <= 0.05
+
+
+# ---- crop framing: keep_fov search + no-padding refinement with numpy coverage in place of the two coverage kernels ----
+
+class _CoverageOracle:
+    """Stand-in for the handle methods crop.py calls (vstab_coverage_bbox, vstab_common_coverage)."""
+
+    @staticmethod
+    def _cov(fwd, src_size, out_size):
+        return [resample_np.coverage_np(np.asarray(m, np.float32).reshape(3, 3), src_size, out_size) for m in fwd.numpy()]
+
+    def coverage_bbox(self, fwd, src_size, out_size, mask_rule=0):
+        import torch
+
+        out = []
+        for c in self._cov(fwd, src_size, out_size):
+            p = np.pad(c, 1, constant_values=False)   # cv2.dilate ignores what lies outside the image
+            d = np.zeros_like(c)
+            for dy in range(3):
+                for dx in range(3):
+                    d |= p[dy:dy + c.shape[0], dx:dx + c.shape[1]]
+            p = np.pad(d, 1, constant_values=True)    # and so does cv2.erode
+            e = np.ones_like(c)
+            for dy in range(3):
+                for dx in range(3):
+                    e &= p[dy:dy + c.shape[0], dx:dx + c.shape[1]]
+            ys, xs = np.nonzero(e)
+            out.append([xs.min(), ys.min(), xs.max(), ys.max()] if len(xs) else [0, 0, -1, -1])
+        return torch.tensor(out, dtype=torch.int32)
+
+    def common_coverage(self, fwd, src_size, out_size, mask_rule=0):
+        import torch
+
+        common = np.ones((out_size[1], out_size[0]), bool)
+        for c in self._cov(fwd, src_size, out_size):
+            common &= c
+        return torch.from_numpy(common.astype(np.uint8))
+
+
+CROP_CPU = [c for c in cases.SMALL_STABILIZER_CASES + cases.CROP_CASES
+            if c["node"] == "flow" and c["framing"] == "crop" and c["name"] in ("flow_trans_crop_121x73", "flow_sim_crop06_480p")]
+
+
+@pytest.mark.parametrize("case", CROP_CPU, ids=[c["name"] for c in CROP_CPU])
+def test_crop_solver_host_path(monkeypatch, case):
+    import torch
+
+    from vstab_b200 import crop
+
+    monkeypatch.setattr(crop._native, "get_handle", lambda device: _CoverageOracle())
+    gold = np.load(os.path.join(GOLDEN_DIR, f"stab_{case['name']}.npz"))
+    with open(os.path.join(GOLDEN_DIR, f"stab_{case['name']}_meta.json")) as fh:
+        gmeta = json.load(fh)
+    from vstab_b200 import stabilizer_core as core
+
+    monkeypatch.setattr(core, "fused_warp", _oracle_warp)
+    clip = _Clip(cases.make_frames(case))
+    clip.device = torch.device("cpu")
+    res = core.stabilize_frames(clip, case["framing"], case["mode"], case["camera_lock"], case["strength"], case["smooth"],
+                                case["keep_fov"], case["padding_rgb"], case["fps"], estimator=_oracle_estimator, flavour="flow",
+                                output="device")
+    _check(res, gmeta, gold=gold)
+    assert float(np.asarray(res.masks).max()) == 0.0
+    cw, ch = res.meta["framing"]["crop_size"]
+    assert abs(cw / ch - case["w"] / case["h"]) <= 1e-6
