@@ -260,3 +260,85 @@ def test_stacked_conversions_ladder_columns_and_gc_pause():
             assert gc.isenabled() == state
         finally:
             gc.enable()
+
+
+def test_node_execute_glue(monkeypatch):
+    """execute() of the three nodes (reference: video_stabilizer_motion_apply.py:86-129, video_stabilizer_flow.py:734-763):
+    padding colour parsing, blur quality -> sample count with the silent "Standard" fallback, progress totals, the
+    interrupt hook, argument order into the drivers, (IMAGE, MASK, JSON) out.  Drivers and tensor adapters are stand-ins."""
+    import numpy as np
+
+    _install_comfy_stubs()
+    sys.modules.pop("vstab_b200.nodes", None)
+    from vstab_b200 import nodes
+
+    bars = []
+
+    class Bar:
+        def __init__(self, total):
+            self.total, self.calls = total, []
+            bars.append(self)
+
+        def update_absolute(self, done, total):
+            self.calls.append((done, total))
+
+    class Ctx:
+        def __len__(self):
+            return 5
+
+    class Result:
+        def __init__(self, meta):
+            self.frames, self.masks, self.meta = "F", "M", meta
+
+    seen = {}
+
+    def fake_apply(context, meta, rgb, **kw):
+        seen["apply"] = (meta, rgb, kw)
+        for _ in range(5 + 5 * 9):
+            kw["progress_callback"]()
+        return Result({"k": 1})
+
+    def fake_stab(context, *a, **kw):
+        seen["stab"] = (a, kw)
+        kw["interrupt_check"]()
+        return Result({"frames": 5})
+
+    monkeypatch.setattr(nodes, "ProgressBar", Bar)
+    monkeypatch.setattr(nodes, "normalize_video_input", lambda frames: Ctx())
+    monkeypatch.setattr(nodes, "reconstruct_video", lambda frames, ctx: ("video", frames))
+    monkeypatch.setattr(nodes, "convert_masks_for_output", lambda masks: ("mask", masks))
+    monkeypatch.setattr(nodes.motion_apply, "apply_motion", fake_apply)
+    monkeypatch.setattr(nodes.flow, "stabilize_frames", fake_stab)
+    monkeypatch.setattr(nodes.classic, "stabilize_frames", fake_stab)
+
+    out = nodes.VideoStabilizerMotionApply.execute("frames", {"motion_meta": {}}, "crop", "bicubic", "#0AC85A", 0.5, "NoSuchQuality")
+    meta, rgb, kw = seen["apply"]
+    assert rgb == (10, 200, 90) and kw["framing_mode"] == "crop" and kw["interpolation"] == "bicubic"
+    assert kw["motion_blur"] == 0.5 and kw["motion_blur_samples"] == 9  # unknown quality -> "Standard"
+    assert out == (("video", "F"), ("mask", "M"), {"k": 1, "motion_apply": {"motion_blur_quality": "Standard"}})
+    total = 5 * 9 + 5
+    assert bars[-1].total == total and bars[-1].calls[-1] == (total, total) and len(bars[-1].calls) == total + 1
+    assert max(d for d, _ in bars[-1].calls) == total
+
+    nodes.VideoStabilizerMotionApply.execute("frames", {}, "expand", "bilinear", "#000000", 0.0, "Ultra")
+    assert seen["apply"][2]["motion_blur_samples"] == 33 and bars[-1].total == 5  # blur off: one tick per frame
+
+    class Interrupted(Exception):
+        pass
+
+    def boom():
+        raise Interrupted
+
+    monkeypatch.setattr(nodes, "model_management", types.SimpleNamespace(throw_exception_if_processing_interrupted=boom))
+    for cls in (nodes.VideoStabilizerFlow, nodes.VideoStabilizerClassic):
+        try:
+            cls.execute("frames", 24.0, "expand", "perspective", True, 0.3, 0.9, 0.2, "#FF0000")
+            raise AssertionError("the interrupt must propagate")
+        except Interrupted:
+            pass
+        a, kw = seen["stab"]
+        assert a == ("expand", "perspective", True, 0.3, 0.9, 0.2, (255, 0, 0), 24.0)
+        assert bars[-1].total == 4 + 5 and kw["progress_bar"] is bars[-1]
+    monkeypatch.setattr(nodes, "model_management", None)
+    out = nodes.VideoStabilizerFlow.execute("frames", 16.0, "crop_and_pad", "similarity", False, 0.7, 0.5, 0.6, "#7F7F7F")
+    assert out == (("video", "F"), ("mask", "M"), {"frames": 5}) and seen["stab"][0][6] == (127, 127, 127)
