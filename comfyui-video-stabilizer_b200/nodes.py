@@ -20,6 +20,7 @@ except ImportError:  # pragma: no cover
     model_management = None
 
 from . import classic, flow, motion_apply
+from .motion_meta import resolve_motion_meta
 from .hostmath import parse_padding_color
 from .pipeline import convert_masks_for_output, normalize_video_input, reconstruct_video
 
@@ -198,6 +199,57 @@ class VideoStabilizerMotionApply(io.ComfyNode):
         return io.NodeOutput(reconstruct_video(result.frames, context), convert_masks_for_output(result.masks), result.meta)
 
 
+class VideoStabilizerInverse(io.ComfyNode):
+    """Deprecated in the reference in favour of Motion Apply, kept for saved workflows
+    (nodes/video_stabilizer_inverse.py:26-100): restores edited stabilized frames to the source canvas."""
+
+    @classmethod
+    def define_schema(cls) -> io.Schema:
+        schema = io.Schema(
+            node_id="video_stabilizer_inverse",
+            display_name="Video Stabilizer Inverse",
+            category="Video/Stabilization",
+            description=("Deprecated: use Video Stabilizer Motion Apply. Restores stabilized frames to the "
+                         "original canvas using stabilization metadata, and emits a padding mask for areas "
+                         "without source pixels."),
+            is_deprecated=True,
+        )
+        schema.inputs = [
+            io.Image.Input("frames", display_name="Frames"),
+            JSONType.Input("meta", display_name="Meta"),
+            io.Color.Input("padding_color", default="#7F7F7F", display_name="Padding Color",
+                           tooltip="HEX padding color used where inverse warping exposes empty pixels."),
+        ]
+        schema.outputs = [
+            io.Image.Output("frames_restored", display_name="Restored Frames"),
+            io.Mask.Output("padding_mask", display_name="Padding Mask"),
+            JSONType.Output("meta", display_name="Meta"),
+        ]
+        return schema
+
+    @classmethod
+    def execute(cls, frames: Any, meta: dict, padding_color: str) -> io.NodeOutput:
+        context = normalize_video_input(frames)
+        inverse_meta = dict(meta)
+        inverse_meta.pop("motion_meta", None)  # force the legacy path: the inverted stabilization_warp
+        motion = resolve_motion_meta(inverse_meta)
+        result = motion_apply.apply_motion(context, inverse_meta, parse_padding_color(padding_color),
+                                           framing_mode="crop_and_pad", interpolation="bilinear")
+        if isinstance(meta, dict) and isinstance(meta.get("motion_meta"), dict):
+            result.meta["motion_meta"] = meta["motion_meta"]
+        result.meta.pop("motion_apply", None)
+        result.meta["inverse_stabilization"] = {
+            "source_size": [int(motion.output_size[0]), int(motion.output_size[1])],
+            "input_size": [int(motion.input_size[0]), int(motion.input_size[1])],
+            "output_size": [int(motion.output_size[0]), int(motion.output_size[1])],
+            "matrix_convention": "stabilized_to_source",
+            "source_matrix_convention": "source_to_stabilized",
+            "framing_mode": meta.get("stabilization_warp", {}).get("framing_mode") if isinstance(meta, dict) else None,
+            "note": "Restores original motion/canvas; pixels discarded by crop framing cannot be recovered.",
+        }
+        return io.NodeOutput(reconstruct_video(result.frames, context), convert_masks_for_output(result.masks), result.meta)
+
+
 class VideoStabilizerB200Extension(ComfyExtension):
     async def get_node_list(self) -> list[type[io.ComfyNode]]:
-        return [VideoStabilizerClassic, VideoStabilizerFlow, VideoStabilizerMotionApply]
+        return [VideoStabilizerClassic, VideoStabilizerFlow, VideoStabilizerMotionApply, VideoStabilizerInverse]

@@ -137,6 +137,69 @@ def gen_ab(ref):
         json.dump(metas, fh)
 
 
+def gen_inverse(ref):
+    """Legacy inverse stabilization on the scenario of the reference's scripts/check_inverse_stabilization.py
+    (:24-131: 7 source frames of 73x45, an expand and a crop stabilization made with cv2): the helper
+    _apply_inverse_stabilization and the deprecated node's execute()."""
+    import importlib
+    import sys
+
+    import cv2
+    import torch
+
+    U = ref.stabilizer_utils
+    width, height = 73, 45
+    yy, xx = np.mgrid[0:height, 0:width]
+    base = np.zeros((height, width, 3), dtype=np.float32)
+    base[..., 0] = xx / max(width - 1, 1)
+    base[..., 1] = yy / max(height - 1, 1)
+    base[..., 2] = (((xx // 6) + (yy // 5)) % 2).astype(np.float32)
+    cv2.rectangle(base, (8, 7), (30, 24), (1.0, 0.2, 0.1), -1)
+    cv2.circle(base, (width - 19, height - 13), 7, (0.1, 0.9, 0.3), -1)
+    center = (width * 0.5, height * 0.5)
+    source = []
+    for idx in range(7):
+        m = cv2.getRotationMatrix2D(center, idx * 0.45, 1.0 + idx * 0.0015)
+        m[0, 2] += idx * 0.65
+        m[1, 2] += idx * -0.35
+        source.append(cv2.warpAffine(base, m, (width, height), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT).astype(np.float32))
+
+    def stabilize(matrices, out_size, framing):
+        frames = [cv2.warpPerspective(f, m, out_size, flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT,
+                                      borderValue=(0.5, 0.5, 0.5)).astype(np.float32) for f, m in zip(source, matrices)]
+        meta = {"frames": len(frames), "framing": {"mode": framing},
+                "stabilization_warp": U._build_stabilization_warp_meta(source_size=(width, height), output_size=out_size,
+                                                                       framing_mode=framing, applied_matrices=matrices)}
+        return np.stack(frames), meta
+
+    shifts = [np.array([[1.0, 0.0, -i * 0.7], [0.0, 1.0, i * 0.4], [0.0, 0.0, 1.0]], dtype=np.float32) for i in range(7)]
+    mins, maxs = U._compute_bounding_boxes(shifts, width, height)
+    translate, out_size = U._prepare_expand_transform(mins, maxs)
+    cases_ = {"expand": stabilize([translate @ m for m in shifts], out_size, "expand")}
+    crop = np.array([[1.12, 0.0, -0.06 * width], [0.0, 1.12, -0.06 * height], [0.0, 0.0, 1.0]], dtype=np.float32)
+    cases_["crop"] = stabilize([crop.copy() for _ in range(7)], (width, height), "crop")
+
+    payload, metas = {"source": np.stack(source)}, {}
+    for name, (frames, meta) in cases_.items():
+        res = U._apply_inverse_stabilization(U._normalize_video_input([f for f in frames]), meta, (127, 127, 127))
+        payload[f"{name}.input"] = frames
+        payload[f"{name}.frames"] = np.stack(res.frames)
+        payload[f"{name}.masks"] = np.stack(res.masks)
+        metas[f"{name}.in"] = meta
+        metas[f"{name}.helper_out"] = res.meta
+    sys.modules["comfy_api.latest"].io.NodeOutput = lambda *a: a
+    node = importlib.import_module("nodes.video_stabilizer_inverse").VideoStabilizerInverse
+    frames, meta = cases_["expand"]
+    video, mask, out_meta = node.execute(torch.from_numpy(frames), meta, "#0AC85A")
+    payload["node.frames"] = video.numpy()
+    payload["node.mask"] = mask.numpy()
+    metas["node.out"] = out_meta
+    np.savez_compressed(os.path.join(GOLDEN, "inverse_73x45.npz"), **payload)
+    with open(os.path.join(GOLDEN, "inverse_73x45_meta.json"), "w") as fh:
+        json.dump(metas, fh)
+    print("inverse", {k: v.shape for k, v in payload.items()})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -144,9 +207,9 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_import.load_reference()
     gens = {"apply": gen_motion_apply, "stab": gen_estimators, "dis": gen_dis, "crop": lambda r: gen_estimators(r, True),
-            "small": lambda r: gen_estimators(r, only_small=True), "ab": gen_ab}
+            "small": lambda r: gen_estimators(r, only_small=True), "ab": gen_ab, "inverse": gen_inverse}
     for key, fn in gens.items():
-        if args.only == key or (args.only is None and key not in ("crop", "small", "ab")):
+        if args.only == key or (args.only is None and key not in ("crop", "small", "ab", "inverse")):
             fn(ref)
 
 

@@ -311,3 +311,68 @@ def test_crop_solver_host_path(monkeypatch, case):
     assert float(np.asarray(res.masks).max()) == 0.0
     cw, ch = res.meta["framing"]["crop_size"]
     assert abs(cw / ch - case["w"] / case["h"]) <= 1e-6
+
+
+# ---- legacy inverse stabilization (helper + deprecated node) --------------------------------------------------------
+
+def _inverse_golden():
+    gold = np.load(os.path.join(GOLDEN_DIR, "inverse_73x45.npz"))
+    with open(os.path.join(GOLDEN_DIR, "inverse_73x45_meta.json")) as fh:
+        return gold, json.load(fh)
+
+
+class _RgbClip(_Clip):
+    channels = 3
+
+
+@pytest.mark.parametrize("name", ["expand", "crop"])
+def test_inverse_stabilization_helper_on_the_cpu(monkeypatch, name):
+    """scripts/check_inverse_stabilization.py scenario; golden = the reference's _apply_inverse_stabilization."""
+    from vstab_b200 import inverse
+
+    monkeypatch.setattr(inverse, "fused_warp", _oracle_sample_warp)
+    gold, metas = _inverse_golden()
+    res = inverse.apply_inverse_stabilization(_RgbClip(gold[f"{name}.input"]), metas[f"{name}.in"], (127, 127, 127))
+    assert np.array_equal(res.frames, gold[f"{name}.frames"]) and np.array_equal(res.masks, gold[f"{name}.masks"])
+    parity.compare_nested(metas[f"{name}.helper_out"], json.loads(json.dumps(res.meta)), "meta", atol=0.0, rtol=0.0)
+    if name == "expand":  # the script's own acceptance numbers (:169-173)
+        err = np.abs(res.frames - gold["source"])
+        assert float(np.quantile(err, 0.99)) <= 0.3 and float(err.mean()) <= 0.035
+    else:
+        assert float(res.masks.max()) > 0.0  # crop framing: some source pixels cannot be recovered (:178-179)
+    bad = json.loads(json.dumps(metas[f"{name}.in"]))
+    bad["stabilization_warp"]["per_frame"][2]["index"] = 7
+    with pytest.raises(ValueError, match=r"per_frame\[2\]\.index must be 2"):
+        inverse.apply_inverse_stabilization(_RgbClip(gold[f"{name}.input"]), bad, (0, 0, 0))
+    with pytest.raises(ValueError, match="Frame count mismatch"):
+        inverse.apply_inverse_stabilization(_RgbClip(gold[f"{name}.input"][:3]), metas[f"{name}.in"], (0, 0, 0))
+    with pytest.raises(ValueError, match="must match stabilization_warp.output_size"):
+        inverse.apply_inverse_stabilization(_RgbClip(gold["source"][:, :40]), metas[f"{name}.in"], (0, 0, 0))
+    with pytest.raises(ValueError, match="stabilization_warp is required"):
+        inverse.apply_inverse_stabilization(_RgbClip(gold["source"]), {}, (0, 0, 0))
+
+
+def test_inverse_node_on_the_cpu(monkeypatch):
+    """The deprecated Video Stabilizer Inverse node (nodes/video_stabilizer_inverse.py:60-100) against its own output."""
+    import sys
+
+    import torch
+
+    from tests.test_abi_and_host import _install_comfy_stubs
+
+    _install_comfy_stubs()
+    sys.modules.pop("vstab_b200.nodes", None)
+    from vstab_b200 import motion_apply as ma, nodes
+
+    gold, metas = _inverse_golden()
+    monkeypatch.setattr(ma, "fused_warp", _oracle_sample_warp)
+    monkeypatch.setattr(nodes, "normalize_video_input", lambda frames: _RgbClip(frames.numpy()))
+    monkeypatch.setattr(nodes, "reconstruct_video", lambda frames, ctx: torch.from_numpy(np.ascontiguousarray(frames)))
+    monkeypatch.setattr(nodes, "convert_masks_for_output", lambda masks: torch.from_numpy(np.ascontiguousarray(masks[..., 0])))
+    video, mask, meta = nodes.VideoStabilizerInverse.execute(torch.from_numpy(gold["expand.input"]), metas["expand.in"], "#0AC85A")
+    assert np.array_equal(video.numpy(), gold["node.frames"]) and np.array_equal(mask.numpy(), gold["node.mask"])
+    parity.compare_nested(metas["node.out"], json.loads(json.dumps(meta)), "meta", atol=0.0, rtol=0.0)
+    schema = nodes.VideoStabilizerInverse.define_schema()
+    assert schema.node_id == "video_stabilizer_inverse" and schema.is_deprecated is True
+    assert [s.args[0] for s in schema.inputs] == ["frames", "meta", "padding_color"]
+    assert [s.args[0] for s in schema.outputs] == ["frames_restored", "padding_mask", "meta"]

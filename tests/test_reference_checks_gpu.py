@@ -212,3 +212,29 @@ def test_reference_ab_gate(node, scenario):
         parity.compare_nested(gmeta, meta, "meta", atol=5e-3, rtol=5e-3)
         assert float(err.mean()) <= 1e-3 and float(err.max()) <= 0.05, (float(err.mean()), float(err.max()))
         assert float((got_m != want_m).mean()) <= 5e-3
+
+
+@pytest.mark.parametrize("name", ["expand", "crop"])
+def test_inverse_stabilization_on_the_check_script_scenario(name):
+    """scripts/check_inverse_stabilization.py:134-181 on the CUDA path; golden = the reference's own helper
+    (tests/golden/inverse_73x45*, scripts/make_golden.py --only inverse)."""
+    import json
+    import os
+
+    from tests.conftest import GOLDEN_DIR
+    from vstab_b200 import inverse
+
+    gold = np.load(os.path.join(GOLDEN_DIR, "inverse_73x45.npz"))
+    with open(os.path.join(GOLDEN_DIR, "inverse_73x45_meta.json")) as fh:
+        metas = json.load(fh)
+    res = inverse.apply_inverse_stabilization(_ctx(gold[f"{name}.input"]), metas[f"{name}.in"], (127, 127, 127))
+    assert res.frames.shape == gold[f"{name}.frames"].shape and res.frames.dtype == np.float32 and res.masks.dtype == np.float32
+    assert float(np.abs(res.frames - gold[f"{name}.frames"]).max()) <= 1e-6  # bilinear: same bits as cv2 in practice
+    assert np.array_equal(res.masks, gold[f"{name}.masks"])
+    inv = res.meta["inverse_stabilization"]
+    assert inv == metas[f"{name}.helper_out"]["inverse_stabilization"] and inv["matrix_convention"] == "stabilized_to_source"
+    if name == "expand":
+        err = np.abs(res.frames - gold["source"])
+        assert float(np.quantile(err, 0.99)) <= 0.3 and float(err.mean()) <= 0.035
+    else:
+        assert float(res.masks.max()) > 0.0
