@@ -25,14 +25,19 @@ class _Clip:
     def __len__(self):
         return len(self.frames)
 
+    def sliced(self, start):
+        return type(self)(self.frames[start:], self.fps)
 
-def _oracle_estimator(context, work_w, work_h, requested):
+
+def _oracle_estimator(context, work_w, work_h, requested, clip_pair_offset=0):
     """flow.estimate_candidates with the oracle in place of K1-K4 / K7-K9: all candidate models of every pair."""
     from vstab_b200.stabilizer_core import PairCandidates
 
     work = None if (work_w, work_h) == (context.width, context.height) else (work_w, work_h)
     gray = [gray_np.gray_for_estimation(f, work) for f in context.frames]
     backend = dis_ref.Backend()  # one object per clip, like the reference (flow.py:312)
+    if clip_pair_offset > 0:     # a shard in the middle of the clip meets the object after its first calc()
+        backend.params.finest_scale = dis_ref.select_scales(work_h, work_w)[0]
     P = len(gray) - 1
     m = np.tile(np.eye(3), (P, 3, 1, 1))
     res, inl, valid, total, ok = (np.zeros((P, 3)) for _ in range(5))

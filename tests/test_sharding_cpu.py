@@ -195,3 +195,62 @@ def test_shards_tell_dis_where_their_pairs_sit_in_the_clip(monkeypatch):
         assert seen[-1] == want, (shard, seen[-1])
         if shard is not None:
             assert shard.pair_range[0] == want
+
+
+def _real_worker(rank, world, port, case_name, out):
+    """One rank of a frame-range sharded Flow run on the CPU: real FrameShard + gloo collectives + the product's host
+    path, with the oracle in place of the GPU stages (tests/test_host_path_cpu.py)."""
+    import functools
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import vstab_loader
+
+    vstab_loader.load()
+    from tests import cases
+    from tests.test_host_path_cpu import _Clip, _oracle_estimator, _oracle_warp
+    from vstab_b200 import stabilizer_core as core
+    from vstab_b200.sharding import FrameShard
+
+    case = next(c for c in cases.SMALL_STABILIZER_CASES if c["name"] == case_name)
+    frames = cases.make_frames(case)
+    shard = FrameShard(rank, world, len(frames), None, torch.device("cpu"))
+    lo, hi = shard.load_range
+    core.fused_warp = _oracle_warp
+    est = shard.wrap_estimator(functools.partial(_oracle_estimator, clip_pair_offset=shard.pair_range[0]))  # as flow.stabilize_frames does
+    res = core.stabilize_frames(_Clip(frames[lo:hi]), case["framing"], case["mode"], case["camera_lock"], case["strength"],
+                                case["smooth"], case["keep_fov"], case["padding_rgb"], case["fps"], estimator=est, flavour="flow",
+                                output="device", shard=shard)
+    out[rank] = (np.asarray(res.frames), np.asarray(res.masks), res.meta)
+    dist.destroy_process_group()
+
+
+def test_two_rank_flow_run_equals_the_reference(monkeypatch):
+    """90x50 is the size where cv2's DIS object changes state after the first pair of a clip: rank 1 starts in the
+    middle of the clip and must estimate its pairs in the later state.  Concatenated frames / merged meta of the two
+    ranks == the single-process run, and both == the unmodified reference's output for the clip."""
+    import json
+
+    from tests import cases, parity
+    from tests.conftest import GOLDEN_DIR
+    from tests.test_host_path_cpu import _run
+    from vstab_b200.sharding import merge_sharded_meta
+
+    name = "flow_sim_pad_90x50"
+    case = next(c for c in cases.SMALL_STABILIZER_CASES if c["name"] == name)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_real_worker, args=(2, _free_port(), name, out), nprocs=2, join=True)
+    frames = np.concatenate([out[0][0], out[1][0]])
+    masks = np.concatenate([out[0][1], out[1][1]])
+    meta = merge_sharded_meta([out[0][2], out[1][2]])
+    single = _run(monkeypatch, cases.make_frames(case), case["framing"], case["mode"], case["camera_lock"], case["strength"],
+                  case["smooth"], case["keep_fov"], case["padding_rgb"], case["fps"])
+    assert np.array_equal(frames, np.asarray(single.frames)) and np.array_equal(masks, np.asarray(single.masks))
+    assert json.loads(json.dumps(meta)) == json.loads(json.dumps(single.meta))
+    gold = np.load(os.path.join(GOLDEN_DIR, f"stab_{name}.npz"))
+    with open(os.path.join(GOLDEN_DIR, f"stab_{name}_meta.json")) as fh:
+        gmeta = json.load(fh)
+    parity.compare_nested(gmeta, json.loads(json.dumps(meta)), "meta", atol=2e-5, rtol=2e-5)
+    err = np.abs(frames - gold["frames"])
+    assert float((err > 2e-5).mean()) <= 1e-3 and float(err.max()) <= 0.04
