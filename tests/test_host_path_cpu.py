@@ -381,3 +381,35 @@ def test_inverse_node_on_the_cpu(monkeypatch):
     assert schema.node_id == "video_stabilizer_inverse" and schema.is_deprecated is True
     assert [s.args[0] for s in schema.inputs] == ["frames", "meta", "padding_color"]
     assert [s.args[0] for s in schema.outputs] == ["frames_restored", "padding_mask", "meta"]
+
+
+def test_check_motion_meta_script_head(monkeypatch):
+    """scripts/check_motion_meta.py:144-205 with the product's modules: v2 block round trip, legacy stabilization_warp
+    inversion, applied block, and the block Motion Apply picks by the size of the frames it is given (a full stabilizer
+    meta replays forwards on source-sized frames and backwards on stabilized-sized ones)."""
+    from vstab_b200 import hostmath as hm, motion_apply as ma, motion_meta as mm
+
+    monkeypatch.setattr(ma, "fused_warp", _oracle_sample_warp)
+    matrices = [np.eye(3), np.array([[1.0, 0.0, 2.5], [0.0, 1.0, -1.25], [0.0, 0.0, 1.0]])]
+    block = mm.build_motion_meta_v2(source="generated_shake", frame_count=2, fps=16.0, input_size=(64, 48), output_size=(64, 48),
+                                    matrices=matrices, generator={"node": "t"})
+    r = mm.resolve_motion_meta({"motion_meta": block})
+    assert r.frame_count == 2 and r.input_size == (64, 48) and r.output_size == (64, 48)
+    warp = hm.build_stabilization_warp_meta(source_size=(80, 50), output_size=(96, 60), framing_mode="expand", applied_matrices=matrices)
+    assert mm.motion_meta_from_stabilization_warp(warp, fps=24.0, source="legacy_stabilization") is not None
+    legacy = mm.resolve_motion_meta({"stabilization_warp": warp})
+    assert legacy.input_size == (96, 60) and legacy.output_size == (80, 50)
+    assert np.allclose(legacy.per_frame[1].matrix, np.linalg.inv(matrices[1]))
+    applied = mm.applied_motion_meta_from_stabilization_warp(warp, fps=24.0, source="estimated_flow")
+    ra = mm.resolve_motion_meta({"motion_meta": applied})
+    assert ra.input_size == (80, 50) and ra.output_size == (96, 60) and np.allclose(ra.per_frame[1].matrix, matrices[1])
+    frames = np.random.default_rng(0).random((2, 50, 80, 3), dtype=np.float32)
+    combined = {"stabilization_warp": warp, "motion_meta": applied}
+    direct = ma.apply_motion(_RgbClip(frames), combined, (127, 127, 127))
+    assert direct.frames.shape[1:3] == (60, 96) and direct.meta["motion_apply"]["source"] == "estimated_flow"
+    back = ma.apply_motion(_RgbClip(direct.frames), combined, (127, 127, 127))
+    assert back.frames.shape[1:3] == (50, 80) and back.meta["motion_apply"]["source"] == "legacy_stabilization"
+    # frame 1 went 2.5 px right / 1.25 px up and back: the interior returns to the source up to two bilinear passes
+    assert float(np.abs(back.frames[0] - frames[0]).max()) <= 1e-6
+    with pytest.raises(ValueError, match="motion_meta or stabilization_warp"):
+        mm.resolve_motion_meta({})
