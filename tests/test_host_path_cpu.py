@@ -161,6 +161,17 @@ def _oracle_sample_warp(context, fwd, out_size, interpolation, border, *, want_m
     return torch.from_numpy(frames), (torch.from_numpy(masks) if want_mask else None), None
 
 
+def _oracle_common_valid_mask(context, input_size, output_size, matrices, progress_callback=None):
+    """motion_apply.common_valid_mask (vstab_common_coverage) in numpy."""
+    from vstab_b200 import motion_apply as ma
+
+    out = np.ones((output_size[1], output_size[0]), dtype=bool)
+    for m in matrices:
+        out &= resample_np.coverage_np(np.asarray(m, np.float32), input_size, output_size)
+    ma._tick(progress_callback, len(matrices))
+    return out
+
+
 SMALL_APPLY = [c for c in cases.MOTION_APPLY_CASES if c["store"] == "full"]
 
 
@@ -168,15 +179,8 @@ SMALL_APPLY = [c for c in cases.MOTION_APPLY_CASES if c["store"] == "full"]
 def test_motion_apply_engine_on_the_cpu(monkeypatch, case):
     from vstab_b200 import motion_apply as ma
 
-    def common(context, input_size, output_size, matrices, progress_callback=None):
-        out = np.ones((output_size[1], output_size[0]), dtype=bool)
-        for m in matrices:
-            out &= resample_np.coverage_np(np.asarray(m, np.float32), input_size, output_size)
-        ma._tick(progress_callback, len(matrices))
-        return out
-
     monkeypatch.setattr(ma, "fused_warp", _oracle_sample_warp)
-    monkeypatch.setattr(ma, "common_valid_mask", common)
+    monkeypatch.setattr(ma, "common_valid_mask", _oracle_common_valid_mask)
     gold = np.load(os.path.join(GOLDEN_DIR, f"apply_{case['name']}.npz"))
     with open(os.path.join(GOLDEN_DIR, f"apply_{case['name']}_meta.json")) as fh:
         meta = json.load(fh)
@@ -413,3 +417,17 @@ def test_check_motion_meta_script_head(monkeypatch):
     assert float(np.abs(back.frames[0] - frames[0]).max()) <= 1e-6
     with pytest.raises(ValueError, match="motion_meta or stabilization_warp"):
         mm.resolve_motion_meta({})
+
+
+def test_check_motion_meta_script_tail_on_the_cpu(monkeypatch):
+    """scripts/check_motion_meta.py:289-415 (identity apply, blur == 0 baseline path, expand canvas, blur determinism,
+    tick counts, crop fallback) and the error messages: the bodies of the GPU tests, run with the numpy resampler."""
+    import tests.test_reference_checks_gpu as g
+    from vstab_b200 import motion_apply as ma
+
+    monkeypatch.setattr(ma, "fused_warp", _oracle_sample_warp)
+    monkeypatch.setattr(ma, "common_valid_mask", _oracle_common_valid_mask)
+    monkeypatch.setattr(g, "_ctx", lambda frames: _RgbClip(np.asarray(frames)))
+    g.test_identity_blur_zero_expand_determinism_and_ticks()
+    g.test_errors_match_the_reference_messages()
+
