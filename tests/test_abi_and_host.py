@@ -342,3 +342,60 @@ def test_node_execute_glue(monkeypatch):
     monkeypatch.setattr(nodes, "model_management", None)
     out = nodes.VideoStabilizerFlow.execute("frames", 16.0, "crop_and_pad", "similarity", False, 0.7, 0.5, 0.6, "#7F7F7F")
     assert out == (("video", "F"), ("mask", "M"), {"frames": 5}) and seen["stab"][0][6] == (127, 127, 127)
+
+
+@pytest.mark.reference
+def test_input_adapters_equal_the_reference_on_its_own_cases(monkeypatch, reference_nodes):
+    """scripts/compare_refactor_behavior.py:289-324 compare_helpers: every container the reference accepts (list,
+    batch, dict, frames wrapped in a leading 1, float64, uint8, a non-contiguous view, torch float32 / uint8) must reach
+    the same normalised clip and the same reconstructed payload.  The adapter rules are torch tensor operations, so
+    they run here with the device pinned to the CPU; "base" is the unmodified reference."""
+    import numpy as np
+    import torch
+
+    from vstab_b200 import pipeline
+
+    monkeypatch.setattr(pipeline, "_require_device", lambda device: torch.device("cpu"))
+    monkeypatch.setattr(pipeline, "_must_stream", lambda *a: False)
+    U = reference_nodes.stabilizer_utils
+    rng = np.random.default_rng(3)
+    frames = [rng.random((45, 73, 3), dtype=np.float32) for _ in range(8)]
+    batch = np.stack(frames, axis=0)
+    u8 = (batch * 255.0).round().clip(0, 255).astype(np.uint8)
+    cases_ = {
+        "list": frames,
+        "batch": batch,
+        "dict": {"frames": batch, "fps": 24.0},
+        "wrapped_frames": [f[np.newaxis, ...] for f in frames],
+        "float64": batch.astype(np.float64),
+        "uint8": u8,
+        "noncontiguous": np.ascontiguousarray(np.stack([f[:, ::-1, :] for f in frames], axis=0))[:, :, ::-1, :],
+        "torch_f32": torch.from_numpy(batch.copy()),
+        "torch_uint8": torch.from_numpy(u8.copy()),
+        "float_0_255": torch.from_numpy(batch * np.float32(255.0)),
+        "gray": torch.from_numpy(batch[..., :1].copy()),
+        "rgba": torch.from_numpy(np.concatenate([batch, batch[..., :1]], axis=-1)),
+        "chw_list": [np.moveaxis(f, -1, 0) for f in frames],
+    }
+    for name, value in cases_.items():
+        base = U._normalize_video_input(value)
+        head = pipeline.normalize_video_input(value)
+        for attr in ("width", "height", "channels", "fps", "template_kind", "template_meta"):
+            assert getattr(base, attr) == getattr(head, attr), (name, attr)
+        assert len(head) == len(base.frames), name
+        got = head.frames.numpy()
+        for i, want in enumerate(base.frames):
+            assert np.array_equal(got[i], want), (name, i, float(np.abs(got[i] - want).max()))
+        b = U._reconstruct_video(base.frames, base)
+        h = pipeline.reconstruct_video(head.frames, head)
+        if isinstance(b, dict):
+            assert set(b) == set(h) and b["fps"] == h["fps"], name
+            b, h = b["frames"], h["frames"]
+        assert b.dtype == h.dtype and tuple(b.shape) == tuple(h.shape) and np.array_equal(b.numpy(), h.numpy()), name
+    for bad in ([], {"fps": 24.0}):
+        for fn in (U._normalize_video_input, pipeline.normalize_video_input):
+            with pytest.raises(ValueError):
+                fn(bad)
+    masks = [rng.random((45, 73, 1)).astype(np.float32) for _ in range(3)]
+    assert np.array_equal(U._convert_masks_for_output(masks).numpy(), pipeline.convert_masks_for_output(np.stack(masks)).numpy())
+    assert tuple(pipeline.convert_masks_for_output(np.zeros((0, 4, 4, 1), np.float32)).shape) == tuple(U._convert_masks_for_output([]).shape) == (1, 1, 1)
