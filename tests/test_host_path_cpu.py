@@ -431,3 +431,22 @@ def test_check_motion_meta_script_tail_on_the_cpu(monkeypatch):
     g.test_identity_blur_zero_expand_determinism_and_ticks()
     g.test_errors_match_the_reference_messages()
 
+
+
+def test_host_path_perspective_camera_lock(monkeypatch):
+    """Perspective ladder + camera_lock (target path 0, smooth >= 0.85) on the 1080p golden clip."""
+    case = next(c for c in cases.STABILIZER_CASES if c["name"] == "flow_persp_lock_1080p")
+    gold = np.load(os.path.join(GOLDEN_DIR, f"stab_{case['name']}.npz"))
+    with open(os.path.join(GOLDEN_DIR, f"stab_{case['name']}_meta.json")) as fh:
+        gmeta = json.load(fh)
+    res = _run(monkeypatch, cases.make_frames(case), case["framing"], case["mode"], case["camera_lock"], case["strength"],
+               case["smooth"], case["keep_fov"], case["padding_rgb"], case["fps"])
+    meta = json.loads(json.dumps(res.meta))
+    assert meta["transform_mode_applied"] == "perspective" and meta["camera_lock"] is True
+    for mine, ref in zip(meta["estimated_motion"]["per_transition"], gmeta["estimated_motion"]["per_transition"]):
+        assert mine["mode"] == ref["mode"] == "perspective"
+        parity.assert_transform_close(mine["matrix"], ref["matrix"], f"pair {ref['index']}")
+    # homography refinement (LM) agrees with cv2 to ~1e-8 per entry, which the 8 perspective parameters carry through
+    parity.compare_nested(gmeta, meta, "meta", atol=2e-4, rtol=2e-4)
+    f, y, x, hh, ww = gold["patch0_at"]
+    assert float(np.abs(np.asarray(res.frames)[f, y:y + hh, x:x + ww] - gold["patch0"]).max()) <= parity.TOL_PIXEL["bilinear"]
