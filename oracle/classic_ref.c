@@ -223,9 +223,16 @@ static inline int dpix(const int16_t* D, int h, int w, int y, int x, int c) {
   return D[((size_t)y * w + x) * 2 + c];
 }
 
-/* prev/next: float [n][2]; status: uint8 [n].  win = 31, max_level = 3, 50 iterations, eps 0.01. */
-void classicref_pyr_lk(const uint8_t* I0, const uint8_t* J0, int h, int w, const float* prev_pts, int n, int win, int max_level,
-                       int max_iter, double eps, float* next_pts, uint8_t* status) {
+/* prev/next: float [n][2]; status: uint8 [n].  win = 31, max_level = 3, 50 iterations, eps 0.01.
+ * cv_order = 0: the window sums (structure tensor A11/A12/A22, mismatch vector b1/b2) run serially over the window --
+ *   what the CUDA tracker is checked against; positions within float rounding of cv2 (<= 2e-3 px, same status flags).
+ * cv_order = 1: the sums in the order of cv2's 128-bit SIMD code, found black-box (minEig through
+ *   OPTFLOW_LK_GET_MIN_EIGENVALS, positions after one iteration): per row the first 24 of the 31 columns go to four
+ *   lane accumulators (A: lane = x mod 4, reduced (l0+l2)+(l1+l3); b: int32 pair sums d[x]g[x]+d[x+4]g[x+4] converted
+ *   to float, eight lanes folded pairwise), columns 24..30 to one scalar accumulator carried across the rows.
+ *   Bit-exact against the wheel: 9288 of 9288 tracks over 30 random frame sizes (tests/test_oracle_classic.py). */
+static void pyr_lk_body(const uint8_t* I0, const uint8_t* J0, int h, int w, const float* prev_pts, int n, int win, int max_level,
+                        int max_iter, double eps, float* next_pts, uint8_t* status, int cv_order) {
   enum { MAXL = 8 };
   uint8_t* Ip[MAXL]; uint8_t* Jp[MAXL]; int16_t* Dp[MAXL]; int hh[MAXL], ww[MAXL];
   int levels = 0;
@@ -261,7 +268,7 @@ void classicref_pyr_lk(const uint8_t* I0, const uint8_t* J0, int h, int w, const
       float a = px - ipx, b = py - ipy;
       int iw00 = (int)lrintf((1.f - a) * (1.f - b) * (1 << W_BITS)), iw01 = (int)lrintf(a * (1.f - b) * (1 << W_BITS));
       int iw10 = (int)lrintf((1.f - a) * b * (1 << W_BITS)), iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
-      float A11 = 0, A12 = 0, A22 = 0;
+      float A11 = 0, A12 = 0, A22 = 0, q11[4] = {0, 0, 0, 0}, q12[4] = {0, 0, 0, 0}, q22[4] = {0, 0, 0, 0};
       for (int y = 0; y < win; y++)
         for (int x = 0; x < win; x++) {
           const int sy = ipy + y, sx = ipx + x;
@@ -272,8 +279,10 @@ void classicref_pyr_lk(const uint8_t* I0, const uint8_t* J0, int h, int w, const
           const int iyval = descale(dpix(D, lh, lw, sy, sx, 1) * iw00 + dpix(D, lh, lw, sy, sx + 1, 1) * iw01 +
                                     dpix(D, lh, lw, sy + 1, sx, 1) * iw10 + dpix(D, lh, lw, sy + 1, sx + 1, 1) * iw11, W_BITS);
           IWin[y * win + x] = (int16_t)ival; DWin[(y * win + x) * 2] = (int16_t)ixval; DWin[(y * win + x) * 2 + 1] = (int16_t)iyval;
-          A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval);
+          if (cv_order && x < (win / 8) * 8) { const int l = x & 3; q11[l] += (float)(ixval * ixval); q12[l] += (float)(ixval * iyval); q22[l] += (float)(iyval * iyval); }
+          else { A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval); }
         }
+      A11 += (q11[0] + q11[2]) + (q11[1] + q11[3]); A12 += (q12[0] + q12[2]) + (q12[1] + q12[3]); A22 += (q22[0] + q22[2]) + (q22[1] + q22[3]);
       A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
       float Dd = A11 * A22 - A12 * A12;
       const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (2 * win * win);
@@ -287,15 +296,26 @@ void classicref_pyr_lk(const uint8_t* I0, const uint8_t* J0, int h, int w, const
         a = nx - inx; b = ny - iny;
         iw00 = (int)lrintf((1.f - a) * (1.f - b) * (1 << W_BITS)); iw01 = (int)lrintf(a * (1.f - b) * (1 << W_BITS));
         iw10 = (int)lrintf((1.f - a) * b * (1 << W_BITS)); iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
-        float b1 = 0, b2 = 0;
-        for (int y = 0; y < win; y++)
+        float b1 = 0, b2 = 0, qb0[4] = {0, 0, 0, 0}, qb1[4] = {0, 0, 0, 0};
+        for (int y = 0; y < win; y++) {
+          int dd[64];
           for (int x = 0; x < win; x++) {
             const int sy = iny + y, sx = inx + x;
-            const int diff = descale(pix(J, lh, lw, sy, sx) * iw00 + pix(J, lh, lw, sy, sx + 1) * iw01 + pix(J, lh, lw, sy + 1, sx) * iw10 +
-                                     pix(J, lh, lw, sy + 1, sx + 1) * iw11, W_BITS - 5) - IWin[y * win + x];
-            b1 += (float)(diff * DWin[(y * win + x) * 2]);
-            b2 += (float)(diff * DWin[(y * win + x) * 2 + 1]);
+            dd[x] = descale(pix(J, lh, lw, sy, sx) * iw00 + pix(J, lh, lw, sy, sx + 1) * iw01 + pix(J, lh, lw, sy + 1, sx) * iw10 +
+                            pix(J, lh, lw, sy + 1, sx + 1) * iw11, W_BITS - 5) - IWin[y * win + x];
           }
+          const int16_t* g0 = DWin + y * win * 2;
+          int x = 0;
+          for (; cv_order && x <= win - 8; x += 8) {
+            const int* d = dd + x; const int16_t* g = g0 + x * 2;
+            qb0[0] += (float)(d[0] * g[0] + d[4] * g[8]);  qb0[1] += (float)(d[0] * g[1] + d[4] * g[9]);
+            qb0[2] += (float)(d[1] * g[2] + d[5] * g[10]); qb0[3] += (float)(d[1] * g[3] + d[5] * g[11]);
+            qb1[0] += (float)(d[2] * g[4] + d[6] * g[12]); qb1[1] += (float)(d[2] * g[5] + d[6] * g[13]);
+            qb1[2] += (float)(d[3] * g[6] + d[7] * g[14]); qb1[3] += (float)(d[3] * g[7] + d[7] * g[15]);
+          }
+          for (; x < win; x++) { b1 += (float)(dd[x] * g0[x * 2]); b2 += (float)(dd[x] * g0[x * 2 + 1]); }
+        }
+        b1 += (qb0[0] + qb1[0]) + (qb0[2] + qb1[2]); b2 += (qb0[1] + qb1[1]) + (qb0[3] + qb1[3]);
         b1 *= FLT_SCALE; b2 *= FLT_SCALE;
         const float ddx = (float)((A12 * b2 - A22 * b1) * Dd), ddy = (float)((A12 * b1 - A11 * b2) * Dd);
         nx += ddx; ny += ddy;
@@ -316,4 +336,14 @@ void classicref_pyr_lk(const uint8_t* I0, const uint8_t* J0, int h, int w, const
   }
   for (int l = 0; l <= levels; l++) { free(Dp[l]); if (l > 0) { free(Ip[l]); free(Jp[l]); } }
   free(IWin); free(DWin);
+}
+
+void classicref_pyr_lk(const uint8_t* I0, const uint8_t* J0, int h, int w, const float* prev_pts, int n, int win, int max_level,
+                       int max_iter, double eps, float* next_pts, uint8_t* status) {
+  pyr_lk_body(I0, J0, h, w, prev_pts, n, win, max_level, max_iter, eps, next_pts, status, 0);
+}
+
+void classicref_pyr_lk_exact(const uint8_t* I0, const uint8_t* J0, int h, int w, const float* prev_pts, int n, int win, int max_level,
+                             int max_iter, double eps, float* next_pts, uint8_t* status) {
+  pyr_lk_body(I0, J0, h, w, prev_pts, n, win, max_level, max_iter, eps, next_pts, status, 1);
 }

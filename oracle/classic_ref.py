@@ -43,14 +43,16 @@ def good_features(img: np.ndarray, max_corners=400, quality=0.01, min_distance=7
     return xy[:k].copy()
 
 
-def pyr_lk(prev_img, next_img, pts, win=31, max_level=3, max_iter=50, eps=0.01):
-    """cv2.calcOpticalFlowPyrLK(prev, next, pts, None, winSize=(win,win), maxLevel, (EPS|COUNT, max_iter, eps)) -> (next_pts, status)."""
+def pyr_lk(prev_img, next_img, pts, win=31, max_level=3, max_iter=50, eps=0.01, exact=False):
+    """cv2.calcOpticalFlowPyrLK(prev, next, pts, None, winSize=(win,win), maxLevel, (EPS|COUNT, max_iter, eps)) -> (next_pts, status).
+    exact=True sums the window terms in the lane order of cv2's SIMD code (bit-exact positions); the default sums them
+    serially, which is what the CUDA tracker is checked against (see classic_ref.c)."""
     a = np.ascontiguousarray(prev_img, dtype=np.uint8)
     b = np.ascontiguousarray(next_img, dtype=np.uint8)
     p = np.ascontiguousarray(np.asarray(pts, dtype=np.float32).reshape(-1, 2))
     n = p.shape[0]
     out = np.zeros((n, 2), np.float32)
     st = np.zeros((n,), np.uint8)
-    lib().classicref_pyr_lk(_p(a), _p(b), C.c_int(a.shape[0]), C.c_int(a.shape[1]), _p(p), C.c_int(n), C.c_int(win), C.c_int(max_level),
+    (lib().classicref_pyr_lk_exact if exact else lib().classicref_pyr_lk)(_p(a), _p(b), C.c_int(a.shape[0]), C.c_int(a.shape[1]), _p(p), C.c_int(n), C.c_int(win), C.c_int(max_level),
                             C.c_int(max_iter), C.c_double(eps), _p(out), _p(st))
     return out, st

@@ -35,3 +35,20 @@ def test_lk_loses_points_that_leave_the_frame():
                                           criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 50, 0.01))
     mine, ms = CR.pyr_lk(p, c, f)
     assert int((st.ravel() != ms).sum()) <= 1
+
+
+@pytest.mark.parametrize("size", [(960, 540), (540, 960), (333, 187), (121, 73), (640, 360)])
+def test_lk_in_cv2_lane_order_is_bit_exact(size):
+    """pyr_lk(exact=True) sums the 31x31 window terms in the lane order of cv2's SIMD code (classic_ref.c): every
+    tracked position carries cv2's bits, every status flag is cv2's.  (The default order is the one the CUDA tracker
+    follows; moving the kernel to this one is what would make Classic as exact as Flow.)"""
+    w, h = size
+    for seed, amount in ((1, 1.5), (2, 6.0)):
+        p, c = cases.make_gray_pair(dict(w=w, h=h, seed=w + seed, amount=amount))
+        f = cv2.goodFeaturesToTrack(p, maxCorners=400, qualityLevel=0.01, minDistance=7, blockSize=21).reshape(-1, 2)
+        nxt, st, _ = cv2.calcOpticalFlowPyrLK(p, c, f.reshape(-1, 1, 2), None, winSize=(31, 31), maxLevel=3,
+                                              criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 50, 0.01))
+        mine, ms = CR.pyr_lk(p, c, f, exact=True)
+        st = st.ravel()
+        assert np.array_equal(st, ms)
+        assert np.array_equal(nxt.reshape(-1, 2)[st == 1], mine[st == 1])
