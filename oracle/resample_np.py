@@ -96,8 +96,13 @@ def _gather(src: np.ndarray, yy: np.ndarray, xx: np.ndarray, border: np.ndarray)
     return np.where(inside[..., None], vals, border[None, None, :].astype(np.float32))
 
 
-def warp_np(src: np.ndarray, m32: np.ndarray, out_size, interp: str, border) -> np.ndarray:
-    """cv2.warpPerspective(src, m32, out_size, INTER_LINEAR|INTER_CUBIC, BORDER_CONSTANT, border)."""
+def warp_np(src: np.ndarray, m32: np.ndarray, out_size, interp: str, border, cubic_rows: bool = False) -> np.ndarray:
+    """cv2.warpPerspective(src, m32, out_size, INTER_LINEAR|INTER_CUBIC, BORDER_CONSTANT, border).
+
+    cubic_rows: order of the 16-term bicubic sum of pixels whose 4x4 footprint lies inside the source.  False: one
+    running sum over the taps, row-major -- what the CUDA resampler does and is checked against (<= 4.8e-7 from cv2).
+    True: cv2's own order, found black-box: the four taps of a row are summed first and the row sums are added to the
+    running sum (remapBicubic's `sum += S[0]*w[4] + S[cn]*w[5] + ...`); bit-exact against the wheel."""
     src = np.asarray(src, dtype=np.float32)
     if src.ndim == 2:
         src = src[..., None]
@@ -125,13 +130,19 @@ def warp_np(src: np.ndarray, m32: np.ndarray, out_size, interp: str, border) -> 
         bx, by = sx - 1, sy - 1
         edge = np.zeros((out_h, out_w, c), dtype=np.float32) + bvec  # cv + sum (S - cv) * w over in-range taps
         for k1 in range(4):
+            row = None
             for k2 in range(4):
                 wgt = (ty[..., k1] * tx[..., k2]).astype(np.float32)
                 yy, xx = by + k1, bx + k2
                 tap = _gather(src, yy, xx, border)
-                out = out + tap * wgt[..., None]
+                if cubic_rows:
+                    row = tap * wgt[..., None] if row is None else row + tap * wgt[..., None]
+                else:
+                    out = out + tap * wgt[..., None]
                 inside = ((yy >= 0) & (yy < h) & (xx >= 0) & (xx < w))[..., None]
                 edge = np.where(inside, edge + (tap - bvec) * wgt[..., None], edge)
+            if cubic_rows:
+                out = row if k1 == 0 else out + row
         interior = (bx >= 0) & (bx < w - 3) & (by >= 0) & (by < h - 3)
         gone = (bx >= w) | (bx + 3 < 0) | (by >= h) | (by + 3 < 0)
         out = np.where(interior[..., None], out, edge)

@@ -82,3 +82,24 @@ def test_apply_oracle_matches_reference_golden(case):
     tol = 0.0 if case["interp"] == "bilinear" and case["blur"] == 0.0 else 2e-6
     assert float(np.abs(out_f - gold["frames"]).max()) <= tol
     assert np.array_equal(out_m, gold["masks"]) if case["blur"] == 0.0 else float(np.abs(out_m - gold["masks"]).max()) <= 1e-6
+
+
+def test_bicubic_in_cv2_row_order_is_bit_exact():
+    """warp_np(cubic_rows=True): the bicubic sum in cv2's own order (row sums first) carries cv2's bits on every pixel,
+    interior and border alike; the default order (one running sum, what the CUDA resampler does) stays within 4.8e-7."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    for k in range(10):
+        w, h = int(rng.integers(40, 300)), int(rng.integers(40, 200))
+        ow, oh = w + int(rng.integers(-5, 30)), h + int(rng.integers(-5, 30))
+        src = rng.random((h, w, 3), dtype=np.float32)
+        th, sc = rng.normal(0, 0.05), 1 + rng.normal(0, 0.05)
+        M = np.array([[sc * np.cos(th), -sc * np.sin(th), rng.normal(0, 6)], [sc * np.sin(th), sc * np.cos(th), rng.normal(0, 6)],
+                      [0, 0, 1]], np.float64)
+        if k % 3 == 0:
+            M[2, :2] = rng.normal(0, 2e-4, 2)
+        M = M.astype(np.float32)
+        border = tuple(float(x) for x in (rng.integers(0, 256, 3) / 255.0).astype(np.float32))
+        ref = cv2.warpPerspective(src, M, (ow, oh), flags=cv2.INTER_CUBIC, borderMode=cv2.BORDER_CONSTANT, borderValue=border)
+        assert np.array_equal(ref, R.warp_np(src, M, (ow, oh), "bicubic", border, cubic_rows=True)), k
+        assert float(np.abs(ref - R.warp_np(src, M, (ow, oh), "bicubic", border)).max()) <= 1e-6
