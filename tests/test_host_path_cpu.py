@@ -450,3 +450,44 @@ def test_host_path_perspective_camera_lock(monkeypatch):
     parity.compare_nested(gmeta, meta, "meta", atol=2e-4, rtol=2e-4)
     f, y, x, hh, ww = gold["patch0_at"]
     assert float(np.abs(np.asarray(res.frames)[f, y:y + hh, x:x + ww] - gold["patch0"]).max()) <= parity.TOL_PIXEL["bilinear"]
+
+
+@pytest.mark.reference
+def test_crop_solvers_equal_the_reference_on_random_paths(monkeypatch, reference_nodes):
+    """keep_fov search + no-padding refinement + aspect rectangle against the unmodified reference's functions
+    (stabilizer_utils.py:448-837) on random stabilisation paths, every keep_fov regime (disabled / met / clamped /
+    failed / no overlap); the two coverage kernels are replaced by their numpy statement."""
+    import torch
+
+    from vstab_b200 import crop, hostmath as hm
+
+    U = reference_nodes.stabilizer_utils
+    monkeypatch.setattr(crop._native, "get_handle", lambda device: _CoverageOracle())
+    rng = np.random.default_rng(17)
+    dev = torch.device("cpu")
+    seen = set()
+    for trial in range(24):
+        w, h = int(rng.integers(48, 200)), int(rng.integers(32, 120))
+        n = int(rng.integers(2, 9))
+        mode = ("translation", "similarity")[trial % 2]
+        amp = float(rng.choice([0.5, 3.0, 12.0, 60.0, 400.0]))
+        deltas = rng.normal(0, 1, (n, 2 if mode == "translation" else 4)) * (np.array([amp, amp]) if mode == "translation" else
+                                                                               np.array([amp, amp, 0.01, 0.01]))
+        keep = float(rng.choice([0.0, 0.3, 0.6, 0.9, 0.97]))
+        margin = max(0.5, 0.02 * max(w, h))
+        want = U._compute_crop_with_keep_fov_parametric(U._params_to_matrix, mode, list(deltas), w, h, keep, margin, return_masks=False)
+        w_final, w_pre, _masks, w_ratio, w_status, w_note, w_scale, w_origin, w_size = want
+        got = crop.compute_crop_with_keep_fov(dev, mode, deltas, w, h, keep, margin)
+        g_final, g_pre, g_ratio, g_status, g_note, g_scale, g_origin, g_size = got
+        assert (g_status, g_note, g_scale) == (w_status, w_note, w_scale), trial
+        assert g_ratio == w_ratio and list(g_origin) == list(w_origin) and list(g_size) == list(w_size), trial
+        assert np.array_equal(np.asarray(g_final), np.stack(w_final)) and np.array_equal(np.asarray(g_pre), np.stack(w_pre)), trial
+        seen.add((w_status, w_note is None))
+        r_final, _m, r_origin, r_size, r_eff = U._refine_no_padding_crop(w_final, w, h, 1)
+        q_final, q_origin, q_size, q_eff = crop.refine_no_padding_crop(dev, np.stack(w_final), w, h, 1)
+        assert q_eff == r_eff and list(q_origin) == list(r_origin) and list(q_size) == list(r_size), trial
+        assert np.array_equal(np.asarray(q_final), np.stack(r_final)), trial
+        mask = rng.random((h, w)) > 0.02
+        mask[: int(rng.integers(0, 6))] = False
+        assert crop.largest_aspect_ratio_rectangle(mask.astype(np.uint8), w, h) == U._largest_aspect_ratio_rectangle(mask.astype(np.uint8), w, h)
+    assert len({s for s, _ in seen}) >= 3, seen  # the draw reached several regimes
