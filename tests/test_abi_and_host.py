@@ -399,3 +399,23 @@ def test_input_adapters_equal_the_reference_on_its_own_cases(monkeypatch, refere
     masks = [rng.random((45, 73, 1)).astype(np.float32) for _ in range(3)]
     assert np.array_equal(U._convert_masks_for_output(masks).numpy(), pipeline.convert_masks_for_output(np.stack(masks)).numpy())
     assert tuple(pipeline.convert_masks_for_output(np.zeros((0, 4, 4, 1), np.float32)).shape) == tuple(U._convert_masks_for_output([]).shape) == (1, 1, 1)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm): one JSON line with the contract's keys,
+    measured on the oracle's cv2 call sequence, no GPU involved."""
+    import json
+    import subprocess
+
+    pytest.importorskip("cv2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True
+    assert line["metric"] == "frames/sec 1080p Flow stabilize" and line["n_gpus"] == 1 and line["steps"] == 1
+    assert line["value"] > 0 and line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["kind"] in ("port", "reference")
+    assert line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"] and "workload" in line["config"]
+    assert line["gpu_launches"] == 0 and line["vs_baseline"] is None and line["dtype"] == "f32" and line["data"] == "synthetic"
