@@ -491,3 +491,56 @@ def test_crop_solvers_equal_the_reference_on_random_paths(monkeypatch, reference
         mask[: int(rng.integers(0, 6))] = False
         assert crop.largest_aspect_ratio_rectangle(mask.astype(np.uint8), w, h) == U._largest_aspect_ratio_rectangle(mask.astype(np.uint8), w, h)
     assert len({s for s, _ in seen}) >= 3, seen  # the draw reached several regimes
+
+
+@pytest.mark.reference
+def test_flow_host_path_equals_the_live_reference_on_random_settings(monkeypatch, reference_nodes):
+    """Random small clips x random node settings (framing, model, camera_lock, strength, smooth, keep_fov, fps, padding
+    colour): the unmodified reference's _stabilize_frames, run here, against the product's host path with the oracle in
+    place of the GPU stages.  Sweeps what the goldens sample: sticky ladder fall-backs on frames with too few grid
+    points, perspective, crop regimes, expand canvases, the keep_fov bypass."""
+    import torch
+
+    import synth
+    from vstab_b200 import crop, stabilizer_core as core
+
+    ref = reference_nodes.video_stabilizer_flow
+    U = reference_nodes.stabilizer_utils
+    monkeypatch.setattr(core, "fused_warp", _oracle_warp)
+    monkeypatch.setattr(crop._native, "get_handle", lambda device: _CoverageOracle())
+    rng = np.random.default_rng(23)
+    modes_seen, framings_seen = set(), set()
+    ran = 0
+    for trial in range(48):
+        w, h = int(rng.integers(24, 140)), int(rng.integers(20, 100))
+        if dis_ref.select_scales(h, w) is None:
+            continue
+        f0, c0 = dis_ref.select_scales(h, w)
+        if min(h >> c0, w >> c0) < 8:      # cv2 itself reads out of bounds on these sizes
+            continue
+        n = int(rng.integers(2, 8))
+        seed = 500 + trial
+        base = synth.base_texture(seed, w, h).numpy()
+        mats = synth.shake_matrices(n, seed, w, h, perspective=bool(trial % 3 == 0), amount=float(rng.choice([0.5, 2.0, 5.0])))
+        frames = synth.render_clip_numpy(base, mats, w, h)
+        framing = str(rng.choice(["crop_and_pad", "expand", "crop"]))
+        mode = str(rng.choice(["translation", "similarity", "perspective"]))
+        args = (framing, mode, bool(rng.random() < 0.3), float(rng.choice([0.0, 0.4, 0.7, 1.0])), float(rng.choice([0.0, 0.5, 1.0])),
+                float(rng.choice([0.0, 0.6, 0.95, 1.0])), tuple(int(v) for v in rng.integers(0, 256, 3)), float(rng.choice([8.0, 16.0, 30.0])))
+        want = ref._stabilize_frames(U._normalize_video_input([f for f in frames]), *args)
+        clip = _Clip(frames)
+        clip.device = torch.device("cpu")
+        clip.untouched = lambda output, fr=frames: (fr, np.zeros(fr.shape[:3] + (1,), np.float32))
+        got = core.stabilize_frames(clip, *args, estimator=_oracle_estimator, flavour="flow", output="device")
+        gmeta, meta = json.loads(json.dumps(want.meta)), json.loads(json.dumps(got.meta))
+        parity.compare_nested(gmeta, meta, f"trial {trial} {args} {w}x{h}x{n}: meta", atol=2e-5, rtol=2e-5)
+        wf, wm = np.asarray(want.frames, np.float32), np.asarray(want.masks, np.float32)
+        gf, gm = np.asarray(got.frames), np.asarray(got.masks)
+        assert gf.shape == wf.shape and gm.shape == wm.shape, trial
+        err = np.abs(gf - wf)
+        assert float((err > 2e-5).mean()) <= 2e-3 and float(err.max()) <= 0.05, (trial, float((err > 2e-5).mean()), float(err.max()))
+        assert float((gm != wm).mean()) <= 2e-3, trial
+        modes_seen.add(meta.get("transform_mode_applied"))
+        framings_seen.add(framing)
+        ran += 1
+    assert ran >= 30 and len(framings_seen) == 3 and len(modes_seen) >= 4, (ran, framings_seen, modes_seen)
