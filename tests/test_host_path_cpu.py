@@ -199,7 +199,7 @@ def test_motion_apply_engine_on_the_cpu(monkeypatch, case):
 
 # ---- Classic: corners + tracks from the C oracle, same host path ------------------------------------------------
 
-def _oracle_classic_estimator(context, work_w, work_h, requested):
+def _oracle_classic_estimator(context, work_w, work_h, requested, exact_lk=False):
     """classic.estimate_candidates with oracle/classic_ref.c in place of K5/K6 and fit_np in place of K7-K9."""
     from oracle import classic_ref as CR
     from vstab_b200.stabilizer_core import PairCandidates
@@ -215,7 +215,7 @@ def _oracle_classic_estimator(context, work_w, work_h, requested):
         detected[p] = len(feats)
         if len(feats) == 0:
             continue
-        nxt, st = CR.pyr_lk(gray[p], gray[p + 1], feats)
+        nxt, st = CR.pyr_lk(gray[p], gray[p + 1], feats, exact=exact_lk)
         prev, curr = feats[st == 1], nxt[st == 1].astype(np.float32)
         valid[p], total[p] = len(prev), 400
         if len(prev) == 0:
@@ -227,6 +227,11 @@ def _oracle_classic_estimator(context, work_w, work_h, requested):
             if A is not None:
                 m[p, 1, :2] = A
                 inl[p, 1], ok[p, 1] = int(mask.sum()), 1
+        if requested == "perspective" and len(prev) >= 4:
+            H, mask = fit_np.find_homography(prev, curr)
+            if H is not None:
+                m[p, 2] = H
+                inl[p, 2], ok[p, 2] = int(mask.sum()), 1
     return PairCandidates(m, res, inl.astype(int), valid.astype(int), total.astype(int), ok.astype(int), min_points=8, detected=detected)
 
 
@@ -544,3 +549,48 @@ def test_flow_host_path_equals_the_live_reference_on_random_settings(monkeypatch
         framings_seen.add(framing)
         ran += 1
     assert ran >= 30 and len(framings_seen) == 3 and len(modes_seen) >= 4, (ran, framings_seen, modes_seen)
+
+
+@pytest.mark.reference
+def test_classic_host_path_equals_the_live_reference_with_exact_lk(monkeypatch, reference_nodes):
+    """The same sweep for Classic, with the tracks summed in cv2's lane order (classic_ref.pyr_lk(exact=True)): corners,
+    tracks, fits, ladder and framing then agree with the unmodified reference to its own 2e-5 -- what the CUDA tracker
+    gains by adopting that order (parity items left for a next round)."""
+    import functools
+
+    import torch
+
+    import synth
+    from vstab_b200 import crop, stabilizer_core as core
+
+    ref = reference_nodes.video_stabilizer_classic
+    U = reference_nodes.stabilizer_utils
+    monkeypatch.setattr(core, "fused_warp", _oracle_warp)
+    monkeypatch.setattr(crop._native, "get_handle", lambda device: _CoverageOracle())
+    est = functools.partial(_oracle_classic_estimator, exact_lk=True)
+    rng = np.random.default_rng(29)
+    modes_seen, ran = set(), 0
+    for trial in range(30):
+        w, h = int(rng.integers(60, 260)), int(rng.integers(48, 160))
+        n = int(rng.integers(2, 7))
+        seed = 700 + trial
+        base = synth.base_texture(seed, w, h).numpy()
+        mats = synth.shake_matrices(n, seed, w, h, perspective=bool(trial % 3 == 0), amount=float(rng.choice([0.5, 2.0, 5.0])))
+        frames = synth.render_clip_numpy(base, mats, w, h)
+        framing = str(rng.choice(["crop_and_pad", "expand", "crop"]))
+        mode = str(rng.choice(["translation", "similarity", "perspective"]))
+        args = (framing, mode, bool(rng.random() < 0.3), float(rng.choice([0.0, 0.4, 0.7, 1.0])), float(rng.choice([0.0, 0.5, 1.0])),
+                float(rng.choice([0.0, 0.6, 0.95, 1.0])), tuple(int(v) for v in rng.integers(0, 256, 3)), float(rng.choice([8.0, 16.0, 30.0])))
+        want = ref._stabilize_frames(U._normalize_video_input([f for f in frames]), *args)
+        clip = _Clip(frames)
+        clip.device = torch.device("cpu")
+        clip.untouched = lambda output, fr=frames: (fr, np.zeros(fr.shape[:3] + (1,), np.float32))
+        got = core.stabilize_frames(clip, *args, estimator=est, flavour="classic", output="device")
+        gmeta, meta = json.loads(json.dumps(want.meta)), json.loads(json.dumps(got.meta))
+        parity.compare_nested(gmeta, meta, f"trial {trial} {args} {w}x{h}x{n}: meta", atol=2e-5, rtol=2e-5)
+        err = np.abs(np.asarray(got.frames) - np.asarray(want.frames, np.float32))
+        assert float((err > 2e-5).mean()) <= 2e-3 and float(err.max()) <= 0.05, (trial, float((err > 2e-5).mean()), float(err.max()))
+        modes_seen.add(meta.get("transform_mode_applied"))
+        ran += 1
+    assert ran == 30 and len(modes_seen) >= 3, (ran, modes_seen)
+
