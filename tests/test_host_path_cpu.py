@@ -594,3 +594,39 @@ def test_classic_host_path_equals_the_live_reference_with_exact_lk(monkeypatch, 
         ran += 1
     assert ran == 30 and len(modes_seen) >= 3, (ran, modes_seen)
 
+
+
+@pytest.mark.reference
+def test_motion_apply_engine_equals_the_live_reference_on_random_settings(monkeypatch, reference_nodes):
+    """Shake Generator metas (every style of the reference's shake_noise, random seeds / amounts) x random Motion Apply
+    settings through the unmodified apply_motion and through the product's engine with the numpy resampler."""
+    from vstab_b200 import motion_apply as ma
+
+    monkeypatch.setattr(ma, "fused_warp", _oracle_sample_warp)
+    monkeypatch.setattr(ma, "common_valid_mask", _oracle_common_valid_mask)
+    R, SN, U = reference_nodes.motion_apply, reference_nodes.shake_noise, reference_nodes.stabilizer_utils
+    rng = np.random.default_rng(31)
+    styles = sorted(SN.STYLES)
+    effective = set()
+    for trial in range(24):
+        w, h, n = int(rng.integers(16, 120)), int(rng.integers(12, 90)), int(rng.integers(1, 7))
+        style = styles[trial % len(styles)]
+        block = SN.generate_shake_motion_meta(recipe=SN.STYLES[style], frame_count=n, width=w, height=h, fps=float(rng.choice([8.0, 16.0, 24.0])),
+                                              amount=float(rng.choice([0.5, 2.0, 8.0, 40.0])), speed=float(rng.choice([0.5, 1.0, 3.0])),
+                                              seed=int(rng.integers(0, 1000)), node="shake_generator", style=style)
+        meta = {"motion_meta": block}
+        frames = rng.random((n, h, w, 3), dtype=np.float32)
+        kw = dict(framing_mode=str(rng.choice(["crop_and_pad", "pad", "crop", "expand"])), interpolation=str(rng.choice(["bilinear", "bicubic"])),
+                  motion_blur=float(rng.choice([0.0, 0.0, 0.5, 1.0])), motion_blur_samples=int(rng.choice([1, 5, 9, 33, 50])))
+        rgb = tuple(int(v) for v in rng.integers(0, 256, 3))
+        ticks = [0, 0]
+        want = R.apply_motion(U._normalize_video_input([f for f in frames]), meta, rgb, progress_callback=lambda: ticks.__setitem__(0, ticks[0] + 1), **kw)
+        got = ma.apply_motion(_RgbClip(frames), json.loads(json.dumps(meta)), rgb, progress_callback=lambda: ticks.__setitem__(1, ticks[1] + 1), **kw)
+        assert ticks[0] == ticks[1], (trial, kw, ticks)
+        assert got.frames.shape == want.frames.shape and got.masks.shape == want.masks.shape, (trial, kw)
+        exact = kw["interpolation"] == "bilinear" and kw["motion_blur"] == 0.0
+        assert float(np.abs(got.frames - want.frames).max()) <= (0.0 if exact else 2e-6), (trial, kw)
+        assert float(np.abs(got.masks - want.masks).max()) <= (0.0 if kw["motion_blur"] == 0.0 else 1e-6), (trial, kw)
+        assert json.loads(json.dumps(got.meta)) == json.loads(json.dumps(want.meta)), (trial, kw)
+        effective.add(got.meta["motion_apply"]["framing_mode"] + ("+fallback" if "framing_fallback" in got.meta else ""))
+    assert {"crop_and_pad", "crop", "expand"} <= {e.split("+")[0] for e in effective}, effective
