@@ -41,6 +41,11 @@ extern "C" void vstab_destroy(vstab_handle* h) {
   cudaSetDevice(h->device);
   if (h->ws) cudaFree(h->ws);
   if (h->plan) cudaFree(h->plan);
+  for (int i = 0; i < h->n_aux; ++i) {
+    cudaStreamDestroy(h->aux_stream[i]);
+    cudaEventDestroy(h->join_event[i]);
+  }
+  if (h->fork_event) cudaEventDestroy(h->fork_event);
   for (int i = 0; i < h->n_area_cache; ++i)
     if (h->area_cache[i].dev) cudaFree(h->area_cache[i].dev);
   free(h);
@@ -49,6 +54,17 @@ extern "C" void vstab_destroy(vstab_handle* h) {
 extern "C" const char* vstab_last_error(const vstab_handle* h) { return h ? h->err : g_vstab_err; }
 
 extern "C" uint64_t vstab_launch_count(const vstab_handle* h) { return h ? h->launches : 0; }
+
+int vstab_aux_streams(vstab_handle* h, int n) {
+  if (n > VSTAB_MAX_AUX_STREAMS) return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_aux_streams: too many helper streams");
+  if (!h->fork_event) VSTAB_CUDA(h, cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
+  while (h->n_aux < n) {
+    VSTAB_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream[h->n_aux], cudaStreamNonBlocking));
+    VSTAB_CUDA(h, cudaEventCreateWithFlags(&h->join_event[h->n_aux], cudaEventDisableTiming));
+    h->n_aux++;
+  }
+  return VSTAB_OK;
+}
 
 int vstab_workspace(vstab_handle* h, size_t bytes, void** out) {
   if (bytes > h->ws_bytes) {

@@ -11,6 +11,7 @@
 #include "area.cuh"
 
 #define VSTAB_AREA_CACHE 32
+#define VSTAB_MAX_AUX_STREAMS 3
 struct vstab_area_cache_entry {
   int ssize, dsize;
   void* dev;
@@ -32,6 +33,12 @@ struct vstab_handle {
   vstab_area_cache_entry area_cache[VSTAB_AREA_CACHE];
   int n_area_cache;
   int area_evict;  // next slot to recycle once the cache is full
+  // helper streams for work that forks from / joins back into the caller's stream inside one call
+  // (DIS pair groups); created on first use
+  cudaStream_t aux_stream[VSTAB_MAX_AUX_STREAMS];
+  cudaEvent_t join_event[VSTAB_MAX_AUX_STREAMS];
+  cudaEvent_t fork_event;
+  int n_aux;
 };
 
 extern char g_vstab_err[512];
@@ -70,6 +77,9 @@ static inline int vstab_fail(vstab_handle* h, int code, const char* fmt, const c
 
 // Returns a device workspace of at least `bytes` (grow-only; synchronises only when growing).
 int vstab_workspace(vstab_handle* h, size_t bytes, void** out);
+
+// Makes sure aux_stream[0..n) / join_event[0..n) / fork_event exist (n <= VSTAB_MAX_AUX_STREAMS).
+int vstab_aux_streams(vstab_handle* h, int n);
 
 static inline int vstab_ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -35,6 +35,12 @@ constexpr float kEps = 0.001f;
 constexpr float kInf = 1e10f;
 constexpr float kAlpha = 20.f, kDelta = 5.f, kGamma = 10.f, kEpsilon = 0.01f, kOmega = 1.6f;
 constexpr int kMaxLevels = 8;
+#ifndef VSTAB_DIS_GROUPS_DEFAULT
+#define VSTAB_DIS_GROUPS_DEFAULT 2
+#endif
+#ifndef VSTAB_VR_MIN_CTAS
+#define VSTAB_VR_MIN_CTAS 5
+#endif
 
 struct Level {
   int w, h, ws, hs;
@@ -193,22 +199,31 @@ __device__ __forceinline__ float patch_eval(const float (&z)[8][2], const float 
   return sum_sq - sum_diff * sum_diff / 64.f;
 }
 
-// One warp per (pair, stripe): 8 patch rows x 4 lanes, anti-diagonal wavefront over the columns.
-// The search is a chain of dependent patch evaluations, so what it costs is the latency of one
-// evaluation: STAGED keeps everything the chain touches in shared memory (both images and the
-// sparse flow of the pair; the bordered I1 of a 240x135 level is 45 KB), which takes the global
-// load round trips out of every link of the chain.  Same arithmetic either way.
+// Anti-diagonal wavefront over the patch columns of OpenCV's 8 fixed stripes: a quad (4 lanes = OpenCV's 4
+// SIMD accumulators) owns one patch row of one stripe.  A stripe has ceil(hs / 8) patch rows -- 4 at the
+// finest level of a 960x540 working image, 2 / 1 / 1 above it -- so one warp (8 quads) carries `spw` =
+// 8 / rows stripes of the same pair at once: every lane works at every level, and the pair needs 8 / spw
+// warps instead of 8.  Those warps are spread over `cpp` CTAs of `wpc` warps (grid = P * cpp) so that the
+// 148 SMs see one or two warps per scheduler: the search is a chain of dependent patch evaluations and what
+// it costs is the issue latency of ONE warp's instruction stream, not throughput.
+// STAGED keeps everything the chain touches in shared memory (both images and the sparse flow of the pair;
+// the bordered I1 of a 240x135 level is 45 KB), which takes the global load round trips out of every link
+// of the chain.  Same arithmetic either way.
 template <bool STAGED>
-__global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P) {
+__global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P, int spw, int cpp) {
   extern __shared__ __align__(16) unsigned char ps_smem[];
-  const int pair = blockIdx.x;
-  const int stripe = threadIdx.x >> 5;
+  const int pair = blockIdx.x / cpp;
+  const int warp_in_pair = (blockIdx.x - pair * cpp) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  const int row_in_stripe = lane >> 2;
+  const int slot = lane >> 2;  // quad index 0..7
   const int l = lane & 3;
   const int w = L.w, h = L.h, ws = L.ws, hs = L.hs, we = w + 2 * kBorder;
   const int stripe_sz = (hs + kStripes - 1) / kStripes;  // ceil(hs / 8)  (<= 8 for working sizes <= 960)
-  const int lo = min(stripe * stripe_sz, hs), hi = min((stripe + 1) * stripe_sz, hs);
+  const int sub = slot / stripe_sz;                       // which of the warp's stripes this quad serves
+  const int row_in_stripe = slot - sub * stripe_sz;
+  const int stripe = warp_in_pair * spw + sub;
+  const bool lane_on = sub < spw && stripe < kStripes;
+  const int lo = lane_on ? min(stripe * stripe_sz, hs) : 0, hi = lane_on ? min((stripe + 1) * stripe_sz, hs) : 0;
   const int rows = hi - lo;
 
   const size_t npx = (size_t)h * w;
@@ -243,7 +258,7 @@ __global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P) {
     Sx = ssx;
     Sy = ssy;
   }
-  if (rows <= 0) return;  // whole warp exits together (after the only CTA-wide barrier)
+  if (warp_in_pair * spw >= kStripes) return;  // whole warp exits together (after the only CTA-wide barrier)
 
   const short* gx = L.Ix + (size_t)pair * npx;
   const short* gy = L.Iy + (size_t)pair * npx;
@@ -255,7 +270,7 @@ __global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P) {
 
   for (int iter = 0; iter < 2; iter++) {
     const int dir = iter == 0 ? 1 : -1;
-    const int nsteps = ws + rows - 1;
+    const int nsteps = ws + stripe_sz - 1;  // same for every quad of the warp (a short last stripe idles)
     for (int step = 0; step < nsteps; step++) {
       const int c = step - row_in_stripe;  // column counted in processing order
       const bool active = row_in_stripe < rows && c >= 0 && c < ws;
@@ -327,7 +342,8 @@ __global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P) {
   if (STAGED) {  // the densification reads the sparse flow from global memory
     float* gSx = L.Sx + (size_t)pair * tp;
     float* gSy = L.Sy + (size_t)pair * tp;
-    for (int k = lo * ws + lane; k < hi * ws; k += 32) {
+    const int s_lo = min(warp_in_pair * spw * stripe_sz, hs), s_hi = min((warp_in_pair + 1) * spw * stripe_sz, hs);
+    for (int k = s_lo * ws + lane; k < s_hi * ws; k += 32) {
       gSx[k] = Sx[k];
       gSy[k] = Sy[k];
     }
@@ -513,7 +529,7 @@ __device__ __forceinline__ void cluster_barrier() {
 // latency, so that is what they cost.  The plane pointers are rebased so that the per-pixel code,
 // which indexes [pair][y][x], lands in the CTA's own copy.
 template <bool ONCHIP>
-__global__ void __launch_bounds__(ONCHIP ? 1024 : 256) vr_fused_kernel(Level L, VrBuf B, int cluster_size) {
+__global__ void __launch_bounds__(ONCHIP ? 1024 : 256, ONCHIP ? 1 : VSTAB_VR_MIN_CTAS) vr_fused_kernel(Level L, VrBuf B, int cluster_size) {
   extern __shared__ __align__(16) float vr_smem[];
   const int pair = blockIdx.x / cluster_size;
   const int crank = blockIdx.x % cluster_size;
@@ -758,7 +774,102 @@ extern "C" int vstab_dis_flow(vstab_handle* hnd, const uint8_t* gray_dev, int n_
 
 namespace {
 
+// The same level restricted to the pairs [p0, ...): per-frame planes start at frame p0, per-pair planes at pair p0.
+Level level_from_pair(const Level& L, int p0) {
+  Level o = L;
+  const size_t npx = (size_t)L.h * L.w, tp = (size_t)L.hs * L.ws;
+  o.I += p0 * npx;
+  o.Iext += (size_t)p0 * (L.h + 2 * kBorder) * (L.w + 2 * kBorder);
+  o.Ix += p0 * npx;
+  o.Iy += p0 * npx;
+  o.T += p0 * 5 * tp;
+  o.Ux += p0 * npx;
+  o.Uy += p0 * npx;
+  o.Sx += p0 * tp;
+  o.Sy += p0 * tp;
+  return o;
+}
+
+int env_int(const char* name, int fallback) {
+  const char* e = getenv(name);
+  return e && atoi(e) > 0 ? atoi(e) : fallback;
+}
+
+// Cluster size of the refinement launch: a pair is one cluster, each CTA a band of rows with about 1024 pixels
+// (4096: 4.66 ms, 1024: 4.44 ms, 256: 4.49 ms for 120 pairs at 960x540).  Round 2 measured the alternatives the
+// occupancy calculator suggests -- 120 pairs in clusters of 8 are 960 CTAs of which only 86 clusters are resident
+// at once, clusters of 6 or 7 all fit -- and they are SLOWER (6: 5.11 ms, 7: 4.53 ms, 8: 4.26 ms): the launch is
+// bound by the throughput of the resident CTAs, not by the second wave (profiles/README.md, round 2).
+int vr_cluster_size(int px) {
+  const int forced = env_int("VSTAB_VR_CLUSTER", 0);
+  if (forced) return forced > 8 ? 8 : forced;
+  int cl = 1;
+  while (cl < 8 && px > 1024 * cl) cl <<= 1;
+  return cl;
+}
+
+// One pyramid level of one pair group on one stream: patch search, densification, refinement, x2 upsampling.
+int dis_level(vstab_handle* hnd, const Level& Lc, const Level* finer, const VrBuf& B, int P, cudaStream_t st) {
+  dim3 gp(vstab_ceil_div(Lc.w, 32), vstab_ceil_div(Lc.h, 8), P);
+  {
+    const int stripe_sz = (Lc.hs + kStripes - 1) / kStripes;
+    int spw = stripe_sz <= 8 ? 8 / stripe_sz : 1;          // stripes carried by one warp
+    if (spw < 1) spw = 1;
+    if (env_int("VSTAB_PS_NOPACK", 0)) spw = 1;
+    const int warps_per_pair = (kStripes + spw - 1) / spw;
+    int wpc = env_int("VSTAB_PS_WPC", 4);                   // warps per CTA
+    if (wpc > warps_per_pair) wpc = warps_per_pair;
+    const int cpp = (warps_per_pair + wpc - 1) / wpc;       // CTAs per pair
+    const size_t n1 = (size_t)(Lc.h + 2 * kBorder) * (Lc.w + 2 * kBorder), n0 = (size_t)Lc.h * Lc.w;
+    const size_t ps_bytes = ((n1 + 15) & ~(size_t)15) + ((n0 + 15) & ~(size_t)15) + 2 * sizeof(float) * Lc.hs * Lc.ws;
+    if (ps_bytes <= (size_t)hnd->max_smem_optin) {
+      VSTAB_CUDA(hnd, cudaFuncSetAttribute(patch_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_bytes));
+      patch_search_kernel<true><<<P * cpp, wpc * 32, ps_bytes, st>>>(Lc, P, spw, cpp);
+    } else {
+      patch_search_kernel<false><<<P * cpp, wpc * 32, 0, st>>>(Lc, P, spw, cpp);
+    }
+  }
+  VSTAB_LAUNCH_CHECK(hnd, "patch_search_kernel");
+  densify_kernel<<<gp, 256, 0, st>>>(Lc, P);
+  VSTAB_LAUNCH_CHECK(hnd, "densify_kernel");
+  // variational refinement: one cluster-fused launch per level
+  {
+    const int px = Lc.w * Lc.h;
+    const size_t onchip_bytes = (size_t)19 * px * sizeof(float);
+    if (onchip_bytes <= (size_t)hnd->max_smem_optin) {
+      VSTAB_CUDA(hnd, cudaFuncSetAttribute(vr_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onchip_bytes));
+      vr_fused_kernel<true><<<P, 1024, onchip_bytes, st>>>(Lc, B, 1);
+      VSTAB_LAUNCH_CHECK(hnd, "vr_fused_kernel");
+    } else {
+      const int cl = vr_cluster_size(px);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(P * cl));
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cl;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      VSTAB_CUDA(hnd, cudaLaunchKernelEx(&cfg, vr_fused_kernel<false>, Lc, B, cl));
+      hnd->launches++;
+    }
+  }
+  if (finer) {
+    dim3 gu(vstab_ceil_div(finer->w, 32), vstab_ceil_div(finer->h, 8), P);
+    upsample_kernel<<<gu, 256, 0, st>>>(Lc, *finer);
+    VSTAB_LAUNCH_CHECK(hnd, "upsample_kernel");
+  }
+  return VSTAB_OK;
+}
+
 // Pairs are processed in chunks so the workspace stays bounded (about 6.5 MB per pair at 960x540).
+// Inside a chunk the pairs are split into up to 4 groups that run the coarse-to-fine chain on their own
+// streams (forked from and joined back into the caller's stream with events): the patch search of one
+// group -- one or two warps per scheduler, long tails on slow pairs -- runs under the refinement of another.
 int dis_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width, Scales sc,
             float* flow_dev, float* grid_dev, int grid_step, cudaStream_t st) {
   const int finest = sc.finest, coarsest = sc.coarsest;
@@ -832,63 +943,46 @@ int dis_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height
       VSTAB_LAUNCH_CHECK(hnd, "tensor_cols_kernel");
     }
 
-    // ---- coarse-to-fine ----
+    // ---- coarse-to-fine, pair groups on their own streams ----
     {
       const size_t n = (size_t)L[coarsest].h * L[coarsest].w * P;
       zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L[coarsest].Ux, n);
       zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L[coarsest].Uy, n);
       hnd->launches += 2;
     }
+    int G = env_int("VSTAB_DIS_GROUPS", VSTAB_DIS_GROUPS_DEFAULT);
+    if (G > VSTAB_MAX_AUX_STREAMS + 1) G = VSTAB_MAX_AUX_STREAMS + 1;
+    if (G > P / 16) G = P / 16 > 0 ? P / 16 : 1;  // small batches: one chain
+    cudaStream_t gs[VSTAB_MAX_AUX_STREAMS + 1];
+    gs[0] = st;
+    if (G > 1) {
+      rc = vstab_aux_streams(hnd, G - 1);
+      if (rc != VSTAB_OK) return rc;
+      VSTAB_CUDA(hnd, cudaEventRecord(hnd->fork_event, st));
+      for (int g = 1; g < G; g++) {
+        gs[g] = hnd->aux_stream[g - 1];
+        VSTAB_CUDA(hnd, cudaStreamWaitEvent(gs[g], hnd->fork_event, 0));
+      }
+    }
     for (int i = coarsest; i >= finest; i--) {
-      dim3 gp(vstab_ceil_div(L[i].w, 32), vstab_ceil_div(L[i].h, 8), P);
-      {
-        const size_t n1 = (size_t)(L[i].h + 2 * kBorder) * (L[i].w + 2 * kBorder), n0 = (size_t)L[i].h * L[i].w;
-        const size_t ps_bytes = ((n1 + 15) & ~(size_t)15) + ((n0 + 15) & ~(size_t)15) + 2 * sizeof(float) * L[i].hs * L[i].ws;
-        if (ps_bytes <= (size_t)hnd->max_smem_optin) {
-          VSTAB_CUDA(hnd, cudaFuncSetAttribute(patch_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_bytes));
-          patch_search_kernel<true><<<P, 256, ps_bytes, st>>>(L[i], P);
-        } else {
-          patch_search_kernel<false><<<P, 256, 0, st>>>(L[i], P);
+      for (int g = 0; g < G; g++) {
+        const int a = (int)((long long)P * g / G), b = (int)((long long)P * (g + 1) / G);
+        if (b <= a) continue;
+        const Level Lg = level_from_pair(L[i], a);
+        Level finer_g;
+        if (i > finest) finer_g = level_from_pair(L[i - 1], a);
+        VrBuf Bg = B;
+        {
+          float** f = (float**)&Bg;
+          for (int k = 0; k < 19; k++) f[k] += (size_t)a * nf;  // a group's scratch is fixed: groups sit at different levels at the same time
         }
+        rc = dis_level(hnd, Lg, i > finest ? &finer_g : nullptr, Bg, b - a, gs[g]);
+        if (rc != VSTAB_OK) return rc;
       }
-      VSTAB_LAUNCH_CHECK(hnd, "patch_search_kernel");
-      densify_kernel<<<gp, 256, 0, st>>>(L[i], P);
-      VSTAB_LAUNCH_CHECK(hnd, "densify_kernel");
-      // variational refinement: one cluster-fused launch per level
-      {
-        const int px = L[i].w * L[i].h;
-        int cl = 1, cl_max = 8;
-        if (const char* e = getenv("VSTAB_VR_CLUSTER_MAX")) cl_max = atoi(e) > 0 ? atoi(e) : 1;
-        // ~1024 pixels per CTA: measured best (4096: 4.66 ms, 1024: 4.44 ms, 256: 4.49 ms for 120 pairs at 960x540)
-        static const int px_per_cta = [] { const char* e = getenv("VSTAB_VR_PX_PER_CTA"); return e && atoi(e) > 0 ? atoi(e) : 1024; }();
-        while (cl < cl_max && px > px_per_cta * cl) cl <<= 1;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(P * cl));
-        cfg.blockDim = dim3(256);
-        cfg.dynamicSmemBytes = 0;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = cl;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        const size_t onchip_bytes = (size_t)19 * px * sizeof(float);
-        if (onchip_bytes <= (size_t)hnd->max_smem_optin) {
-          VSTAB_CUDA(hnd, cudaFuncSetAttribute(vr_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onchip_bytes));
-          vr_fused_kernel<true><<<P, 1024, onchip_bytes, st>>>(L[i], B, 1);
-          VSTAB_LAUNCH_CHECK(hnd, "vr_fused_kernel");
-        } else {
-          VSTAB_CUDA(hnd, cudaLaunchKernelEx(&cfg, vr_fused_kernel<false>, L[i], B, cl));
-          hnd->launches++;
-        }
-      }
-      if (i > finest) {
-        dim3 gu(vstab_ceil_div(L[i - 1].w, 32), vstab_ceil_div(L[i - 1].h, 8), P);
-        upsample_kernel<<<gu, 256, 0, st>>>(L[i], L[i - 1]);
-        VSTAB_LAUNCH_CHECK(hnd, "upsample_kernel");
-      }
+    }
+    for (int g = 1; g < G; g++) {
+      VSTAB_CUDA(hnd, cudaEventRecord(hnd->join_event[g - 1], gs[g]));
+      VSTAB_CUDA(hnd, cudaStreamWaitEvent(st, hnd->join_event[g - 1], 0));
     }
     const float mul = (float)(1 << finest);
     if (flow_dev) {

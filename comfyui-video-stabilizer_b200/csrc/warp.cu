@@ -253,6 +253,26 @@ __device__ __forceinline__ void interior_tile(const double* __restrict__ s_minv,
   }
 }
 
+// remapBicubic with the whole 4x4 footprint inside the source, in cv2's own order of additions (found black-box,
+// oracle/resample_np.py warp_np(cubic_rows=True), bit-exact against the wheel): the four products of a tap row are
+// summed left to right, then the row sums are added top to bottom -- not one running sum over the 16 taps.
+// t: first tap (row k1, column k2, channel ch at t[k1 * row_stride + k2 * 3 + ch]).
+__device__ __forceinline__ void cubic_rows_sum(const float* __restrict__ t, int row_stride, const float (&wx)[4], const float (&wy)[4],
+                                               float (&v)[3]) {
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+    const float* r = t + k1 * row_stride;
+    const float w0 = __fmul_rn(wy[k1], wx[0]), w1 = __fmul_rn(wy[k1], wx[1]);
+    const float w2 = __fmul_rn(wy[k1], wx[2]), w3 = __fmul_rn(wy[k1], wx[3]);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float row = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[ch], w0), __fmul_rn(r[3 + ch], w1)), __fmul_rn(r[6 + ch], w2)),
+                                  __fmul_rn(r[9 + ch], w3));
+      v[ch] = k1 == 0 ? row : __fadd_rn(v[ch], row);
+    }
+  }
+}
+
 // General tile: any sample count, both interpolations, border handling, coverage mask and padded
 // count.  Uses the staged box where it can and global loads elsewhere; only warp-level
 // synchronisation inside, so it serves both the one-tile-per-CTA kernel and the streaming kernel.
@@ -386,34 +406,30 @@ __device__ __forceinline__ void general_tile_body(const WarpParams& p, const flo
         }
         const int bxs = sx - 1, bys = sy - 1;
         if (bxs >= 0 && bxs < p.sw - 3 && bys >= 0 && bys < p.sh - 3) {
-          vr = vg = vb = 0.f;
+          // footprint inside the source: cv2's row sums (cubic_rows_sum)
+          float v3[3];
           if (t_on && bxs >= t_x0 && bxs + 3 <= t_x1 && bys >= t_y0 && bys + 3 <= t_y1) {
-            const float* s0 = t_smem + (bys - t_y0) * t_pitch + (bxs - t_x0) * 3;
-#pragma unroll
-            for (int k1 = 0; k1 < 4; ++k1) {
-#pragma unroll
-              for (int k2 = 0; k2 < 4; ++k2) {
-                const float w = __fmul_rn(wy[k1], wx[k2]);
-                const float* t = s0 + k1 * t_pitch + k2 * 3;
-                vr = __fadd_rn(vr, __fmul_rn(t[0], w));
-                vg = __fadd_rn(vg, __fmul_rn(t[1], w));
-                vb = __fadd_rn(vb, __fmul_rn(t[2], w));
-              }
-            }
+            cubic_rows_sum(t_smem + (bys - t_y0) * t_pitch + (bxs - t_x0) * 3, t_pitch, wx, wy, v3);
           } else {
 #pragma unroll
             for (int k1 = 0; k1 < 4; ++k1) {
+              float row[3] = {0.f, 0.f, 0.f};
 #pragma unroll
               for (int k2 = 0; k2 < 4; ++k2) {
                 const float w = __fmul_rn(wy[k1], wx[k2]);
                 float r, g, b;
                 fetch_rgb(p, frame, tile, bys + k1, bxs + k2, r, g, b);
-                vr = __fadd_rn(vr, __fmul_rn(r, w));
-                vg = __fadd_rn(vg, __fmul_rn(g, w));
-                vb = __fadd_rn(vb, __fmul_rn(b, w));
+                row[0] = k2 == 0 ? __fmul_rn(r, w) : __fadd_rn(row[0], __fmul_rn(r, w));
+                row[1] = k2 == 0 ? __fmul_rn(g, w) : __fadd_rn(row[1], __fmul_rn(g, w));
+                row[2] = k2 == 0 ? __fmul_rn(b, w) : __fadd_rn(row[2], __fmul_rn(b, w));
               }
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) v3[ch] = k1 == 0 ? row[ch] : __fadd_rn(v3[ch], row[ch]);
             }
           }
+          vr = v3[0];
+          vg = v3[1];
+          vb = v3[2];
         } else {
           // remapBicubic border branch: cv + sum over in-range taps of (S - cv) * w
           vr = p.border[0];
@@ -686,18 +702,27 @@ __device__ __forceinline__ void blur_tile(const WarpParams& p, const float* __re
             const float4 wx4 = *reinterpret_cast<const float4*>(s_cubic + (ix & 31) * 4);
             const float4 wy4 = *reinterpret_cast<const float4*>(s_cubic + (iy & 31) * 4);
             const float wx[4] = {wx4.x, wx4.y, wx4.z, wx4.w}, wy[4] = {wy4.x, wy4.y, wy4.z, wy4.w};
-            vr = (EDGE && mode) ? p.border[0] : 0.f;
-            vg = (EDGE && mode) ? p.border[1] : 0.f;
-            vb = (EDGE && mode) ? p.border[2] : 0.f;
+            if (EDGE && mode) {
+              // remapBicubic's border branch: one running sum that starts at the border colour (t holds S - cv, zeros for skipped taps)
+              vr = p.border[0];
+              vg = p.border[1];
+              vb = p.border[2];
 #pragma unroll
-            for (int k1 = 0; k1 < 4; ++k1) {
+              for (int k1 = 0; k1 < 4; ++k1) {
 #pragma unroll
-              for (int k2 = 0; k2 < 4; ++k2) {
-                const float w = __fmul_rn(wy[k1], wx[k2]);
-                vr = __fadd_rn(vr, __fmul_rn(t[(k1 * 4 + k2) * 3 + 0], w));
-                vg = __fadd_rn(vg, __fmul_rn(t[(k1 * 4 + k2) * 3 + 1], w));
-                vb = __fadd_rn(vb, __fmul_rn(t[(k1 * 4 + k2) * 3 + 2], w));
+                for (int k2 = 0; k2 < 4; ++k2) {
+                  const float w = __fmul_rn(wy[k1], wx[k2]);
+                  vr = __fadd_rn(vr, __fmul_rn(t[(k1 * 4 + k2) * 3 + 0], w));
+                  vg = __fadd_rn(vg, __fmul_rn(t[(k1 * 4 + k2) * 3 + 1], w));
+                  vb = __fadd_rn(vb, __fmul_rn(t[(k1 * 4 + k2) * 3 + 2], w));
+                }
               }
+            } else {
+              float v3[3];
+              cubic_rows_sum(t, 12, wx, wy, v3);
+              vr = v3[0];
+              vg = v3[1];
+              vb = v3[2];
             }
           }
           ar = __fadd_rn(ar, vr);
@@ -1131,21 +1156,11 @@ __device__ __forceinline__ void stream_interior(const double* __restrict__ s_min
           v[ch] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s0[ch], w00), __fmul_rn(s0[3 + ch], w01)), __fmul_rn(s1[ch], w10)),
                             __fmul_rn(s1[3 + ch], w11));
       } else {
-        // remapBicubic away from the border: sum over the 4x4 taps of S * (wy * wx), rows outer (general_tile_body's order)
+        // remapBicubic away from the border: row sums of S * (wy * wx), added top to bottom (cubic_rows_sum)
         const float4 wx4 = *reinterpret_cast<const float4*>(s_cubic + (ix & 31) * 4);
         const float4 wy4 = *reinterpret_cast<const float4*>(s_cubic + (iy & 31) * 4);
         const float wx[4] = {wx4.x, wx4.y, wx4.z, wx4.w}, wy[4] = {wy4.x, wy4.y, wy4.z, wy4.w};
-        const float* s0 = tile0 + ((iy >> 5) - 1) * S_PITCH + ((ix >> 5) - 1) * 3;
-        v[0] = v[1] = v[2] = 0.f;
-#pragma unroll
-        for (int k1 = 0; k1 < 4; ++k1) {
-#pragma unroll
-          for (int k2 = 0; k2 < 4; ++k2) {
-            const float w = __fmul_rn(wy[k1], wx[k2]);
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) v[ch] = __fadd_rn(v[ch], __fmul_rn(s0[k1 * S_PITCH + k2 * 3 + ch], w));
-          }
-        }
+        cubic_rows_sum(tile0 + ((iy >> 5) - 1) * S_PITCH + ((ix >> 5) - 1) * 3, S_PITCH, wx, wy, v);
       }
       float* o = VEC ? scratch + rr * (TW * 3) + (lane + cc * 32) * 3 : dst_tile + ((size_t)(warp + rr * NWARPS) * ow + lane + cc * 32) * 3;
       o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
@@ -1243,7 +1258,7 @@ __device__ __forceinline__ void stream_edge(const WarpParams& p, const double* _
           v[ch] = any_in ? r : bc;
         }
       } else {
-        // remapBicubic: all 16 taps inside the frame -> plain sum from 0; otherwise the border branch,
+        // remapBicubic: all 16 taps inside the frame -> row sums (cubic_rows_sum); otherwise the border branch,
         // cv + sum over the in-range taps of (S - cv) * w (nothing in range leaves cv itself)
         const float4 wx4 = *reinterpret_cast<const float4*>(s_cubic + (ix & 31) * 4);
         const float4 wy4 = *reinterpret_cast<const float4*>(s_cubic + (iy & 31) * 4);
@@ -1251,16 +1266,7 @@ __device__ __forceinline__ void stream_edge(const WarpParams& p, const double* _
         const int bxs = sx - 1, bys = sy - 1;
         const float* s0 = tile0 + bys * S_PITCH + bxs * 3;
         if (bxs >= 0 && bxs < p.sw - 3 && bys >= 0 && bys < p.sh - 3) {
-          v[0] = v[1] = v[2] = 0.f;
-#pragma unroll
-          for (int k1 = 0; k1 < 4; ++k1) {
-#pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              const float w = __fmul_rn(wy[k1], wx[k2]);
-#pragma unroll
-              for (int ch = 0; ch < 3; ++ch) v[ch] = __fadd_rn(v[ch], __fmul_rn(s0[k1 * S_PITCH + k2 * 3 + ch], w));
-            }
-          }
+          cubic_rows_sum(s0, S_PITCH, wx, wy, v);
         } else {
           v[0] = br; v[1] = bg; v[2] = bb;
 #pragma unroll

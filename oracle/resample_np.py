@@ -96,13 +96,14 @@ def _gather(src: np.ndarray, yy: np.ndarray, xx: np.ndarray, border: np.ndarray)
     return np.where(inside[..., None], vals, border[None, None, :].astype(np.float32))
 
 
-def warp_np(src: np.ndarray, m32: np.ndarray, out_size, interp: str, border, cubic_rows: bool = False) -> np.ndarray:
+def warp_np(src: np.ndarray, m32: np.ndarray, out_size, interp: str, border, cubic_rows: bool = True) -> np.ndarray:
     """cv2.warpPerspective(src, m32, out_size, INTER_LINEAR|INTER_CUBIC, BORDER_CONSTANT, border).
 
-    cubic_rows: order of the 16-term bicubic sum of pixels whose 4x4 footprint lies inside the source.  False: one
-    running sum over the taps, row-major -- what the CUDA resampler does and is checked against (<= 4.8e-7 from cv2).
-    True: cv2's own order, found black-box: the four taps of a row are summed first and the row sums are added to the
-    running sum (remapBicubic's `sum += S[0]*w[4] + S[cn]*w[5] + ...`); bit-exact against the wheel."""
+    cubic_rows: order of the 16-term bicubic sum of pixels whose 4x4 footprint lies inside the source.  True (default,
+    what the CUDA resampler does since round 2): cv2's own order, found black-box: the four taps of a row are summed
+    first and the row sums are added to the running sum (remapBicubic's `sum += S[0]*w[4] + S[cn]*w[5] + ...`);
+    bit-exact against the wheel.  False: one running sum over the 16 taps, row-major (<= 4.8e-7 from cv2; kept to show
+    the difference)."""
     src = np.asarray(src, dtype=np.float32)
     if src.ndim == 2:
         src = src[..., None]
