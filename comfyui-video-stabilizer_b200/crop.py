@@ -177,14 +177,20 @@ def refine_no_padding_crop(device, final: np.ndarray, width: int, height: int, s
 
 def solve_crop_framing(context, base_mode, delta_full, path, target_path, keep_fov_clamped, transform_mode, camera_lock,
                        strength, smooth, fps_requested, fps_effective, padding_rgb, flow_keys, is_flow, attach, progress,
-                       check, output):
+                       check, output, shard=None):
     """The crop branch of _stabilize_frames.  Returns either a finished StabilizationResult (the
-    keep_fov ~= 1 bypass) or (final_matrices, apply_matrices, framing-meta additions, scale)."""
+    keep_fov ~= 1 bypass) or (final_matrices, apply_matrices, framing-meta additions, scale).
+
+    shard: frame-range shard of the clip (sharding.FrameShard) or None.  `context` then holds only the rank's
+    load range (own frames + halo); every clip-wide quantity comes from `path` / `delta_full`, which all ranks
+    hold in full after the candidate all-gather."""
     from .stabilizer_core import StabilizationResult
 
     width, height = context.width, context.height
-    n = len(context)
+    n = len(context) if shard is None else shard.total_frames
     if keep_fov_clamped >= 0.9999:
+        # per-frame lists: the rank's share of the clip (clip-wide indices), like stabilizer_core does
+        m_lo, m_hi = (0, n) if shard is None else shard.meta_frame_range
         meta = {
             "frames": n,
             "note": "keep_fov~=1.0 in crop mode; returning original frames.",
@@ -209,20 +215,36 @@ def solve_crop_framing(context, base_mode, delta_full, path, target_path, keep_f
             **flow_keys,
             "stabilization_warp": hm.build_stabilization_warp_meta(
                 source_size=(width, height), output_size=(width, height), framing_mode="crop",
-                applied_matrices=[np.eye(3, dtype=np.float32) for _ in range(n)],
+                applied_matrices=[np.eye(3, dtype=np.float32) for _ in range(m_hi - m_lo)], first_index=m_lo,
             ),
             "estimated_motion": {
                 "per_transition": [],
-                "path": path.tolist(),
-                "target_path": target_path.tolist(),
-                "target_path_effective": path.tolist(),
+                "path": path[m_lo:m_hi].tolist(),
+                "target_path": target_path[m_lo:m_hi].tolist(),
+                "target_path_effective": path[m_lo:m_hi].tolist(),
             },
             "padding_fraction_mean": 0.0,
             "padding_fraction_max": 0.0,
         }
         progress.finish()
-        frames, masks = context.untouched(output)
-        return StabilizationResult(frames, masks, attach(meta))
+        frames, masks = (context if shard is None else shard.owned_context(context)).untouched(output)
+        if shard is None or (m_lo, m_hi) == (0, n):
+            meta = attach(meta)
+        else:
+            from .motion_meta import applied_motion_meta_from_matrices
+
+            if m_hi > m_lo:
+                try:
+                    meta["motion_meta"] = applied_motion_meta_from_matrices(
+                        np.tile(np.eye(3, dtype=np.float32), (m_hi - m_lo, 1, 1)), source_size=(width, height),
+                        output_size=(width, height), fps=fps_effective, source="estimated_flow" if is_flow else "estimated_classic",
+                        first_index=m_lo,
+                    )
+                except (KeyError, TypeError, ValueError, np.linalg.LinAlgError):
+                    pass
+            meta["shard"] = {"rank": shard.rank, "world": shard.world, "frame_range": list(shard.frame_range),
+                             "meta_frame_range": [m_lo, m_hi]}
+        return StabilizationResult(frames, masks, meta)
 
     safety_margin_px = max(0.5, 0.02 * max(width, height))
     final, pre_crop, _ratio, status, note, scale, _origin, _size = compute_crop_with_keep_fov(

@@ -398,16 +398,35 @@ struct LkPyr {
 };
 
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
-__device__ __forceinline__ float warp_sum(float v) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+
+// Per-warp shared memory of the tracker: the template window (I, Ix, Iy as int16, [y][x][3]) and a double-buffered
+// row of float terms through which the lanes hand their products to the lanes that own a summation chain.
+constexpr int kLkWinBytes = (kWin * kWin * 3 * 2 + 15) & ~15;   // 5776
+constexpr int kLkRowFloats = 2 * 3 * 40;                         // A sums: 2 buffers x 3 quantities x 40 slots
+constexpr int kLkWarpBytes = kLkWinBytes + kLkRowFloats * 4;     // 6736
+
+// tail + ((q0 + q2) + (q1 + q3)): the final fold of cv2's lane accumulators; chain lanes first..first+3 and `tail`.
+__device__ __forceinline__ float lk_fold(float acc, int first, int tail) {
+  const float q0 = __shfl_sync(0xffffffffu, acc, first), q1 = __shfl_sync(0xffffffffu, acc, first + 1);
+  const float q2 = __shfl_sync(0xffffffffu, acc, first + 2), q3 = __shfl_sync(0xffffffffu, acc, first + 3);
+  const float t = __shfl_sync(0xffffffffu, acc, tail);
+  return t + ((q0 + q2) + (q1 + q3));
 }
 
-// One warp per (pair, feature).  8 warps per CTA share nothing but the launch.
+// One warp per (pair, feature); lane x owns column x of the 31x31 window and walks down its rows (lane 31 idles).
+//
+// The window sums are float sums of integer terms, and above 2^24 their value depends on the order of the additions.
+// cv2's order (its 128-bit SIMD code, found black-box, see oracle/classic_ref.c pyr_lk_body cv_order = 1): of every
+// window row the first 24 columns go to four lane accumulators -- structure tensor: lane = x mod 4; mismatch vector:
+// int32 pair sums d[x] g[x] + d[x+4] g[x+4] of the 8-column blocks, lane = x mod 4 -- and columns 24..30 to one scalar
+// accumulator that runs on across the rows; at the end tail + ((l0 + l2) + (l1 + l3)).  These are 5 sequential chains
+// per sum (4 x 186 + 217 terms for A, 4 x 93 + 217 for b).  Here every lane computes the term of its column, the
+// terms of a row go through a small shared-memory row buffer, and 15 (A11, A12, A22) / 10 (b1, b2) lanes each own
+// one chain and add their 3..7 terms of the row in order.  Same terms, same order, same bits as the wheel.
 __global__ void __launch_bounds__(256) lk_track_kernel(LkPyr P, int n_pairs, int max_corners, const float* __restrict__ feats,
                                                        const int* __restrict__ n_feats, float* __restrict__ prev_out,
                                                        float* __restrict__ curr_out) {
-  extern __shared__ short s_win[];  // [8 warps][961][3]: I, Ix, Iy of the template window
+  extern __shared__ __align__(16) unsigned char s_lk[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = blockIdx.x * 8 + warp;
   if (gid >= n_pairs * max_corners) return;
@@ -420,10 +439,21 @@ __global__ void __launch_bounds__(256) lk_track_kernel(LkPyr P, int n_pairs, int
     return;
   }
   const float fx = feats[((size_t)pair * max_corners + fi) * 2], fy = feats[((size_t)pair * max_corners + fi) * 2 + 1];
-  short* win = s_win + warp * (kWin * kWin * 3);
+  short* win = reinterpret_cast<short*>(s_lk + warp * kLkWarpBytes);
+  float* rb = reinterpret_cast<float*>(s_lk + warp * kLkWarpBytes + kLkWinBytes);
   const float half = (kWin - 1) * 0.5f;
   const float FLT_SCALE = 1.f / (1 << 20);
   const int W_BITS = 14;
+  const int x = lane;
+  const bool col_on = x < kWin;
+  // where this column's terms go in the row buffers, and which chain (if any) this lane adds up
+  const int a_slot = x < 24 ? (x & 3) * 8 + (x >> 2) : 32 + (x - 24);          // A: 4 chains x 6 columns, tail x 7
+  const int b_slot = x < 24 ? (x & 3) * 4 + (x >> 3) : 16 + (x - 24);          // b: 4 chains x 3 blocks, tail x 7
+  const bool b_store = col_on && (x >= 24 || (x & 7) < 4);
+  const bool a_chain = lane < 15, a_tail = lane >= 12;
+  const int a_base = (a_tail ? lane - 12 : lane >> 2) * 40 + (a_tail ? 32 : (lane & 3) * 8);
+  const bool b_chain = lane < 10, b_tail = lane >= 8;
+  const int b_base = (b_tail ? lane - 8 : lane >> 2) * 24 + (b_tail ? 16 : (lane & 3) * 4);
   bool status = true;
   float nx = 0.f, ny = 0.f;
   for (int level = P.levels; level >= 0; level--) {
@@ -440,40 +470,52 @@ __global__ void __launch_bounds__(256) lk_track_kernel(LkPyr P, int n_pairs, int
     float a = px - ipx, b = py - ipy;
     int iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS)), iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
     int iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS)), iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
-    float A11 = 0, A12 = 0, A22 = 0;
+    float A11, A12, A22;
     __syncwarp();
     {
-      // template window: intensities from the padded copy (no reflection), derivatives zero outside the frame;
-      // (y, x) of pixel k = lane + 32 j advance by (+1, +1) with a wrap, like the iteration loop below
-      const unsigned char* Ip = L.ext + (size_t)pair * (lh + 2 * kLkPad) * pw + (ipy + kLkPad) * pw + (ipx + kLkPad);
-      const bool inside = ipx >= 0 && ipy >= 0 && ipx + kWin < lw && ipy + kWin < lh;  // with the +1 taps
-      int x = lane >= kWin ? lane - kWin : lane, y = lane >= kWin ? 1 : 0;
-      short* wq = win + lane * 3;
-      for (int k = lane; k < kWin * kWin; k += 32) {
-        const unsigned char* q = Ip + y * pw + x;
-        const int ival = descale(q[0] * iw00 + q[1] * iw01 + q[pw] * iw10 + q[pw + 1] * iw11, W_BITS - 5);
-        const int sy = ipy + y, sx = ipx + x;
-        short2 d00, d01, d10, d11;
-        if (inside) {
-          const short2* dq = D + sy * lw + sx;
-          d00 = dq[0]; d01 = dq[1]; d10 = dq[lw]; d11 = dq[lw + 1];
-        } else {
-          const bool in00 = sx >= 0 && sy >= 0 && sx < lw && sy < lh, in01 = sx + 1 >= 0 && sy >= 0 && sx + 1 < lw && sy < lh;
-          const bool in10 = sx >= 0 && sy + 1 >= 0 && sx < lw && sy + 1 < lh, in11 = sx + 1 >= 0 && sy + 1 >= 0 && sx + 1 < lw && sy + 1 < lh;
-          const short2 zero = make_short2(0, 0);
-          d00 = in00 ? D[sy * lw + sx] : zero; d01 = in01 ? D[sy * lw + sx + 1] : zero;
-          d10 = in10 ? D[(sy + 1) * lw + sx] : zero; d11 = in11 ? D[(sy + 1) * lw + sx + 1] : zero;
+      // template window: intensities from the padded copy (no reflection), derivatives zero outside the frame.
+      // Walking down a column, the lower two taps of a row are the upper two of the next one.
+      const int cx = col_on ? x : 0;
+      const unsigned char* q = L.ext + (size_t)pair * (lh + 2 * kLkPad) * pw + (ipy + kLkPad) * pw + (ipx + kLkPad) + cx;
+      const int sx = ipx + cx;
+      const bool in_x0 = sx >= 0 && sx < lw, in_x1 = sx + 1 >= 0 && sx + 1 < lw;
+      const short2 zero = make_short2(0, 0);
+      int i0 = q[0], i1 = q[1];
+      short2 d0 = (in_x0 && ipy >= 0 && ipy < lh) ? D[ipy * lw + sx] : zero;
+      short2 d1 = (in_x1 && ipy >= 0 && ipy < lh) ? D[ipy * lw + sx + 1] : zero;
+      float acc = 0.f;
+      short* wq = win + cx * 3;
+      for (int y = 0; y < kWin; y++) {
+        q += pw;
+        const int sy1 = ipy + y + 1;
+        const bool in_y1 = sy1 >= 0 && sy1 < lh;
+        const int j0 = q[0], j1 = q[1];
+        const short2 e0 = (in_x0 && in_y1) ? D[sy1 * lw + sx] : zero;
+        const short2 e1 = (in_x1 && in_y1) ? D[sy1 * lw + sx + 1] : zero;
+        const int ival = descale(i0 * iw00 + i1 * iw01 + j0 * iw10 + j1 * iw11, W_BITS - 5);
+        const int ixval = descale(d0.x * iw00 + d1.x * iw01 + e0.x * iw10 + e1.x * iw11, W_BITS);
+        const int iyval = descale(d0.y * iw00 + d1.y * iw01 + e0.y * iw10 + e1.y * iw11, W_BITS);
+        i0 = j0; i1 = j1; d0 = e0; d1 = e1;
+        float* rrow = rb + (y & 1) * 120;
+        if (col_on) {
+          wq[0] = (short)ival; wq[1] = (short)ixval; wq[2] = (short)iyval;
+          rrow[a_slot] = (float)(ixval * ixval);
+          rrow[40 + a_slot] = (float)(ixval * iyval);
+          rrow[80 + a_slot] = (float)(iyval * iyval);
         }
-        const int ixval = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, W_BITS);
-        const int iyval = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, W_BITS);
-        wq[0] = (short)ival; wq[1] = (short)ixval; wq[2] = (short)iyval;
-        wq += 32 * 3;
-        A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval);
-        x += 1; y += 1;
-        if (x >= kWin) { x -= kWin; y += 1; }
+        wq += kWin * 3;
+        __syncwarp();
+        if (a_chain) {
+          const float4 v0 = *reinterpret_cast<const float4*>(rrow + a_base);
+          const float4 v1 = *reinterpret_cast<const float4*>(rrow + a_base + 4);
+          acc += v0.x; acc += v0.y; acc += v0.z; acc += v0.w; acc += v1.x; acc += v1.y;
+          if (a_tail) acc += v1.z;
+        }
       }
+      A11 = lk_fold(acc, 0, 12) * FLT_SCALE;
+      A12 = lk_fold(acc, 4, 13) * FLT_SCALE;
+      A22 = lk_fold(acc, 8, 14) * FLT_SCALE;
     }
-    A11 = warp_sum(A11) * FLT_SCALE; A12 = warp_sum(A12) * FLT_SCALE; A22 = warp_sum(A22) * FLT_SCALE;
     __syncwarp();
     float Dd = A11 * A22 - A12 * A12;
     const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (2 * kWin * kWin);
@@ -487,28 +529,38 @@ __global__ void __launch_bounds__(256) lk_track_kernel(LkPyr P, int n_pairs, int
       a = wx - inx; b = wy - iny;
       iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS)); iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
       iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS)); iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
-      float b1 = 0, b2 = 0;
+      float b1, b2;
       {
-        // (y, x) of pixel k = lane + 32 j advance by (+1, +1) with a wrap instead of a division -- same pixels,
-        // same order, same sums.  The tracker is issue-bound on integer work, so the walk keeps one running byte
-        // offset into the padded frame and one running window pointer instead of recomputing them per pixel.
-        const unsigned char* Jp = Jext + (iny + kLkPad) * pw + (inx + kLkPad);
-        int x = lane >= kWin ? lane - kWin : lane;
-        unsigned off = (lane >= kWin ? (unsigned)pw : 0u) + (unsigned)x;
-        const unsigned step_off = (unsigned)pw + 1u, wrap_off = (unsigned)(pw - kWin);
-        const short* wp = win + lane * 3;
-        for (int k = lane; k < kWin * kWin; k += 32) {
-          const unsigned char* q = Jp + off;
-          const int diff = descale(q[0] * iw00 + q[1] * iw01 + q[pw] * iw10 + q[pw + 1] * iw11, W_BITS - 5) - wp[0];
-          b1 += (float)(diff * wp[1]);
-          b2 += (float)(diff * wp[2]);
-          wp += 32 * 3;
-          x += 1;
-          off += step_off;
-          if (x >= kWin) { x -= kWin; off += wrap_off; }
+        const int cx = col_on ? x : 0;
+        const unsigned char* q = Jext + (iny + kLkPad) * pw + (inx + kLkPad) + cx;
+        int i0 = q[0], i1 = q[1];
+        const short* wp = win + cx * 3;
+        float acc = 0.f;
+        for (int y = 0; y < kWin; y++) {
+          q += pw;
+          const int j0 = q[0], j1 = q[1];
+          const int diff = descale(i0 * iw00 + i1 * iw01 + j0 * iw10 + j1 * iw11, W_BITS - 5) - wp[0];
+          i0 = j0; i1 = j1;
+          const int p1 = diff * wp[1], p2 = diff * wp[2];
+          wp += kWin * 3;
+          // columns 0..23: int32 pair sums of the columns x and x + 4 of an 8-column block, held by the lower column
+          const int s1 = p1 + __shfl_down_sync(0xffffffffu, p1, 4), s2 = p2 + __shfl_down_sync(0xffffffffu, p2, 4);
+          float* rrow = rb + (y & 1) * 48;
+          if (b_store) {
+            rrow[b_slot] = (float)(x < 24 ? s1 : p1);
+            rrow[24 + b_slot] = (float)(x < 24 ? s2 : p2);
+          }
+          __syncwarp();
+          if (b_chain) {
+            const float4 v0 = *reinterpret_cast<const float4*>(rrow + b_base);
+            const float4 v1 = *reinterpret_cast<const float4*>(rrow + b_base + 4);
+            acc += v0.x; acc += v0.y; acc += v0.z;
+            if (b_tail) { acc += v0.w; acc += v1.x; acc += v1.y; acc += v1.z; }
+          }
         }
+        b1 = lk_fold(acc, 0, 8) * FLT_SCALE;
+        b2 = lk_fold(acc, 4, 9) * FLT_SCALE;
       }
-      b1 = warp_sum(b1) * FLT_SCALE; b2 = warp_sum(b2) * FLT_SCALE;
       const float ddx = (A12 * b2 - A22 * b1) * Dd, ddy = (A12 * b1 - A11 * b2) * Dd;
       wx += ddx; wy += ddy;
       nx = wx + half; ny = wy + half;
@@ -645,7 +697,7 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
     pyr.lv[l].ext = ext;
   }
   // ---- track ----
-  const size_t smem = sizeof(short) * 8 * kWin * kWin * 3;
+  const size_t smem = (size_t)8 * kLkWarpBytes;
   VSTAB_CUDA(hnd, cudaFuncSetAttribute(lk_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   lk_track_kernel<<<vstab_ceil_div(P * max_corners, 8), 256, smem, st>>>(pyr, P, max_corners, feats, detected_dev, prev_dev, curr_dev);
   VSTAB_LAUNCH_CHECK(hnd, "lk_track_kernel");

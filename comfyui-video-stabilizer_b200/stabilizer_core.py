@@ -270,7 +270,7 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
             "fps_effective": fps_effective,
         }
         progress.finish()
-        frames, masks = context.untouched(output)
+        frames, masks = (context if shard is None else shard.owned_context(context)).untouched(output)
         return StabilizationResult(frames, masks, attach(meta))
 
     # ---- estimation: all candidate models of every pair -----------------------------------------
@@ -318,7 +318,7 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
         crop = solve_crop_framing(
             context, base_mode, delta_full, path, target_path, keep_fov_clamped, transform_mode, camera_lock,
             strength, smooth, fps_requested, fps_effective, padding_rgb, flow_keys, is_flow, attach, progress,
-            check, output,
+            check, output, shard=shard,
         )
         if isinstance(crop, StabilizationResult):
             return crop

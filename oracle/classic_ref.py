@@ -43,10 +43,11 @@ def good_features(img: np.ndarray, max_corners=400, quality=0.01, min_distance=7
     return xy[:k].copy()
 
 
-def pyr_lk(prev_img, next_img, pts, win=31, max_level=3, max_iter=50, eps=0.01, exact=False):
+def pyr_lk(prev_img, next_img, pts, win=31, max_level=3, max_iter=50, eps=0.01, exact=True):
     """cv2.calcOpticalFlowPyrLK(prev, next, pts, None, winSize=(win,win), maxLevel, (EPS|COUNT, max_iter, eps)) -> (next_pts, status).
-    exact=True sums the window terms in the lane order of cv2's SIMD code (bit-exact positions); the default sums them
-    serially, which is what the CUDA tracker is checked against (see classic_ref.c)."""
+    exact=True (default; what the CUDA tracker does since round 2) sums the window terms in the lane order of cv2's SIMD
+    code: bit-exact positions and status against the wheel.  exact=False sums them serially (<= 2e-3 px off; kept to show
+    the difference, see classic_ref.c)."""
     a = np.ascontiguousarray(prev_img, dtype=np.uint8)
     b = np.ascontiguousarray(next_img, dtype=np.uint8)
     p = np.ascontiguousarray(np.asarray(pts, dtype=np.float32).reshape(-1, 2))

@@ -31,11 +31,11 @@ def test_gftt_lk_matches_oracle(handle, size):
         assert int(det[p]) == len(feats)
         assert np.array_equal(prev[p, : len(feats)], feats)       # identical corners, identical order
         assert np.isnan(prev[p, len(feats):]).all()
-        want, st = CR.pyr_lk(gray[p], gray[p + 1], feats)
+        want, st = CR.pyr_lk(gray[p], gray[p + 1], feats, exact=True)  # cv2's lane order: bit-exact against the wheel
         got = curr[p, : len(feats)]
         lost = np.isnan(got).any(axis=1)
         assert int((lost != (st == 0)).sum()) == 0
-        assert float(np.abs(got[~lost] - want[~lost]).max()) <= 2e-3  # float accumulation order only
+        assert np.array_equal(got[~lost], want[~lost]), float(np.abs(got[~lost] - want[~lost]).max())
 
 
 CLASSIC_CASES = [c for c in cases.STABILIZER_CASES if c["node"] == "classic"]
@@ -60,7 +60,8 @@ def test_classic_matches_reference_golden(case):
         assert abs(mine["confidence"] - ref["confidence"]) <= 0.01
     for mine, ref in zip(meta["stabilization_warp"]["per_frame"], gmeta["stabilization_warp"]["per_frame"]):
         parity.assert_transform_close(mine["applied_matrix"], ref["applied_matrix"], f"frame {ref['index']}")
-    parity.compare_nested(gmeta, json.loads(json.dumps(meta)), "meta", atol=5e-3, rtol=5e-3)
+    # corners and tracks carry cv2's bits; what remains is the float32 rounding of the fitted matrices (like Flow)
+    parity.compare_nested(gmeta, json.loads(json.dumps(meta)), "meta", atol=2e-5, rtol=2e-5)
     f, y, x, hh, ww = gold["patch0_at"]
-    assert float(np.abs(res.frames[f, y:y + hh, x:x + ww] - gold["patch0"]).max()) <= 5e-3  # matrices differ by ~1e-3 px
+    assert float(np.abs(res.frames[f, y:y + hh, x:x + ww] - gold["patch0"]).max()) <= 1e-3
     assert tuple(res.frames.shape) == tuple(gold["shape"])
