@@ -29,6 +29,9 @@ class _Clip:
     def sliced(self, start):
         return type(self)(self.frames[start:], self.fps)
 
+    def untouched(self, output):
+        return self.frames, np.zeros(self.frames.shape[:3] + (1,), np.float32)
+
 
 def _oracle_estimator(context, work_w, work_h, requested, clip_pair_offset=0):
     """flow.estimate_candidates with the oracle in place of K1-K4 / K7-K9: all candidate models of every pair."""

@@ -4,6 +4,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -212,13 +213,22 @@ def _real_worker(rank, world, port, case_name, out):
     from vstab_b200 import stabilizer_core as core
     from vstab_b200.sharding import FrameShard
 
-    case = next(c for c in cases.SMALL_STABILIZER_CASES if c["name"] == case_name)
+    case = dict(next(c for c in cases.SMALL_STABILIZER_CASES if c["name"] == case_name.split("@")[0]))
+    if "@" in case_name:  # "name@keep_fov": the same clip with another keep_fov
+        case["keep_fov"] = float(case_name.split("@")[1])
     frames = cases.make_frames(case)
     shard = FrameShard(rank, world, len(frames), None, torch.device("cpu"))
     lo, hi = shard.load_range
     core.fused_warp = _oracle_warp
+    if case["framing"] == "crop":  # numpy coverage in place of the two coverage kernels
+        from tests.test_host_path_cpu import _CoverageOracle
+        from vstab_b200 import crop
+
+        crop._native.get_handle = lambda device: _CoverageOracle()
     est = shard.wrap_estimator(functools.partial(_oracle_estimator, clip_pair_offset=shard.pair_range[0]))  # as flow.stabilize_frames does
-    res = core.stabilize_frames(_Clip(frames[lo:hi]), case["framing"], case["mode"], case["camera_lock"], case["strength"],
+    clip = _Clip(frames[lo:hi])
+    clip.device = torch.device("cpu")
+    res = core.stabilize_frames(clip, case["framing"], case["mode"], case["camera_lock"], case["strength"],
                                 case["smooth"], case["keep_fov"], case["padding_rgb"], case["fps"], estimator=est, flavour="flow",
                                 output="device", shard=shard)
     out[rank] = (np.asarray(res.frames), np.asarray(res.masks), res.meta)
@@ -254,3 +264,39 @@ def test_two_rank_flow_run_equals_the_reference(monkeypatch):
     parity.compare_nested(gmeta, json.loads(json.dumps(meta)), "meta", atol=2e-5, rtol=2e-5)
     err = np.abs(frames - gold["frames"])
     assert float((err > 2e-5).mean()) <= 1e-3 and float(err.max()) <= 0.04
+
+
+@pytest.mark.parametrize("keep_fov", [1.0, 0.6])
+def test_two_rank_crop_framing_equals_the_single_process_run(monkeypatch, keep_fov):
+    """`crop` framing under frame-range shards: the keep_fov ~= 1 bypass must hand back each rank's OWN
+    frames (not its halo frame) with clip-wide frame counts and indices, and the keep_fov search / no-padding refinement
+    must solve for the whole clip on every rank.  Concatenated frames / masks and the merged meta == single process."""
+    import json
+
+    import torch as _torch
+
+    from tests import cases
+    from tests.test_host_path_cpu import _Clip, _CoverageOracle, _oracle_estimator, _oracle_warp
+    from vstab_b200 import crop, stabilizer_core as core
+    from vstab_b200.sharding import merge_sharded_meta
+
+    name = "flow_trans_crop_121x73"
+    case = next(c for c in cases.SMALL_STABILIZER_CASES if c["name"] == name)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_real_worker, args=(2, _free_port(), f"{name}@{keep_fov}", out), nprocs=2, join=True)
+    frames = np.concatenate([out[0][0], out[1][0]])
+    masks = np.concatenate([out[0][1], out[1][1]])
+    meta = merge_sharded_meta([out[0][2], out[1][2]])
+    monkeypatch.setattr(core, "fused_warp", _oracle_warp)
+    monkeypatch.setattr(crop._native, "get_handle", lambda device: _CoverageOracle())
+    clip = _Clip(cases.make_frames(case))
+    clip.device = _torch.device("cpu")
+    single = core.stabilize_frames(clip, case["framing"], case["mode"], case["camera_lock"], case["strength"], case["smooth"],
+                                   keep_fov, case["padding_rgb"], case["fps"], estimator=_oracle_estimator, flavour="flow", output="device")
+    assert frames.shape == np.asarray(single.frames).shape
+    assert np.array_equal(frames, np.asarray(single.frames)) and np.array_equal(masks, np.asarray(single.masks))
+    assert json.loads(json.dumps(meta)) == json.loads(json.dumps(single.meta))
+    assert meta["frames"] == case["n"] and [e["index"] for e in meta["stabilization_warp"]["per_frame"]] == list(range(case["n"]))
+    if keep_fov >= 0.9999:
+        assert np.array_equal(frames, cases.make_frames(case)) and meta["transform_mode_applied"] == "identity"
