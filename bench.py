@@ -10,19 +10,26 @@ N > 1 the clip is N x 121 frames sharded by contiguous frame range (one halo fra
 NCCL all-gather of the per-pair candidate table, one of the per-frame padded-pixel counts): weak
 scaling.  One "step" = one full pass of the hot path over the (sharded) clip.
 
-  value   frames/s with the clip already resident in HBM and the results left in HBM
-  e2e     frames/s through the node-level API with HOST tensors: pinned-host -> HBM upload of
-          the frames and HBM -> pinned-host download of frames + masks inside the timed region
+  value     frames/s with the clip already resident in HBM and the results left in HBM
+  e2e       frames/s through the NODE (`nodes.VideoStabilizerFlow.execute`, the call ComfyUI makes) with a
+            PAGEABLE CPU IMAGE tensor in and CPU tensors out: upload and download inside the timed region.
+            `e2e.pinned_driver` is the same through the driver with a pinned input (what round 1 reported);
+            `e2e.host_link` is the measured ceiling of this box's host link (plain pinned cudaMemcpyAsync up and
+            down, one copy per call) and `e2e.frac_of_link` = time the bytes need at that rate / time taken
   roofline  fused resampler (vstab_warp_fused): algorithmic bytes (12HW read + 12H'W' + 4H'W'
-          written per frame) / CUDA-event duration of its launches inside the timed steps,
-          against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the reference's OpenCV path (oracle/cv_path.py: same cv2 calls per frame / pair as
-          the reference's _stabilize_frames) timed once on the host cores over the same clip
+            written per frame) / CUDA-event duration of its launches inside the timed steps,
+            against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref, a copy of /root/reference made by build()) through its own
+            node `VideoStabilizerFlow.execute` on the host cores over the same clip; `oracle/cv_path.py` (a port
+            of its cv2 call sequence) only when the copy is absent
+  parity    the GPU result of the full 121-frame clip against that CPU result: per-pair transforms, applied
+            matrices, pixels, masks, meta tree (north_star tolerances)
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -37,10 +44,9 @@ import torch
 
 WIDTH, HEIGHT, FRAMES_PER_GPU = 1920, 1080, 121
 PARAMS = dict(framing="crop_and_pad", mode="similarity", camera_lock=False, strength=0.7, smooth=0.5, keep_fov=0.6,
-              padding_rgb=(127, 127, 127), fps=16.0)
+              padding_rgb=(127, 127, 127), padding_color="#7F7F7F", fps=16.0)
 WORKLOAD = "Video Stabilizer Flow DIS, similarity, crop_and_pad, strength=0.7 smooth=0.5, 121 synthetic jittered 1920x1080 f32 frames per GPU"
 METRIC = "frames/sec 1080p Flow stabilize"
-REFERENCE_SAMPLE_FRAMES = 41
 
 
 def measured_peak_gbs():
@@ -110,30 +116,71 @@ def settle_gc():
     gc.freeze()
 
 
-def run_reference_arm(args):
-    """The reference's own CPU implementation of the path on the host cores (oracle/cv_path.py:
-    the Python reference cannot travel to the GPU box; this restates its cv2 call sequence and is
-    checked against the unmodified reference in tests/test_cv_path_vs_reference.py)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+# ------------------------------------------------------------------------------------ the CPU reference ----
+
+def cpu_clip(n_frames: int) -> torch.Tensor:
+    """The first `n_frames` of the bench clip rendered on the host with cv2 (bilinear, same matrices and base
+    texture as the GPU render: the fused resampler is bit-exact against cv2 for bilinear, so the clips agree)."""
     import cv2
 
     import synth
-    from oracle import cv_path
 
-    n = REFERENCE_SAMPLE_FRAMES
     base = synth.base_texture(0, WIDTH, HEIGHT)
-    mats = synth.shake_matrices(FRAMES_PER_GPU, 0, WIDTH, HEIGHT)[:n]
+    mats = synth.shake_matrices(FRAMES_PER_GPU, 0, WIDTH, HEIGHT)[:n_frames]
     fwd = synth.render_matrices(mats)
-    frames = np.stack([cv2.warpPerspective(base.numpy(), fwd[i], (WIDTH, HEIGHT), flags=cv2.INTER_LINEAR) for i in range(n)])
-    clip = torch.from_numpy(frames)
+    frames = np.stack([cv2.warpPerspective(base.numpy(), fwd[i], (WIDTH, HEIGHT), flags=cv2.INTER_LINEAR) for i in range(n_frames)])
+    return torch.from_numpy(frames)
+
+
+class CpuReference:
+    """One callable for the CPU arm: the unmodified reference's node when baseline/_ref exists, else the port."""
+
+    def __init__(self):
+        import cv2
+
+        from baseline import refload
+
+        self.cv2 = cv2
+        if refload.available():
+            self.kind = "reference"
+            self.ref = refload.load()
+            self.what = "unmodified reference (baseline/_ref) VideoStabilizerFlow.execute"
+        else:
+            from oracle import cv_path  # the one other place bench.py may execute oracle/ (task statement, section 4)
+
+            self.kind = "port"
+            self.cv_path = cv_path
+            self.what = "oracle/cv_path.py (port of the reference's cv2 call sequence; baseline/_ref absent)"
+
+    def __call__(self, clip: torch.Tensor):
+        """-> (frames [N,H,W,3] CPU tensor, masks [N,H,W] CPU tensor, meta)."""
+        p = PARAMS
+        if self.kind == "reference":
+            out = self.ref.video_stabilizer_flow.VideoStabilizerFlow.execute(
+                clip, p["fps"], p["framing"], p["mode"], p["camera_lock"], p["strength"], p["smooth"], p["keep_fov"], p["padding_color"])
+            return out[0], out[1], out[2]
+        f, m, meta = self.cv_path.stabilize(clip, "flow", p["framing"], p["mode"], p["camera_lock"], p["strength"], p["smooth"],
+                                            p["keep_fov"], p["padding_rgb"], p["fps"])
+        return torch.from_numpy(f), torch.from_numpy(m[..., 0]), meta
+
+    def describe(self, n):
+        return (f"{self.what}, all {n} frames of the clip per step, cv2 {self.cv2.__version__} with {self.cv2.getNumThreads()} threads")
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores, same clip, same
+    parameters, all 121 frames of one GPU's share per step (at N > 1 the sharded clip is N x 121 frames; the CPU arm
+    keeps timing 121 -- a bounded sample, and a rate).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cpu = CpuReference()
+    clip = cpu_clip(FRAMES_PER_GPU)
+    n = FRAMES_PER_GPU
 
     def step():
         t0 = time.perf_counter()
-        out_f, out_m, _ = cv_path.stabilize(clip, "flow", PARAMS["framing"], PARAMS["mode"], PARAMS["camera_lock"], PARAMS["strength"],
-                                            PARAMS["smooth"], PARAMS["keep_fov"], PARAMS["padding_rgb"], PARAMS["fps"])
-        torch.from_numpy(out_f), torch.from_numpy(out_m[..., 0])
+        cpu(clip)
         return time.perf_counter() - t0
 
     for _ in range(args.warmup):
@@ -142,16 +189,127 @@ def run_reference_arm(args):
     times = [step() for _ in range(args.steps)]
     sec = float(np.mean(times))
     fps = n / sec
-    sample = f"{n} of the 121 frames per step (same clip, same parameters), cv2 {cv2.__version__} with {cv2.getNumThreads()} threads"
+    sample = cpu.describe(n)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": host_cores(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": host_cores(), "kind": cpu.kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- parity ----
+
+def _decompose(m):
+    m = np.asarray(m, dtype=np.float64)
+    m = m / m[2, 2]
+    return m[0, 2], m[1, 2], math.degrees(math.atan2(m[1, 0], m[0, 0])), math.hypot(m[0, 0], m[1, 0])
+
+
+def _nested_diff(a, b, path, out):
+    """Key-set equality + largest numeric difference of two JSON trees (reference: scripts/compare_refactor_behavior.py:196-217)."""
+    if isinstance(a, dict):
+        if not isinstance(b, dict) or set(a) != set(b):
+            out["keys_equal"] = False
+            out.setdefault("first_key_mismatch", path)
+            return
+        for k in a:
+            _nested_diff(a[k], b[k], f"{path}.{k}", out)
+    elif isinstance(a, (list, tuple)):
+        if not isinstance(b, (list, tuple)) or len(a) != len(b):
+            out["keys_equal"] = False
+            out.setdefault("first_key_mismatch", path)
+            return
+        for i, (x, y) in enumerate(zip(a, b)):
+            _nested_diff(x, y, f"{path}[{i}]", out)
+    elif isinstance(a, bool) or a is None or isinstance(a, str):
+        if a != b:
+            out["values_equal"] = False
+            out.setdefault("first_value_mismatch", path)
+    elif isinstance(a, (int, float)):
+        if not isinstance(b, (int, float)) or isinstance(b, bool):
+            out["values_equal"] = False
+            out.setdefault("first_value_mismatch", path)
+            return
+        d = abs(float(a) - float(b))
+        rel = d / max(abs(float(a)), abs(float(b)), 1e-300)
+        if d > out["max_abs"]:
+            out["max_abs"], out["max_abs_at"] = d, path
+        out["max_excess"] = max(out["max_excess"], min(d / 2e-5, rel / 2e-5) if d > 0 else 0.0)
+
+
+def parity_block(gpu_res, ref_frames, ref_masks, ref_meta, dev):
+    """GPU result (device tensors + meta) of the full bench clip against the CPU reference's."""
+    meta = json.loads(json.dumps(gpu_res.meta))
+    ref_meta = json.loads(json.dumps(ref_meta))
+    worst = [0.0, 0.0, 0.0]
+    modes_equal = True
+    for mine, ref in zip(meta["estimated_motion"]["per_transition"], ref_meta["estimated_motion"]["per_transition"]):
+        a, b = _decompose(mine["matrix"]), _decompose(ref["matrix"])
+        worst = [max(worst[0], abs(a[0] - b[0]), abs(a[1] - b[1])), max(worst[1], abs(a[2] - b[2])), max(worst[2], abs(a[3] - b[3]))]
+        modes_equal &= mine["mode"] == ref["mode"]
+    applied = max(float(np.abs(np.asarray(x["applied_matrix"]) - np.asarray(y["applied_matrix"])).max())
+                  for x, y in zip(meta["stabilization_warp"]["per_frame"], ref_meta["stabilization_warp"]["per_frame"]))
+    tree = {"keys_equal": True, "values_equal": True, "max_abs": 0.0, "max_abs_at": None, "max_excess": 0.0}
+    _nested_diff(ref_meta, meta, "meta", tree)
+    # pixels and masks, chunk by chunk on the device
+    gf, gm = gpu_res.frames, gpu_res.masks[..., 0]
+    n = gf.shape[0]
+    px_max, px_bad, mask_bad, px_total = 0.0, 0, 0, 0
+    same_shape = tuple(gf.shape) == tuple(ref_frames.shape) and tuple(gm.shape) == tuple(ref_masks.shape)
+    if same_shape:
+        for a in range(0, n, 16):
+            b = min(a + 16, n)
+            rf = ref_frames[a:b].to(dev, non_blocking=True)
+            rm = ref_masks[a:b].to(dev, non_blocking=True)
+            d = (gf[a:b] - rf).abs()
+            px_max = max(px_max, float(d.max()))
+            px_bad += int((d > 1e-3).sum())
+            px_total += d.numel()
+            mask_bad += int((gm[a:b] != rm).sum())
+    within = (modes_equal and worst[0] <= 0.05 and worst[1] <= 0.01 and worst[2] <= 1e-4 and same_shape and px_max <= 1e-3
+              and tree["keys_equal"] and tree["values_equal"])
+    return {
+        "against": "CPU reference result of the same 121-frame clip (cpu_baseline leg)", "pairs": len(meta["estimated_motion"]["per_transition"]),
+        "pair_modes_equal": modes_equal,
+        "pair_transform_max_delta": {"translation_px": worst[0], "rotation_deg": worst[1], "scale": worst[2]},
+        "applied_matrix_max_abs_diff": applied,
+        "pixel_max_abs_err": px_max, "pixels_over_1e-3": px_bad, "pixels": px_total,
+        "mask_mismatch_px": mask_bad, "mask_px": int(gm.numel()),
+        "meta": {"keys_equal": tree["keys_equal"], "non_numeric_equal": tree["values_equal"], "max_abs_diff": tree["max_abs"],
+                 "max_abs_diff_at": tree["max_abs_at"], "within_2e-5_abs_or_rel": tree["max_excess"] <= 1.0},
+        "tolerances": "north_star: 0.05 px / 0.01 deg / 1e-4 scale per pair, 1e-3 pixels (bilinear), mask bit-exact given identical matrices",
+        "within_north_star": bool(within),
+    }
+
+
+# -------------------------------------------------------------------------------------- host link ----
+
+def host_link_probe(dev, world, barrier):
+    """Ceiling of the host link of THIS box for the e2e figure: plain pinned cudaMemcpyAsync (torch copy_) of 1 GiB,
+    host->device and device->host, one copy per call, every rank at the same time (all N GPUs pull on the host
+    memory system together, like the e2e step does).  GB/s per GPU, best of 3."""
+    nbytes = 1 << 30
+    host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    devbuf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    host.fill_(1)
+    out = {}
+    for name, (dst, src) in {"h2d": (devbuf, host), "d2h": (host, devbuf)}.items():
+        best = 0.0
+        for _ in range(3):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        out[name + "_gbs"] = best
+    del host, devbuf
+    return out
 
 
 def main():
@@ -182,6 +340,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    placement = pipeline.bind_host_to_gpu(local_rank, world)  # NUMA node / core share of this rank (pinned buffers follow)
     total_frames = FRAMES_PER_GPU * world
     shard = None
     if world > 1:
@@ -276,15 +435,20 @@ def main():
     # ---- end to end through the public API with host tensors ----
     e2e = None
     if not args.no_e2e:
-        own_lo, own_hi = shard.frame_range if shard is not None else (0, total_frames)
-        host_clip = torch.empty(clip_dev.shape, dtype=torch.float32, pin_memory=True)
-        host_clip.copy_(clip_dev)
+        from baseline import refload
+
+        refload.install_stubs()  # ComfyUI is not in this image: comfy_api.latest / comfy.utils stand-ins (sockets, NodeOutput, ProgressBar)
+        from vstab_b200 import nodes
+
+        link = host_link_probe(dev, world, barrier)
+        pinned_clip = torch.empty(clip_dev.shape, dtype=torch.float32, pin_memory=True)
+        pinned_clip.copy_(clip_dev)
         torch.cuda.synchronize()
-        h2d = host_clip.numel() * 4
+        h2d = pinned_clip.numel() * 4
         d2h_holder = {}
 
-        def e2e_step():
-            ctx = pipeline.normalize_video_input(host_clip, dev)
+        def pinned_driver_step():
+            ctx = pipeline.normalize_video_input(pinned_clip, dev)
             res = flow.stabilize_frames(ctx, PARAMS["framing"], PARAMS["mode"], PARAMS["camera_lock"], PARAMS["strength"], PARAMS["smooth"],
                                         PARAMS["keep_fov"], PARAMS["padding_rgb"], PARAMS["fps"], output="host", shard=shard)
             frames_out = pipeline.reconstruct_video(res.frames, ctx)
@@ -292,28 +456,50 @@ def main():
             d2h_holder["bytes"] = frames_out.numel() * 4 + masks_out.numel() * 4
 
         e2e_steps = max(2, min(args.steps, 3))
-        e2e_ms, _, _ = timed(e2e_step, e2e_steps, 1)
-        e2e_ms /= e2e_steps
-        e2e = {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d * world),
-               "d2h_bytes_per_step": int(d2h_holder["bytes"] * world), "ms_per_step": e2e_ms,
-               "note": "pinned host clip -> HBM, results -> pinned host, both inside the timed region"}
-        del host_clip
+        pin_ms, _, _ = timed(pinned_driver_step, e2e_steps, 1)
+        pin_ms /= e2e_steps
+        d2h = d2h_holder["bytes"]
+        ideal_ms = (h2d / (link["h2d_gbs"] * 1e9) + d2h / (link["d2h_gbs"] * 1e9)) * 1e3
+        e2e = {"unit": "frames/s", "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
+               "host_link": {**link, "how": "plain pinned cudaMemcpyAsync of 1 GiB each way, one copy per call, all ranks at once, best of 3",
+                             "ms_for_the_step_bytes": ideal_ms, "placement": placement},
+               "pinned_driver": {"value": total_frames / (pin_ms * 1e-3), "ms_per_step": pin_ms, "frac_of_link": ideal_ms / pin_ms,
+                                 "note": "pinned host clip -> flow.stabilize_frames(output='host') -> pinned results (round 1's e2e)"}}
+        if world == 1:
+            # the node call ComfyUI makes, with what ComfyUI hands over: a pageable CPU IMAGE tensor
+            pageable = torch.empty(clip_dev.shape, dtype=torch.float32)
+            pageable.copy_(pinned_clip)
 
-    # ---- CPU baseline on the host cores (rank 0, N == 1 only) ----
+            def node_step():
+                out = nodes.VideoStabilizerFlow.execute(pageable, PARAMS["fps"], PARAMS["framing"], PARAMS["mode"], PARAMS["camera_lock"],
+                                                        PARAMS["strength"], PARAMS["smooth"], PARAMS["keep_fov"], PARAMS["padding_color"])
+                assert out[0].shape[0] == total_frames and not out[0].is_cuda and not out[1].is_cuda
+
+            node_ms, _, _ = timed(node_step, e2e_steps, 1)
+            node_ms /= e2e_steps
+            e2e.update({"value": total_frames / (node_ms * 1e-3), "ms_per_step": node_ms, "frac_of_link": ideal_ms / node_ms,
+                        "note": "nodes.VideoStabilizerFlow.execute(pageable CPU IMAGE) -> CPU IMAGE + MASK + meta; upload and download inside the timed region"})
+            del pageable
+        else:
+            # sharded runs have no single-process node call: every rank drives its frame range through the driver
+            e2e.update({"value": e2e["pinned_driver"]["value"], "ms_per_step": pin_ms, "frac_of_link": ideal_ms / pin_ms,
+                        "note": "per-rank pinned host shard -> flow.stabilize_frames(shard, output='host') -> pinned results"})
+        del pinned_clip
+
+    # ---- CPU baseline on the host cores + parity of the GPU result against it (rank 0, N == 1 only) ----
     cpu = None
+    parity = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        import cv2
-
-        from oracle import cv_path
-
+        ref = CpuReference()
         host = clip_dev.cpu()
         t0 = time.perf_counter()
-        out_f, out_m, _ = cv_path.stabilize(host, "flow", PARAMS["framing"], PARAMS["mode"], PARAMS["camera_lock"], PARAMS["strength"],
-                                            PARAMS["smooth"], PARAMS["keep_fov"], PARAMS["padding_rgb"], PARAMS["fps"])
+        ref_frames, ref_masks, ref_meta = ref(host)
         sec = time.perf_counter() - t0
-        cpu = {"value": FRAMES_PER_GPU / sec, "unit": "frames/s", "cores": host_cores(), "kind": "port",
-               "sample": f"the full 121-frame clip once ({sec:.1f} s), cv2 {cv2.__version__} with {cv2.getNumThreads()} threads"}
-        del out_f, out_m, host
+        cpu = {"value": FRAMES_PER_GPU / sec, "unit": "frames/s", "cores": host_cores(), "kind": ref.kind,
+               "sample": f"{ref.describe(FRAMES_PER_GPU)}, once ({sec:.1f} s)"}
+        del host
+        parity = parity_block(device_step(), ref_frames, ref_masks, ref_meta, dev)
+        del ref_frames, ref_masks
 
     launches_t = torch.tensor([launches], dtype=torch.float64, device=dev)
     if world > 1:
@@ -325,7 +511,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_total": total_frames, "sharding": "frame-range, 1 halo frame, all-gather of per-pair candidates" if world > 1 else "none",
                        "l2": "inputs larger than L2 (3.0 GB clip per GPU vs 126 MB)", "parallelism": f"frame-shard x{world}"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_t.item()), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": int(launches_t.item()), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

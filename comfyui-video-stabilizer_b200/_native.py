@@ -268,22 +268,31 @@ class Handle:
         return prev, curr, det
 
     # -- K4 + K7..K9 -----------------------------------------------------------------------------
-    def fit_grid(self, grid_flow: torch.Tensor, grid_step: int, mode_mask: int = 7) -> torch.Tensor:
-        """grid_flow [P,gh,gw,2] sampled flow -> raw result words [P,3,12] float64 (see FitResult)."""
+    def _fit_out(self, p: int, device, out: Optional[torch.Tensor]) -> torch.Tensor:
+        if out is None:
+            return torch.zeros((p, 3, FIT_RESULT_DOUBLES), dtype=torch.float64, device=device)
+        _check_cuda(out, torch.float64, "out")
+        if tuple(out.shape) != (p, 3, FIT_RESULT_DOUBLES):
+            raise VstabNativeError(f"out must be [{p},3,{FIT_RESULT_DOUBLES}] float64")
+        return out
+
+    def fit_grid(self, grid_flow: torch.Tensor, grid_step: int, mode_mask: int = 7, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """grid_flow [P,gh,gw,2] sampled flow -> raw result words [P,3,12] float64 (see FitResult).
+        out: zero-initialised destination (e.g. a slice of an all-gather send buffer)."""
         _check_cuda(grid_flow, torch.float32, "grid_flow")
         if not hasattr(self.lib, "vstab_fit_batch"):
             raise VstabNativeError("libvstab.so was built without vstab_fit_batch")
         p, gh, gw, _ = grid_flow.shape
-        out = torch.zeros((p, 3, FIT_RESULT_DOUBLES), dtype=torch.float64, device=grid_flow.device)
+        out = self._fit_out(p, grid_flow.device, out)
         self._check(self.lib.vstab_fit_batch(self._h, None, grid_flow.data_ptr(), p, gh * gw, gw, gh, int(grid_step), int(mode_mask), out.data_ptr(), _stream_ptr(grid_flow.device)))
         return out
 
-    def fit_points(self, prev: torch.Tensor, curr: torch.Tensor, mode_mask: int = 7) -> torch.Tensor:
+    def fit_points(self, prev: torch.Tensor, curr: torch.Tensor, mode_mask: int = 7, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """prev/curr [P,K,2] correspondences (NaN rows = invalid) -> raw result words [P,3,12] float64."""
         _check_cuda(prev, torch.float32, "prev")
         _check_cuda(curr, torch.float32, "curr")
         p, k, _ = prev.shape
-        out = torch.zeros((p, 3, FIT_RESULT_DOUBLES), dtype=torch.float64, device=prev.device)
+        out = self._fit_out(p, prev.device, out)
         self._check(self.lib.vstab_fit_batch(self._h, prev.data_ptr(), curr.data_ptr(), p, k, 0, 0, 0, int(mode_mask), out.data_ptr(), _stream_ptr(prev.device)))
         return out
 

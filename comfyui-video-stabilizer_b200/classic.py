@@ -15,20 +15,20 @@ import torch
 from . import _native, pipeline
 from .flow import mode_mask_for
 from .pipeline import VideoContext
-from .stabilizer_core import PairCandidates, StabilizationResult, stabilize_frames as _core
+from .stabilizer_core import DeviceCandidates, PairCandidates, StabilizationResult, stabilize_frames as _core
 
 MAX_CORNERS = 400
 
 
-def estimate_candidates(context: VideoContext, work_w: int, work_h: int, requested_mode: str) -> PairCandidates:
-    """K1/K2 -> K5 (corners of frame i) -> K6 (track into frame i+1) -> K7-K9 candidates per pair."""
+def estimate_candidates(context: VideoContext, work_w: int, work_h: int, requested_mode: str,
+                        out_raw: Optional[torch.Tensor] = None) -> DeviceCandidates:
+    """K1/K2 -> K5 (corners of frame i) -> K6 (track into frame i+1) -> K7-K9 candidates per pair; enqueued only,
+    the table stays in HBM (out_raw: see flow.estimate_candidates)."""
     h = _native.get_handle(context.device)
     gray = pipeline.gray_working(context, (work_w, work_h))
     prev, curr, detected = h.gftt_lk(gray, MAX_CORNERS)  # [P,400,2] each, NaN rows = not found / lost
-    raw = h.fit_points(prev, curr, mode_mask_for(requested_mode))
-    d = _native.decode_fit_results(raw)
-    return PairCandidates(d["matrix"], d["residual"], d["n_inliers"], d["n_valid"], d["n_total"], d["ok"],
-                          min_points=8, detected=detected.cpu().numpy().astype(np.int64))
+    raw = h.fit_points(prev, curr, mode_mask_for(requested_mode), out=out_raw)
+    return DeviceCandidates(raw, min_points=8, detected=detected)
 
 
 def stabilize_frames(

@@ -16,7 +16,7 @@ import torch
 
 from . import _native, pipeline
 from .pipeline import VideoContext
-from .stabilizer_core import PairCandidates, StabilizationResult, stabilize_frames as _core
+from .stabilizer_core import DeviceCandidates, PairCandidates, StabilizationResult, stabilize_frames as _core
 
 SAMPLE_STEP = 8  # flow.py:138 sample_step
 
@@ -28,9 +28,11 @@ def mode_mask_for(requested: str) -> int:
 
 
 def estimate_candidates(context: VideoContext, work_w: int, work_h: int, requested_mode: str,
-                        first_pair: int = 0, last_pair: Optional[int] = None, clip_pair_offset: int = 0) -> PairCandidates:
+                        first_pair: int = 0, last_pair: Optional[int] = None, clip_pair_offset: int = 0,
+                        out_raw: Optional[torch.Tensor] = None) -> DeviceCandidates:
     """K1/K2 -> K3 -> K4/K7-K9 for pairs [first_pair, last_pair) of the clip held by `context`
-    (pair i = frames i, i+1).  Everything stays on the device until the [P,3] result table.
+    (pair i = frames i, i+1).  Everything is enqueued and stays on the device: the [P,3] result table is returned
+    as it sits in HBM (out_raw: where the fit kernels write it -- a frame-range shard passes its all-gather send buffer).
     clip_pair_offset: clip-wide index of the context's pair 0 (a frame-range shard holds a slice of the
     clip; on small frames cv2's DIS treats the first pair of a clip differently, see vstab_dis_flow_at)."""
     h = _native.get_handle(context.device)
@@ -38,9 +40,8 @@ def estimate_candidates(context: VideoContext, work_w: int, work_h: int, request
     last_pair = n - 1 if last_pair is None else last_pair
     gray = pipeline.gray_working(context, (work_w, work_h), first_pair, last_pair + 1)
     _, grid = h.dis_flow(gray, want_flow=False, grid_step=SAMPLE_STEP, first_pair=clip_pair_offset + first_pair)
-    raw = h.fit_grid(grid, SAMPLE_STEP, mode_mask_for(requested_mode))
-    d = _native.decode_fit_results(raw)
-    return PairCandidates(d["matrix"], d["residual"], d["n_inliers"], d["n_valid"], d["n_total"], d["ok"], min_points=12)
+    raw = h.fit_grid(grid, SAMPLE_STEP, mode_mask_for(requested_mode), out=out_raw)
+    return DeviceCandidates(raw, min_points=12)
 
 
 def stabilize_frames(

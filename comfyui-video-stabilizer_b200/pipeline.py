@@ -139,16 +139,112 @@ def frames_per_chunk(height: int, width: int, channels: int = 3) -> int:
     return max(1, CHUNK_BYTES // (height * width * channels * 4))
 
 
+_BOUNCE: Dict[Any, List[torch.Tensor]] = {}
+BOUNCE_BYTES = 256 << 20
+
+
+def _bounce_buffers(nbytes: int) -> List[torch.Tensor]:
+    """Two pinned staging buffers per process (grow-only), for host tensors that are not page-locked."""
+    bufs = _BOUNCE.get("up")
+    if bufs is None or bufs[0].numel() < nbytes:
+        bufs = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        _BOUNCE["up"] = bufs
+    return bufs
+
+
 def _upload_batched(t: torch.Tensor, device: torch.device) -> torch.Tensor:
-    """CPU [N,H,W,C] tensor -> device, chunked so pinned sources overlap with later kernels."""
+    """CPU [N,H,W,C] tensor -> device, in chunks.
+
+    Pinned sources go up with one asynchronous copy per chunk.  A PAGEABLE source -- what ComfyUI hands a node --
+    would make every cudaMemcpyAsync a synchronous, single-threaded staging copy inside the driver; instead each chunk
+    is copied into one of two pinned bounce buffers by torch's multi-threaded host copy while the DMA of the previous
+    chunk is still in flight, so the upload runs at min(host memcpy rate, link rate)."""
     if t.is_cuda:
         return t.to(device)
     n = t.shape[0]
     out = torch.empty(t.shape, dtype=t.dtype, device=device)
-    step = max(1, CHUNK_BYTES // max(1, t[0].numel() * t.element_size()))
-    for a in range(0, n, step):
-        out[a : a + step].copy_(t[a : a + step], non_blocking=True)
+    if torch.device(device).type != "cuda":  # host-side tests drive the adapters without a GPU
+        out.copy_(t)
+        return out
+    frame_bytes = max(1, t[0].numel() * t.element_size())
+    if t.is_pinned():
+        step = max(1, CHUNK_BYTES // frame_bytes)
+        for a in range(0, n, step):
+            out[a : a + step].copy_(t[a : a + step], non_blocking=True)
+        return out
+    step = max(1, BOUNCE_BYTES // frame_bytes)
+    bufs = _bounce_buffers(step * frame_bytes)
+    stream = torch.cuda.current_stream(device)
+    busy: List[Optional[torch.cuda.Event]] = [None, None]
+    for k, a in enumerate(range(0, n, step)):
+        b = min(a + step, n)
+        slot = k & 1
+        if busy[slot] is not None:
+            busy[slot].synchronize()  # the DMA that last read this buffer is done
+        stage = bufs[slot][: (b - a) * frame_bytes].view(t.dtype).view((b - a,) + tuple(t.shape[1:]))
+        stage.copy_(t[a:b])  # host -> pinned, torch's parallel copy
+        out[a:b].copy_(stage, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        busy[slot] = ev
     return out
+
+
+def bind_host_to_gpu(local_rank: int, world: int) -> Dict[str, Any]:
+    """One-process-per-GPU deployments: run this rank's host threads on the cores of the GPU's NUMA node (a fair share
+    of them when several ranks share a node) and prefer that node's memory for the pinned staging buffers, so that
+    uploads and downloads do not cross the socket interconnect.  Best effort -- containers often pin the cpuset or hide
+    sysfs; the returned dict says what was done.  Never called by the nodes themselves (a ComfyUI host owns its own
+    affinity); bench.py and torchrun-style launchers call it once per rank."""
+    import os
+
+    info: Dict[str, Any] = {"numa_node": None, "cpus": None, "mempolicy": None}
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        prop = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{getattr(prop, 'pci_domain_id', 0):04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        node = -1
+        try:
+            with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+                node = int(fh.read().strip())
+        except OSError:
+            pass
+        info["pci"] = bdf
+        cpus = allowed
+        if node >= 0:
+            info["numa_node"] = node
+            try:
+                with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+                    local = set()
+                    for part in fh.read().strip().split(","):
+                        lo, _, hi = part.partition("-")
+                        local.update(range(int(lo), int(hi or lo) + 1))
+                near = [c for c in allowed if c in local]
+                if near:
+                    cpus = near
+            except OSError:
+                pass
+        if world > 1:
+            # ranks whose GPUs sit on the same node share its cores evenly; without NUMA information all ranks
+            # share the allowed set the same way (keeps N ranks x intra-op threads from oversubscribing the box)
+            share = max(1, len(cpus) // world) if cpus is allowed or node < 0 else max(1, len(cpus) * 2 // world)
+            start = (local_rank * share) % max(len(cpus) - share + 1, 1)
+            cpus = cpus[start : start + share]
+        if cpus and set(cpus) != set(allowed):
+            os.sched_setaffinity(0, cpus)
+        torch.set_num_threads(max(1, min(len(cpus), 16)))
+        info["cpus"] = f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else None
+        if node >= 0:
+            import ctypes
+
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            rc = libc.syscall(238, 1, ctypes.byref(mask), 16 * 64 + 1)  # set_mempolicy(MPOL_PREFERRED, node)
+            info["mempolicy"] = "preferred" if rc == 0 else f"unchanged (errno {ctypes.get_errno()})"
+    except Exception as exc:  # pragma: no cover - depends on the box
+        info["error"] = f"{type(exc).__name__}: {exc}"
+    return info
 
 
 def _frame_to_hwc(arr: np.ndarray):
@@ -336,6 +432,28 @@ def convert_masks_for_output(masks: Any) -> torch.Tensor:
     return masks.contiguous()
 
 
+PINNED_RESULT_LIMIT = 64 << 30  # VSTAB_PINNED_RESULT_LIMIT_MB overrides
+
+
+def _host_result(shape) -> torch.Tensor:
+    """Host tensor a result is downloaded into: page-locked (the download then runs at link rate) unless the clip is
+    larger than the pinned budget or the allocation fails -- then plain pageable memory, like the reference's numpy
+    result (the copies still work, the driver stages them)."""
+    import os
+
+    nbytes = 4
+    for d in shape:
+        nbytes *= int(d)
+    limit = os.environ.get("VSTAB_PINNED_RESULT_LIMIT_MB")
+    limit = int(limit) << 20 if limit is not None else PINNED_RESULT_LIMIT
+    if nbytes <= limit:
+        try:
+            return torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        except RuntimeError:
+            pass
+    return torch.empty(shape, dtype=torch.float32)
+
+
 _POOL: Dict[Any, torch.Tensor] = {}
 
 
@@ -365,8 +483,12 @@ def fused_warp(
     mask_rule: int = _native.MASK_RULE_P,
     output: Literal["host", "device"] = "host",
     defer: bool = False,
+    pad_transform=None,
 ):
     """Run the fused resampler over the whole clip.
+
+    pad_transform: device -> device callable applied to the [N] int32 padded-pixel counts right after the last launch
+    (frame-range shards all-gather them there); the returned counts are then whatever it produced.
 
     With defer=True everything is enqueued and a callable is returned; calling it waits for the
     GPU and yields (frames, masks, pad_counts).  The caller can build its host-side results while
@@ -391,19 +513,26 @@ def fused_warp(
         )
     if output == "device":
         dst_buf = _pooled((n, oh, ow, 3), dev, "warp_dst")
+        if context.frames.untyped_storage().data_ptr() == dst_buf.untyped_storage().data_ptr():
+            # the clip IS the previous result (e.g. Flow with output="device" fed into Motion Apply at the same
+            # size): resampling it into the pooled buffer would read and write the same memory
+            dst_buf = torch.empty((n, oh, ow, 3), dtype=torch.float32, device=dev)
         mask_buf = _pooled((n, oh, ow), dev, "warp_mask") if want_mask else None
         dst, mask, pad = _timed_warp(
             h, context.frames, fwd_t, (ow, oh), interpolation, border,
             mask_rule=mask_rule, want_mask=want_mask, want_pad_count=want_pad_count, out=dst_buf, mask_out=mask_buf,
         )
 
+        if pad is not None and pad_transform is not None:
+            pad = pad_transform(pad)
+
         def finish_device():
             return dst, mask, (pad.cpu().numpy().astype(np.int64) if pad is not None else None)
 
         return finish_device if defer else finish_device()
 
-    frames_cpu = torch.empty((n, oh, ow, 3), dtype=torch.float32, pin_memory=True)
-    masks_cpu = torch.empty((n, oh, ow), dtype=torch.float32, pin_memory=True) if want_mask else None
+    frames_cpu = _host_result((n, oh, ow, 3))
+    masks_cpu = _host_result((n, oh, ow)) if want_mask else None
     pads: List[torch.Tensor] = []
     step = frames_per_chunk(oh, ow, 4)
     if context.streamed:
@@ -441,10 +570,17 @@ def fused_warp(
             ev = torch.cuda.Event()
             ev.record(copy_stream)
             copied[k % len(bufs)] = ev
-    def finish_host():
+    pad_all = None
+    if pads:
+        pad_all = torch.cat(pads) if len(pads) > 1 else pads[0]
+        if pad_transform is not None:
+            pad_all = pad_transform(pad_all)
+    keep_alive = (bufs, fwd_t)  # the copy stream still reads the staging buffers after this function returns
+
+    def finish_host(_keep=keep_alive):
         copy_stream.synchronize()
         main.synchronize()
-        pad_np = torch.cat(pads).cpu().numpy().astype(np.int64) if pads else None
+        pad_np = pad_all.cpu().numpy().astype(np.int64) if pad_all is not None else None
         return frames_cpu, masks_cpu, pad_np
 
     return finish_host if defer else finish_host()

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .stabilizer_core import PairCandidates
+from .stabilizer_core import DeviceCandidates, PairCandidates
 
 TABLE_COLS = 43
 META_OWN_RANGE, META_EVERY_RANK = -2, -1
@@ -85,11 +85,26 @@ class FrameShard:
         return out
 
     # -- hooks used by stabilizer_core.stabilize_frames ------------------------------------------
+    @property
+    def on_gpu(self) -> bool:
+        return self.device is not None and self.device.type == "cuda"
+
     def wrap_estimator(self, estimate: Callable) -> Callable:
-        """The local context holds frames load_range; every consecutive local pair is ours."""
+        """The local context holds frames load_range; every consecutive local pair is ours.  On GPUs the fit
+        kernels write their result table straight into this rank's all-gather send buffer (no staging copy)."""
 
         def run(context, work_w, work_h, requested_mode):
-            if len(context) < 2:
+            n_local = max(len(context) - 1, 0)
+            if self.on_gpu:
+                cap = max(max(self.pair_counts()), 1)
+                send = torch.zeros((cap, 3, 12), dtype=torch.float64, device=self.device)
+                if n_local == 0:
+                    return DeviceCandidates(send[:0], min_points=0, send=send)
+                cands = estimate(context, work_w, work_h, requested_mode, out_raw=send[:n_local])
+                if isinstance(cands, DeviceCandidates):
+                    cands.send = send
+                return cands
+            if n_local == 0:
                 z = np.zeros
                 return PairCandidates(z((0, 3, 3, 3)), z((0, 3)), z((0, 3), int), z((0, 3), int), z((0, 3), int), z((0, 3), int))
             return estimate(context, work_w, work_h, requested_mode)
@@ -108,7 +123,65 @@ class FrameShard:
         host = recv.cpu().numpy()
         return np.concatenate([host[r, : counts[r]] for r in range(self.world)], axis=0)
 
-    def gather_candidates(self, local: PairCandidates) -> PairCandidates:
+    def _gather_device_table(self, local: DeviceCandidates) -> PairCandidates:
+        """NCCL all-gather of the fit kernels' output, device to device, then ONE blocking copy of the gathered
+        table (344 B per pair) to the host.  min_points / detected travel with it (Classic: a second tiny gather)."""
+        counts = self.pair_counts()
+        n_local = int(local.raw.shape[0])
+        if n_local != counts[self.rank]:
+            raise RuntimeError(f"rank {self.rank}: estimated {n_local} pairs, expected {counts[self.rank]}")
+        cap = max(max(counts), 1)
+        send = local.send
+        if send is None:
+            send = torch.zeros((cap, 3, 12), dtype=torch.float64, device=self.device)
+            send[:n_local] = local.raw
+        recv = torch.empty((self.world * cap, 3, 12), dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        # every rank runs the same node, so min_points and the presence of `detected` agree; a rank without pairs
+        # cannot know them, hence the MAX over ranks rides along in the same small collective
+        info = torch.zeros((cap + 2,), dtype=torch.int32, device=self.device)
+        info[0] = int(local.min_points)
+        if local.detected is not None:
+            info[1] = 1
+            info[2 : 2 + n_local] = local.detected.to(torch.int32)
+        infos = torch.empty((self.world, cap + 2), dtype=torch.int32, device=self.device)
+        dist.all_gather_into_tensor(infos.view(-1), info, group=self.group)
+        host = recv.cpu().numpy().reshape(self.world, cap, 3, 12)
+        infos_h = infos.cpu().numpy()
+        table = np.concatenate([host[r, : counts[r]] for r in range(self.world)], axis=0)
+        min_points = int(infos_h[:, 0].max())
+        detected = None
+        if int(infos_h[:, 1].max()) > 0:
+            detected = np.concatenate([infos_h[r, 2 : 2 + counts[r]] for r in range(self.world)], axis=0)
+        return PairCandidates.from_raw(table, min_points, detected)
+
+    def device_pad_gather(self):
+        """fused_warp hook (pad_transform): all-gather the per-frame padded-pixel counts device to device on the
+        stream that just launched the resampler.  None on the CPU (gloo tests use gather_pad_counts)."""
+        if not self.on_gpu:
+            return None
+        sizes = [b - a for a, b in (split_range(self.total_frames, self.world, r) for r in range(self.world))]
+        cap = max(max(sizes), 1)
+
+        def gather(pad: torch.Tensor) -> torch.Tensor:
+            send = torch.zeros((cap,), dtype=torch.int32, device=self.device)
+            send[: pad.shape[0]] = pad
+            recv = torch.empty((self.world * cap,), dtype=torch.int32, device=self.device)
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+            return recv
+
+        return gather
+
+    def unpack_pad_counts(self, gathered: np.ndarray) -> np.ndarray:
+        """Host view of device_pad_gather's result: [world * cap] -> clip-wide [total_frames] int64."""
+        sizes = [b - a for a, b in (split_range(self.total_frames, self.world, r) for r in range(self.world))]
+        cap = max(max(sizes), 1)
+        g = np.asarray(gathered).reshape(self.world, cap)
+        return np.concatenate([g[r, : sizes[r]] for r in range(self.world)]).astype(np.int64)
+
+    def gather_candidates(self, local):
+        if isinstance(local, DeviceCandidates):
+            return self._gather_device_table(local)
         counts = self.pair_counts()
         if local.matrix.shape[0] != counts[self.rank]:
             raise RuntimeError(f"rank {self.rank}: estimated {local.matrix.shape[0]} pairs, expected {counts[self.rank]}")

@@ -76,7 +76,34 @@ class PairCandidates:
         )
 
 
-Estimator = Callable[[VideoContext, int, int, str], PairCandidates]
+    @staticmethod
+    def from_raw(raw: np.ndarray, min_points: int, detected: Optional[np.ndarray] = None) -> "PairCandidates":
+        """raw [P,3,12] float64 words of vstab_fit_result (include/vstab.h) -> columns."""
+        arr = np.ascontiguousarray(raw, dtype=np.float64).reshape(-1, 3, 12)
+        ints = arr[..., 10:12].copy().view(np.int32)  # [P,3,4]: n_inliers, n_valid, n_total, ok
+        return PairCandidates(
+            matrix=arr[..., :9].reshape(arr.shape[0], 3, 3, 3).copy(), residual=arr[..., 9].copy(), n_inliers=ints[..., 0].copy(),
+            n_valid=ints[..., 1].copy(), n_total=ints[..., 2].copy(), ok=ints[..., 3].copy(), min_points=min_points,
+            detected=None if detected is None else np.asarray(detected).astype(np.int64),
+        )
+
+
+@dataclass
+class DeviceCandidates:
+    """The candidate table as the fit kernels left it in HBM: nothing has waited for the GPU yet.  A frame-range
+    shard all-gathers `raw` device to device (sharding.FrameShard.gather_candidates); `to_host()` is the one
+    blocking copy of the estimation phase."""
+    raw: torch.Tensor                 # [P,3,12] float64 words (vstab_fit_result), CUDA
+    min_points: int
+    detected: Optional[torch.Tensor] = None  # Classic: [P] int32, CUDA
+    send: Optional[torch.Tensor] = None      # [cap,3,12] all-gather send buffer `raw` is a view of (sharded runs)
+
+    def to_host(self) -> PairCandidates:
+        det = None if self.detected is None else self.detected.cpu().numpy()
+        return PairCandidates.from_raw(self.raw.cpu().numpy(), self.min_points, det)
+
+
+Estimator = Callable[[VideoContext, int, int, str], Any]  # -> PairCandidates | DeviceCandidates
 
 
 def _accepts_requested(cands: PairCandidates, mode: str) -> np.ndarray:
@@ -280,10 +307,12 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
 
     t0 = time.perf_counter()
     cands = estimator(context, work_w, work_h, transform_mode)
-    t0 = _mark("estimate (gray+flow/track+fit, waits for the GPU)", t0)
+    t0 = _mark("estimate (gray+flow/track+fit enqueued)", t0)
     if shard is not None:
         cands = shard.gather_candidates(cands)
-        t0 = _mark("all-gather candidates", t0)
+    if isinstance(cands, DeviceCandidates):
+        cands = cands.to_host()
+    t0 = _mark("candidate table on the host (waits for the GPU; all-gather when sharded)", t0)
     chosen, active_mode, stacked = replay_mode_ladder(cands, transform_mode, with_residual=is_flow)
     t0 = _mark("ladder", t0)
     progress.advance(estimation_steps)
@@ -375,9 +404,13 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
     final_matrices = np.asarray(final_matrices, dtype=np.float32)
     fwd = final_matrices[lo:hi].reshape(-1, 1, 9)
     t0 = _mark("host path/framing solve", t0)
+    # sharded runs on GPUs: the per-frame padded-pixel counts are all-gathered device to device right behind the
+    # resampler (they only feed the meta), and come back with the one copy that waits for it
+    pad_gather = shard.device_pad_gather() if shard is not None else None
     pending = fused_warp(
         context if shard is None else shard.owned_context(context), fwd, output_size, "bilinear",
         hm.border_value(padding_rgb), want_mask=True, want_pad_count=True, output=output, defer=True,
+        **({"pad_transform": pad_gather} if pad_gather is not None else {}),
     )
 
     # the kernels above are in flight: build the meta tree on the host meanwhile.  Sharded runs materialise
@@ -418,7 +451,7 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
     frames_out, masks_out, pad_counts = pending()
     t0 = _mark("wait for warp + pad counts", t0)
     if shard is not None:
-        pad_counts = shard.gather_pad_counts(pad_counts)
+        pad_counts = shard.unpack_pad_counts(pad_counts) if pad_gather is not None else shard.gather_pad_counts(pad_counts)
         t0 = _mark("all-gather pad counts", t0)
     pixels = int(output_size[0]) * int(output_size[1])
     padded_ratios = hm.padded_fractions(pad_counts, pixels)

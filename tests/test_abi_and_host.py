@@ -403,7 +403,8 @@ def test_input_adapters_equal_the_reference_on_its_own_cases(monkeypatch, refere
 
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm): one JSON line with the contract's keys,
-    measured on the oracle's cv2 call sequence, no GPU involved."""
+    measured on the unmodified reference's own node (baseline/_ref, copied from /root/reference by build()) or, where that copy
+    is absent, on the oracle's port of its cv2 call sequence; all 121 frames per step, no GPU involved."""
     import json
     import subprocess
 
@@ -419,3 +420,7 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["kind"] in ("port", "reference")
     assert line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"] and "workload" in line["config"]
     assert line["gpu_launches"] == 0 and line["vs_baseline"] is None and line["dtype"] == "f32" and line["data"] == "synthetic"
+    from baseline import refload
+
+    assert line["cpu_baseline"]["kind"] == ("reference" if refload.available() else "port")
+    assert "all 121 frames" in line["cpu_baseline"]["sample"]
