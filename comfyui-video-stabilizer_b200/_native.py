@@ -19,6 +19,28 @@ LIB_PATH = os.environ.get("VSTAB_LIB") or os.path.join(_PKG_DIR, "libvstab.so") 
 INTERP = {"bilinear": 0, "bicubic": 1}
 MASK_RULE_P = 0
 MASK_RULE_C = 1
+MASK_RULE_AUTO = 2
+
+
+def mask_rule_auto(threads: int) -> int:
+    """VSTAB_MASK_RULE_AUTO_THREADS(threads) of include/vstab.h: the rule cv2 would pick per call on a machine whose
+    cv2.getNumThreads() is `threads` (Rule P unless one of its destination stripes misses the source)."""
+    return MASK_RULE_AUTO | (max(1, int(threads)) << 8)
+
+
+def default_mask_rule() -> int:
+    """The nodes' mask rule.  Rule P (= cv2 with one thread, and cv2 at any thread count for ordinary stabilisation
+    jitter) unless the environment asks for the reference machine's behaviour: VSTAB_MASK_RULE=auto (thread count =
+    this host's CPU count, like cv2's default), auto:<threads>, P or C.  The node schema is untouched."""
+    v = os.environ.get("VSTAB_MASK_RULE", "P").strip().lower()
+    if v in ("p", "0", ""):
+        return MASK_RULE_P
+    if v in ("c", "1"):
+        return MASK_RULE_C
+    if v.startswith("auto"):
+        _, _, t = v.partition(":")
+        return mask_rule_auto(int(t) if t else (os.cpu_count() or 1))
+    raise VstabNativeError(f"VSTAB_MASK_RULE={v!r}: expected P, C, auto or auto:<threads>")
 STAGE_AUTO = 0
 STAGE_GLOBAL = 1
 MODE_INDEX = {"translation": 0, "similarity": 1, "perspective": 2}
@@ -214,8 +236,9 @@ class Handle:
         )
         return dst, mask, pad
 
-    def common_coverage(self, fwd: torch.Tensor, src_size, out_size, mask_rule: int = MASK_RULE_P) -> torch.Tensor:
+    def common_coverage(self, fwd: torch.Tensor, src_size, out_size, mask_rule: Optional[int] = None) -> torch.Tensor:
         _check_cuda(fwd, torch.float32, "fwd")
+        mask_rule = default_mask_rule() if mask_rule is None else mask_rule
         n = int(fwd.shape[0])
         sw, sh = int(src_size[0]), int(src_size[1])
         ow, oh = int(out_size[0]), int(out_size[1])
@@ -223,9 +246,10 @@ class Handle:
         self._check(self.lib.vstab_common_coverage(self._h, fwd.data_ptr(), n, sh, sw, oh, ow, int(mask_rule), out.data_ptr(), _stream_ptr(fwd.device)))
         return out
 
-    def coverage_bbox(self, fwd: torch.Tensor, src_size, out_size, mask_rule: int = MASK_RULE_P) -> torch.Tensor:
+    def coverage_bbox(self, fwd: torch.Tensor, src_size, out_size, mask_rule: Optional[int] = None) -> torch.Tensor:
         """fwd [N,9] f32 -> int32 [N,4] (xmin, ymin, xmax, ymax) of the 3x3-closed coverage; xmax < 0 = empty."""
         _check_cuda(fwd, torch.float32, "fwd")
+        mask_rule = default_mask_rule() if mask_rule is None else mask_rule
         n = int(fwd.shape[0])
         sw, sh = int(src_size[0]), int(src_size[1])
         ow, oh = int(out_size[0]), int(out_size[1])

@@ -41,6 +41,7 @@ extern "C" void vstab_destroy(vstab_handle* h) {
   cudaSetDevice(h->device);
   if (h->ws) cudaFree(h->ws);
   if (h->plan) cudaFree(h->plan);
+  if (h->rules) cudaFree(h->rules);
   for (int i = 0; i < h->n_aux; ++i) {
     cudaStreamDestroy(h->aux_stream[i]);
     cudaEventDestroy(h->join_event[i]);

@@ -33,6 +33,9 @@ struct vstab_handle {
   vstab_area_cache_entry area_cache[VSTAB_AREA_CACHE];
   int n_area_cache;
   int area_evict;  // next slot to recycle once the cache is full
+  // grow-only per-(frame, sample) mask rules of VSTAB_MASK_RULE_AUTO launches
+  void* rules;
+  size_t rules_bytes;
   // helper streams for work that forks from / joins back into the caller's stream inside one call
   // (DIS pair groups); created on first use
   cudaStream_t aux_stream[VSTAB_MAX_AUX_STREAMS];

@@ -66,6 +66,7 @@ struct WarpParams {
   int n, sh, sw, oh, ow;
   int samples;
   int mask_rule;
+  const unsigned char* __restrict__ rules;  // VSTAB_MASK_RULE_AUTO: rule of every (frame, sample), else nullptr
   int stage_mode;
   int stage_capacity;  // floats available for the staged source tile
   int vec_store;       // ow % 4 == 0 && dst 16B aligned
@@ -75,6 +76,68 @@ struct WarpParams {
 };
 
 __constant__ float c_cubic_tab[32][4];
+
+// Mask rule of one (frame, shutter sample): the launch-wide rule, or what mask_rule_auto_kernel chose for it.
+__device__ __forceinline__ int sample_rule(const WarpParams& p, int frame_idx, int s) {
+  return p.rules ? (int)p.rules[(size_t)frame_idx * p.samples + s] : p.mask_rule;
+}
+
+// VSTAB_MASK_RULE_AUTO: which rule cv2 itself applies to one warpPerspective(ones, M, INTER_NEAREST) call.
+// The wheel's IPP path handles the destination in `stripes` horizontal stripes -- min(cv2.getNumThreads(),
+// ceil(W' H' / 2^14)) of them, stripe s = rows [(s H' + S/2) / S, ((s+1) H' + S/2) / S) -- and when the source frame
+// (forward-mapped quad of its pixel centres) misses ONE of them entirely the whole call falls back to OpenCV's own code,
+// which rounds the source coordinate before the range test (Rule C).  Found black-box and pinned against the live wheel
+// in tests/test_oracle_resample.py (random warps + boundary sweeps, 0 mismatches); oracle: resample_np.auto_rule.
+__device__ __forceinline__ int clip_halfplane(double (&px)[10], double (&py)[10], int n, double a, double b, double c) {
+  double qx[10], qy[10];
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    const int j = i + 1 == n ? 0 : i + 1;
+    const double fp = a * px[i] + b * py[i] + c, fq = a * px[j] + b * py[j] + c;
+    if (fp >= 0.0 && m < 10) { qx[m] = px[i]; qy[m] = py[i]; ++m; }
+    if ((fp >= 0.0) != (fq >= 0.0) && m < 10) {
+      const double t = fp / (fp - fq);
+      qx[m] = px[i] + t * (px[j] - px[i]);
+      qy[m] = py[i] + t * (py[j] - py[i]);
+      ++m;
+    }
+  }
+  for (int i = 0; i < m; ++i) { px[i] = qx[i]; py[i] = qy[i]; }
+  return m;
+}
+
+__global__ void mask_rule_auto_kernel(const float* __restrict__ fwd, int count, int sh, int sw, int oh, int ow, int threads,
+                                      unsigned char* __restrict__ rules) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float* m = fwd + (size_t)i * 9;
+  const double cx[4] = {0.0, (double)(sw - 1), (double)(sw - 1), 0.0}, cy[4] = {0.0, 0.0, (double)(sh - 1), (double)(sh - 1)};
+  double qx[4], qy[4];
+  for (int k = 0; k < 4; ++k) {
+    const double X = (double)m[0] * cx[k] + (double)m[1] * cy[k] + (double)m[2];
+    const double Y = (double)m[3] * cx[k] + (double)m[4] * cy[k] + (double)m[5];
+    const double W = (double)m[6] * cx[k] + (double)m[7] * cy[k] + (double)m[8];
+    qx[k] = X / W;
+    qy[k] = Y / W;
+  }
+  long long area_stripes = ((long long)ow * oh + 16383) / 16384;
+  int S = threads < area_stripes ? threads : (int)area_stripes;
+  if (S < 1) S = 1;
+  int rule = VSTAB_MASK_RULE_P;
+  for (int s = 0; s < S && rule == VSTAB_MASK_RULE_P; ++s) {
+    const int r0 = (int)(((long long)s * oh + S / 2) / S), r1 = (int)(((long long)(s + 1) * oh + S / 2) / S);
+    if (r1 <= r0) continue;
+    double px[10], py[10];
+    for (int k = 0; k < 4; ++k) { px[k] = qx[k]; py[k] = qy[k]; }
+    int n = 4;
+    n = clip_halfplane(px, py, n, 1.0, 0.0, 0.0);                       // x >= 0
+    if (n) n = clip_halfplane(px, py, n, -1.0, 0.0, (double)(ow - 1));  // x <= W' - 1
+    if (n) n = clip_halfplane(px, py, n, 0.0, 1.0, -(double)r0);        // y >= r0
+    if (n) n = clip_halfplane(px, py, n, 0.0, -1.0, (double)(r1 - 1));  // y <= r1 - 1
+    if (n == 0) rule = VSTAB_MASK_RULE_C;
+  }
+  rules[i] = (unsigned char)rule;
+}
 
 struct StagedTile {
   const float* smem;  // staged box, row pitch = pitch floats
@@ -318,6 +381,7 @@ __device__ __forceinline__ void general_tile_body(const WarpParams& p, const flo
     // affine maps (last row 0 0 w): W is the same double for every pixel => one division per CTA
     const bool affine = (m[6] == 0.0) && (m[7] == 0.0);
     const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
+    const int rule = sample_rule(p, frame_idx, s);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int rr = q >> 1, cc = q & 1;
@@ -341,13 +405,13 @@ __device__ __forceinline__ void general_tile_body(const WarpParams& p, const flo
         const double rw = sc * 0.03125;  // fl(32/W)/32 == fl(1/W): scaling by 2^-5 is exact
         const double qx = X * rw, qy = Y * rw;
         const double band = 1e-6;
-        if (p.mask_rule == VSTAB_MASK_RULE_P && qx > band && qx < x_hi - band && qy > band && qy < y_hi - band) {
+        if (rule == VSTAB_MASK_RULE_P && qx > band && qx < x_hi - band && qy > band && qy < y_hi - band) {
           ok = true;
-        } else if (p.mask_rule == VSTAB_MASK_RULE_P && (qx < -band || qx > x_hi + band || qy < -band || qy > y_hi + band)) {
+        } else if (rule == VSTAB_MASK_RULE_P && (qx < -band || qx > x_hi + band || qy < -band || qy > y_hi + band)) {
           ok = false;
         } else {
           double cxs = __ddiv_rn(X, W), cys = __ddiv_rn(Y, W);
-          if (p.mask_rule == VSTAB_MASK_RULE_C) {
+          if (rule == VSTAB_MASK_RULE_C) {
             cxs = rint(cxs);
             cys = rint(cys);
           }
@@ -656,13 +720,14 @@ __device__ __forceinline__ void blur_tile(const WarpParams& p, const float* __re
             const double rw = sc * 0.03125;
             const double qx = X * rw, qy = Y * rw;
             const double band = 1e-6;
-            if (p.mask_rule == VSTAB_MASK_RULE_P && qx > band && qx < x_hi - band && qy > band && qy < y_hi - band) {
+            const int rule = sample_rule(p, frame_idx, s);
+            if (rule == VSTAB_MASK_RULE_P && qx > band && qx < x_hi - band && qy > band && qy < y_hi - band) {
               ok = true;
-            } else if (p.mask_rule == VSTAB_MASK_RULE_P && (qx < -band || qx > x_hi + band || qy < -band || qy > y_hi + band)) {
+            } else if (rule == VSTAB_MASK_RULE_P && (qx < -band || qx > x_hi + band || qy < -band || qy > y_hi + band)) {
               ok = false;
             } else {
               double cxs = __ddiv_rn(X, W), cys = __ddiv_rn(Y, W);
-              if (p.mask_rule == VSTAB_MASK_RULE_C) {
+              if (rule == VSTAB_MASK_RULE_C) {
                 cxs = rint(cxs);
                 cys = rint(cys);
               }
@@ -1194,6 +1259,7 @@ __device__ __forceinline__ void stream_edge(const WarpParams& p, const double* _
   const double x_hi = (double)(p.sw - 1), y_hi = (double)(p.sh - 1);
   const float br = p.border[0], bg = p.border[1], bb = p.border[2];
   const int ow = p.ow;
+  const int rule = sample_rule(p, frame_idx, 0);
   unsigned padded = 0;
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
@@ -1218,13 +1284,13 @@ __device__ __forceinline__ void stream_edge(const WarpParams& p, const double* _
         const double rw = sc * 0.03125;
         const double qx = X * rw, qy = Y * rw;
         const double band = 1e-6;
-        if (p.mask_rule == VSTAB_MASK_RULE_P && qx > band && qx < x_hi - band && qy > band && qy < y_hi - band) {
+        if (rule == VSTAB_MASK_RULE_P && qx > band && qx < x_hi - band && qy > band && qy < y_hi - band) {
           ok = true;
-        } else if (p.mask_rule == VSTAB_MASK_RULE_P && (qx < -band || qx > x_hi + band || qy < -band || qy > y_hi + band)) {
+        } else if (rule == VSTAB_MASK_RULE_P && (qx < -band || qx > x_hi + band || qy < -band || qy > y_hi + band)) {
           ok = false;
         } else {
           double cxs = __ddiv_rn(X, W), cys = __ddiv_rn(Y, W);
-          if (p.mask_rule == VSTAB_MASK_RULE_C) {
+          if (rule == VSTAB_MASK_RULE_C) {
             cxs = rint(cxs);
             cys = rint(cys);
           }
@@ -1450,7 +1516,7 @@ __global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __g
 // AND-reduction of INTER_NEAREST coverage over n matrices (crop solvers).
 __global__ void __launch_bounds__(256) common_coverage_kernel(const float* __restrict__ fwd, int n,
                                                               int sh, int sw, int oh, int ow,
-                                                              int mask_rule,
+                                                              int mask_rule, const unsigned char* __restrict__ rules,
                                                               unsigned char* __restrict__ common) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_minv = reinterpret_cast<double*>(smem_raw);  // [chunk][9]
@@ -1472,7 +1538,7 @@ __global__ void __launch_bounds__(256) common_coverage_kernel(const float* __res
         const double Y = __dadd_rn(__dadd_rn(__dmul_rn(m[3], dx), __dmul_rn(m[4], dy)), m[5]);
         const double W = __dadd_rn(__dadd_rn(__dmul_rn(m[6], dx), __dmul_rn(m[7], dy)), m[8]);
         double cxs = __ddiv_rn(X, W), cys = __ddiv_rn(Y, W);
-        if (mask_rule == VSTAB_MASK_RULE_C) {
+        if ((rules ? (int)rules[base + k] : mask_rule) == VSTAB_MASK_RULE_C) {
           cxs = rint(cxs);
           cys = rint(cys);
         }
@@ -1486,7 +1552,8 @@ __global__ void __launch_bounds__(256) common_coverage_kernel(const float* __res
 
 // Per-frame INTER_NEAREST coverage as bytes (crop solvers: the closing + bounding box below).
 __global__ void __launch_bounds__(256) coverage_u8_kernel(const float* __restrict__ fwd, int sh, int sw, int oh, int ow,
-                                                          int mask_rule, unsigned char* __restrict__ cov) {
+                                                          int mask_rule, const unsigned char* __restrict__ rules,
+                                                          unsigned char* __restrict__ cov) {
   __shared__ double s_m[9];
   const int f = blockIdx.z;
   if (threadIdx.x == 0) vstab_invert3(fwd + (size_t)f * 9, s_m);
@@ -1499,7 +1566,7 @@ __global__ void __launch_bounds__(256) coverage_u8_kernel(const float* __restric
   const double Y = __dadd_rn(__dadd_rn(__dmul_rn(s_m[3], dx), __dmul_rn(s_m[4], dy)), s_m[5]);
   const double W = __dadd_rn(__dadd_rn(__dmul_rn(s_m[6], dx), __dmul_rn(s_m[7], dy)), s_m[8]);
   double cxs = __ddiv_rn(X, W), cys = __ddiv_rn(Y, W);
-  if (mask_rule == VSTAB_MASK_RULE_C) {
+  if ((rules ? (int)rules[f] : mask_rule) == VSTAB_MASK_RULE_C) {
     cxs = rint(cxs);
     cys = rint(cys);
   }
@@ -1603,6 +1670,41 @@ void build_cubic_tab(float tab[32][4]) {
 
 }  // namespace
 
+namespace {
+// Splits the ABI's mask_rule argument and, for VSTAB_MASK_RULE_AUTO, fills the handle's per-matrix rule table.
+// *rules_out stays nullptr for the two fixed rules.
+int resolve_mask_rule(vstab_handle* h, const float* fwd_dev, int count, int src_h, int src_w, int out_h, int out_w,
+                      int mask_rule, cudaStream_t st, int* rule_out, const unsigned char** rules_out) {
+  const int rule = mask_rule & 0xff, threads = mask_rule >> 8;
+  *rule_out = rule;
+  *rules_out = nullptr;
+  if (rule == VSTAB_MASK_RULE_P || rule == VSTAB_MASK_RULE_C) {
+    if (threads != 0) return vstab_fail(h, VSTAB_ERR_INVALID, "mask_rule: a thread count only goes with VSTAB_MASK_RULE_AUTO");
+    return VSTAB_OK;
+  }
+  if (rule != VSTAB_MASK_RULE_AUTO || threads < 1) return vstab_fail(h, VSTAB_ERR_INVALID, "unknown mask rule (AUTO needs VSTAB_MASK_RULE_AUTO_THREADS(t >= 1))");
+  if (threads == 1 || count == 0) {  // one stripe only misses the source when the whole output does: Rule P
+    *rule_out = VSTAB_MASK_RULE_P;
+    return VSTAB_OK;
+  }
+  if ((size_t)count > h->rules_bytes) {
+    VSTAB_CUDA(h, cudaDeviceSynchronize());
+    if (h->rules) cudaFree(h->rules);
+    h->rules = nullptr;
+    h->rules_bytes = 0;
+    const size_t want = (size_t)count + 4096;
+    if (cudaMalloc(&h->rules, want) != cudaSuccess) return vstab_fail(h, VSTAB_ERR_NOMEM, "mask rule table: cudaMalloc failed");
+    h->rules_bytes = want;
+  }
+  mask_rule_auto_kernel<<<vstab_ceil_div(count, 128), 128, 0, st>>>(fwd_dev, count, src_h, src_w, out_h, out_w, threads,
+                                                                     (unsigned char*)h->rules);
+  VSTAB_LAUNCH_CHECK(h, "mask_rule_auto_kernel");
+  *rule_out = VSTAB_MASK_RULE_P;
+  *rules_out = (const unsigned char*)h->rules;
+  return VSTAB_OK;
+}
+}  // namespace
+
 extern "C" int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, int src_h, int src_w,
                                 const float* fwd_dev, int samples, int interp, int out_h,
                                 int out_w, const float* border_host, int mask_rule,
@@ -1617,8 +1719,11 @@ extern "C" int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, in
     return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_warp_fused: samples must be in 1..33");
   if (interp != VSTAB_INTERP_BILINEAR && interp != VSTAB_INTERP_BICUBIC)
     return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_warp_fused: unknown interpolation");
-  if (mask_rule != VSTAB_MASK_RULE_P && mask_rule != VSTAB_MASK_RULE_C)
-    return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_warp_fused: unknown mask rule");
+  {
+    const int r = mask_rule & 0xff;
+    if (r != VSTAB_MASK_RULE_P && r != VSTAB_MASK_RULE_C && r != VSTAB_MASK_RULE_AUTO)
+      return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_warp_fused: unknown mask rule");
+  }
   if (src_w > 32767 || src_h > 32767)
     return vstab_fail(h, VSTAB_ERR_UNSUPPORTED, "vstab_warp_fused: source larger than 32767 px");
   if (n == 0) return VSTAB_OK;
@@ -1646,7 +1751,12 @@ extern "C" int vstab_warp_fused(vstab_handle* h, const float* src_dev, int n, in
   p.oh = out_h;
   p.ow = out_w;
   p.samples = samples;
-  p.mask_rule = mask_rule;
+  {
+    const unsigned char* rules = nullptr;
+    const int rc = resolve_mask_rule(h, fwd_dev, n * samples, src_h, src_w, out_h, out_w, mask_rule, st, &p.mask_rule, &rules);
+    if (rc != VSTAB_OK) return rc;
+    p.rules = rules;
+  }
   p.stage_mode = stage_mode;
   p.vec_store = (out_w % 4 == 0) && (((uintptr_t)dst_dev & 15) == 0);
   p.vec_load = (src_w % 4 == 0) && (((uintptr_t)src_dev & 15) == 0);
@@ -1756,9 +1866,15 @@ extern "C" int vstab_common_coverage(vstab_handle* h, const float* fwd_dev, int 
     return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_common_coverage: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   VSTAB_ENTER(h);
+  int rule = mask_rule;
+  const unsigned char* rules = nullptr;
+  {
+    const int rc = resolve_mask_rule(h, fwd_dev, n, src_h, src_w, out_h, out_w, mask_rule, st, &rule, &rules);
+    if (rc != VSTAB_OK) return rc;
+  }
   dim3 grid(vstab_ceil_div(out_w, 32), vstab_ceil_div(out_h, 8));
   common_coverage_kernel<<<grid, 256, sizeof(double) * 64 * 9, st>>>(fwd_dev, n, src_h, src_w, out_h,
-                                                                    out_w, mask_rule, common_dev);
+                                                                    out_w, rule, rules, common_dev);
   VSTAB_LAUNCH_CHECK(h, "common_coverage_kernel");
   return VSTAB_OK;
 }
@@ -1776,12 +1892,16 @@ extern "C" int vstab_coverage_bbox(vstab_handle* h, const float* fwd_dev, int n,
   int rc = vstab_workspace(h, (size_t)chunk * out_h * out_w, &ws);
   if (rc != VSTAB_OK) return rc;
   unsigned char* cov = (unsigned char*)ws;
+  int rule = mask_rule;
+  const unsigned char* rules = nullptr;
+  rc = resolve_mask_rule(h, fwd_dev, n, src_h, src_w, out_h, out_w, mask_rule, st, &rule, &rules);
+  if (rc != VSTAB_OK) return rc;
   bbox_init_kernel<<<vstab_ceil_div(n, 128), 128, 0, st>>>(bbox_dev, n);
   VSTAB_LAUNCH_CHECK(h, "bbox_init_kernel");
   for (int f0 = 0; f0 < n; f0 += chunk) {
     const int F = (n - f0) < chunk ? (n - f0) : chunk;
     dim3 grid(vstab_ceil_div(out_w, 32), vstab_ceil_div(out_h, 8), F);
-    coverage_u8_kernel<<<grid, 256, 0, st>>>(fwd_dev + (size_t)f0 * 9, src_h, src_w, out_h, out_w, mask_rule, cov);
+    coverage_u8_kernel<<<grid, 256, 0, st>>>(fwd_dev + (size_t)f0 * 9, src_h, src_w, out_h, out_w, rule, rules ? rules + f0 : nullptr, cov);
     VSTAB_LAUNCH_CHECK(h, "coverage_u8_kernel");
     closed_bbox_kernel<<<grid, 256, 0, st>>>(cov, out_h, out_w, bbox_dev + (size_t)f0 * 4);
     VSTAB_LAUNCH_CHECK(h, "closed_bbox_kernel");

@@ -40,7 +40,13 @@ def gc_paused():
     dicts per clip; allocating them with the collector on triggers a generation-0 pass every 700
     containers, promotes the survivors and soon a full collection over every object of the process
     (tens of ms with torch loaded) -- measured 8 ms median / 125 ms worst per call for a 968-frame meta
-    against 4 ms with the collector paused.  Reference counting still frees everything as usual."""
+    against 4 ms with the collector paused.  Reference counting still frees everything as usual.
+    A host application that wants its collector left alone sets VSTAB_GC_PAUSE=0."""
+    import os
+
+    if os.environ.get("VSTAB_GC_PAUSE", "1") == "0":
+        yield
+        return
     was_enabled = gc.isenabled()
     gc.disable()
     try:

@@ -43,7 +43,7 @@ def _size_pair(owner: str, block: Dict[str, Any], key: str) -> Tuple[int, int]:
     return w, h
 
 
-def _matrix_entry(owner: str, entry: Any, position: int, key: str) -> np.ndarray:
+def _matrix_entry(owner: str, entry: Any, position: int, key: str, require_finite: bool = True) -> np.ndarray:
     where = f"{owner}.per_frame[{position}]"
     if not isinstance(entry, dict):
         raise ValueError(f"{where} must be an object.")
@@ -54,7 +54,7 @@ def _matrix_entry(owner: str, entry: Any, position: int, key: str) -> np.ndarray
     m = np.asarray(entry[key], dtype=np.float64)
     if m.shape != (3, 3):
         raise ValueError(f"{where}.{key} must be 3x3.")
-    if not np.isfinite(m).all():
+    if require_finite and not np.isfinite(m).all():
         raise ValueError(f"{where}.{key} must contain finite numbers.")
     try:
         np.linalg.inv(m)
@@ -63,19 +63,20 @@ def _matrix_entry(owner: str, entry: Any, position: int, key: str) -> np.ndarray
     return m
 
 
-def _matrix_entries(owner: str, entries: list, key: str) -> List[np.ndarray]:
+def _matrix_entries(owner: str, entries: list, key: str, require_finite: bool = True) -> List[np.ndarray]:
     """All per_frame matrices, validated.  Vectorised happy path (one stacked isfinite + inv);
     any irregularity re-runs the per-entry checks so the first offending entry is reported with
-    exactly the reference's message."""
+    exactly the reference's message.  require_finite=False: the legacy inverse helper of the reference
+    (stabilizer_utils.py:898-927) has no finiteness check, only shape and invertibility."""
     try:
         if all(isinstance(e, dict) and e.get("index") == i and key in e for i, e in enumerate(entries)):
             stack = np.asarray([e[key] for e in entries], dtype=np.float64)
-            if stack.shape == (len(entries), 3, 3) and np.isfinite(stack).all():
+            if stack.shape == (len(entries), 3, 3) and (not require_finite or np.isfinite(stack).all()):
                 np.linalg.inv(stack)
                 return list(stack)
     except (ValueError, TypeError, np.linalg.LinAlgError):
         pass
-    return [_matrix_entry(owner, e, i, key) for i, e in enumerate(entries)]
+    return [_matrix_entry(owner, e, i, key, require_finite) for i, e in enumerate(entries)]
 
 
 def validate_motion_meta(block: Dict[str, Any]) -> None:

@@ -480,7 +480,7 @@ def fused_warp(
     *,
     want_mask: bool = True,
     want_pad_count: bool = False,
-    mask_rule: int = _native.MASK_RULE_P,
+    mask_rule: Optional[int] = None,
     output: Literal["host", "device"] = "host",
     defer: bool = False,
     pad_transform=None,
@@ -504,6 +504,8 @@ def fused_warp(
     dev = context.device
     n = len(context)
     ow, oh = int(out_size[0]), int(out_size[1])
+    if mask_rule is None:
+        mask_rule = _native.default_mask_rule()  # Rule P unless VSTAB_MASK_RULE says otherwise
     fwd_t = torch.from_numpy(np.ascontiguousarray(fwd, dtype=np.float32)).to(dev, non_blocking=True)
     if fwd_t.dim() == 2:
         fwd_t = fwd_t.view(n, 1, 9)

@@ -38,6 +38,27 @@ def _mark(label, t0):
     return time.perf_counter()
 
 
+class _Nvtx:
+    """NVTX ranges around the phases of a call (estimate / table / ladder / solve / resample / meta / finish), visible in
+    Nsight Systems and in ncu's NVTX filters.  On when a CUDA device is there; VSTAB_NVTX=0 switches them off."""
+
+    def __init__(self):
+        import os
+
+        self.on = os.environ.get("VSTAB_NVTX", "1") != "0" and torch.cuda.is_available()
+        self.open = False
+
+    def phase(self, name: Optional[str]) -> None:
+        if not self.on:
+            return
+        if self.open:
+            torch.cuda.nvtx.range_pop()
+            self.open = False
+        if name is not None:
+            torch.cuda.nvtx.range_push(f"vstab.{name}")
+            self.open = True
+
+
 @dataclass
 class StabilizationResult:
     frames: Any  # [N,H',W',3] float32 (numpy view of a pinned CPU tensor, or CUDA tensor)
@@ -248,14 +269,18 @@ def stabilize_frames(
     output: str = "host",
     shard=None,
 ) -> StabilizationResult:
-    with hm.gc_paused():
-        return _stabilize_frames(context, framing_mode, transform_mode, camera_lock, strength, smooth, keep_fov, padding_rgb,
-                                 frame_rate, estimator=estimator, flavour=flavour, progress_bar=progress_bar,
-                                 interrupt_check=interrupt_check, output=output, shard=shard)
+    nvtx = _Nvtx()
+    try:
+        with hm.gc_paused():
+            return _stabilize_frames(context, framing_mode, transform_mode, camera_lock, strength, smooth, keep_fov, padding_rgb,
+                                     frame_rate, estimator=estimator, flavour=flavour, progress_bar=progress_bar,
+                                     interrupt_check=interrupt_check, output=output, shard=shard, nvtx=nvtx)
+    finally:
+        nvtx.phase(None)
 
 
 def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, strength, smooth, keep_fov, padding_rgb, frame_rate, *,
-                      estimator, flavour, progress_bar, interrupt_check, output, shard) -> StabilizationResult:
+                      estimator, flavour, progress_bar, interrupt_check, output, shard, nvtx) -> StabilizationResult:
     is_flow = flavour == "flow"
     total_frames = len(context)
     width, height = context.width, context.height
@@ -306,13 +331,16 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
     import time
 
     t0 = time.perf_counter()
+    nvtx.phase("estimate")
     cands = estimator(context, work_w, work_h, transform_mode)
     t0 = _mark("estimate (gray+flow/track+fit enqueued)", t0)
+    nvtx.phase("candidate_table")
     if shard is not None:
         cands = shard.gather_candidates(cands)
     if isinstance(cands, DeviceCandidates):
         cands = cands.to_host()
     t0 = _mark("candidate table on the host (waits for the GPU; all-gather when sharded)", t0)
+    nvtx.phase("ladder+solve")
     chosen, active_mode, stacked = replay_mode_ladder(cands, transform_mode, with_residual=is_flow)
     t0 = _mark("ladder", t0)
     progress.advance(estimation_steps)
@@ -404,6 +432,7 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
     final_matrices = np.asarray(final_matrices, dtype=np.float32)
     fwd = final_matrices[lo:hi].reshape(-1, 1, 9)
     t0 = _mark("host path/framing solve", t0)
+    nvtx.phase("resample")
     # sharded runs on GPUs: the per-frame padded-pixel counts are all-gathered device to device right behind the
     # resampler (they only feed the meta), and come back with the one copy that waits for it
     pad_gather = shard.device_pad_gather() if shard is not None else None
@@ -417,6 +446,7 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
     # the per-frame lists only for shard.meta_frame_range (by default the rank's own frames: the per-frame
     # meta is sharded like the frames it describes, sharding.merge_sharded_meta() reassembles it); entries
     # keep their clip-wide indices.  Transitions go with the frame they end in.
+    nvtx.phase("meta")
     m_lo, m_hi = (0, total_frames) if shard is None else shard.meta_frame_range
     t_lo, t_hi = max(m_lo, 1) - 1, max(m_hi - 1, max(m_lo, 1) - 1)
     per_transition = []
@@ -448,6 +478,7 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
     )
 
     t0 = _mark("meta build (overlaps the warp)", t0)
+    nvtx.phase("finish")
     frames_out, masks_out, pad_counts = pending()
     t0 = _mark("wait for warp + pad counts", t0)
     if shard is not None:

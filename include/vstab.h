@@ -49,6 +49,12 @@ extern "C" {
 /* padding-mask footprint rule of warpPerspective(ones, INTER_NEAREST) */
 #define VSTAB_MASK_RULE_P 0 /* closed rectangle on continuous coordinates (cv2 4.13 IPP HAL) */
 #define VSTAB_MASK_RULE_C 1 /* classic: round-half-even, then range check */
+/* What cv2 itself does per call: Rule P, unless one of the wheel's min(threads, ceil(W'H'/2^14)) destination
+ * stripes misses the source frame entirely -- then Rule C for that whole (frame, sample).  The thread count of the
+ * reference machine (cv2.getNumThreads(), by default its logical CPU count) rides in the upper bits of mask_rule:
+ * VSTAB_MASK_RULE_AUTO_THREADS(8).  With 1 thread AUTO == Rule P. */
+#define VSTAB_MASK_RULE_AUTO 2
+#define VSTAB_MASK_RULE_AUTO_THREADS(t) (VSTAB_MASK_RULE_AUTO | ((t) << 8))
 
 /* source-tile staging of the fused resampler (debug / A-B switch) */
 #define VSTAB_STAGE_AUTO 0   /* shared-memory tile when the footprint fits, else global gather */

@@ -171,6 +171,52 @@ def coverage_np(m32: np.ndarray, src_size, out_size, rule: int = RULE_P) -> np.n
     return ok
 
 
+def _clip_halfplane(poly, a, b, c):
+    """Sutherland-Hodgman: the part of the polygon with a x + b y + c >= 0."""
+    out = []
+    for i, p in enumerate(poly):
+        q = poly[(i + 1) % len(poly)]
+        fp, fq = a * p[0] + b * p[1] + c, a * q[0] + b * q[1] + c
+        if fp >= 0:
+            out.append(p)
+        if (fp >= 0) != (fq >= 0):
+            t = fp / (fp - fq)
+            out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
+    return out
+
+
+def mask_stripes(out_size, threads: int):
+    """Row ranges [r0, r1) of the destination stripes the wheel's IPP path of warpPerspective(INTER_NEAREST) works in:
+    min(cv2.getNumThreads(), ceil(W' H' / 2^14)) stripes, boundaries (s H' + S // 2) // S.  Found black-box (threshold of
+    the Rule P -> Rule C flip under vertical shifts, 11 sizes x 7 thread counts)."""
+    ow, oh = int(out_size[0]), int(out_size[1])
+    s = max(1, min(int(threads), -(-(ow * oh) // 16384)))
+    return [((k * oh + s // 2) // s, ((k + 1) * oh + s // 2) // s) for k in range(s)]
+
+
+def auto_rule(m32, src_size, out_size, threads: int) -> int:
+    """The rule cv2 applies to ONE warpPerspective(ones, m32, out_size, INTER_NEAREST) call: Rule P, unless
+    the forward-mapped quad of the source's pixel centres misses one destination stripe entirely -- then the IPP call is
+    refused and OpenCV's own code (Rule C) handles the whole image."""
+    w, h = int(src_size[0]), int(src_size[1])
+    ow = int(out_size[0])
+    m = np.asarray(m32, dtype=np.float32).astype(np.float64).reshape(3, 3)
+    quad = []
+    for x, y in ((0.0, 0.0), (w - 1.0, 0.0), (w - 1.0, h - 1.0), (0.0, h - 1.0)):
+        X, Y, W = (m[0, 0] * x + m[0, 1] * y + m[0, 2], m[1, 0] * x + m[1, 1] * y + m[1, 2], m[2, 0] * x + m[2, 1] * y + m[2, 2])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            quad.append((float(np.float64(X) / np.float64(W)), float(np.float64(Y) / np.float64(W))))
+    for r0, r1 in mask_stripes(out_size, threads):
+        if r1 <= r0:
+            continue
+        poly = quad
+        for a, b, c in ((1.0, 0.0, 0.0), (-1.0, 0.0, ow - 1.0), (0.0, 1.0, -float(r0)), (0.0, -1.0, float(r1 - 1))):
+            poly = _clip_halfplane(poly, a, b, c)
+            if not poly:
+                return RULE_C
+    return RULE_P
+
+
 def mask_np(m32, src_size, out_size, rule: int = RULE_P) -> np.ndarray:
     """Padding mask exactly as the reference post-processes it (flow.py:583-584)."""
     mask = np.float32(1.0) - coverage_np(m32, src_size, out_size, rule).astype(np.float32)

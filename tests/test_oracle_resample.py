@@ -104,3 +104,54 @@ def test_bicubic_in_cv2_row_order_is_bit_exact():
         assert np.array_equal(ref, R.warp_np(src, M, (ow, oh), "bicubic", border, cubic_rows=True)), k
         assert np.array_equal(ref, R.warp_np(src, M, (ow, oh), "bicubic", border)), k
         assert float(np.abs(ref - R.warp_np(src, M, (ow, oh), "bicubic", border, cubic_rows=False)).max()) <= 1e-6
+
+
+def _cv_rule(m, src, out):
+    """Which rule the live wheel applied to this call (None when both rules give the same mask)."""
+    ones = np.ones((src[1], src[0]), np.float32)
+    cov = cv2.warpPerspective(ones, m, out, flags=cv2.INTER_NEAREST, borderMode=cv2.BORDER_CONSTANT, borderValue=0.0) > 0.5
+    dp = int((cov != R.coverage_np(m, src, out, R.RULE_P)).sum())
+    dc = int((cov != R.coverage_np(m, src, out, R.RULE_C)).sum())
+    assert dp == 0 or dc == 0, (dp, dc)  # one of the two rules always explains the wheel's mask exactly
+    return None if dp == dc == 0 else (R.RULE_P if dp == 0 else R.RULE_C)
+
+
+@pytest.mark.parametrize("threads", [8, 4, 3])
+def test_mask_rule_auto_matches_what_cv2_picks(threads):
+    """the wheel switches the WHOLE call to Rule C when one of its destination stripes misses
+    the source.  resample_np.auto_rule restates the predicate (stripe count = min(threads, ceil(W'H'/2^14)), boundaries
+    (s H' + S/2) // S, forward quad of the source's pixel centres vs the stripe's pixel-centre rectangle); here against
+    the live wheel on random large off-canvas warps and on shifts one row either side of every flip."""
+    if (os.cpu_count() or 1) < threads:
+        pytest.skip("not enough CPUs for this cv2 thread count")
+    cv2.setNumThreads(threads)
+    try:
+        if cv2.getNumThreads() != threads:
+            pytest.skip("cv2 did not accept the thread count")
+        rng = np.random.default_rng(threads)
+        decided = 0
+        for trial in range(150):
+            w, h = [(832, 480), (320, 200), (640, 360), (400, 300), (200, 120), (256, 256)][trial % 6]
+            out = (w, h) if trial % 3 else (w + int(rng.integers(-40, 80)), h + int(rng.integers(-40, 80)))
+            th, sc = rng.normal(0, 0.15), 1 + rng.normal(0, 0.15)
+            m = np.array([[sc * np.cos(th), -sc * np.sin(th), rng.normal(0, 0.6 * w) + 0.3],
+                          [sc * np.sin(th), sc * np.cos(th), rng.normal(0, 0.6 * h)], [0, 0, 1]])
+            if trial % 4 == 0:
+                m[2, :2] = rng.normal(0, 3e-4, 2)
+            m = m.astype(np.float32)
+            want = _cv_rule(m, (w, h), out)
+            if want is not None:
+                decided += 1
+                assert R.auto_rule(m, (w, h), out, threads) == want, (trial, (w, h), out)
+        assert decided >= 100
+        for w, h in [(832, 480), (400, 300), (640, 360)]:
+            stripes = R.mask_stripes((w, h), threads)
+            for edge, b in (("top", stripes[0][1]), ("bottom", h - stripes[-1][0])):
+                for d in (-1.5, -1.0, -0.5, -0.1, 0.0, 0.1, 0.5, 1.0):
+                    ty = (b + d) if edge == "top" else -(b + d)
+                    m = np.array([[1, 0, -0.3], [0, 1, ty], [0, 0, 1]], np.float32)
+                    want = _cv_rule(m, (w, h), (w, h))
+                    assert want is not None and R.auto_rule(m, (w, h), (w, h), threads) == want, (w, h, edge, d)
+    finally:
+        cv2.setNumThreads(-1)
+    assert R.auto_rule(np.array([[1, 0, -0.3], [0, 1, 300.0], [0, 0, 1]], np.float32), (832, 480), (832, 480), 1) == R.RULE_P

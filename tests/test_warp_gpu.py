@@ -184,3 +184,70 @@ def test_full_size_properties_1080p(handle):
     assert torch.equal(dst[:, : h - 5, 7:], src[:, 5:, : w - 7])
     assert int(pad[0]) == w * h - (w - 7) * (h - 5)
     assert torch.equal(mask[:, : h - 5, 7:], torch.zeros_like(mask[:, : h - 5, 7:]))
+
+
+@pytest.mark.parametrize("threads", [8, 4])
+def test_mask_rule_auto_follows_cv2_per_frame_and_sample(handle, threads):
+    """VSTAB_MASK_RULE_AUTO_THREADS(t): every (frame, shutter sample) gets the rule cv2 would pick for that call on a
+    machine with t cv2 threads -- Rule P, or Rule C when one of the wheel's destination stripes misses the source
+    (oracle: resample_np.auto_rule, pinned against the live wheel in tests/test_oracle_resample.py).  Shifts on both
+    sides of the flip, single sample and motion blur whose samples straddle it; pixels must not change at all."""
+    from vstab_b200 import _native
+    from vstab_b200.motion_apply import sample_matrices
+
+    rng = np.random.default_rng(17)
+    w, h = 832, 480
+    first = R.mask_stripes((w, h), threads)[0][1]
+    shifts = [first - 2.0, first - 0.5, first + 0.5, first + 30.0, -(h - R.mask_stripes((w, h), threads)[-1][0]) - 1.0, 5.0]
+    src = rng.random((len(shifts), h, w, 3), dtype=np.float32)
+    mats = np.stack([np.array([[1, 0, -0.3], [0, 1, ty], [0, 0, 1]], np.float32) for ty in shifts])
+    rules = [R.auto_rule(m, (w, h), (w, h), threads) for m in mats]
+    assert R.RULE_P in rules and R.RULE_C in rules
+    got, mask, pad = _run(handle, src, mats.reshape(-1, 1, 9), (w, h), "bilinear", (0.5, 0.5, 0.5), mask_rule=_native.mask_rule_auto(threads))
+    ref, _, _ = _run(handle, src, mats.reshape(-1, 1, 9), (w, h), "bilinear", (0.5, 0.5, 0.5))
+    assert np.array_equal(got, ref)  # the rule only concerns the mask
+    for i, m in enumerate(mats):
+        want = R.mask_np(m, (w, h), (w, h), rules[i])
+        assert np.array_equal(mask[i], want), (i, shifts[i], rules[i])
+        assert int(pad[i]) == int(want.sum())
+    # one thread: AUTO is Rule P
+    _, mask1, _ = _run(handle, src, mats.reshape(-1, 1, 9), (w, h), "bilinear", (0.5, 0.5, 0.5), mask_rule=_native.mask_rule_auto(1))
+    for i, m in enumerate(mats):
+        assert np.array_equal(mask1[i], R.mask_np(m, (w, h), (w, h), R.RULE_P))
+    # motion blur: the shutter samples of frame 0 move across the flip
+    seq = [np.array([[1, 0, -0.3], [0, 1, first - 6.0], [0, 0, 1]], np.float64), np.array([[1, 0, -0.3], [0, 1, first + 10.0], [0, 0, 1]], np.float64)]
+    fwd = sample_matrices(seq, 1.0, 9)
+    gotb, maskb, _ = _run(handle, src[:2], fwd, (w, h), "bilinear", (0.5, 0.5, 0.5), mask_rule=_native.mask_rule_auto(threads))
+    for i in range(2):
+        cov = np.zeros((h, w), np.float32)
+        seen = set()
+        for k in range(9):
+            m32 = np.asarray(fwd[i, k], np.float32).reshape(3, 3)
+            rule = R.auto_rule(m32, (w, h), (w, h), threads)
+            seen.add(rule)
+            cov += R.coverage_np(m32, (w, h), (w, h), rule).astype(np.float32)
+        want = np.float32(1.0) - cov / np.float32(9)
+        want[want < 1e-3] = 0.0
+        assert np.array_equal(maskb[i], want), i
+        if i == 0:
+            assert seen == {R.RULE_P, R.RULE_C}
+
+
+def test_mask_rule_auto_in_the_crop_coverage_kernels(handle):
+    from vstab_b200 import _native
+
+    w, h, threads = 640, 360, 8
+    first = R.mask_stripes((w, h), threads)[0][1]
+    mats = np.stack([np.array([[1, 0, -0.3], [0, 1, ty], [0, 0, 1]], np.float32) for ty in (3.0, first + 4.0, first - 3.0)])
+    fwd = torch.from_numpy(mats.reshape(-1, 9)).cuda()
+    rules = [R.auto_rule(m, (w, h), (w, h), threads) for m in mats]
+    assert rules == [R.RULE_P, R.RULE_C, R.RULE_P]
+    common = handle.common_coverage(fwd, (w, h), (w, h), _native.mask_rule_auto(threads)).cpu().numpy() > 0
+    want = np.ones((h, w), bool)
+    for m, r in zip(mats, rules):
+        want &= R.coverage_np(m, (w, h), (w, h), r)
+    assert np.array_equal(common, want)
+    box = handle.coverage_bbox(fwd, (w, h), (w, h), _native.mask_rule_auto(threads)).cpu().numpy()
+    for i, (m, r) in enumerate(zip(mats, rules)):
+        ys, xs = np.nonzero(R.coverage_np(m, (w, h), (w, h), r))
+        assert box[i, 0] == xs.min() and box[i, 2] == xs.max() and box[i, 1] == ys.min() and box[i, 3] == ys.max(), (i, box[i])
