@@ -45,6 +45,7 @@ extern "C" void vstab_destroy(vstab_handle* h) {
   for (int i = 0; i < h->n_aux; ++i) {
     cudaStreamDestroy(h->aux_stream[i]);
     cudaEventDestroy(h->join_event[i]);
+    cudaEventDestroy(h->stagger_event[i]);
   }
   if (h->fork_event) cudaEventDestroy(h->fork_event);
   for (int i = 0; i < h->n_area_cache; ++i)
@@ -62,6 +63,7 @@ int vstab_aux_streams(vstab_handle* h, int n) {
   while (h->n_aux < n) {
     VSTAB_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream[h->n_aux], cudaStreamNonBlocking));
     VSTAB_CUDA(h, cudaEventCreateWithFlags(&h->join_event[h->n_aux], cudaEventDisableTiming));
+    VSTAB_CUDA(h, cudaEventCreateWithFlags(&h->stagger_event[h->n_aux], cudaEventDisableTiming));
     h->n_aux++;
   }
   return VSTAB_OK;

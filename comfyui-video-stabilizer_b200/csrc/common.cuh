@@ -40,6 +40,7 @@ struct vstab_handle {
   // (DIS pair groups); created on first use
   cudaStream_t aux_stream[VSTAB_MAX_AUX_STREAMS];
   cudaEvent_t join_event[VSTAB_MAX_AUX_STREAMS];
+  cudaEvent_t stagger_event[VSTAB_MAX_AUX_STREAMS];
   cudaEvent_t fork_event;
   int n_aux;
 };

@@ -38,6 +38,9 @@ constexpr int kMaxLevels = 8;
 #ifndef VSTAB_DIS_GROUPS_DEFAULT
 #define VSTAB_DIS_GROUPS_DEFAULT 2
 #endif
+#ifndef VSTAB_DIS_STAGGER_DEFAULT
+#define VSTAB_DIS_STAGGER_DEFAULT 0
+#endif
 #ifndef VSTAB_VR_MIN_CTAS
 #define VSTAB_VR_MIN_CTAS 5
 #endif
@@ -144,18 +147,33 @@ struct Bil {
   int off;  // offset of the top-left sample in the bordered image
 };
 
+// Integer <-> float conversions without the XU pipe.  I2F / F2I / FRND run at 16 lanes per clock per SM, and the
+// patch search converts a 9 x 4 texel window per evaluation: ncu showed that pipe 96 % busy on the slowest SM
+// (profiles/r02_dis_ncu.txt).  The classic 2^23 bias does the same conversions exactly on the FMA / ALU pipes.
+__device__ __forceinline__ float u8_to_float(unsigned v) { return __int_as_float(0x4B000000u | v) - 8388608.0f; }   // 0 <= v < 2^23
+__device__ __forceinline__ float s16_to_float(int v) { return __int_as_float(0x4B400000 + v) - 12582912.0f; }      // |v| < 2^22
+// floorf(x) and (int)x for 0 <= x < 2^22: x + 2^23 leaves rint(x) in the mantissa; step back when that rounded up
+__device__ __forceinline__ float floor_pos(float x, int& as_int) {
+  const float t = x + 8388608.0f;
+  const float r = t - 8388608.0f;
+  const bool up = r > x;
+  as_int = (__float_as_int(t) & 0x7FFFFF) - (up ? 1 : 0);
+  return up ? r - 1.0f : r;
+}
+
 __device__ __forceinline__ Bil bil_weights(float i, float j, float Ux, float Uy, int w, int h, int we) {
   const float i_lo = kBorder - kPatch + 1.0f, i_hi = kBorder + h - 1.0f;
   const float j_lo = kBorder - kPatch + 1.0f, j_hi = kBorder + w - 1.0f;
-  const float iI = fminf(fmaxf(i + Uy + kBorder, i_lo), i_hi);
+  const float iI = fminf(fmaxf(i + Uy + kBorder, i_lo), i_hi);   // >= 9: floor == truncation
   const float jI = fminf(fmaxf(j + Ux + kBorder, j_lo), j_hi);
-  const float di = iI - floorf(iI), dj = jI - floorf(jI);
+  int ii, ji;
+  const float di = iI - floor_pos(iI, ii), dj = jI - floor_pos(jI, ji);
   Bil b;
   b.w11 = di * dj;
   b.w10 = di * (1 - dj);
   b.w01 = (1 - di) * dj;
   b.w00 = (1 - di) * (1 - dj);
-  b.off = (int)iI * we + (int)jI;
+  b.off = ii * we + ji;
   return b;
 }
 
@@ -165,29 +183,77 @@ __device__ __forceinline__ float quad_reduce(float v, unsigned mask) {
   return t + __shfl_xor_sync(mask, t, 1);
 }
 
+// ---- packed float32x2 multiplies (Blackwell FMUL2): two IEEE round-to-nearest products per instruction.
+// A lane owns pixel columns l and l + 4 of a patch, and OpenCV's code does the same operation on both, so every
+// product of the inner loop is issued once for the pair -- same bits, fewer instructions in a kernel whose cost is the
+// length of one warp's instruction stream.  Only the PRODUCTS are packed: ptxas 12.9 contracts mul.rn.f32x2 +
+// add.rn.f32x2 into a fused FFMA2 even under -fmad=false and with explicit .rn (checked with cuobjdump), which would
+// change the rounding, so the sums stay scalar FADDs, which it leaves alone.
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 pack2(float x, float y) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f2 a, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ float hsum2(f2 a) {
+  float x, y;
+  unpack2(a, x, y);
+  return __fadd_rn(x, y);
+}
+
+// The 9 x (2 + 2) texels of I1 a lane needs for one patch position, converted to float once and kept in registers:
+// consecutive Gauss-Newton steps of a patch move it by a fraction of a pixel, so the integer offset -- and with it
+// every texel -- usually stays the same and only the four bilinear weights change.
+struct I1Cache {
+  f2 lo[9];   // (I1[r][l],     I1[r][l + 4])
+  f2 hi[9];   // (I1[r][l + 1], I1[r][l + 5])
+  int off;    // offset of the cached window in the bordered image, -1 = empty
+};
+
+__device__ __forceinline__ void i1_load(I1Cache& c, const unsigned char* __restrict__ I1e, int s1, int off, int l) {
+  if (off == c.off) return;
+  const unsigned char* p = I1e + off + l;
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    c.lo[r] = pack2(u8_to_float(p[r * s1]), u8_to_float(p[r * s1 + 4]));
+    c.hi[r] = pack2(u8_to_float(p[r * s1 + 1]), u8_to_float(p[r * s1 + 5]));
+  }
+  c.off = off;
+}
+
 // One 8x8 patch evaluation by a quad: lane l handles pixel columns l and l+4 of every row.
 // kind 0: mean-normalised SSD only; kind 1: SSD + gradient-weighted sums (processPatchMeanNorm).
 // The template patch (I0 and its gradients) is the same for every evaluation of a patch, so the
-// caller converts it to float once (z / gx / gy: [row][0] = column l, [row][1] = column l+4).
+// caller converts it to float once (z / gx / gy: .x = column l, .y = column l+4).
 template <int KIND>
-__device__ __forceinline__ float patch_eval(const float (&z)[8][2], const float (&gxv)[8][2], const float (&gyv)[8][2],
-                                            const unsigned char* __restrict__ I1p, int s1, const Bil& b, int l, float xgs,
-                                            float ygs, float& dUx, float& dUy, unsigned mask) {
+__device__ __forceinline__ float patch_eval(const f2 (&z)[8], const f2 (&gxv)[8], const f2 (&gyv)[8], const I1Cache& c,
+                                            const Bil& b, float xgs, float ygs, float& dUx, float& dUy, unsigned mask) {
   float sd = 0.f, sq = 0.f, mx = 0.f, my = 0.f;
-  float a0 = I1p[l], a1 = I1p[l + 1], a4 = I1p[l + 4], a5 = I1p[l + 5];
+  const f2 w00 = pack2(b.w00, b.w00), w01 = pack2(b.w01, b.w01), w10 = pack2(b.w10, b.w10), w11 = pack2(b.w11, b.w11);
 #pragma unroll
   for (int r = 0; r < 8; r++) {
-    const unsigned char* nb = I1p + (r + 1) * s1;
-    const float b0 = nb[l], b1 = nb[l + 1], b4 = nb[l + 4], b5 = nb[l + 5];
-    const float dl = b.w00 * a0 + b.w01 * a1 + b.w10 * b0 + b.w11 * b1 - z[r][0];
-    const float dr = b.w00 * a4 + b.w01 * a5 + b.w10 * b4 + b.w11 * b5 - z[r][1];
+    // (dl, dr) = ((w00 a + w01 a') + w10 b) + w11 b' - z in OpenCV's order: four packed products, scalar sums
+    float p0x, p0y, p1x, p1y, p2x, p2y, p3x, p3y, zx, zy;
+    unpack2(mul2(w00, c.lo[r]), p0x, p0y);
+    unpack2(mul2(w01, c.hi[r]), p1x, p1y);
+    unpack2(mul2(w10, c.lo[r + 1]), p2x, p2y);
+    unpack2(mul2(w11, c.hi[r + 1]), p3x, p3y);
+    unpack2(z[r], zx, zy);
+    const float dl = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(p0x, p1x), p2x), p3x), zx);
+    const float dr = __fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(p0y, p1y), p2y), p3y), zy);
+    const f2 d = pack2(dl, dr);
     if (KIND == 1) {
-      mx = mx + (dl * gxv[r][0] + dr * gxv[r][1]);
-      my = my + (dl * gyv[r][0] + dr * gyv[r][1]);
+      mx = __fadd_rn(mx, hsum2(mul2(d, gxv[r])));
+      my = __fadd_rn(my, hsum2(mul2(d, gyv[r])));
     }
-    sq = sq + (dl * dl + dr * dr);
-    sd = sd + (dl + dr);
-    a0 = b0; a1 = b1; a4 = b4; a5 = b5;
+    sq = __fadd_rn(sq, hsum2(mul2(d, d)));
+    sd = __fadd_rn(sd, __fadd_rn(dl, dr));
   }
   const float sum_diff = quad_reduce(sd, mask);
   const float sum_sq = quad_reduce(sq, mask);
@@ -209,8 +275,11 @@ __device__ __forceinline__ float patch_eval(const float (&z)[8][2], const float 
 // STAGED keeps everything the chain touches in shared memory (both images and the sparse flow of the pair;
 // the bordered I1 of a 240x135 level is 45 KB), which takes the global load round trips out of every link
 // of the chain.  Same arithmetic either way.
+#ifndef VSTAB_PS_MIN_CTAS
+#define VSTAB_PS_MIN_CTAS 1
+#endif
 template <bool STAGED>
-__global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P, int spw, int cpp) {
+__global__ void __launch_bounds__(256, VSTAB_PS_MIN_CTAS) patch_search_kernel(Level L, int P, int spw, int cpp) {
   extern __shared__ __align__(16) unsigned char ps_smem[];
   const int pair = blockIdx.x / cpp;
   const int warp_in_pair = (blockIdx.x - pair * cpp) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -288,30 +357,32 @@ __global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P, int s
           sy = Sy[k];
         }
         const unsigned char* I0p = I0 + i * w + j;
-        float z[8][2], gxv[8][2], gyv[8][2];
+        f2 z[8], gxv[8], gyv[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-          z[r][0] = I0p[r * w + l];
-          z[r][1] = I0p[r * w + l + 4];
-          gxv[r][0] = gx[(i + r) * w + j + l];
-          gxv[r][1] = gx[(i + r) * w + j + l + 4];
-          gyv[r][0] = gy[(i + r) * w + j + l];
-          gyv[r][1] = gy[(i + r) * w + j + l + 4];
+          z[r] = pack2(u8_to_float(I0p[r * w + l]), u8_to_float(I0p[r * w + l + 4]));
+          gxv[r] = pack2(s16_to_float(gx[(i + r) * w + j + l]), s16_to_float(gx[(i + r) * w + j + l + 4]));
+          gyv[r] = pack2(s16_to_float(gy[(i + r) * w + j + l]), s16_to_float(gy[(i + r) * w + j + l + 4]));
         }
         float dux, duy;
+        I1Cache i1c;
+        i1c.off = -1;
         // spatial propagation: own / previous column / previous row of this pass
         Bil b = bil_weights((float)i, (float)j, sx, sy, w, h, we);
-        float min_ssd = patch_eval<0>(z, gxv, gyv, I1e + b.off, we, b, l, 0.f, 0.f, dux, duy, qmask);
+        i1_load(i1c, I1e, we, b.off, l);
+        float min_ssd = patch_eval<0>(z, gxv, gyv, i1c, b, 0.f, 0.f, dux, duy, qmask);
         if (c > 0) {
           const float cx = Sx[k - dir], cy = Sy[k - dir];
           b = bil_weights((float)i, (float)j, cx, cy, w, h, we);
-          const float s = patch_eval<0>(z, gxv, gyv, I1e + b.off, we, b, l, 0.f, 0.f, dux, duy, qmask);
+          i1_load(i1c, I1e, we, b.off, l);
+          const float s = patch_eval<0>(z, gxv, gyv, i1c, b, 0.f, 0.f, dux, duy, qmask);
           if (s < min_ssd) { min_ssd = s; sx = cx; sy = cy; }
         }
         if (row_in_stripe > 0) {
           const float cx = Sx[k - dir * ws], cy = Sy[k - dir * ws];
           b = bil_weights((float)i, (float)j, cx, cy, w, h, we);
-          const float s = patch_eval<0>(z, gxv, gyv, I1e + b.off, we, b, l, 0.f, 0.f, dux, duy, qmask);
+          i1_load(i1c, I1e, we, b.off, l);
+          const float s = patch_eval<0>(z, gxv, gyv, i1c, b, 0.f, 0.f, dux, duy, qmask);
           if (s < min_ssd) { min_ssd = s; sx = cx; sy = cy; }
         }
         float cur_Ux = sx, cur_Uy = sy;
@@ -323,7 +394,8 @@ __global__ void __launch_bounds__(256) patch_search_kernel(Level L, int P, int s
         float prev_ssd = kInf;
         for (int t = 0; t < inner; t++) {
           b = bil_weights((float)i, (float)j, cur_Ux, cur_Uy, w, h, we);
-          const float ssd = patch_eval<1>(z, gxv, gyv, I1e + b.off, we, b, l, xgs, ygs, dux, duy, qmask);
+          i1_load(i1c, I1e, we, b.off, l);
+          const float ssd = patch_eval<1>(z, gxv, gyv, i1c, b, xgs, ygs, dux, duy, qmask);
           const float dx = invH11 * dux + invH12 * duy;
           const float dy = invH12 * dux + invH22 * duy;
           cur_Ux -= dx;
@@ -809,15 +881,20 @@ int vr_cluster_size(int px) {
 }
 
 // One pyramid level of one pair group on one stream: patch search, densification, refinement, x2 upsampling.
-int dis_level(vstab_handle* hnd, const Level& Lc, const Level* finer, const VrBuf& B, int P, cudaStream_t st) {
+int dis_level(vstab_handle* hnd, const Level& Lc, const Level* finer, const VrBuf& B, int P, cudaStream_t st,
+              cudaEvent_t after_search = nullptr) {
   dim3 gp(vstab_ceil_div(Lc.w, 32), vstab_ceil_div(Lc.h, 8), P);
   {
     const int stripe_sz = (Lc.hs + kStripes - 1) / kStripes;
-    int spw = stripe_sz <= 8 ? 8 / stripe_sz : 1;          // stripes carried by one warp
+    // Stripes carried by one warp.  Packing 8 / rows stripes into a warp halves the instruction count of the
+    // launch (342 M -> 158 M at the finest level) but NOT its duration: the cost is the length of one warp's
+    // instruction stream at ~0.31 IPC, and a warp with 8 busy quads runs every Gauss-Newton loop as long as its
+    // slowest quad.  Measured on 120 pairs (scripts/dis_sweep.py): one stripe per warp 4.00 ms, packed 4.25 ms.
+    int spw = 1;
+    if (env_int("VSTAB_PS_PACK", 0)) spw = stripe_sz <= 8 ? 8 / stripe_sz : 1;
     if (spw < 1) spw = 1;
-    if (env_int("VSTAB_PS_NOPACK", 0)) spw = 1;
     const int warps_per_pair = (kStripes + spw - 1) / spw;
-    int wpc = env_int("VSTAB_PS_WPC", 4);                   // warps per CTA
+    int wpc = env_int("VSTAB_PS_WPC", 8);                   // warps per CTA
     if (wpc > warps_per_pair) wpc = warps_per_pair;
     const int cpp = (warps_per_pair + wpc - 1) / wpc;       // CTAs per pair
     const size_t n1 = (size_t)(Lc.h + 2 * kBorder) * (Lc.w + 2 * kBorder), n0 = (size_t)Lc.h * Lc.w;
@@ -830,6 +907,7 @@ int dis_level(vstab_handle* hnd, const Level& Lc, const Level* finer, const VrBu
     }
   }
   VSTAB_LAUNCH_CHECK(hnd, "patch_search_kernel");
+  if (after_search) VSTAB_CUDA(hnd, cudaEventRecord(after_search, st));
   densify_kernel<<<gp, 256, 0, st>>>(Lc, P);
   VSTAB_LAUNCH_CHECK(hnd, "densify_kernel");
   // variational refinement: one cluster-fused launch per level
@@ -964,10 +1042,15 @@ int dis_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height
         VSTAB_CUDA(hnd, cudaStreamWaitEvent(gs[g], hnd->fork_event, 0));
       }
     }
-    for (int i = coarsest; i >= finest; i--) {
-      for (int g = 0; g < G; g++) {
-        const int a = (int)((long long)P * g / G), b = (int)((long long)P * (g + 1) / G);
-        if (b <= a) continue;
+    // Groups that start together run in lockstep -- patch search under patch search, refinement under refinement --
+    // and gain nothing.  So group g + 1 is released only when group g has finished the patch search of level
+    // `stagger` levels above the finest: from then on the (latency-bound, 2 warps per scheduler) finest-level search
+    // of one group sits under the (throughput-bound) finest-level refinement of the group before it.
+    const int stagger = env_int("VSTAB_DIS_STAGGER", VSTAB_DIS_STAGGER_DEFAULT) - 1;  // env 0 / unset-to-0 = off, k = release after PS of level finest + k - 1
+    for (int g = 0; g < G; g++) {
+      const int a = (int)((long long)P * g / G), b = (int)((long long)P * (g + 1) / G);
+      if (b <= a) continue;
+      for (int i = coarsest; i >= finest; i--) {
         const Level Lg = level_from_pair(L[i], a);
         Level finer_g;
         if (i > finest) finer_g = level_from_pair(L[i - 1], a);
@@ -976,8 +1059,11 @@ int dis_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height
           float** f = (float**)&Bg;
           for (int k = 0; k < 19; k++) f[k] += (size_t)a * nf;  // a group's scratch is fixed: groups sit at different levels at the same time
         }
-        rc = dis_level(hnd, Lg, i > finest ? &finer_g : nullptr, Bg, b - a, gs[g]);
+        cudaEvent_t after_search = nullptr;
+        if (stagger >= 0 && g + 1 < G && i == (finest + stagger < coarsest ? finest + stagger : coarsest)) after_search = hnd->stagger_event[g];
+        rc = dis_level(hnd, Lg, i > finest ? &finer_g : nullptr, Bg, b - a, gs[g], after_search);
         if (rc != VSTAB_OK) return rc;
+        if (after_search) VSTAB_CUDA(hnd, cudaStreamWaitEvent(gs[g + 1], after_search, 0));
       }
     }
     for (int g = 1; g < G; g++) {

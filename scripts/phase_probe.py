@@ -28,7 +28,7 @@ out["fit_sim+trans_ms"], raw = t(lambda: h.fit_grid(grid, 8, 3))
 out["fit_sim_only_ms"], _ = t(lambda: h.fit_grid(grid, 8, 2))
 out["fit_all_ms"], _ = t(lambda: h.fit_grid(grid, 8, 7))
 out["decode_ms"], d = t(lambda: _native.decode_fit_results(raw))
-out["estimate_total_ms"], cands = t(lambda: flow.estimate_candidates(ctx, 960, 540, "similarity"))
+out["estimate_total_ms"], cands = t(lambda: flow.estimate_candidates(ctx, 960, 540, "similarity").to_host())
 t0 = time.perf_counter()
 for _ in range(5):
     chosen, active, _ = core.replay_mode_ladder(cands, "similarity", with_residual=True)
