@@ -94,6 +94,10 @@ def load_library() -> C.CDLL:
         lib.vstab_working_size.restype = i32
         lib.vstab_gray_working.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp]
         lib.vstab_gray_working.restype = i32
+        lib.vstab_gray_working_adapt.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp, vp]
+        lib.vstab_gray_working_adapt.restype = i32
+        lib.vstab_range_normalize.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+        lib.vstab_range_normalize.restype = i32
         lib.vstab_warp_fused.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, fp, i32, i32, vp, vp, vp, vp]
         lib.vstab_warp_fused.restype = i32
         lib.vstab_common_coverage.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
@@ -191,6 +195,29 @@ class Handle:
         out = torch.empty((n, wh, ww), dtype=torch.uint8, device=rgb.device)
         self._check(self.lib.vstab_gray_working(self._h, rgb.data_ptr(), n, h, w, out.data_ptr(), wh, ww, _stream_ptr(rgb.device)))
         return out
+
+    def gray_working_adapt(self, rgb: torch.Tensor, work_size: tuple[int, int] | None = None):
+        """K1 + K2 with the input adapter's range rule fused in (include/vstab.h, vstab_gray_working_adapt):
+        rgb [N,H,W,3] f32 cuda, READ AND WRITTEN (frames whose max exceeds 1.5 are divided by 255 in place)
+        -> (gray [N,h,w] u8, flags [N] int32 on the device: 1 = that frame was 0..255 content and has been rescaled)."""
+        _check_cuda(rgb, torch.float32, "rgb")
+        n, h, w, c = rgb.shape
+        if c != 3:
+            raise VstabNativeError("rgb must have 3 channels")
+        ww, wh = work_size if work_size is not None else working_size(w, h)
+        out = torch.empty((n, wh, ww), dtype=torch.uint8, device=rgb.device)
+        flags = torch.empty((n,), dtype=torch.int32, device=rgb.device)
+        self._check(self.lib.vstab_gray_working_adapt(self._h, rgb.data_ptr(), n, h, w, out.data_ptr(), wh, ww, flags.data_ptr(),
+                                                      _stream_ptr(rgb.device)))
+        return out, flags
+
+    def range_normalize(self, frames: torch.Tensor) -> torch.Tensor:
+        """The adapter's range rule alone, in place: frames [N,H,W,C] f32 cuda -> flags [N] int32 (1 = rescaled by 1/255)."""
+        _check_cuda(frames, torch.float32, "frames")
+        n, h, w, c = frames.shape
+        flags = torch.empty((n,), dtype=torch.int32, device=frames.device)
+        self._check(self.lib.vstab_range_normalize(self._h, frames.data_ptr(), n, h, w, c, flags.data_ptr(), _stream_ptr(frames.device)))
+        return flags
 
     # -- K10 + K11 + K12 -------------------------------------------------------------------------
     def warp_fused(

@@ -84,7 +84,7 @@ def _stabilizer_outputs():
 
 def _run_stabilizer(driver, frames, frame_rate, framing_mode, transform_mode, camera_lock, strength, smooth, keep_fov,
                     padding_color):
-    context = normalize_video_input(frames)
+    context = normalize_video_input(frames, defer_range=True)  # the range rule rides on the luma kernel's read
     total = len(context)
     bar = ProgressBar(max(0, total - 1) + total)
     result = driver.stabilize_frames(

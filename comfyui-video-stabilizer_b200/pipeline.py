@@ -65,6 +65,9 @@ class VideoContext:
     template_meta: Dict[str, Any] = field(default_factory=dict)
     host: Optional[torch.Tensor] = None  # [N,H,W,C] float32 / uint8 CPU tensor (streamed clips only)
     stream_device: Optional[torch.device] = None
+    # float32 clip whose per-frame range rule (max > 1.5 => / 255) has not run yet: the estimation's luma kernel applies
+    # it in the same read of the source (gray_working below); paths without an estimation pass call settle_range()
+    range_pending: bool = False
 
     def __len__(self) -> int:
         return int((self.frames if self.frames is not None else self.host).shape[0])
@@ -85,9 +88,16 @@ class VideoContext:
             return dataclasses.replace(self, frames=self.frames[start:])
         return dataclasses.replace(self, host=self.host[start:])
 
+    def settle_range(self) -> None:
+        """Apply a pending range rule now (own kernels, in place; no host round trip)."""
+        if self.range_pending and self.frames is not None:
+            _native.get_handle(self.frames.device).range_normalize(self.frames)
+        self.range_pending = False
+
     def chunk(self, a: int, b: int) -> torch.Tensor:
         """Frames [a, b) as a normalised [b-a,H,W,3] float32 device tensor."""
         if self.frames is not None:
+            self.settle_range()
             return self.frames[a:b]
         dev = self.host[a:b].to(self.stream_device, non_blocking=True)
         return _normalize_device(dev)[0]
@@ -99,6 +109,7 @@ class VideoContext:
         """(frames, all-zero masks) for the paths that hand the input back unchanged
         (keep_fov bypass, single frame): device tensors, or numpy arrays for output="host"."""
         n = len(self)
+        self.settle_range()
         if self.streamed:
             if output != "host":
                 raise _native.VstabNativeError("a streamed clip can only be returned with output='host'")
@@ -119,6 +130,13 @@ def gray_working(context: VideoContext, size: Tuple[int, int], first: int = 0, l
     h = _native.get_handle(context.device)
     last = len(context) if last is None else last
     if not context.streamed:
+        if context.range_pending:
+            if (first, last) == (0, len(context)):
+                # the adapter's `max > 1.5 => / 255` rides on the luma kernel's read of the source
+                gray, _flags = h.gray_working_adapt(context.frames, size)
+                context.range_pending = False
+                return gray
+            context.settle_range()
         return h.gray_working(context.frames[first:last], size)
     step = context.chunk_frames()
     parts = [h.gray_working(context.chunk(a, min(a + step, last)), size) for a in range(first, last, step)]
@@ -273,9 +291,10 @@ def _ensure_rgb_host(arr: np.ndarray) -> np.ndarray:
     return arr
 
 
-def _normalize_device(dev: torch.Tensor, source_ptr: Optional[int] = None) -> Tuple[torch.Tensor, str]:
+def _normalize_device(dev: torch.Tensor, source_ptr: Optional[int] = None, defer_range: bool = False) -> Tuple[torch.Tensor, str]:
     """Adapter rules of _to_numpy_frame / _ensure_rgb (stabilizer_utils.py:96-147) on a device chunk
-    [n,H,W,C] (float32 or uint8): per-frame `max > 1.5 => /255`, 1 channel repeated, alpha dropped."""
+    [n,H,W,C] (float32 or uint8): per-frame `max > 1.5 => /255`, 1 channel repeated, alpha dropped.
+    defer_range: leave the range rule of a float32 CUDA clip to the estimation's luma kernel (value_range "deferred")."""
     device = dev.device
     # IEEE division by a TENSOR 255 (torch turns division by a Python scalar into a multiplication
     # by the reciprocal on CUDA, which is 1 ulp off numpy's `arr /= 255.0` for some values)
@@ -283,8 +302,18 @@ def _normalize_device(dev: torch.Tensor, source_ptr: Optional[int] = None) -> Tu
     if dev.dtype == torch.uint8:
         frames = torch.div(dev.to(torch.float32), div255)
         value_range = "0_255"
+    elif dev.is_cuda:
+        # float32 on the device: the range rule runs in libvstab (vstab_range_normalize), in place on the uploaded copy
+        frames = dev.contiguous()
+        if source_ptr is not None and frames.data_ptr() == source_ptr:
+            frames = frames.clone()  # the caller handed us its own CUDA tensor: never write into it
+        if defer_range and frames.shape[3] == 3:  # the reference's max() runs over ALL channels, alpha included
+            value_range = "deferred"
+        else:
+            flags = _native.get_handle(frames.device).range_normalize(frames)
+            value_range = "0_255" if int(flags[0]) == 1 else "0_1"
     else:
-        frames = dev
+        frames = dev  # host tensors (CPU-side tests of the adapter rules)
         peaks = frames.reshape(frames.shape[0], -1).amax(dim=1)
         big = peaks > 1.5
         value_range = "0_255" if bool(big[0]) else "0_1"
@@ -314,7 +343,7 @@ def _must_stream(n: int, height: int, width: int, device: torch.device) -> bool:
     return need > 0.7 * free - 4 * CHUNK_BYTES
 
 
-def normalize_video_input(value: Any, device=None) -> VideoContext:
+def normalize_video_input(value: Any, device=None, defer_range: bool = False) -> VideoContext:
     """ComfyUI IMAGE (or list / dict of frames) -> clip resident in HBM.
 
     Fast path: a 4-D torch tensor [B,H,W,C] (float32 / uint8) is uploaded as a whole and the
@@ -357,8 +386,9 @@ def normalize_video_input(value: Any, device=None) -> VideoContext:
             adapter = FrameAdapter(origin_dtype, False, value_range, "torch", bool(squeeze))
             return VideoContext(None, adapter, ww, hh, 3, fps, kind, extra, host=seq.contiguous(), stream_device=device)
         dev = _upload_batched(seq.contiguous(), device)
-        frames, value_range = _normalize_device(dev, source_ptr=seq.data_ptr())
-        adapter = FrameAdapter(origin_dtype, False, value_range, "torch", bool(squeeze))
+        frames, value_range = _normalize_device(dev, source_ptr=seq.data_ptr(), defer_range=defer_range)
+        pending = value_range == "deferred"
+        adapter = FrameAdapter(origin_dtype, False, "0_1" if pending else value_range, "torch", bool(squeeze))
     else:
         host: List[np.ndarray] = []
         adapter = None
@@ -388,7 +418,9 @@ def normalize_video_input(value: Any, device=None) -> VideoContext:
         frames = _upload_batched(stacked, device)
 
     n, h, w, c = frames.shape
-    return VideoContext(frames, adapter, int(w), int(h), int(c), fps, kind, extra)
+    ctx = VideoContext(frames, adapter, int(w), int(h), int(c), fps, kind, extra)
+    ctx.range_pending = bool(fast and pending)
+    return ctx
 
 
 def download(t: torch.Tensor, pin: bool = True) -> torch.Tensor:

@@ -144,6 +144,23 @@ VSTAB_API int vstab_common_coverage(vstab_handle* h, const float* fwd_dev, int n
 VSTAB_API int vstab_coverage_bbox(vstab_handle* h, const float* fwd_dev, int n, int src_h, int src_w,
                                   int out_h, int out_w, int mask_rule, int32_t* bbox_dev, void* stream);
 
+/*
+ * K1 + K2 with the input adapter's range rule fused into the same read of the source.
+ * Replaces, for float32 frames, the per-frame `arr.max() > 1.5  =>  arr /= 255.0` of
+ * nodes/stabilizer_utils.py:96-147 (_to_numpy_frame) together with :236-276 (_make_gray_for_estimation):
+ * the luma kernel notes per frame whether it saw an element > 1.5 (bit 0) or a NaN (bit 1; numpy's max() is then
+ * NaN and the test false).  Frames with flags == 1 are 0..255 content: their working image is recomputed from
+ * value / 255 and the frame is divided by 255 IN PLACE, all on `stream`, without a host round trip.
+ * rgb_dev is therefore read AND written; flags_dev [n] uint32 is zeroed by the call.
+ */
+VSTAB_API int vstab_gray_working_adapt(vstab_handle* h, float* rgb_dev, int n, int height, int width, uint8_t* gray_dev,
+                                       int work_h, int work_w, uint32_t* flags_dev, void* stream);
+
+/* The range rule alone (Motion Apply and the legacy inverse have no estimation pass): one read for the flags, then
+ * the in-place division of the frames with flags == 1.  rgb_dev [n][height][width][channels] float32. */
+VSTAB_API int vstab_range_normalize(vstab_handle* h, float* rgb_dev, int n, int height, int width, int channels,
+                                    uint32_t* flags_dev, void* stream);
+
 /* ---- K3 + K4 : DIS dense optical flow, batched over frame pairs ------------------------- */
 
 /*

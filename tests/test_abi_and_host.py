@@ -304,7 +304,7 @@ def test_node_execute_glue(monkeypatch):
         return Result({"frames": 5})
 
     monkeypatch.setattr(nodes, "ProgressBar", Bar)
-    monkeypatch.setattr(nodes, "normalize_video_input", lambda frames: Ctx())
+    monkeypatch.setattr(nodes, "normalize_video_input", lambda frames, **kw: Ctx())
     monkeypatch.setattr(nodes, "reconstruct_video", lambda frames, ctx: ("video", frames))
     monkeypatch.setattr(nodes, "convert_masks_for_output", lambda masks: ("mask", masks))
     monkeypatch.setattr(nodes.motion_apply, "apply_motion", fake_apply)
