@@ -90,6 +90,8 @@ def load_library() -> C.CDLL:
         lib.vstab_last_error.restype = C.c_char_p
         lib.vstab_launch_count.argtypes = [vp]
         lib.vstab_launch_count.restype = C.c_uint64
+        lib.vstab_host_libm.argtypes = [i32, vp, vp, vp, i32]
+        lib.vstab_host_libm.restype = i32
         lib.vstab_working_size.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32)]
         lib.vstab_working_size.restype = i32
         lib.vstab_gray_working.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp]
@@ -119,6 +121,27 @@ def load_library() -> C.CDLL:
             raise VstabNativeError("libvstab.so ABI version mismatch; rebuild it")
         _lib = lib
         return lib
+
+
+_LIBM_OPS = {"atan2": 0, "log": 1, "exp": 2, "cos": 3, "sin": 4}
+
+
+def host_libm(op: str, a, b=None):
+    """glibc libm over a float64 array (vstab_host_libm): bit-identical to map(math.<op>, ...), without a Python call per
+    element.  Host-only: needs the library, not a GPU."""
+    import numpy as np
+
+    lib = load_library()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    out = np.empty_like(a)
+    bp = None
+    if b is not None:
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        bp = b.ctypes.data_as(C.c_void_p)
+    rc = lib.vstab_host_libm(_LIBM_OPS[op], a.ctypes.data_as(C.c_void_p), bp, out.ctypes.data_as(C.c_void_p), int(a.size))
+    if rc != 0:
+        raise VstabNativeError(f"vstab_host_libm({op}) failed: {rc}")
+    return out
 
 
 def working_size(width: int, height: int) -> tuple[int, int]:

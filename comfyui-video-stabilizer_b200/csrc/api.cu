@@ -1,6 +1,7 @@
 // api.cu -- handle lifecycle and error plumbing of libvstab.so (see include/vstab.h).
 #include "common.cuh"
 
+#include <math.h>
 #include <stdlib.h>
 
 char g_vstab_err[512] = "";
@@ -56,6 +57,23 @@ extern "C" void vstab_destroy(vstab_handle* h) {
 extern "C" const char* vstab_last_error(const vstab_handle* h) { return h ? h->err : g_vstab_err; }
 
 extern "C" uint64_t vstab_launch_count(const vstab_handle* h) { return h ? h->launches : 0; }
+
+// Host helper, no GPU involved: glibc libm over an array.  The trajectory solve between the estimation and the
+// resampler runs in float64 on the host like the reference (nodes/stabilizer_utils.py:300-358 uses math.atan2 / log /
+// exp / cos / sin per frame); at 1000-2000 frames per clip those per-element Python calls were the largest part of it
+// on every rank.  Python's math module calls these very libm functions, so the results carry the same bits.
+extern "C" int vstab_host_libm(int op, const double* a, const double* b, double* out, int n) {
+  if (!a || !out || n < 0 || (op == VSTAB_LIBM_ATAN2 && !b)) return VSTAB_ERR_INVALID;
+  switch (op) {
+    case VSTAB_LIBM_ATAN2: for (int i = 0; i < n; ++i) out[i] = atan2(a[i], b[i]); break;
+    case VSTAB_LIBM_LOG: for (int i = 0; i < n; ++i) out[i] = log(a[i]); break;
+    case VSTAB_LIBM_EXP: for (int i = 0; i < n; ++i) out[i] = exp(a[i]); break;
+    case VSTAB_LIBM_COS: for (int i = 0; i < n; ++i) out[i] = cos(a[i]); break;
+    case VSTAB_LIBM_SIN: for (int i = 0; i < n; ++i) out[i] = sin(a[i]); break;
+    default: return VSTAB_ERR_INVALID;
+  }
+  return VSTAB_OK;
+}
 
 int vstab_aux_streams(vstab_handle* h, int n) {
   if (n > VSTAB_MAX_AUX_STREAMS) return vstab_fail(h, VSTAB_ERR_INVALID, "vstab_aux_streams: too many helper streams");

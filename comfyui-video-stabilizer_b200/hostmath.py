@@ -116,6 +116,25 @@ def params_to_matrix(params, base_mode: str) -> np.ndarray:
     return np.array(rows, dtype=np.float32)
 
 
+_MATH = {"atan2": math.atan2, "log": math.log, "exp": math.exp, "cos": math.cos, "sin": math.sin}
+
+
+def _libm(op: str, a, b=None) -> np.ndarray:
+    """Element-wise libm over float64 arrays, the bits of Python's math.<op> (what the reference calls per frame).
+    Through libvstab's host helper when the library is built (one C loop instead of a Python call per element: the
+    O(frames) part of the trajectory solve every rank repeats); through map(math.<op>) otherwise."""
+    try:
+        from . import _native
+
+        return _native.host_libm(op, a, b)
+    except Exception:  # library not built (host-only checkouts): the slow, equally exact route
+        fn = _MATH[op]
+        a = np.asarray(a, dtype=np.float64)
+        if b is None:
+            return np.fromiter(map(fn, a.tolist()), dtype=np.float64, count=a.size)
+        return np.fromiter(map(fn, a.tolist(), np.asarray(b, dtype=np.float64).tolist()), dtype=np.float64, count=a.size)
+
+
 def matrices_to_params(matrices: np.ndarray, base_mode: str) -> np.ndarray:
     """Stacked matrix_to_params: [P,3,3] float32 -> [P,K] float64, same bits as the per-matrix
     version (float32 products for a*a + c*c, libm atan2 / log per element)."""
@@ -131,11 +150,11 @@ def matrices_to_params(matrices: np.ndarray, base_mode: str) -> np.ndarray:
         out[:, 1] = m[:, 1, 2]
         # libm per element through map(): no interpreter frame per item.  float32 -> Python float is exact,
         # so atan2 sees the same doubles as math.atan2(np.float32, np.float32) does in the reference.
-        out[:, 2] = np.fromiter(map(math.atan2, c.tolist(), a.tolist()), dtype=np.float64, count=n)
+        out[:, 2] = _libm("atan2", c.astype(np.float64), a.astype(np.float64))
         # max(v, 1e-10) keeps v when v > 1e-10 compared in v's own dtype (NEP 50: the Python float is weak)
         floor = mag2.dtype.type(1e-10)
         clamped = np.where(mag2 > floor, mag2.astype(np.float64), 1e-10)
-        out[:, 3] = np.fromiter(map(math.log, np.sqrt(clamped).tolist()), dtype=np.float64, count=n)  # sqrt is IEEE-exact
+        out[:, 3] = _libm("log", np.sqrt(clamped))  # sqrt is IEEE-exact
         return out
     one = m.dtype.type(1.0)
     return np.stack(
@@ -155,10 +174,10 @@ def params_to_matrices(params: np.ndarray, base_mode: str) -> np.ndarray:
         out[:, 0, 2] = p[:, 0]
         out[:, 1, 2] = p[:, 1]
     elif base_mode == "similarity":
-        ang = p[:, 2].tolist()
-        k = np.fromiter(map(math.exp, p[:, 3].tolist()), dtype=np.float64, count=n)
-        cs = np.fromiter(map(math.cos, ang), dtype=np.float64, count=n)
-        sn = np.fromiter(map(math.sin, ang), dtype=np.float64, count=n)
+        ang = np.ascontiguousarray(p[:, 2])
+        k = _libm("exp", p[:, 3])
+        cs = _libm("cos", ang)
+        sn = _libm("sin", ang)
         out[:, 0, 0] = k * cs
         out[:, 0, 1] = -k * sn
         out[:, 1, 0] = k * sn

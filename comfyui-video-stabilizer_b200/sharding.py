@@ -89,6 +89,11 @@ class FrameShard:
     def on_gpu(self) -> bool:
         return self.device is not None and self.device.type == "cuda"
 
+    # Send buffer of the candidate all-gather, float64 words: cap x 36 table words (the fit kernels write them there
+    # themselves), then min_points, a "has detected counts" flag and cap per-pair detected counts (Classic).
+    def _send_words(self, cap: int) -> int:
+        return cap * 36 + 2 + cap
+
     def wrap_estimator(self, estimate: Callable) -> Callable:
         """The local context holds frames load_range; every consecutive local pair is ours.  On GPUs the fit
         kernels write their result table straight into this rank's all-gather send buffer (no staging copy)."""
@@ -97,10 +102,11 @@ class FrameShard:
             n_local = max(len(context) - 1, 0)
             if self.on_gpu:
                 cap = max(max(self.pair_counts()), 1)
-                send = torch.zeros((cap, 3, 12), dtype=torch.float64, device=self.device)
+                send = torch.zeros((self._send_words(cap),), dtype=torch.float64, device=self.device)
+                table = send[: cap * 36].view(cap, 3, 12)
                 if n_local == 0:
-                    return DeviceCandidates(send[:0], min_points=0, send=send)
-                cands = estimate(context, work_w, work_h, requested_mode, out_raw=send[:n_local])
+                    return DeviceCandidates(table[:0], min_points=0, send=send)
+                cands = estimate(context, work_w, work_h, requested_mode, out_raw=table[:n_local])
                 if isinstance(cands, DeviceCandidates):
                     cands.send = send
                 return cands
@@ -124,35 +130,32 @@ class FrameShard:
         return np.concatenate([host[r, : counts[r]] for r in range(self.world)], axis=0)
 
     def _gather_device_table(self, local: DeviceCandidates) -> PairCandidates:
-        """NCCL all-gather of the fit kernels' output, device to device, then ONE blocking copy of the gathered
-        table (344 B per pair) to the host.  min_points / detected travel with it (Classic: a second tiny gather)."""
+        """ONE all-gather (NCCL, device to device) of the fit kernels' output plus the few words every rank must agree
+        on, then ONE blocking copy of the gathered buffer (~300 B per pair) to the host."""
         counts = self.pair_counts()
         n_local = int(local.raw.shape[0])
         if n_local != counts[self.rank]:
             raise RuntimeError(f"rank {self.rank}: estimated {n_local} pairs, expected {counts[self.rank]}")
         cap = max(max(counts), 1)
+        words = self._send_words(cap)
         send = local.send
-        if send is None:
-            send = torch.zeros((cap, 3, 12), dtype=torch.float64, device=self.device)
-            send[:n_local] = local.raw
-        recv = torch.empty((self.world * cap, 3, 12), dtype=torch.float64, device=self.device)
+        if send is None or send.numel() != words:
+            send = torch.zeros((words,), dtype=torch.float64, device=self.device)
+            send[: cap * 36].view(cap, 3, 12)[:n_local] = local.raw
+        # min_points and the presence of `detected` agree on every rank that has pairs (same node); a rank without
+        # pairs cannot know them, so the host takes the maximum over ranks
+        tail = [float(local.min_points), 1.0 if local.detected is not None else 0.0]
+        send[cap * 36 : cap * 36 + 2] = torch.tensor(tail, dtype=torch.float64).to(self.device, non_blocking=True)
+        if local.detected is not None and n_local:
+            send[cap * 36 + 2 : cap * 36 + 2 + n_local] = local.detected.to(torch.float64)
+        recv = torch.empty((self.world * words,), dtype=torch.float64, device=self.device)
         dist.all_gather_into_tensor(recv, send, group=self.group)
-        # every rank runs the same node, so min_points and the presence of `detected` agree; a rank without pairs
-        # cannot know them, hence the MAX over ranks rides along in the same small collective
-        info = torch.zeros((cap + 2,), dtype=torch.int32, device=self.device)
-        info[0] = int(local.min_points)
-        if local.detected is not None:
-            info[1] = 1
-            info[2 : 2 + n_local] = local.detected.to(torch.int32)
-        infos = torch.empty((self.world, cap + 2), dtype=torch.int32, device=self.device)
-        dist.all_gather_into_tensor(infos.view(-1), info, group=self.group)
-        host = recv.cpu().numpy().reshape(self.world, cap, 3, 12)
-        infos_h = infos.cpu().numpy()
-        table = np.concatenate([host[r, : counts[r]] for r in range(self.world)], axis=0)
-        min_points = int(infos_h[:, 0].max())
+        host = recv.cpu().numpy().reshape(self.world, words)
+        table = np.concatenate([host[r, : cap * 36].reshape(cap, 3, 12)[: counts[r]] for r in range(self.world)], axis=0)
+        min_points = int(host[:, cap * 36].max())
         detected = None
-        if int(infos_h[:, 1].max()) > 0:
-            detected = np.concatenate([infos_h[r, 2 : 2 + counts[r]] for r in range(self.world)], axis=0)
+        if host[:, cap * 36 + 1].max() > 0:
+            detected = np.rint(np.concatenate([host[r, cap * 36 + 2 : cap * 36 + 2 + counts[r]] for r in range(self.world)])).astype(np.int64)
         return PairCandidates.from_raw(table, min_points, detected)
 
     def device_pad_gather(self):

@@ -161,6 +161,18 @@ VSTAB_API int vstab_gray_working_adapt(vstab_handle* h, float* rgb_dev, int n, i
 VSTAB_API int vstab_range_normalize(vstab_handle* h, float* rgb_dev, int n, int height, int width, int channels,
                                     uint32_t* flags_dev, void* stream);
 
+/*
+ * Host-side helper (no device work): out[i] = f(a[i] [, b[i]]) with glibc's libm, for the float64 trajectory maths that
+ * stays on the host like in the reference (nodes/stabilizer_utils.py:300-358 _matrix_to_params / _params_to_matrix:
+ * math.atan2, math.log, math.exp, math.cos, math.sin per frame).  Same libm as Python's math module => same bits.
+ */
+#define VSTAB_LIBM_ATAN2 0 /* atan2(a, b) */
+#define VSTAB_LIBM_LOG 1
+#define VSTAB_LIBM_EXP 2
+#define VSTAB_LIBM_COS 3
+#define VSTAB_LIBM_SIN 4
+VSTAB_API int vstab_host_libm(int op, const double* a, const double* b, double* out, int n);
+
 /* ---- K3 + K4 : DIS dense optical flow, batched over frame pairs ------------------------- */
 
 /*

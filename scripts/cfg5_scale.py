@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--e2e-frames", type=int, default=32)
     ap.add_argument("--cpu-frames", type=int, default=0)
+    ap.add_argument("--probe", action="store_true", help="per-rank kernel timings + NVML clocks / power / throttle reasons")
     args = ap.parse_args()
 
     import torch.distributed as dist
@@ -122,9 +123,81 @@ def main():
         torch.cuda.empty_cache()
         return info
 
+    def kernel_probe(frames_per_gpu):
+        """Every rank times its own kernels with CUDA events -- gray, DIS, fit, resampler, each alone, all ranks at the same
+        moment (barrier first) -- while NVML is sampled: tells apart "the GPUs got slower" (clocks, power cap when 8 GPUs
+        stream from HBM at once) from "the ranks wait for each other / for the host"."""
+        import threading
+
+        total = frames_per_gpu * world
+        mats = synth.shake_matrices(total, 0, W, H, perspective=True)
+        lo, hi = sharding.FrameShard(rank, world, total).load_range if world > 1 else (0, total)
+        base = synth.base_texture(0, W, H).to(dev)
+        clip = synth.render_clip_cuda(h, base, mats, W, H, lo, hi)
+        del base
+        n = clip.shape[0]
+        samples = {"sm": [], "mem": [], "power": [], "reasons": set()}
+        stop = threading.Event()
+
+        def sample():
+            try:
+                import pynvml as nv
+
+                nv.nvmlInit()
+                hd = nv.nvmlDeviceGetHandleByIndex(local)
+                while not stop.is_set():
+                    samples["sm"].append(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM))
+                    samples["mem"].append(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_MEM))
+                    samples["power"].append(nv.nvmlDeviceGetPowerUsage(hd) / 1000.0)
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(hd)
+                    for name, bit in (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal", 0x20), ("hw_thermal", 0x40), ("hw_power_brake", 0x80)):
+                        if mask & bit:
+                            samples["reasons"].add(name)
+                    stop.wait(0.005)
+            except Exception as exc:
+                samples["reasons"].add(f"nvml:{type(exc).__name__}")
+
+        th = threading.Thread(target=sample, daemon=True)
+        th.start()
+
+        def timed(fn, reps=3):
+            fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                r = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps, r
+
+        out = {}
+        out["gray_ms"], gray = timed(lambda: h.gray_working(clip, (960, 540)))
+        out["dis_ms"], (_, grid) = timed(lambda: h.dis_flow(gray, want_flow=False, grid_step=8))
+        out["fit_ms"], _ = timed(lambda: h.fit_grid(grid, 8, 7))
+        fwd = torch.from_numpy(np.tile(np.array([1.001, -0.002, 3.3, 0.002, 0.999, -2.1, 1e-6, 0, 1], np.float32), (n, 1, 1))).to(dev)
+        dst = torch.empty((n, H, W, 3), dtype=torch.float32, device=dev)
+        msk = torch.empty((n, H, W), dtype=torch.float32, device=dev)
+        out["warp_ms"], _ = timed(lambda: h.warp_fused(clip, fwd, (W, H), "bilinear", (0.5, 0.5, 0.5), out=dst, mask_out=msk, want_pad_count=True))
+        stop.set()
+        th.join(timeout=2)
+        out["sm_mhz_min_median"] = [int(min(samples["sm"] or [0])), int(np.median(samples["sm"] or [0]))]
+        out["mem_mhz_min"] = int(min(samples["mem"] or [0]))
+        out["power_w_max"] = round(max(samples["power"] or [0]), 1)
+        out["reasons"] = sorted(samples["reasons"])
+        del clip, dst, msk, gray, grid
+        torch.cuda.empty_cache()
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, out)
+            return gathered
+        return [out]
+
     line = {"config": "BASELINE configs[4]: Flow DIS, perspective, camera_lock, 3840x2160 f32, frame-range sharded", "n_gpus": world,
             "frames_per_gpu": args.frames_per_gpu, "steps": args.steps, "warmup": args.warmup, "placement_rank0": placement}
     line["device_resident"] = run_case(args.frames_per_gpu, args.steps, args.warmup, host_io=False)
+    if args.probe:
+        line["kernel_probe_per_rank"] = kernel_probe(args.frames_per_gpu)
     if args.e2e_frames > 0:
         line["e2e"] = run_case(args.e2e_frames, max(1, min(args.steps, 2)), 2, host_io=True)
         line["e2e"]["note"] = f"{args.e2e_frames} frames per GPU: pinned host shard -> HBM -> pinned host results inside the timed region"

@@ -200,16 +200,44 @@ def gen_inverse(ref):
     print("inverse", {k: v.shape for k, v in payload.items()})
 
 
+def gen_full(ref, only_name=None):
+    """The BASELINE.json configurations as quoted (121 / 241 / 121 frames, and 4K): summaries + the whole meta."""
+    for case in cases.FULL_CASES:
+        if only_name and case["name"] != only_name:
+            continue
+        name = case["name"]
+        frames = cases.make_frames(case)
+        ctx = ref.stabilizer_utils._normalize_video_input([f for f in frames])
+        if case["kind"] == "apply":
+            meta_in = cases.make_motion_meta(case, ref)
+            with open(os.path.join(GOLDEN, f"full_{name}_motion_meta.json"), "w") as fh:
+                json.dump(meta_in, fh)
+            res = ref.motion_apply.apply_motion(ctx, meta_in, case["padding_rgb"], framing_mode=case["framing"], interpolation=case["interp"],
+                                                motion_blur=case["blur"], motion_blur_samples=case["samples"])
+        else:
+            mod = ref.video_stabilizer_flow if case["node"] == "flow" else ref.video_stabilizer_classic
+            res = mod._stabilize_frames(ctx, case["framing"], case["mode"], case["camera_lock"], case["strength"], case["smooth"],
+                                        case["keep_fov"], case["padding_rgb"], case["fps"])
+        with open(os.path.join(GOLDEN, f"full_{name}_meta.json"), "w") as fh:
+            json.dump(res.meta, fh)
+        out_frames, out_masks = np.asarray(res.frames, dtype=np.float32), np.asarray(res.masks, dtype=np.float32)
+        np.savez_compressed(os.path.join(GOLDEN, f"full_{name}.npz"), **_summaries(out_frames, out_masks, case["patches"]))
+        print("full", name, out_frames.shape, flush=True)
+        del frames, ctx, res, out_frames, out_masks
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
+    ap.add_argument("--name", default=None, help="with --only full: one case")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_import.load_reference()
     gens = {"apply": gen_motion_apply, "stab": gen_estimators, "dis": gen_dis, "crop": lambda r: gen_estimators(r, True),
-            "small": lambda r: gen_estimators(r, only_small=True), "ab": gen_ab, "inverse": gen_inverse}
+            "small": lambda r: gen_estimators(r, only_small=True), "ab": gen_ab, "inverse": gen_inverse,
+            "full": lambda r: gen_full(r, args.name)}
     for key, fn in gens.items():
-        if args.only == key or (args.only is None and key not in ("crop", "small", "ab", "inverse")):
+        if args.only == key or (args.only is None and key not in ("crop", "small", "ab", "inverse", "full")):
             fn(ref)
 
 

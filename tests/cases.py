@@ -17,6 +17,28 @@ def make_frames(case) -> np.ndarray:
     if kind == "noise":  # white noise: worst case for resampling parity (gradient ~1/px)
         rng = np.random.default_rng(case["seed"])
         return rng.random((n, h, w, 3), dtype=np.float32)
+    if kind == "texture_fast":
+        # the same clip as "texture" for the BASELINE-length cases: rendered by the fused resampler when a GPU is there
+        # (the -m gpu tests) and by cv2 where the goldens are made -- bilinear is bit-exact across oracle, cv2 and kernel
+        # (tests/test_oracle_resample.py, tests/test_warp_gpu.py), so both sides see the same bytes
+        import synth
+        import torch
+
+        mats = synth.shake_matrices(n, case["seed"], w, h, perspective=case.get("perspective", False), amount=case.get("amount", 1.0))
+        base = synth.base_texture(case["seed"], w, h)
+        if torch.cuda.is_available():
+            import vstab_loader
+
+            vstab_loader.load()
+            from vstab_b200 import _native
+
+            dev = torch.device("cuda", torch.cuda.current_device())
+            return synth.render_clip_cuda(_native.get_handle(dev), base.to(dev), mats, w, h).cpu().numpy()
+        import cv2
+
+        fwd = synth.render_matrices(mats)
+        return np.stack([cv2.warpPerspective(base.numpy(), fwd[i], (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT,
+                                             borderValue=(0.5, 0.5, 0.5)) for i in range(n)])
     if kind == "texture":  # smooth trackable texture rendered through shake matrices
         import synth
 
@@ -116,6 +138,27 @@ CROP_CASES = [
     dict(name="classic_sim_crop06_720p", node="classic", n=7, w=1280, h=720, seed=55, frames="texture", framing="crop",
          mode="similarity", camera_lock=False, strength=1.0, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=24.0,
          store="summary", patches=[(3, 300, 600, 48, 64)]),
+]
+
+
+# The BASELINE.json configurations AS QUOTED (full clip lengths): summaries (per-frame sums, three
+# patches, the whole meta tree) of the unmodified reference's output, scripts/make_golden.py --only full.
+FULL_CASES = [
+    dict(name="cfg2_flow_1080p_121", kind="stab", node="flow", n=121, w=1920, h=1080, seed=0, frames="texture_fast", framing="crop_and_pad",
+         mode="similarity", camera_lock=False, strength=0.7, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=16.0,
+         patches=[(0, 0, 0, 48, 64), (60, 500, 900, 48, 64), (120, 1030, 1850, 48, 64)]),
+    dict(name="cfg3_classic_sim_720p_241", kind="stab", node="classic", n=241, w=1280, h=720, seed=3, frames="texture_fast", framing="crop_and_pad",
+         mode="similarity", camera_lock=False, strength=0.7, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=16.0,
+         patches=[(0, 0, 0, 48, 64), (120, 300, 600, 48, 64), (240, 670, 1210, 48, 64)]),
+    dict(name="cfg3_classic_trans_720p_241", kind="stab", node="classic", n=241, w=1280, h=720, seed=3, frames="texture_fast", framing="crop_and_pad",
+         mode="translation", camera_lock=False, strength=0.7, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=16.0,
+         patches=[(0, 0, 0, 48, 64), (120, 300, 600, 48, 64), (240, 670, 1210, 48, 64)]),
+    dict(name="cfg4_apply_1080p_121", kind="apply", n=121, w=1920, h=1080, seed=4, frames="texture_fast", meta="shake", amount=1.0, framing="expand",
+         interp="bicubic", blur=0.5, samples=33, padding_rgb=PAD,
+         patches=[(0, 0, 0, 48, 64), (60, 500, 900, 48, 64), (120, 1030, 1850, 48, 64)]),
+    dict(name="cfg5_flow_persp_lock_4k_6", kind="stab", node="flow", n=6, w=3840, h=2160, seed=5, frames="texture_fast", perspective=True,
+         framing="crop_and_pad", mode="perspective", camera_lock=True, strength=0.7, smooth=0.5, keep_fov=0.6, padding_rgb=PAD, fps=16.0,
+         patches=[(0, 0, 0, 48, 64), (3, 1000, 1800, 48, 64), (5, 2100, 3770, 48, 64)]),
 ]
 
 
