@@ -950,7 +950,22 @@ extern "C" int vstab_fit_batch(vstab_handle* h, const float* prev_dev, const flo
 
   prepare_kernel<<<n_pairs, kThreads, 0, st>>>(prev_dev, curr_dev, n_pts, grid_w, grid_step, P, C, nvalid);
   VSTAB_LAUNCH_CHECK(h, "fit prepare_kernel");
-  if (mode_mask & (1 << VSTAB_MODE_TRANSLATION)) {
+  // The three models of a pair are independent (disjoint outputs) and each kernel is a chain of short serial phases
+  // per pair (RNG replay, 8x8 / 9x9 solves by one thread, LM steps), so they run side by side on forked streams:
+  // 250 pairs of a perspective clip, all three models: 3.05 ms back to back.
+  const bool want_t = mode_mask & (1 << VSTAB_MODE_TRANSLATION), want_s = mode_mask & (1 << VSTAB_MODE_SIMILARITY);
+  const bool want_p = mode_mask & (1 << VSTAB_MODE_PERSPECTIVE);
+  cudaStream_t st_s = st, st_p = st;
+  const int forks = (want_s && want_t ? 1 : 0) + (want_p && (want_t || want_s) ? 1 : 0);
+  if (forks > 0) {
+    const int rcs = vstab_aux_streams(h, forks);
+    if (rcs != VSTAB_OK) return rcs;
+    VSTAB_CUDA(h, cudaEventRecord(h->fork_event, st));
+    int k = 0;
+    if (want_s && want_t) { st_s = h->aux_stream[k++]; VSTAB_CUDA(h, cudaStreamWaitEvent(st_s, h->fork_event, 0)); }
+    if (want_p && (want_t || want_s)) { st_p = h->aux_stream[k++]; VSTAB_CUDA(h, cudaStreamWaitEvent(st_p, h->fork_event, 0)); }
+  }
+  if (want_t) {
     int cap = 1;
     while (cap < n_pts) cap <<= 1;
     const size_t smem = sizeof(unsigned) * 2 * cap;
@@ -958,13 +973,18 @@ extern "C" int vstab_fit_batch(vstab_handle* h, const float* prev_dev, const flo
     translation_kernel<<<n_pairs, 1024, smem, st>>>(P, C, nvalid, n_pts, cap, out);
     VSTAB_LAUNCH_CHECK(h, "fit translation_kernel");
   }
-  if (mode_mask & (1 << VSTAB_MODE_SIMILARITY)) {
-    similarity_kernel<<<n_pairs, kThreads, 0, st>>>(P, C, nvalid, n_pts, out);
+  if (want_s) {
+    similarity_kernel<<<n_pairs, kThreads, 0, st_s>>>(P, C, nvalid, n_pts, out);
     VSTAB_LAUNCH_CHECK(h, "fit similarity_kernel");
   }
-  if (mode_mask & (1 << VSTAB_MODE_PERSPECTIVE)) {
-    perspective_kernel<<<n_pairs, kThreads, 0, st>>>(P, C, nvalid, n_pts, flags, out);
+  if (want_p) {
+    perspective_kernel<<<n_pairs, kThreads, 0, st_p>>>(P, C, nvalid, n_pts, flags, out);
     VSTAB_LAUNCH_CHECK(h, "fit perspective_kernel");
+  }
+  {
+    int k = 0;
+    if (st_s != st) { VSTAB_CUDA(h, cudaEventRecord(h->join_event[k], st_s)); VSTAB_CUDA(h, cudaStreamWaitEvent(st, h->join_event[k], 0)); k++; }
+    if (st_p != st) { VSTAB_CUDA(h, cudaEventRecord(h->join_event[k], st_p)); VSTAB_CUDA(h, cudaStreamWaitEvent(st, h->join_event[k], 0)); k++; }
   }
   return VSTAB_OK;
 }

@@ -28,6 +28,16 @@ MODE_NAMES = _native.MODE_NAMES
 
 # set to a list to collect (label, seconds) host-side phase timings of the last call (bench / debugging)
 PHASE_LOG = None
+# set to a list to collect (label, torch.cuda.Event) marks recorded on the launching stream at the phase boundaries of
+# the last call: elapsed_time between consecutive marks is what the GPU (not the host) spent there, collectives included
+GPU_MARKS = None
+
+
+def _gpu_mark(label, device):
+    if GPU_MARKS is not None and device is not None and torch.device(device).type == "cuda":
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(device))
+        GPU_MARKS.append((label, ev))
 
 
 def _mark(label, t0):
@@ -332,11 +342,15 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
 
     t0 = time.perf_counter()
     nvtx.phase("estimate")
+    mark_dev = getattr(context, "device", None)
+    _gpu_mark("start", mark_dev)
     cands = estimator(context, work_w, work_h, transform_mode)
+    _gpu_mark("estimation kernels", mark_dev)
     t0 = _mark("estimate (gray+flow/track+fit enqueued)", t0)
     nvtx.phase("candidate_table")
     if shard is not None:
         cands = shard.gather_candidates(cands)
+    _gpu_mark("candidate all-gather", mark_dev)
     if isinstance(cands, DeviceCandidates):
         cands = cands.to_host()
     t0 = _mark("candidate table on the host (waits for the GPU; all-gather when sharded)", t0)
@@ -436,12 +450,14 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
     # sharded runs on GPUs: the per-frame padded-pixel counts are all-gathered device to device right behind the
     # resampler (they only feed the meta), and come back with the one copy that waits for it
     pad_gather = shard.device_pad_gather() if shard is not None else None
+    _gpu_mark("idle while the host solves the trajectory", mark_dev)
     pending = fused_warp(
         context if shard is None else shard.owned_context(context), fwd, output_size, "bilinear",
         hm.border_value(padding_rgb), want_mask=True, want_pad_count=True, output=output, defer=True,
         **({"pad_transform": pad_gather} if pad_gather is not None else {}),
     )
 
+    _gpu_mark("resampler + pad-count all-gather", mark_dev)
     # the kernels above are in flight: build the meta tree on the host meanwhile.  Sharded runs materialise
     # the per-frame lists only for shard.meta_frame_range (by default the rank's own frames: the per-frame
     # meta is sharded like the frames it describes, sharding.merge_sharded_meta() reassembles it); entries

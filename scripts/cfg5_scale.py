@@ -105,6 +105,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         # host-side phases of one more step, slowest rank's view
         core.PHASE_LOG = []
+        core.GPU_MARKS = []
         barrier()
         del out
         t0 = time.perf_counter()
@@ -112,10 +113,18 @@ def main():
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
         phases = {a[:40]: round(b * 1e3, 3) for a, b in core.PHASE_LOG}
+        marks = core.GPU_MARKS
+        gpu = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 3) for i in range(1, len(marks))}
         core.PHASE_LOG = None
+        core.GPU_MARKS = None
+        if world > 1:
+            every = [None] * world
+            dist.all_gather_object(every, gpu)
+            gpu = {k: [e.get(k) for e in every] for k in gpu}
         meta = out[2]
         info = {"frames_total": total, "ms_per_step": float(ms.item()), "frames_per_s": total / (float(ms.item()) * 1e-3),
-                "mode_applied": meta["transform_mode_applied"], "rank0_step_wall_ms": round(wall, 3), "rank0_phases_ms": phases}
+                "mode_applied": meta["transform_mode_applied"], "rank0_step_wall_ms": round(wall, 3), "rank0_phases_ms": phases,
+                "gpu_ms_between_marks_per_rank": gpu}
         if host_io:
             info["h2d_bytes_per_step"] = int(src.numel() * 4 * world)
             info["d2h_bytes_per_step"] = int((out[0].numel() + out[1].numel()) * 4 * world)
