@@ -1126,6 +1126,14 @@ __global__ void __launch_bounds__(256) warp_plan_kernel(const float* __restrict_
     else if ((mxx + HI <= ox + S_BW - 1) && need_h <= S_BH && (tx0 + TW <= ow) && (ty0 + S_TH <= oh) &&
              (mnx - LO >= -30000) && (mny - LO >= -30000) && (mxx + HI <= 30000) && (mxy + HI <= 30000))
       flags |= 8;  // edge tile: the staged box holds every tap position, some of them outside the frame
+    else if (INTERP == VSTAB_INTERP_BILINEAR && (tx0 + TW <= ow) && (ty0 + S_TH <= oh) && (mnx - LO >= -30000) && (mny - LO >= -30000) &&
+             (mxx + HI <= 30000) && (mxy + HI <= 30000)) {
+      // mixed tile: footprint larger than the box (minifying map).  The box sits on the middle of the footprint; pixels
+      // whose taps fall outside it gather from global memory (stream_edge<MIXED>)
+      ox = ((mnx + mxx) / 2 - S_BW / 2) & ~3;
+      oy = (mny + mxy) / 2 - S_BH / 2;
+      flags |= 2 | 8;
+    }
   }
   TilePlan pl;
   pl.ox = ox;
@@ -1249,10 +1257,16 @@ __device__ __forceinline__ void stream_interior(const double* __restrict__ s_min
 // fits the staged box.  Same arithmetic as stream_interior plus what the frame border needs: per-tap
 // BORDER_CONSTANT substitution (the TMA engine zero-filled those texels), remapBilinear's "footprint
 // entirely outside" rule, the coverage test of the padding mask and the padded-pixel count.
-template <int INTERP, bool AFFINE, bool VEC>
+// MIXED (bilinear only): the tile's source footprint is LARGER than the staged box (the map minifies: zoom-out, or the
+// far side of a projective correction).  Same arithmetic, but every pixel first asks whether its 2x2 footprint lies in
+// the box -- then it is served from shared memory like an edge pixel -- and gathers its taps from global memory (L1)
+// otherwise.  Before round 2 such tiles took the general path and a frame with 10 % minification ran at 2.5 TB/s, with
+// 20 % at 1.7 TB/s (scripts/warp_persp_probe.py): the late frames of a camera-locked perspective clip.
+template <int INTERP, bool AFFINE, bool VEC, bool MIXED = false>
 __device__ __forceinline__ void stream_edge(const WarpParams& p, const double* __restrict__ s_minv, const float* __restrict__ tile0,
                                             int tx0, int ty0, int frame_idx, int warp, int lane, float* __restrict__ scratch,
-                                            float* __restrict__ dst_tile, float* __restrict__ mask_tile, const float* __restrict__ s_cubic) {
+                                            float* __restrict__ dst_tile, float* __restrict__ mask_tile, const float* __restrict__ s_cubic,
+                                            int box_x0 = 0, int box_y0 = 0) {
   const double m0 = s_minv[0], m1 = s_minv[1], m2 = s_minv[2], m3 = s_minv[3], m4 = s_minv[4], m5 = s_minv[5];
   const double m8 = s_minv[8];
   const double sc_affine = (m8 != 0.0) ? __ddiv_rn(32.0, m8) : 0.0;
@@ -1315,6 +1329,15 @@ __device__ __forceinline__ void stream_edge(const WarpParams& p, const double* _
         const bool any_in = (x0in || x1in) && (y0in || y1in);  // else: remapBilinear returns the border colour itself
         const float* s0 = tile0 + sy * S_PITCH + sx * 3;
         const float* s1 = s0 + S_PITCH;
+        int step1 = S_PITCH;
+        if (MIXED && !(sx >= box_x0 && sx + 1 <= box_x0 + S_BW - 1 && sy >= box_y0 && sy + 1 <= box_y0 + S_BH - 1)) {
+          // footprint (partly) outside the staged box: the same four taps from the frame itself; taps outside the
+          // frame are never dereferenced (in00..in11 select the border colour)
+          s0 = p.src + ((size_t)frame_idx * p.sh + sy) * (size_t)p.sw * 3 + (ptrdiff_t)sx * 3;
+          step1 = p.sw * 3;
+          s1 = s0 + step1;
+        }
+        (void)step1;
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           const float bc = ch == 0 ? br : (ch == 1 ? bg : bb);
@@ -1441,6 +1464,20 @@ __global__ void __launch_bounds__(NTHREADS, S_CTAS) warp_stream_kernel(const __g
     const int ox = meta->ox, oy = meta->oy;
     if (flags & 4) {
       // empty slot: nothing to resample, the stage still goes through the hand-over below
+    } else if ((flags & 10) == 10) {
+      if (INTERP == VSTAB_INTERP_BILINEAR) {  // the plan only marks bilinear tiles as mixed
+        const bool affine = (meta->minv[6] == 0.0) && (meta->minv[7] == 0.0);
+        float* dst_tile = p.dst + (((size_t)frame_idx * p.oh + ty0) * p.ow + tx0) * 3;
+        float* mask_tile = p.mask ? p.mask + ((size_t)frame_idx * p.oh + ty0) * p.ow + tx0 : nullptr;
+        const float* tile0 = box - (oy * S_PITCH + ox * 3);
+        if (p.vec_store) {
+          if (affine) stream_edge<VSTAB_INTERP_BILINEAR, true, true, true>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile, s_cubic, ox, oy);
+          else stream_edge<VSTAB_INTERP_BILINEAR, false, true, true>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile, s_cubic, ox, oy);
+        } else {
+          if (affine) stream_edge<VSTAB_INTERP_BILINEAR, true, false, true>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile, s_cubic, ox, oy);
+          else stream_edge<VSTAB_INTERP_BILINEAR, false, false, true>(p, meta->minv, tile0, tx0, ty0, frame_idx, warp, lane, scratch, dst_tile, mask_tile, s_cubic, ox, oy);
+        }
+      }
     } else if (flags & 2) {
       const bool affine = (meta->minv[6] == 0.0) && (meta->minv[7] == 0.0);
       float* dst_tile = p.dst + (((size_t)frame_idx * p.oh + ty0) * p.ow + tx0) * 3;

@@ -161,7 +161,9 @@ class FrameShard:
     def device_pad_gather(self):
         """fused_warp hook (pad_transform): all-gather the per-frame padded-pixel counts device to device on the
         stream that just launched the resampler.  None on the CPU (gloo tests use gather_pad_counts)."""
-        if not self.on_gpu:
+        import os
+
+        if not self.on_gpu or os.environ.get("VSTAB_PAD_GATHER") == "host":  # "host": A/B switch, gather after the download
             return None
         sizes = [b - a for a, b in (split_range(self.total_frames, self.world, r) for r in range(self.world))]
         cap = max(max(sizes), 1)

@@ -106,6 +106,7 @@ def main():
         # host-side phases of one more step, slowest rank's view
         core.PHASE_LOG = []
         core.GPU_MARKS = []
+        pipeline.WARP_LAUNCH_LOG = []
         barrier()
         del out
         t0 = time.perf_counter()
@@ -114,7 +115,10 @@ def main():
         wall = (time.perf_counter() - t0) * 1e3
         phases = {a[:40]: round(b * 1e3, 3) for a, b in core.PHASE_LOG}
         marks = core.GPU_MARKS
+        warp_ms = round(sum(a.elapsed_time(b) for a, b, _, _ in pipeline.WARP_LAUNCH_LOG), 3)
+        pipeline.WARP_LAUNCH_LOG = None
         gpu = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 3) for i in range(1, len(marks))}
+        gpu["of which: resampler launches (CUDA events around vstab_warp_fused)"] = warp_ms
         core.PHASE_LOG = None
         core.GPU_MARKS = None
         if world > 1:

@@ -81,3 +81,45 @@ def test_stream_kernel_is_deterministic_on_a_long_clip(handle):
             first = got
         else:
             assert all(np.array_equal(a, b) for a, b in zip(first, got))
+
+
+@pytest.mark.parametrize("kind", ["zoom_out_0.9", "zoom_out_0.6", "zoom_out_0.35", "projective_far_side", "projective_strong", "rotate_zoom_out"])
+def test_minifying_maps_take_the_mixed_tiles_and_keep_every_bit(handle, kind):
+    """Maps that MINIFY (zoom-out, the far side of a projective correction: the late frames of a camera-locked perspective
+    clip, BASELINE config 5) have tile footprints larger than the staged TMA box.  Round 2 serves them as "mixed" tiles
+    (box where it reaches, L1 gathers elsewhere) instead of the general path: same bits as the global-gather kernel and
+    as the numpy oracle, mask and padded counts included."""
+    from oracle import resample_np as R
+
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(99)
+    n, h, w = 3, 288, 512
+    src_np = rng.random((n, h, w, 3), dtype=np.float32)
+    cx, cy = w / 2, h / 2
+    mats = []
+    for i in range(n):
+        if kind.startswith("zoom_out"):
+            s = float(kind.split("_")[-1]) + 0.01 * i
+            m = np.array([[s, 0, cx - s * cx + 3.3 * i], [0, s, cy - s * cy - 2.1 * i], [0, 0, 1.0]])
+        elif kind == "rotate_zoom_out":
+            s, th = 0.7, 0.2 + 0.05 * i
+            c, sn = s * np.cos(th), s * np.sin(th)
+            m = np.array([[c, -sn, cx - c * cx + sn * cy], [sn, c, cy - sn * cx - c * cy], [0, 0, 1.0]])
+        else:
+            g = (4e-4 if kind == "projective_far_side" else 2.5e-3) * (1 + 0.3 * i)
+            m = np.array([[1, 0, 2.0 * i], [0, 1, -1.0 * i], [g, g / 2, 1.0]])
+        mats.append(m)
+    mats = np.asarray(mats, dtype=np.float32)
+    src = torch.from_numpy(src_np).to(dev)
+    fwd = torch.from_numpy(mats.reshape(n, 1, 9)).to(dev)
+    border = (0.25, 0.5, 0.75)
+    res = []
+    for stage in (0, 1):
+        dst, mask, pad = handle.warp_fused(src, fwd, (w, h), "bilinear", border, want_pad_count=True, stage_mode=stage)
+        torch.cuda.synchronize()
+        res.append((dst.cpu().numpy(), mask.cpu().numpy(), pad.cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    for i in range(n):
+        want = R.warp_np(src_np[i], mats[i], (w, h), "bilinear", border)
+        assert np.array_equal(res[0][0][i], want), (kind, i, float(np.abs(res[0][0][i] - want).max()))
+        assert np.array_equal(res[0][1][i], R.mask_np(mats[i], (w, h), (w, h)))
