@@ -489,6 +489,11 @@ def _host_result(shape) -> torch.Tensor:
 _POOL: Dict[Any, torch.Tensor] = {}
 
 
+def release_pool() -> None:
+    """Give the pooled device result buffers (output="device") back to torch's allocator."""
+    _POOL.clear()
+
+
 def _pooled(shape, device, tag: str) -> torch.Tensor:
     """Device-resident result buffers are reused from call to call (output="device" hands out views
     of them: consume a result before asking for the next one).  Avoids re-allocating gigabytes per
