@@ -251,3 +251,29 @@ def test_mask_rule_auto_in_the_crop_coverage_kernels(handle):
     fixed = {r: handle.coverage_bbox(fwd, (w, h), (w, h), r).cpu().numpy() for r in (R.RULE_P, R.RULE_C)}
     for i, r in enumerate(rules):  # bounding box of the 3x3-closed coverage: what the same kernel returns under that frame's rule
         assert np.array_equal(box[i], fixed[r][i]), (i, box[i])
+
+
+def test_mask_rule_env_reaches_the_nodes_engine(monkeypatch):
+    """VSTAB_MASK_RULE=auto:<threads> (no schema change): Motion Apply with an off-canvas shift of more than H'/8 rows gets
+    cv2's Rule C mask for that frame and Rule P for the others, as the reference does on a machine with 8 cv2 threads."""
+    from vstab_b200 import motion_apply, pipeline
+    from vstab_b200.motion_meta import build_motion_meta_v2
+
+    w, h = 640, 360
+    rng = np.random.default_rng(4)
+    frames = rng.random((3, h, w, 3), dtype=np.float32)
+    mats = [np.array([[1, 0, -0.3], [0, 1, ty], [0, 0, 1]], np.float64) for ty in (2.0, 60.0, -7.0)]
+    meta = {"motion_meta": build_motion_meta_v2(source="test", frame_count=3, fps=16.0, input_size=(w, h), output_size=(w, h), matrices=mats)}
+    want_rules = [R.auto_rule(np.asarray(m, np.float32), (w, h), (w, h), 8) for m in mats]
+    assert want_rules == [R.RULE_P, R.RULE_C, R.RULE_P]
+    out = {}
+    for env in ("P", "auto:8"):
+        monkeypatch.setenv("VSTAB_MASK_RULE", env)
+        ctx = pipeline.normalize_video_input(torch.from_numpy(frames))
+        out[env] = motion_apply.apply_motion(ctx, meta, (127, 127, 127), framing_mode="crop_and_pad", interpolation="bilinear")
+    for i, m in enumerate(mats):
+        m32 = np.asarray(m, np.float32)
+        assert np.array_equal(out["P"].masks[i, ..., 0], R.mask_np(m32, (w, h), (w, h), R.RULE_P))
+        assert np.array_equal(out["auto:8"].masks[i, ..., 0], R.mask_np(m32, (w, h), (w, h), want_rules[i]))
+    assert np.array_equal(out["P"].frames, out["auto:8"].frames)
+    assert not np.array_equal(out["P"].masks[1], out["auto:8"].masks[1])
