@@ -454,7 +454,10 @@ def main():
                                         PARAMS["keep_fov"], PARAMS["padding_rgb"], PARAMS["fps"], output="host", shard=shard)
             frames_out = pipeline.reconstruct_video(res.frames, ctx)
             masks_out = pipeline.convert_masks_for_output(res.masks)
-            d2h_holder["bytes"] = frames_out.numel() * 4 + masks_out.numel() * 4
+            # what actually crossed the link: float32 frames + the 0 / 1 padding mask as one byte per pixel (widened to the
+            # float32 MASK on the host inside the timed region); pipeline counts the bytes of the copies it issues
+            d2h_holder["bytes"] = pipeline.LAST_D2H_BYTES
+            d2h_holder["result_bytes"] = frames_out.numel() * 4 + masks_out.numel() * 4
 
         e2e_steps = max(2, min(args.steps, 3))
         pin_ms, _, _ = timed(pinned_driver_step, e2e_steps, 1)
@@ -462,6 +465,8 @@ def main():
         d2h = d2h_holder["bytes"]
         ideal_ms = (h2d / (link["h2d_gbs"] * 1e9) + d2h / (link["d2h_gbs"] * 1e9)) * 1e3
         e2e = {"unit": "frames/s", "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
+               "result_bytes_per_step": int(d2h_holder["result_bytes"] * world),
+               "mask_on_the_link": "uint8 (binary mask, widened to float32 on the host)" if pipeline.mask_bytes_enabled() else "float32",
                "host_link": {**link, "how": "plain pinned cudaMemcpyAsync of 1 GiB each way, one copy per call, all ranks at once, best of 3",
                              "ms_for_the_step_bytes": ideal_ms, "placement": placement},
                "pinned_driver": {"value": total_frames / (pin_ms * 1e-3), "ms_per_step": pin_ms, "frac_of_link": ideal_ms / pin_ms,

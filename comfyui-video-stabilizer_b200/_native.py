@@ -92,6 +92,12 @@ def load_library() -> C.CDLL:
         lib.vstab_launch_count.restype = C.c_uint64
         lib.vstab_host_libm.argtypes = [i32, vp, vp, vp, i32]
         lib.vstab_host_libm.restype = i32
+        lib.vstab_host_trajectory.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, C.POINTER(i32)]
+        lib.vstab_host_trajectory.restype = i32
+        lib.vstab_host_framing.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp]
+        lib.vstab_host_framing.restype = i32
+        lib.vstab_host_shift.argtypes = [vp, i32, C.c_float, C.c_float, vp]
+        lib.vstab_host_shift.restype = i32
         lib.vstab_working_size.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32)]
         lib.vstab_working_size.restype = i32
         lib.vstab_gray_working.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp]
@@ -106,6 +112,8 @@ def load_library() -> C.CDLL:
         lib.vstab_common_coverage.restype = i32
         lib.vstab_coverage_bbox.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
         lib.vstab_coverage_bbox.restype = i32
+        lib.vstab_mask_pack_u8.argtypes = [vp, vp, C.c_size_t, vp, vp, vp]
+        lib.vstab_mask_pack_u8.restype = i32
         if hasattr(lib, "vstab_dis_flow"):
             lib.vstab_dis_flow.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, vp]
             lib.vstab_dis_flow.restype = i32
@@ -142,6 +150,60 @@ def host_libm(op: str, a, b=None):
     if rc != 0:
         raise VstabNativeError(f"vstab_host_libm({op}) failed: {rc}")
     return out
+
+
+def host_trajectory(raw, detected, min_points: int, mode: str, source_size, working_size):
+    """vstab_host_trajectory: raw [P,3,12] float64 fit words -> (matrices [P,3,3] float32 at full size, path [P+1,K]
+    float64), or None when some pair does not accept `mode` itself (the caller replays the fallback ladder)."""
+    import numpy as np
+
+    lib = load_library()
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    p = raw.shape[0]
+    det = None
+    if detected is not None:
+        det = np.ascontiguousarray(detected, dtype=np.int32)
+    k = (2, 4, 8)[MODE_INDEX[mode]]
+    matrices = np.empty((p, 3, 3), dtype=np.float32)
+    path = np.empty((p + 1, k), dtype=np.float64)
+    first = C.c_int(0)
+    ww, wh = (0, 0) if working_size is None else (int(working_size[0]), int(working_size[1]))
+    rc = lib.vstab_host_trajectory(raw.ctypes.data, None if det is None else det.ctypes.data, p, int(min_points), MODE_INDEX[mode],
+                                   int(source_size[0]), int(source_size[1]), ww, wh, matrices.ctypes.data, path.ctypes.data,
+                                   C.byref(first))
+    if rc != 0:
+        raise VstabNativeError(f"vstab_host_trajectory failed: {rc}")
+    if first.value != p:
+        return None
+    return matrices, path
+
+
+def host_framing(diffs, mode: str, width: int, height: int):
+    """vstab_host_framing: diffs [N,K] float64 -> (apply [N,3,3] float32, mins [N,2], maxs [N,2], box [9])."""
+    import numpy as np
+
+    lib = load_library()
+    diffs = np.ascontiguousarray(diffs, dtype=np.float64)
+    n = diffs.shape[0]
+    apply = np.empty((n, 3, 3), dtype=np.float32)
+    mins = np.empty((n, 2), dtype=np.float64)
+    maxs = np.empty((n, 2), dtype=np.float64)
+    box = np.empty((9,), dtype=np.float64)
+    rc = lib.vstab_host_framing(diffs.ctypes.data, n, MODE_INDEX[mode], int(width), int(height), apply.ctypes.data,
+                                mins.ctypes.data, maxs.ctypes.data, box.ctypes.data)
+    if rc != 0:
+        raise VstabNativeError(f"vstab_host_framing failed: {rc}")
+    return apply, mins, maxs, box
+
+
+def host_shift(apply, off_x, off_y):
+    """vstab_host_shift: translate affine float32 matrices; None when a matrix is not affine (use the float32 matmul)."""
+    import numpy as np
+
+    lib = load_library()
+    out = np.empty_like(apply)
+    rc = lib.vstab_host_shift(apply.ctypes.data, int(apply.shape[0]), float(np.float32(off_x)), float(np.float32(off_y)), out.ctypes.data)
+    return out if rc == 0 else None
 
 
 def working_size(width: int, height: int) -> tuple[int, int]:
@@ -285,6 +347,15 @@ class Handle:
             )
         )
         return dst, mask, pad
+
+    def mask_pack_u8(self, mask: torch.Tensor, out: torch.Tensor, odd: torch.Tensor) -> None:
+        """Binary float32 mask -> bytes (vstab_mask_pack_u8); `odd` (uint32 [1], zeroed by the caller) collects bit 0 when a
+        value other than 0 / 1 shows up."""
+        _check_cuda(mask, torch.float32, "mask")
+        _check_cuda(out, torch.uint8, "out")
+        if not (mask.is_contiguous() and out.is_contiguous()) or out.numel() != mask.numel():
+            raise VstabNativeError("mask_pack_u8: contiguous buffers of equal length expected")
+        self._check(self.lib.vstab_mask_pack_u8(self._h, mask.data_ptr(), mask.numel(), out.data_ptr(), odd.data_ptr(), _stream_ptr(mask.device)))
 
     def common_coverage(self, fwd: torch.Tensor, src_size, out_size, mask_rule: Optional[int] = None) -> torch.Tensor:
         _check_cuda(fwd, torch.float32, "fwd")

@@ -202,6 +202,46 @@ def left_multiply(shift: np.ndarray, matrices: np.ndarray) -> np.ndarray:
     return np.matmul(np.asarray(shift)[None], np.asarray(matrices))
 
 
+def native_trajectory(cands, mode: str, source_size, working_size):
+    """Acceptance test + float32 transforms at full size + cumulative path through libvstab's host helper
+    (vstab_host_trajectory): (matrices [P,3,3] float32, path [P+1,K] float64), or None when a pair falls back to another
+    model or the library is not built -- the caller then takes the numpy route above, which computes the same bits."""
+    try:
+        from . import _native
+
+        return _native.host_trajectory(cands.raw_words(), cands.detected, cands.min_points, mode, source_size, working_size)
+    except (OSError, RuntimeError, AttributeError):  # library not built (host-only checkouts)
+        return None
+
+
+def native_framing(diffs: np.ndarray, mode: str, width: int, height: int):
+    """params_to_matrices + compute_bounding_boxes + inner / outer rectangle in one C pass (vstab_host_framing):
+    (apply [N,3,3] float32, mins, maxs, box[9]) or None without the library."""
+    try:
+        from . import _native
+
+        return _native.host_framing(diffs, mode, width, height)
+    except (OSError, RuntimeError, AttributeError):  # library not built (host-only checkouts)
+        return None
+
+
+def translate_matrices(matrices: np.ndarray, off_x: float, off_y: float, affine: bool = False) -> np.ndarray:
+    """[[1, 0, off_x], [0, 1, off_y], [0, 0, 1]] (float32) @ m for every m: the recentring / expand shift of the framing
+    modes.  Affine stacks go through vstab_host_shift (one inexact addition per element, so independent of the BLAS);
+    anything else through the float32 matmul the reference runs."""
+    if affine:
+        try:
+            from . import _native
+
+            out = _native.host_shift(np.ascontiguousarray(matrices, dtype=np.float32), off_x, off_y)
+            if out is not None:
+                return out
+        except (OSError, RuntimeError, AttributeError):  # library not built (host-only checkouts)
+            pass
+    shift = np.array([[1.0, 0.0, off_x], [0.0, 1.0, off_y], [0.0, 0.0, 1.0]], dtype=np.float32)
+    return left_multiply(shift, matrices)
+
+
 def smoothing_window(smooth: float, fps: float) -> int:
     fps = float(max(1.0, fps))
     seconds = 3.0 / 16.0 + smooth * (13.0 / 16.0 - 3.0 / 16.0)
@@ -217,14 +257,15 @@ def smooth_path(path: np.ndarray, smooth: float, fps: float) -> np.ndarray:
     window = smoothing_window(smooth, fps)
     half = window // 2
     taps = np.ones(window, dtype=np.float64) / float(window)
-    out = np.zeros_like(path)
-    n = path.shape[0]
-    padded = np.empty(n + 2 * half, dtype=path.dtype)  # np.pad(mode="edge") written out: it costs 35 us per call
-    for col in range(path.shape[1]):
-        padded[:half] = path[0, col]
-        padded[half : half + n] = path[:, col]
-        padded[half + n :] = path[n - 1, col]
-        out[:, col] = np.convolve(padded, taps, mode="valid")
+    n, cols = path.shape
+    # np.pad(mode="edge") written out for all columns at once (it costs 35 us per call): one contiguous row per column
+    padded = np.empty((cols, n + 2 * half), dtype=path.dtype)
+    padded[:, half : half + n] = path.T
+    padded[:, :half] = path[0][:, None]
+    padded[:, half + n :] = path[n - 1][:, None]
+    out = np.empty_like(path)
+    for col in range(cols):
+        out[:, col] = np.convolve(padded[col], taps, mode="valid")
     return out
 
 

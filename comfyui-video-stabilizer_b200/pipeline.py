@@ -466,6 +466,16 @@ def convert_masks_for_output(masks: Any) -> torch.Tensor:
 
 PINNED_RESULT_LIMIT = 64 << 30  # VSTAB_PINNED_RESULT_LIMIT_MB overrides
 
+# bytes the last fused_warp(output="host") call copied device -> host (frames + mask as it crossed the link); bench.py reads it
+LAST_D2H_BYTES = 0
+
+
+def mask_bytes_enabled() -> bool:
+    """Binary masks travel device -> host as uint8 unless VSTAB_MASK_BYTES=0 (A/B switch; the results are identical)."""
+    import os
+
+    return os.environ.get("VSTAB_MASK_BYTES", "1") != "0"
+
 
 def _host_result(shape) -> torch.Tensor:
     """Host tensor a result is downloaded into: page-locked (the download then runs at link rate) unless the clip is
@@ -572,6 +582,9 @@ def fused_warp(
 
     frames_cpu = _host_result((n, oh, ow, 3))
     masks_cpu = _host_result((n, oh, ow)) if want_mask else None
+    # a single-sample mask is exactly 0 / 1: it crosses the link as bytes (a quarter of the float32 MASK, ~10 % of the
+    # whole transfer) and is widened into masks_cpu by the host while the frames are still being copied
+    pack_mask = want_mask and fwd_t.shape[1] == 1 and mask_bytes_enabled()
     pads: List[torch.Tensor] = []
     step = frames_per_chunk(oh, ow, 4)
     if context.streamed:
@@ -582,13 +595,18 @@ def fused_warp(
         (
             torch.empty((min(step, n), oh, ow, 3), dtype=torch.float32, device=dev),
             torch.empty((min(step, n), oh, ow), dtype=torch.float32, device=dev) if want_mask else None,
+            torch.empty((min(step, n), oh, ow), dtype=torch.uint8, device=dev) if pack_mask else None,
         )
         for _ in range(2 if n > step else 1)
     ]
+    mask_bytes_cpu = torch.empty((n, oh, ow), dtype=torch.uint8, pin_memory=True) if pack_mask else None
+    odd = torch.zeros((1,), dtype=torch.int32, device=dev) if pack_mask else None
+    mask_ready: List[Tuple[int, int, torch.cuda.Event]] = []
     copied = [None] * len(bufs)
+    d2h_bytes = 0
     for k, a in enumerate(range(0, n, step)):
         b = min(a + step, n)
-        dbuf, mbuf = bufs[k % len(bufs)]
+        dbuf, mbuf, ubuf = bufs[k % len(bufs)]
         if copied[k % len(bufs)] is not None:
             main.wait_event(copied[k % len(bufs)])  # buffer free again
         # streamed clips: the upload of chunk k+1 (this stream) overlaps the download of chunk k (copy stream)
@@ -597,18 +615,30 @@ def fused_warp(
             mask_rule=mask_rule, want_mask=want_mask, want_pad_count=want_pad_count,
             out=dbuf[: b - a], mask_out=(mbuf[: b - a] if mbuf is not None else None),
         )
+        if pack_mask:
+            h.mask_pack_u8(mask, ubuf[: b - a], odd)
         if pad is not None:
             pads.append(pad)
         done = torch.cuda.Event()
         done.record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done)
+            if pack_mask:  # the mask first: the host widens it while the frames of the chunk are on the link
+                mask_bytes_cpu[a:b].copy_(ubuf[: b - a], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+                mask_ready.append((a, b, ready))
+                d2h_bytes += (b - a) * oh * ow
             frames_cpu[a:b].copy_(dst, non_blocking=True)
-            if masks_cpu is not None:
+            d2h_bytes += (b - a) * oh * ow * 12
+            if masks_cpu is not None and not pack_mask:
                 masks_cpu[a:b].copy_(mask, non_blocking=True)
+                d2h_bytes += (b - a) * oh * ow * 4
             ev = torch.cuda.Event()
             ev.record(copy_stream)
             copied[k % len(bufs)] = ev
+    global LAST_D2H_BYTES
+    LAST_D2H_BYTES = d2h_bytes
     pad_all = None
     if pads:
         pad_all = torch.cat(pads) if len(pads) > 1 else pads[0]
@@ -617,9 +647,14 @@ def fused_warp(
     keep_alive = (bufs, fwd_t)  # the copy stream still reads the staging buffers after this function returns
 
     def finish_host(_keep=keep_alive):
+        for a, b, ready in mask_ready:
+            ready.synchronize()
+            masks_cpu[a:b].copy_(mask_bytes_cpu[a:b])  # uint8 -> float32 on the host cores (torch's parallel copy)
         copy_stream.synchronize()
         main.synchronize()
         pad_np = pad_all.cpu().numpy().astype(np.int64) if pad_all is not None else None
+        if odd is not None and int(odd.item()) != 0:
+            raise _native.VstabNativeError("a single-sample padding mask held a value other than 0 / 1: refusing to return it as bytes")
         return frames_cpu, masks_cpu, pad_np
 
     return finish_host if defer else finish_host()

@@ -17,6 +17,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
+import math
+
 import numpy as np
 import torch
 
@@ -87,6 +89,20 @@ class PairCandidates:
     ok: np.ndarray          # [P,3] int
     min_points: int = 12    # Flow: 12 finite grid points; Classic: 8 tracked features
     detected: Optional[np.ndarray] = None  # Classic: corners found per pair (<12 => identity)
+    raw: Optional[np.ndarray] = None       # [P,3,12] float64 words the columns were decoded from (vstab_fit_result)
+
+    def raw_words(self) -> np.ndarray:
+        """The table as [P,3,12] vstab_fit_result words (what vstab_host_trajectory reads): the block it was decoded
+        from, or the columns packed again (tables that were built or gathered as columns)."""
+        if self.raw is not None:
+            return self.raw
+        p = self.matrix.shape[0]
+        arr = np.zeros((p, 3, 12), dtype=np.float64)
+        arr[..., :9] = np.asarray(self.matrix, dtype=np.float64).reshape(p, 3, 9)
+        arr[..., 9] = self.residual
+        ints = np.stack([self.n_inliers, self.n_valid, self.n_total, self.ok], axis=-1).astype(np.int32)
+        arr[..., 10:12] = np.ascontiguousarray(ints).view(np.float64).reshape(p, 3, 2)
+        return arr
 
     def to_array(self) -> np.ndarray:
         """Flat float64 [P, 3*14 + 1] table (what shards all-gather)."""
@@ -115,7 +131,7 @@ class PairCandidates:
         return PairCandidates(
             matrix=arr[..., :9].reshape(arr.shape[0], 3, 3, 3).copy(), residual=arr[..., 9].copy(), n_inliers=ints[..., 0].copy(),
             n_valid=ints[..., 1].copy(), n_total=ints[..., 2].copy(), ok=ints[..., 3].copy(), min_points=min_points,
-            detected=None if detected is None else np.asarray(detected).astype(np.int64),
+            detected=None if detected is None else np.asarray(detected).astype(np.int64), raw=arr,
         )
 
 
@@ -130,8 +146,28 @@ class DeviceCandidates:
     send: Optional[torch.Tensor] = None      # [cap,3,12] all-gather send buffer `raw` is a view of (sharded runs)
 
     def to_host(self) -> PairCandidates:
+        return self.to_host_words().decode()
+
+    def to_host_words(self) -> "HostWords":
+        """The blocking copy alone; the columns are decoded when somebody asks for them (HostWords.decode)."""
         det = None if self.detected is None else self.detected.cpu().numpy()
-        return PairCandidates.from_raw(self.raw.cpu().numpy(), self.min_points, det)
+        return HostWords(self.raw.cpu().numpy(), self.min_points, det)
+
+
+@dataclass
+class HostWords:
+    """The candidate table on the host as the fit kernels wrote it ([P,3,12] vstab_fit_result words).  The trajectory
+    helper of libvstab reads the words directly; the per-column view (PairCandidates) is only needed by the fallback
+    ladder and by the meta builder, which runs while the resampler is in flight."""
+    raw: np.ndarray
+    min_points: int
+    detected: Optional[np.ndarray] = None
+
+    def raw_words(self) -> np.ndarray:
+        return self.raw
+
+    def decode(self) -> PairCandidates:
+        return PairCandidates.from_raw(self.raw, self.min_points, self.detected)
 
 
 Estimator = Callable[[VideoContext, int, int, str], Any]  # -> PairCandidates | DeviceCandidates
@@ -237,6 +273,29 @@ def replay_mode_ladder(cands: PairCandidates, requested_mode: str, *, with_resid
         resid.append(res if with_residual else None)
     stacked = np.concatenate([mats32, np.stack(tail, axis=0)], axis=0) if tail else mats32
     return LadderEntries(stacked, modes, confs, resid), active, stacked
+
+
+def accepted_ladder_entries(cands: PairCandidates, mode: str, *, with_residual: bool) -> LadderEntries:
+    """LadderEntries columns (mode, confidence, residual) of a clip whose every pair accepted `mode` itself: what
+    replay_mode_ladder returns in that case, without the matrix stack (vstab_host_trajectory produced it already)."""
+    k = _native.MODE_INDEX[mode]
+    total = cands.matrix.shape[0]
+    n_valid = cands.n_valid.max(axis=1)
+    if mode == "translation":
+        denom = cands.detected if cands.detected is not None else cands.n_total[:, k]
+        confs = (n_valid / denom.astype(np.float64)).tolist()
+    else:
+        confs = (cands.n_inliers[:, k] / n_valid.astype(np.float64)).tolist()
+    resid = cands.residual[:, k].tolist() if with_residual else [None] * total
+    return LadderEntries(None, [mode] * total, confs, resid)
+
+
+def _native_host_solve() -> bool:
+    """The trajectory solve runs in libvstab's host helpers (csrc/hostsolve.cu) unless VSTAB_HOST_SOLVE=0 asks for the
+    numpy formulation of hostmath.py -- same operations, same bits (tests/test_host_solve_cpu.py), ~0.4 ms slower."""
+    import os
+
+    return os.environ.get("VSTAB_HOST_SOLVE", "1") != "0"
 
 
 class _Progress:
@@ -352,22 +411,30 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
         cands = shard.gather_candidates(cands)
     _gpu_mark("candidate all-gather", mark_dev)
     if isinstance(cands, DeviceCandidates):
-        cands = cands.to_host()
+        cands = cands.to_host_words()
     t0 = _mark("candidate table on the host (waits for the GPU; all-gather when sharded)", t0)
     nvtx.phase("ladder+solve")
-    chosen, active_mode, stacked = replay_mode_ladder(cands, transform_mode, with_residual=is_flow)
+    base_mode = transform_mode
+    use_native = _native_host_solve()
+    solved = hm.native_trajectory(cands, transform_mode, (width, height), work) if use_native else None
+    if solved is not None:
+        # every pair accepted the requested model: per-pair float32 transforms at full size and the cumulative path in
+        # one C pass; the ladder's meta columns are put together after the resampler is launched
+        matrices, path = solved
+        chosen, active_mode = None, transform_mode
+    else:
+        if isinstance(cands, HostWords):
+            cands = cands.decode()
+        chosen, active_mode, stacked = replay_mode_ladder(cands, transform_mode, with_residual=is_flow)
+        if work is not None:
+            stacked = hm.rescale_transforms_to_full(stacked, (width, height), work)
+        matrices = stacked  # [P,3,3] float32, full-resolution per-pair transforms
+        delta_params = hm.matrices_to_params(matrices, base_mode)
+        path = np.zeros((total_frames, delta_params.shape[1]), dtype=np.float64)
+        np.cumsum(delta_params, axis=0, out=path[1:])  # sequential adds, same as path[i] = path[i-1] + delta
     t0 = _mark("ladder", t0)
     progress.advance(estimation_steps)
     check()
-
-    base_mode = transform_mode
-    if work is not None:
-        stacked = hm.rescale_transforms_to_full(stacked, (width, height), work)
-    matrices = stacked  # [P,3,3] float32, full-resolution per-pair transforms
-    delta_params = hm.matrices_to_params(matrices, base_mode)
-
-    path = np.zeros((total_frames, delta_params.shape[1]), dtype=np.float64)
-    np.cumsum(delta_params, axis=0, out=path[1:])  # sequential adds, same as path[i] = path[i-1] + delta
 
     strength = float(np.clip(strength, 0.0, 1.0))
     smooth = float(np.clip(smooth, 0.0, 1.0))
@@ -396,13 +463,22 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
         final_matrices, apply_matrices, crop_meta, stabilization_scale = crop
         output_size = (width, height)
     else:
-        apply_matrices = hm.params_to_matrices(delta_full, base_mode)  # [N,3,3] float32
-        final_matrices = apply_matrices
         output_size = (width, height)
         crop_meta = None
 
-    mins, maxs = hm.compute_bounding_boxes(apply_matrices, width, height)
-    inner = hm.inner_rectangle(mins, maxs)
+    # bounding boxes of the frame corners under the applied matrices: box = (inner rectangle, union, all-affine flag)
+    framed = hm.native_framing(delta_full, base_mode, width, height) if use_native and framing_mode != "crop" else None
+    if framed is not None:
+        apply_matrices, mins, maxs, box = framed
+        final_matrices = apply_matrices
+        inner = (box[0], box[1], box[2], box[3])
+    else:
+        box = None
+        if framing_mode != "crop":
+            apply_matrices = hm.params_to_matrices(delta_full, base_mode)  # [N,3,3] float32
+            final_matrices = apply_matrices
+        mins, maxs = hm.compute_bounding_boxes(apply_matrices, width, height)
+        inner = hm.inner_rectangle(mins, maxs)
     framing_meta: Dict[str, Any] = {
         "mode": framing_mode,
         "input_size": [width, height],
@@ -421,8 +497,7 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
         iw, ih = max(1.0, x1 - x0), max(1.0, y1 - y0)
         off_x = width * 0.5 - (x0 + x1) * 0.5
         off_y = height * 0.5 - (y0 + y1) * 0.5
-        shift = np.array([[1.0, 0.0, off_x], [0.0, 1.0, off_y], [0.0, 0.0, 1.0]], dtype=np.float32)
-        final_matrices = hm.left_multiply(shift, apply_matrices)
+        final_matrices = hm.translate_matrices(apply_matrices, off_x, off_y, affine=box is not None and box[8] == 1.0)
         framing_meta.update(
             {
                 "safe_region_origin": [x0, y0],
@@ -432,14 +507,14 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
             }
         )
     else:
-        shift, output_size = hm.prepare_expand_transform(mins, maxs)
-        final_matrices = hm.left_multiply(shift, apply_matrices)
+        if box is not None:
+            x_lo, y_lo, x_hi, y_hi = (float(v) for v in box[4:8])
+            output_size = (max(int(math.ceil(x_hi - x_lo)), 1), max(int(math.ceil(y_hi - y_lo)), 1))
+            final_matrices = hm.translate_matrices(apply_matrices, -x_lo, -y_lo, affine=box[8] == 1.0)
+        else:
+            shift, output_size = hm.prepare_expand_transform(mins, maxs)
+            final_matrices = hm.left_multiply(shift, apply_matrices)
         framing_meta["expanded_size"] = list(output_size)
-
-    effective_diffs = hm.matrices_to_params(np.asarray(apply_matrices), base_mode) if framing_mode == "crop" else np.array(delta_full)
-    stabilization_scale = float(np.clip(stabilization_scale, 0.0, 1.0))
-    strength_effective = strength * stabilization_scale
-    effective_target_path = path + effective_diffs
 
     # ---- warp + mask: one fused launch per chunk -------------------------------------------------
     lo, hi = (0, total_frames) if shard is None else shard.frame_range
@@ -463,6 +538,14 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
     # meta is sharded like the frames it describes, sharding.merge_sharded_meta() reassembles it); entries
     # keep their clip-wide indices.  Transitions go with the frame they end in.
     nvtx.phase("meta")
+    if chosen is None:
+        if isinstance(cands, HostWords):
+            cands = cands.decode()
+        chosen = accepted_ladder_entries(cands, transform_mode, with_residual=is_flow)
+    effective_diffs = hm.matrices_to_params(np.asarray(apply_matrices), base_mode) if framing_mode == "crop" else np.array(delta_full)
+    stabilization_scale = float(np.clip(stabilization_scale, 0.0, 1.0))
+    strength_effective = strength * stabilization_scale
+    effective_target_path = path + effective_diffs
     m_lo, m_hi = (0, total_frames) if shard is None else shard.meta_frame_range
     t_lo, t_hi = max(m_lo, 1) - 1, max(m_hi - 1, max(m_lo, 1) - 1)
     per_transition = []

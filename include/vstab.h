@@ -145,6 +145,16 @@ VSTAB_API int vstab_coverage_bbox(vstab_handle* h, const float* fwd_dev, int n, 
                                   int out_h, int out_w, int mask_rule, int32_t* bbox_dev, void* stream);
 
 /*
+ * Padding mask of a single-sample resampling (values exactly 0.0f / 1.0f) packed to one byte per pixel for the
+ * device->host copy: the MASK output of nodes/video_stabilizer_flow.py:560-588 / classic.py:491-519 goes back as a
+ * quarter of its float32 bytes and is widened on the host (pipeline.fused_warp, output="host").
+ * mask_dev [n] float32, out_dev [n] uint8 (both 16-byte aligned), odd_dev: one uint32 the caller zeroed; bit 0 is set
+ * when a value other than 0 / 1 was seen (a soft motion-blur mask must not take this route).
+ */
+VSTAB_API int vstab_mask_pack_u8(vstab_handle* h, const float* mask_dev, size_t n, uint8_t* out_dev, uint32_t* odd_dev,
+                                 void* stream);
+
+/*
  * K1 + K2 with the input adapter's range rule fused into the same read of the source.
  * Replaces, for float32 frames, the per-frame `arr.max() > 1.5  =>  arr /= 255.0` of
  * nodes/stabilizer_utils.py:96-147 (_to_numpy_frame) together with :236-276 (_make_gray_for_estimation):
@@ -172,6 +182,34 @@ VSTAB_API int vstab_range_normalize(vstab_handle* h, float* rgb_dev, int n, int 
 #define VSTAB_LIBM_COS 3
 #define VSTAB_LIBM_SIN 4
 VSTAB_API int vstab_host_libm(int op, const double* a, const double* b, double* out, int n);
+
+/*
+ * Host-side trajectory solve (no device work), the common case of the path between the fit kernels and the resampler
+ * in one pass each instead of some 80 numpy operations -- the GPU idles while it runs.  Same IEEE operations in the same
+ * order and widths as the reference (and as hostmath.py, which stays the general path and the test oracle for these).
+ *
+ * vstab_host_trajectory: nodes/video_stabilizer_flow.py:156-210 / classic.py:104-158 (acceptance test of the requested
+ * model), stabilizer_utils.py:279-297 (_rescale_transform_to_full), :300-326 (_matrix_to_params), flow.py:341-349 (cumsum).
+ *   raw            [n_pairs][3] vstab_fit_result as copied from the device (12 eight-byte words each)
+ *   detected       [n_pairs] corners found per pair (Classic: < 12 => identity) or NULL
+ *   mode           VSTAB_MODE_* requested;  work_w/work_h = 0: estimation ran at full size (no rescale)
+ *   matrices       out [n_pairs][9] float32 full-resolution per-pair transforms
+ *   path           out [n_pairs + 1][K] float64 cumulative parameters, K = 2 / 4 / 8
+ *   first_fallback out: n_pairs when every pair accepts the requested model; otherwise the first pair that does not --
+ *                  the sticky fallback ladder starts there, the outputs are NOT written and the caller replays it.
+ * vstab_host_framing: stabilizer_utils.py:329-358 (_params_to_matrix) and :1010-1032 (_compute_bounding_boxes).
+ *   diffs [n_frames][K] float64 -> apply [n_frames][9] float32, mins / maxs [n_frames][2] float64 (corner bounding boxes),
+ *   box [9]: inner rectangle x0 y0 x1 y1 (max of minima, min of maxima), union x0 y0 x1 y1, 1.0 if all matrices are
+ *   finite with a (0, 0, 1) last row.
+ * vstab_host_shift: [[1,0,ox],[0,1,oy],[0,0,1]] @ apply for such matrices (flow.py:471-489; the float32 product has one
+ *   inexact operation per element there, so its bits do not depend on the BLAS); VSTAB_ERR_UNSUPPORTED otherwise.
+ */
+VSTAB_API int vstab_host_trajectory(const double* raw, const int32_t* detected, int n_pairs, int min_points, int mode,
+                                    int src_w, int src_h, int work_w, int work_h, float* matrices, double* path,
+                                    int* first_fallback);
+VSTAB_API int vstab_host_framing(const double* diffs, int n_frames, int mode, int width, int height, float* apply,
+                                 double* mins, double* maxs, double* box);
+VSTAB_API int vstab_host_shift(const float* apply, int n_frames, float off_x, float off_y, float* out);
 
 /* ---- K3 + K4 : DIS dense optical flow, batched over frame pairs ------------------------- */
 
