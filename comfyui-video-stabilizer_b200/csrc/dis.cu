@@ -23,6 +23,7 @@
 
 namespace {
 
+//@emul-begin (tests/emul/vr_emul.cpp compiles the marked regions for the host)
 constexpr int kBorder = 16;
 constexpr int kPatch = 8;
 constexpr int kStride = 4;
@@ -40,6 +41,12 @@ constexpr int kMaxLevels = 8;
 #endif
 #ifndef VSTAB_DIS_STAGGER_DEFAULT
 #define VSTAB_DIS_STAGGER_DEFAULT 0
+#endif
+#ifndef VSTAB_VR_RESIDENT_DEFAULT
+#define VSTAB_VR_RESIDENT_DEFAULT 2
+#endif
+#ifndef VSTAB_VR_RESIDENT_THREADS_DEFAULT
+#define VSTAB_VR_RESIDENT_THREADS_DEFAULT 1024
 #endif
 #ifndef VSTAB_VR_MIN_CTAS
 #define VSTAB_VR_MIN_CTAS 5
@@ -59,6 +66,7 @@ struct Level {
   float* Sx;           // [P][hs][ws]
   float* Sy;
 };
+//@emul-end
 
 __device__ __forceinline__ int reflect101(int p, int len) {
   if (len == 1) return 0;
@@ -459,6 +467,7 @@ __global__ void __launch_bounds__(256) densify_kernel(Level L, int P) {
 }
 
 // ---- variational refinement --------------------------------------------------------------------
+//@emul-begin
 
 struct VrBuf {  // all [P][h][w] float
   float *avg, *Iz, *Ix, *Iy, *Ixx, *Ixy, *Iyy, *Ixz, *Iyz;
@@ -480,6 +489,7 @@ __device__ __forceinline__ float at_clamped(const float* p, size_t base, int y, 
 // separated by cluster barriers (barrier.cluster release/acquire orders the global-memory traffic
 // between the CTAs of the cluster), so the ~70 dependent launches per level collapse into one.
 
+template <bool STATE = true>
 __device__ __forceinline__ void vr_px_warp(const Level& L, const VrBuf& B, int pair, int x, int y) {
   const int w = L.w, h = L.h;
   const size_t k = (size_t)pair * h * w + (size_t)y * w + x;
@@ -500,10 +510,12 @@ __device__ __forceinline__ void vr_px_warp(const Level& L, const VrBuf& B, int p
   const float i0 = (float)I0[y * w + x];
   B.avg[k] = 0.5f * (i0 + warped);
   B.Iz[k] = warped - i0;
-  B.tu[k] = L.Ux[k];
-  B.tv[k] = L.Uy[k];
-  B.du[k] = 0.f;
-  B.dv[k] = 0.f;
+  if (STATE) {  // the resident variant keeps du / dv in shared memory and forms tu / tv on the fly
+    B.tu[k] = L.Ux[k];
+    B.tv[k] = L.Uy[k];
+    B.du[k] = 0.f;
+    B.dv[k] = 0.f;
+  }
 }
 
 __device__ __forceinline__ void vr_px_deriv1(const Level& L, const VrBuf& B, int pair, int x, int y) {
@@ -590,10 +602,13 @@ __device__ __forceinline__ void vr_px_sor(const Level& L, const VrBuf& B, int pa
   B.dv[k] = dv;
 }
 
+#ifndef VSTAB_HOST_EMUL
 __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
+#define VSTAB_DYNAMIC_SMEM(name) extern __shared__ __align__(16) float name[]
+#endif
 
 // ONCHIP: the level is small enough for all 19 planes of a pair to live in the shared memory of ONE CTA
 // (19 * h * w * 4 bytes: 39 KB at 30x17, 155 KB at 60x34): 1024 threads, __syncthreads between the
@@ -602,7 +617,7 @@ __device__ __forceinline__ void cluster_barrier() {
 // which indexes [pair][y][x], lands in the CTA's own copy.
 template <bool ONCHIP>
 __global__ void __launch_bounds__(ONCHIP ? 1024 : 256, ONCHIP ? 1 : VSTAB_VR_MIN_CTAS) vr_fused_kernel(Level L, VrBuf B, int cluster_size) {
-  extern __shared__ __align__(16) float vr_smem[];
+  VSTAB_DYNAMIC_SMEM(vr_smem);
   const int pair = blockIdx.x / cluster_size;
   const int crank = blockIdx.x % cluster_size;
   const int w = L.w, h = L.h;
@@ -656,6 +671,212 @@ __global__ void __launch_bounds__(ONCHIP ? 1024 : 256, ONCHIP ? 1 : VSTAB_VR_MIN
 #undef FOR_PX
 }
 
+// ---- variational refinement, resident variant ----------------------------------------------------
+//
+// The SOR state of a band of <= 4096 checkerboard cells per colour lives in the shared memory of ONE 1024-thread CTA:
+// du, dv, the smoothness weights and three of the five system coefficients as colour-split planes
+// [colour][band row + 1 halo row above and below][column / 2], A11 and A22 of a thread's own eight pixels in registers.
+// A half-sweep then touches no global memory at all (the cluster version above streams 19 loads per update through
+// L2 at ~700 cycles each); the eight derivative planes a pixel needs once per outer iteration stay in global memory
+// (written and read by the same thread).  A pair is one CTA (<= 8192 px, e.g. 120x67) or a cluster of 2 / 4 / 8 CTAs,
+// each a band of rows; after a half-sweep the first and last row of a band are pushed into the halo rows of the
+// neighbouring CTAs through distributed shared memory, and barrier.cluster orders the pushes.
+// Same per-pixel arithmetic as vr_px_* above, expression by expression (this file is compiled with -fmad=false).
+constexpr int kResCells = 4096;  // checkerboard cells per colour and CTA: 1024 threads x 4 or 512 threads x 8
+
+#ifndef VSTAB_HOST_EMUL
+__device__ __forceinline__ void st_cluster(float* local, unsigned rank, float v) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(local), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(r), "f"(v) : "memory");
+}
+#endif
+
+template <bool CLUSTER, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf B, int cluster_size) {
+  constexpr int kResThreads = THREADS, kResPpt = kResCells / THREADS;
+  VSTAB_DYNAMIC_SMEM(rs);
+  const int pair = blockIdx.x / cluster_size;
+  const int crank = blockIdx.x % cluster_size;
+  const int w = L.w, h = L.h, half_w = (w + 1) >> 1;
+  const int rows_per = (h + cluster_size - 1) / cluster_size;
+  const int r0 = min(crank * rows_per, h), r1 = min(r0 + rows_per, h), rows = r1 - r0;
+  const int cs = (rows_per + 2) * half_w;  // cells of one colour, halo rows included
+  float* const s_du = rs;
+  float* const s_dv = rs + 2 * cs;
+  float* const s_wg = rs + 4 * cs;
+  float* const s_a12 = rs + 6 * cs;
+  float* const s_b1 = rs + 8 * cs;
+  float* const s_b2 = rs + 10 * cs;
+  const int ncell = rows * half_w;
+  const size_t pbase = (size_t)pair * h * w;
+  const float* __restrict__ u0 = L.Ux + pbase;
+  const float* __restrict__ v0 = L.Uy + pbase;
+#define RES_SYNC() do { if (CLUSTER) cluster_barrier(); else __syncthreads(); } while (0)
+
+  // own cells: cell i = tid + 1024 m of the band -> (row, column pair); the same cell in both colours.
+  // packed: bits 0..12 plane index (halo row included), 13..22 image row, 23..31 column pair; -1 = none
+  int own[kResPpt];
+#pragma unroll
+  for (int m = 0; m < kResPpt; m++) {
+    const int i = threadIdx.x + kResThreads * m;
+    if (i < ncell) {
+      const int ly = i / half_w, j = i - ly * half_w;
+      own[m] = ((ly + 1) * half_w + j) | ((r0 + ly) << 13) | (j << 23);
+    } else {
+      own[m] = -1;
+    }
+  }
+#define RES_CELL(c, m)                                             \
+  int cell = own[m];                                               \
+  asm volatile("" : "+r"(cell)); /* decode here, not hoisted out of the sweep loop for all sixteen cells at once */ \
+  const int sidx = cell & 8191, y = (cell >> 13) & 1023;           \
+  const int j = (cell >> 23) & 511, q = (y + (c)) & 1, x = 2 * j + q; \
+  const bool live = cell >= 0 && x < w;                            \
+  const int ci = (c) * cs + sidx, oi = (1 - (c)) * cs + sidx;      \
+  const size_t k = (size_t)y * w + x;
+
+  // phases without per-cell register state walk the band with a rolled loop (cell -> row / column pair by division)
+#define RES_FOR_CELLS(...)                                              \
+  _Pragma("unroll 1") for (int c = 0; c < 2; c++)                       \
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ncell; i += kResThreads) { \
+    const int ly = i / half_w, j = i - ly * half_w, y = r0 + ly;        \
+    const int q = (y + c) & 1, x = 2 * j + q;                           \
+    if (x < w) {                                                        \
+      const int sidx = (ly + 1) * half_w + j;                           \
+      const int ci = c * cs + sidx, oi = (1 - c) * cs + sidx;           \
+      const size_t k = (size_t)y * w + x;                               \
+      (void)ci; (void)oi; (void)k;                                      \
+      __VA_ARGS__;                                                      \
+    }                                                                   \
+  }
+
+  for (int i = threadIdx.x; i < 4 * cs; i += kResThreads) rs[i] = 0.f;  // du, dv (halo rows too)
+  RES_FOR_CELLS(vr_px_warp<false>(L, B, pair, x, y))
+  RES_SYNC();
+  RES_FOR_CELLS(vr_px_deriv1(L, B, pair, x, y))
+  RES_SYNC();
+  RES_FOR_CELLS(vr_px_deriv2(L, B, pair, x, y))
+
+  float a11r[2][kResPpt], a22r[2][kResPpt];
+  for (int it = 0; it < kVrIter; it++) {
+    // ---- smoothness weights (vr_px_weight) from tu = u0 + du, tv = v0 + dv of the cell, its right and its lower neighbour
+    RES_FOR_CELLS({
+      const bool has_r = x + 1 < w, has_d = y + 1 < h;
+      const size_t kr = has_r ? k + 1 : k, kd = has_d ? k + w : k;
+      const int sr = has_r ? oi + q : ci, sd = has_d ? oi + half_w : ci;
+      float tu = u0[k], tv = v0[k], tur = u0[kr], tvr = v0[kr], tud = u0[kd], tvd = v0[kd];
+      if (it > 0) {
+        tu = tu + s_du[ci]; tv = tv + s_dv[ci];
+        tur = tur + s_du[sr]; tvr = tvr + s_dv[sr];
+        tud = tud + s_du[sd]; tvd = tvd + s_dv[sd];
+      }
+      const float ux = tur - tu, vx = tvr - tv, uy = tud - tu, vy = tvd - tv;
+      const float eps2 = kEpsilon * kEpsilon;
+      const float wgt = (kAlpha / 2) / sqrtf(ux * ux + vx * vx + uy * uy + vy * vy + eps2);
+      s_wg[ci] = wgt;
+      if (CLUSTER && y == r1 - 1 && r1 < h) st_cluster(&s_wg[c * cs + j], crank + 1, wgt);  // last row -> top halo of the band below
+    })
+    RES_SYNC();
+    // ---- linear system (vr_px_system): A11, A22 stay in registers, A12, b1, b2 in shared memory
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+      for (int m = 0; m < kResPpt; m++) {
+        RES_CELL(c, m)
+        if (live) {
+          const size_t gk = pbase + k;
+          const float zeta2 = 0.1f * 0.1f, eps2 = kEpsilon * kEpsilon, gamma2 = kGamma / 2, delta2 = kDelta / 2;
+          const float ix = B.Ix[gk], iy = B.Iy[gk], iz = B.Iz[gk], ixx = B.Ixx[gk], ixy = B.Ixy[gk], iyy = B.Iyy[gk];
+          const float ixz = B.Ixz[gk], iyz = B.Iyz[gk], dU = s_du[ci], dV = s_dv[ci];
+          float derivNorm = ix * ix + iy * iy + zeta2;
+          const float Ik1z = iz + ix * dU + iy * dV;
+          float weight = (delta2 / sqrtf(Ik1z * Ik1z / derivNorm + eps2)) / derivNorm;
+          float a11 = weight * (ix * ix) + zeta2;
+          float a12 = weight * (ix * iy);
+          float a22 = weight * (iy * iy) + zeta2;
+          float bb1 = -weight * (iz * ix);
+          float bb2 = -weight * (iz * iy);
+          derivNorm = ixx * ixx + ixy * ixy + zeta2;
+          const float derivNorm2 = iyy * iyy + ixy * ixy + zeta2;
+          const float Ik1zx = ixz + ixx * dU + ixy * dV;
+          const float Ik1zy = iyz + ixy * dU + iyy * dV;
+          weight = gamma2 / sqrtf(Ik1zx * Ik1zx / derivNorm + Ik1zy * Ik1zy / derivNorm2 + eps2);
+          a11 += weight * (ixx * ixx / derivNorm + ixy * ixy / derivNorm2);
+          a12 += weight * (ixx * ixy / derivNorm + ixy * iyy / derivNorm2);
+          a22 += weight * (ixy * ixy / derivNorm + iyy * iyy / derivNorm2);
+          bb1 += -weight * (ixx * ixz / derivNorm + ixy * iyz / derivNorm2);
+          bb2 += -weight * (ixy * ixz / derivNorm + iyy * iyz / derivNorm2);
+          const bool red = ((x + y) & 1) == 0;
+          const float wc = s_wg[ci];
+          const bool own_h = x < w - 1, left_h = x > 0;
+          float own_ux = 0.f, own_vx = 0.f, left_ux = 0.f, left_vx = 0.f, wl = 0.f;
+          if (own_h) { own_ux = wc * (u0[k + 1] - u0[k]); own_vx = wc * (v0[k + 1] - v0[k]); }
+          if (left_h) { wl = s_wg[oi + q - 1]; left_ux = wl * (u0[k] - u0[k - 1]); left_vx = wl * (v0[k] - v0[k - 1]); }
+          if (red) { ADD_OWN_H(); ADD_LEFT_H(); } else { ADD_LEFT_H(); ADD_OWN_H(); }
+          const bool own_v = y < h - 1, up_v = y > 0;
+          float own_uy = 0.f, own_vy = 0.f, up_uy = 0.f, up_vy = 0.f, wu = 0.f;
+          if (own_v) { own_uy = wc * (u0[k + w] - u0[k]); own_vy = wc * (v0[k + w] - v0[k]); }
+          if (up_v) { wu = s_wg[oi - half_w]; up_uy = wu * (u0[k] - u0[k - w]); up_vy = wu * (v0[k] - v0[k - w]); }
+          if (red) { ADD_OWN_V(); ADD_UP_V(); } else { ADD_UP_V(); ADD_OWN_V(); }
+          a11r[c][m] = a11;
+          a22r[c][m] = a22;
+          s_a12[ci] = a12;
+          s_b1[ci] = bb1;
+          s_b2[ci] = bb2;
+        }
+        asm volatile("" ::: "memory");  // one cell at a time: keeps the unrolled cells from piling their loads up in registers
+      }
+    // the sweeps read what this thread itself just wrote and du / dv, which nobody has touched since the last barrier
+    for (int s = 0; s < kSorIter; s++) {
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+#pragma unroll
+        for (int m = 0; m < kResPpt; m++) {
+          RES_CELL(c, m)
+          (void)k;
+          if (live) {
+            const bool has_l = x > 0, has_r = x + 1 < w, has_u = y > 0, has_d = y + 1 < h;
+            const float wl = has_l ? s_wg[oi + q - 1] : 0.f, dul = has_l ? s_du[oi + q - 1] : 0.f, dvl = has_l ? s_dv[oi + q - 1] : 0.f;
+            const float dur = has_r ? s_du[oi + q] : 0.f, dvr = has_r ? s_dv[oi + q] : 0.f;
+            const float wu = has_u ? s_wg[oi - half_w] : 0.f, duu = has_u ? s_du[oi - half_w] : 0.f, dvu = has_u ? s_dv[oi - half_w] : 0.f;
+            const float dud = has_d ? s_du[oi + half_w] : 0.f, dvd = has_d ? s_dv[oi + half_w] : 0.f;
+            const float wc = s_wg[ci];
+            const float sigmaU = wl * dul + wc * dur + wu * duu + wc * dud;
+            const float sigmaV = wl * dvl + wc * dvr + wu * dvu + wc * dvd;
+            float du = s_du[ci], dv = s_dv[ci];
+            du += kOmega * ((sigmaU + s_b1[ci] - dv * s_a12[ci]) / a11r[c][m] - du);
+            dv += kOmega * ((sigmaV + s_b2[ci] - du * s_a12[ci]) / a22r[c][m] - dv);
+            s_du[ci] = du;
+            s_dv[ci] = dv;
+            if (CLUSTER) {
+              if (y == r0 && crank > 0) {  // first row of the band -> bottom halo of the band above
+                st_cluster(&s_du[c * cs + (rows_per + 1) * half_w + j], crank - 1, du);
+                st_cluster(&s_dv[c * cs + (rows_per + 1) * half_w + j], crank - 1, dv);
+              }
+              if (y == r1 - 1 && r1 < h) {  // last row -> top halo of the band below
+                st_cluster(&s_du[c * cs + j], crank + 1, du);
+                st_cluster(&s_dv[c * cs + j], crank + 1, dv);
+              }
+            }
+          }
+          asm volatile("" ::: "memory");
+        }
+        RES_SYNC();
+      }
+    }
+  }
+  // total flow of the level = u0 + du (the update phase of the last iteration)
+  RES_FOR_CELLS({
+    L.Ux[pbase + k] = u0[k] + s_du[ci];
+    L.Uy[pbase + k] = v0[k] + s_dv[ci];
+  })
+#undef RES_FOR_CELLS
+#undef RES_CELL
+#undef RES_SYNC
+}
+
+//@emul-end
 // ---- flow upsampling ---------------------------------------------------------------------------
 
 // next level = 2 * resize(linear) in the arithmetic of the 1-channel float path of the wheel (IPP):
@@ -880,6 +1101,23 @@ int vr_cluster_size(int px) {
   return cl;
 }
 
+// Cluster size of the resident refinement (vr_resident_kernel): the smallest of 1 / 2 / 4 / 8 row bands whose
+// checkerboard cells fit the CTA (4096 per colour) and whose six planes fit its shared memory; 0 = use the streaming
+// cluster kernel.  VSTAB_VR_RESIDENT: 0 = off, 1 = single-CTA levels only, 2 (default) = clusters too.
+int vr_resident_cluster(const vstab_handle* hnd, int h, int w) {
+  const char* e = getenv("VSTAB_VR_RESIDENT");
+  const int mode = e ? atoi(e) : VSTAB_VR_RESIDENT_DEFAULT;
+  if (mode <= 0 || h > 1023 || w > 1022) return 0;
+  const int half_w = (w + 1) / 2;
+  for (int cl = 1; cl <= 8; cl <<= 1) {
+    const int rows_per = (h + cl - 1) / cl;
+    const size_t bytes = (size_t)12 * (rows_per + 2) * half_w * sizeof(float);
+    if (rows_per * half_w <= kResCells && (rows_per + 2) * half_w <= 8191 && bytes <= (size_t)hnd->max_smem_optin)
+      return (cl == 1 || mode >= 2) ? cl : 0;
+  }
+  return 0;
+}
+
 // One pyramid level of one pair group on one stream: patch search, densification, refinement, x2 upsampling.
 int dis_level(vstab_handle* hnd, const Level& Lc, const Level* finer, const VrBuf& B, int P, cudaStream_t st,
               cudaEvent_t after_search = nullptr) {
@@ -918,6 +1156,28 @@ int dis_level(vstab_handle* hnd, const Level& Lc, const Level* finer, const VrBu
       VSTAB_CUDA(hnd, cudaFuncSetAttribute(vr_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onchip_bytes));
       vr_fused_kernel<true><<<P, 1024, onchip_bytes, st>>>(Lc, B, 1);
       VSTAB_LAUNCH_CHECK(hnd, "vr_fused_kernel");
+    } else if (const int rcl = vr_resident_cluster(hnd, Lc.h, Lc.w)) {
+      const int rows_per = (Lc.h + rcl - 1) / rcl, half_w = (Lc.w + 1) / 2;
+      const size_t bytes = (size_t)12 * (rows_per + 2) * half_w * sizeof(float);
+      const int threads = env_int("VSTAB_VR_RESIDENT_THREADS", VSTAB_VR_RESIDENT_THREADS_DEFAULT) == 512 ? 512 : 1024;
+      void (*kernel)(Level, VrBuf, int) =
+          rcl == 1 ? (threads == 512 ? vr_resident_kernel<false, 512> : vr_resident_kernel<false, 1024>)
+                   : (threads == 512 ? vr_resident_kernel<true, 512> : vr_resident_kernel<true, 1024>);
+      VSTAB_CUDA(hnd, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(P * rcl));
+      cfg.blockDim = dim3(threads);
+      cfg.dynamicSmemBytes = bytes;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = rcl;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = rcl > 1 ? 1 : 0;
+      VSTAB_CUDA(hnd, cudaLaunchKernelEx(&cfg, kernel, Lc, B, rcl));
+      hnd->launches++;
     } else {
       const int cl = vr_cluster_size(px);
       cudaLaunchConfig_t cfg = {};

@@ -15,7 +15,8 @@ mats = synth.shake_matrices(N, 0, W, H)
 clip = synth.render_clip_cuda(h, synth.base_texture(0, W, H).to(dev), mats, W, H)
 gray = h.gray_working(clip, (960, 540))
 del clip
-KNOBS = ("VSTAB_PS_NOPACK", "VSTAB_PS_WPC", "VSTAB_DIS_GROUPS", "VSTAB_VR_CLUSTER", "VSTAB_DIS_STAGGER", "VSTAB_PS_SPW")
+KNOBS = ("VSTAB_PS_NOPACK", "VSTAB_PS_WPC", "VSTAB_DIS_GROUPS", "VSTAB_VR_CLUSTER", "VSTAB_DIS_STAGGER", "VSTAB_PS_SPW", "VSTAB_VR_RESIDENT",
+         "VSTAB_VR_RESIDENT_THREADS")
 
 def run(cfg, reps=5):
     for k in KNOBS:
