@@ -675,14 +675,24 @@ __global__ void __launch_bounds__(ONCHIP ? 1024 : 256, ONCHIP ? 1 : VSTAB_VR_MIN
 //
 // The SOR state of a band of <= 4096 checkerboard cells per colour lives in the shared memory of ONE 1024-thread CTA:
 // du, dv, the smoothness weights and three of the five system coefficients as colour-split planes
-// [colour][band row + 1 halo row above and below][column / 2], A11 and A22 of a thread's own eight pixels in registers.
-// A half-sweep then touches no global memory at all (the cluster version above streams 19 loads per update through
-// L2 at ~700 cycles each); the eight derivative planes a pixel needs once per outer iteration stay in global memory
-// (written and read by the same thread).  A pair is one CTA (<= 8192 px, e.g. 120x67) or a cluster of 2 / 4 / 8 CTAs,
-// each a band of rows; after a half-sweep the first and last row of a band are pushed into the halo rows of the
-// neighbouring CTAs through distributed shared memory, and barrier.cluster orders the pushes.
-// Same per-pixel arithmetic as vr_px_* above, expression by expression (this file is compiled with -fmad=false).
-constexpr int kResCells = 4096;  // checkerboard cells per colour and CTA: 1024 threads x 4 or 512 threads x 8
+// [colour][band row + 1 halo row above and below][column / 2 + 1 pad cell left and right], A11 and A22 of a thread's own
+// eight pixels in registers.  A half-sweep then touches no global memory at all (the cluster version above streams
+// 19 loads per update through L2 at ~700 cycles each); the derivative planes a pixel needs once per outer iteration
+// stay in global memory (written and read by the same thread).  A pair is one CTA (<= 8192 px, e.g. 120x67) or a cluster
+// of 2 / 4 / 8 CTAs, each a band of rows; after a half-sweep the first and last row of a band are pushed into the halo
+// rows of the neighbouring CTAs through distributed shared memory, and barrier.cluster orders the pushes.
+//
+// Same per-pixel arithmetic as vr_px_* above, expression by expression (this file is compiled with -fmad=false):
+//  * the planes have a compile-time size, so every operand of an update is one LDS at [cell + immediate];
+//  * pad cells, halo rows outside the image and dead cells (odd widths) hold +0 in du, dv and the weight plane and are
+//    never written: `x > 0 ? w[k-1] * du[k-1] : 0 * 0` and its three siblings become plain loads (0 * 0 = +0 either way);
+//  * the quotients of the gradient-constancy term that do not depend on du / dv -- (Ixx Ixx / n1 + Ixy Ixy / n2) and its
+//    four siblings -- are formed once per pixel instead of in each of the five outer iterations (11 of the 16 IEEE
+//    divisions of a system evaluation), by the same expressions on the same operands.
+constexpr int kResCells = 4096;   // checkerboard cells per colour and CTA: 1024 threads x 4 or 512 threads x 8
+constexpr int kResColour = 4416;  // floats per colour of a plane: (rows + 2 halo rows) x (cells per row + 2 pad cells) fits
+constexpr int kResPlane = 2 * kResColour;
+constexpr int kResSmemFloats = 6 * kResPlane;  // du, dv, weight, A12, b1, b2
 
 #ifndef VSTAB_HOST_EMUL
 __device__ __forceinline__ void st_cluster(float* local, unsigned rank, float v) {
@@ -695,46 +705,40 @@ __device__ __forceinline__ void st_cluster(float* local, unsigned rank, float v)
 template <bool CLUSTER, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf B, int cluster_size) {
   constexpr int kResThreads = THREADS, kResPpt = kResCells / THREADS;
+  constexpr int DU = 0, DV = kResPlane, WG = 2 * kResPlane, A12 = 3 * kResPlane, B1 = 4 * kResPlane, B2 = 5 * kResPlane;
   VSTAB_DYNAMIC_SMEM(rs);
   const int pair = blockIdx.x / cluster_size;
   const int crank = blockIdx.x % cluster_size;
   const int w = L.w, h = L.h, half_w = (w + 1) >> 1;
+  const int rstride = half_w + 2;  // cells per plane row: one pad cell on either side
   const int rows_per = (h + cluster_size - 1) / cluster_size;
   const int r0 = min(crank * rows_per, h), r1 = min(r0 + rows_per, h), rows = r1 - r0;
-  const int cs = (rows_per + 2) * half_w;  // cells of one colour, halo rows included
-  float* const s_du = rs;
-  float* const s_dv = rs + 2 * cs;
-  float* const s_wg = rs + 4 * cs;
-  float* const s_a12 = rs + 6 * cs;
-  float* const s_b1 = rs + 8 * cs;
-  float* const s_b2 = rs + 10 * cs;
   const int ncell = rows * half_w;
   const size_t pbase = (size_t)pair * h * w;
   const float* __restrict__ u0 = L.Ux + pbase;
   const float* __restrict__ v0 = L.Uy + pbase;
+  // the five quotient sums live in planes the streaming kernel uses for other things
+  float* const q11 = B.A11;
+  float* const q12 = B.A12;
+  float* const q22 = B.A22;
+  float* const qb1 = B.b1;
+  float* const qb2 = B.b2;
 #define RES_SYNC() do { if (CLUSTER) cluster_barrier(); else __syncthreads(); } while (0)
 
-  // own cells: cell i = tid + 1024 m of the band -> (row, column pair); the same cell in both colours.
-  // packed: bits 0..12 plane index (halo row included), 13..22 image row, 23..31 column pair; -1 = none
-  int own[kResPpt];
+  // own cells: cell i = tid + THREADS m of the band -> (row, column pair); the same cell in both colours.
+  // packed: bits 0..12 index inside a colour (halo row and pad cell included), 13 parity of the image row, 14 / 15 the
+  //         cell is a pixel of the image in colour 0 / 1, 16..22 row of the band, 23..31 column pair
+  unsigned own_s[kResPpt];
 #pragma unroll
   for (int m = 0; m < kResPpt; m++) {
     const int i = threadIdx.x + kResThreads * m;
+    own_s[m] = 0;
     if (i < ncell) {
-      const int ly = i / half_w, j = i - ly * half_w;
-      own[m] = ((ly + 1) * half_w + j) | ((r0 + ly) << 13) | (j << 23);
-    } else {
-      own[m] = -1;
+      const int ly = i / half_w, j = i - ly * half_w, y = r0 + ly;
+      const int live0 = 2 * j + (y & 1) < w, live1 = 2 * j + 1 - (y & 1) < w;
+      own_s[m] = (unsigned)((ly + 1) * rstride + j + 1) | ((y & 1) << 13) | (live0 << 14) | (live1 << 15) | (ly << 16) | ((unsigned)j << 23);
     }
   }
-#define RES_CELL(c, m)                                             \
-  int cell = own[m];                                               \
-  asm volatile("" : "+r"(cell)); /* decode here, not hoisted out of the sweep loop for all sixteen cells at once */ \
-  const int sidx = cell & 8191, y = (cell >> 13) & 1023;           \
-  const int j = (cell >> 23) & 511, q = (y + (c)) & 1, x = 2 * j + q; \
-  const bool live = cell >= 0 && x < w;                            \
-  const int ci = (c) * cs + sidx, oi = (1 - (c)) * cs + sidx;      \
-  const size_t k = (size_t)y * w + x;
 
   // phases without per-cell register state walk the band with a rolled loop (cell -> row / column pair by division)
 #define RES_FOR_CELLS(...)                                              \
@@ -743,20 +747,32 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
     const int ly = i / half_w, j = i - ly * half_w, y = r0 + ly;        \
     const int q = (y + c) & 1, x = 2 * j + q;                           \
     if (x < w) {                                                        \
-      const int sidx = (ly + 1) * half_w + j;                           \
-      const int ci = c * cs + sidx, oi = (1 - c) * cs + sidx;           \
+      const int sidx = (ly + 1) * rstride + j + 1;                      \
+      const int ci = c * kResColour + sidx, oi = (1 - c) * kResColour + sidx; \
       const size_t k = (size_t)y * w + x;                               \
       (void)ci; (void)oi; (void)k;                                      \
       __VA_ARGS__;                                                      \
     }                                                                   \
   }
 
-  for (int i = threadIdx.x; i < 4 * cs; i += kResThreads) rs[i] = 0.f;  // du, dv (halo rows too)
+  for (int i = threadIdx.x; i < 3 * kResPlane; i += kResThreads) rs[i] = 0.f;  // du, dv, weights: pads and halo rows too
   RES_FOR_CELLS(vr_px_warp<false>(L, B, pair, x, y))
   RES_SYNC();
   RES_FOR_CELLS(vr_px_deriv1(L, B, pair, x, y))
   RES_SYNC();
-  RES_FOR_CELLS(vr_px_deriv2(L, B, pair, x, y))
+  RES_FOR_CELLS({
+    vr_px_deriv2(L, B, pair, x, y);
+    const size_t gk = pbase + k;
+    const float zeta2 = 0.1f * 0.1f;
+    const float ixx = B.Ixx[gk], ixy = B.Ixy[gk], iyy = B.Iyy[gk], ixz = B.Ixz[gk], iyz = B.Iyz[gk];
+    const float derivNorm = ixx * ixx + ixy * ixy + zeta2;
+    const float derivNorm2 = iyy * iyy + ixy * ixy + zeta2;
+    q11[gk] = (ixx * ixx / derivNorm + ixy * ixy / derivNorm2);
+    q12[gk] = (ixx * ixy / derivNorm + ixy * iyy / derivNorm2);
+    q22[gk] = (ixy * ixy / derivNorm + iyy * iyy / derivNorm2);
+    qb1[gk] = (ixx * ixz / derivNorm + ixy * iyz / derivNorm2);
+    qb2[gk] = (ixy * ixz / derivNorm + iyy * iyz / derivNorm2);
+  })
 
   float a11r[2][kResPpt], a22r[2][kResPpt];
   for (int it = 0; it < kVrIter; it++) {
@@ -764,18 +780,18 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
     RES_FOR_CELLS({
       const bool has_r = x + 1 < w, has_d = y + 1 < h;
       const size_t kr = has_r ? k + 1 : k, kd = has_d ? k + w : k;
-      const int sr = has_r ? oi + q : ci, sd = has_d ? oi + half_w : ci;
+      const int sr = has_r ? oi + q : ci, sd = has_d ? oi + rstride : ci;
       float tu = u0[k], tv = v0[k], tur = u0[kr], tvr = v0[kr], tud = u0[kd], tvd = v0[kd];
       if (it > 0) {
-        tu = tu + s_du[ci]; tv = tv + s_dv[ci];
-        tur = tur + s_du[sr]; tvr = tvr + s_dv[sr];
-        tud = tud + s_du[sd]; tvd = tvd + s_dv[sd];
+        tu = tu + rs[DU + ci]; tv = tv + rs[DV + ci];
+        tur = tur + rs[DU + sr]; tvr = tvr + rs[DV + sr];
+        tud = tud + rs[DU + sd]; tvd = tvd + rs[DV + sd];
       }
       const float ux = tur - tu, vx = tvr - tv, uy = tud - tu, vy = tvd - tv;
       const float eps2 = kEpsilon * kEpsilon;
       const float wgt = (kAlpha / 2) / sqrtf(ux * ux + vx * vx + uy * uy + vy * vy + eps2);
-      s_wg[ci] = wgt;
-      if (CLUSTER && y == r1 - 1 && r1 < h) st_cluster(&s_wg[c * cs + j], crank + 1, wgt);  // last row -> top halo of the band below
+      rs[WG + ci] = wgt;
+      if (CLUSTER && y == r1 - 1 && r1 < h) st_cluster(&rs[WG + c * kResColour + j + 1], crank + 1, wgt);  // last row -> top halo of the band below
     })
     RES_SYNC();
     // ---- linear system (vr_px_system): A11, A22 stay in registers, A12, b1, b2 in shared memory
@@ -783,12 +799,15 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
     for (int c = 0; c < 2; c++)
 #pragma unroll
       for (int m = 0; m < kResPpt; m++) {
-        RES_CELL(c, m)
-        if (live) {
-          const size_t gk = pbase + k;
+        unsigned cs_ = own_s[m];
+        asm volatile("" : "+r"(cs_));  // decode here, not hoisted out of the iteration loop for all cells at once
+        if ((cs_ >> (14 + c)) & 1) {
+          const int sidx = cs_ & 8191, y = r0 + ((cs_ >> 16) & 127), q = (y + c) & 1, x = 2 * (int)(cs_ >> 23) + q;
+          const int ci = c * kResColour + sidx, oi = (1 - c) * kResColour + sidx;
+          const size_t k = (size_t)y * w + x, gk = pbase + k;
           const float zeta2 = 0.1f * 0.1f, eps2 = kEpsilon * kEpsilon, gamma2 = kGamma / 2, delta2 = kDelta / 2;
           const float ix = B.Ix[gk], iy = B.Iy[gk], iz = B.Iz[gk], ixx = B.Ixx[gk], ixy = B.Ixy[gk], iyy = B.Iyy[gk];
-          const float ixz = B.Ixz[gk], iyz = B.Iyz[gk], dU = s_du[ci], dV = s_dv[ci];
+          const float ixz = B.Ixz[gk], iyz = B.Iyz[gk], dU = rs[DU + ci], dV = rs[DV + ci];
           float derivNorm = ix * ix + iy * iy + zeta2;
           const float Ik1z = iz + ix * dU + iy * dV;
           float weight = (delta2 / sqrtf(Ik1z * Ik1z / derivNorm + eps2)) / derivNorm;
@@ -802,28 +821,28 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
           const float Ik1zx = ixz + ixx * dU + ixy * dV;
           const float Ik1zy = iyz + ixy * dU + iyy * dV;
           weight = gamma2 / sqrtf(Ik1zx * Ik1zx / derivNorm + Ik1zy * Ik1zy / derivNorm2 + eps2);
-          a11 += weight * (ixx * ixx / derivNorm + ixy * ixy / derivNorm2);
-          a12 += weight * (ixx * ixy / derivNorm + ixy * iyy / derivNorm2);
-          a22 += weight * (ixy * ixy / derivNorm + iyy * iyy / derivNorm2);
-          bb1 += -weight * (ixx * ixz / derivNorm + ixy * iyz / derivNorm2);
-          bb2 += -weight * (ixy * ixz / derivNorm + iyy * iyz / derivNorm2);
+          a11 += weight * q11[gk];
+          a12 += weight * q12[gk];
+          a22 += weight * q22[gk];
+          bb1 += -weight * qb1[gk];
+          bb2 += -weight * qb2[gk];
           const bool red = ((x + y) & 1) == 0;
-          const float wc = s_wg[ci];
+          const float wc = rs[WG + ci];
           const bool own_h = x < w - 1, left_h = x > 0;
           float own_ux = 0.f, own_vx = 0.f, left_ux = 0.f, left_vx = 0.f, wl = 0.f;
           if (own_h) { own_ux = wc * (u0[k + 1] - u0[k]); own_vx = wc * (v0[k + 1] - v0[k]); }
-          if (left_h) { wl = s_wg[oi + q - 1]; left_ux = wl * (u0[k] - u0[k - 1]); left_vx = wl * (v0[k] - v0[k - 1]); }
+          if (left_h) { wl = rs[WG + oi + q - 1]; left_ux = wl * (u0[k] - u0[k - 1]); left_vx = wl * (v0[k] - v0[k - 1]); }
           if (red) { ADD_OWN_H(); ADD_LEFT_H(); } else { ADD_LEFT_H(); ADD_OWN_H(); }
           const bool own_v = y < h - 1, up_v = y > 0;
           float own_uy = 0.f, own_vy = 0.f, up_uy = 0.f, up_vy = 0.f, wu = 0.f;
           if (own_v) { own_uy = wc * (u0[k + w] - u0[k]); own_vy = wc * (v0[k + w] - v0[k]); }
-          if (up_v) { wu = s_wg[oi - half_w]; up_uy = wu * (u0[k] - u0[k - w]); up_vy = wu * (v0[k] - v0[k - w]); }
+          if (up_v) { wu = rs[WG + oi - rstride]; up_uy = wu * (u0[k] - u0[k - w]); up_vy = wu * (v0[k] - v0[k - w]); }
           if (red) { ADD_OWN_V(); ADD_UP_V(); } else { ADD_UP_V(); ADD_OWN_V(); }
           a11r[c][m] = a11;
           a22r[c][m] = a22;
-          s_a12[ci] = a12;
-          s_b1[ci] = bb1;
-          s_b2[ci] = bb2;
+          rs[A12 + ci] = a12;
+          rs[B1 + ci] = bb1;
+          rs[B2 + ci] = bb2;
         }
         asm volatile("" ::: "memory");  // one cell at a time: keeps the unrolled cells from piling their loads up in registers
       }
@@ -833,30 +852,35 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
       for (int c = 0; c < 2; c++) {
 #pragma unroll
         for (int m = 0; m < kResPpt; m++) {
-          RES_CELL(c, m)
-          (void)k;
-          if (live) {
-            const bool has_l = x > 0, has_r = x + 1 < w, has_u = y > 0, has_d = y + 1 < h;
-            const float wl = has_l ? s_wg[oi + q - 1] : 0.f, dul = has_l ? s_du[oi + q - 1] : 0.f, dvl = has_l ? s_dv[oi + q - 1] : 0.f;
-            const float dur = has_r ? s_du[oi + q] : 0.f, dvr = has_r ? s_dv[oi + q] : 0.f;
-            const float wu = has_u ? s_wg[oi - half_w] : 0.f, duu = has_u ? s_du[oi - half_w] : 0.f, dvu = has_u ? s_dv[oi - half_w] : 0.f;
-            const float dud = has_d ? s_du[oi + half_w] : 0.f, dvd = has_d ? s_dv[oi + half_w] : 0.f;
-            const float wc = s_wg[ci];
+          unsigned cs_ = own_s[m];
+          asm volatile("" : "+r"(cs_));
+          if ((cs_ >> (14 + c)) & 1) {
+            const int co = c * kResColour, oo = (1 - c) * kResColour;
+            float* const p = rs + (cs_ & 8191);           // the cell; planes and colours are immediates from here
+            const float* const ph = p + (((cs_ >> 13) + c) & 1);  // other colour, same row: left neighbour at ph[-1], right at ph[0]
+            const float* const pu = p - rstride;
+            const float* const pd = p + rstride;
+            const float wl = ph[WG + oo - 1], dul = ph[DU + oo - 1], dvl = ph[DV + oo - 1];
+            const float dur = ph[DU + oo], dvr = ph[DV + oo];
+            const float wu = pu[WG + oo], duu = pu[DU + oo], dvu = pu[DV + oo];
+            const float dud = pd[DU + oo], dvd = pd[DV + oo];
+            const float wc = p[WG + co];
             const float sigmaU = wl * dul + wc * dur + wu * duu + wc * dud;
             const float sigmaV = wl * dvl + wc * dvr + wu * dvu + wc * dvd;
-            float du = s_du[ci], dv = s_dv[ci];
-            du += kOmega * ((sigmaU + s_b1[ci] - dv * s_a12[ci]) / a11r[c][m] - du);
-            dv += kOmega * ((sigmaV + s_b2[ci] - du * s_a12[ci]) / a22r[c][m] - dv);
-            s_du[ci] = du;
-            s_dv[ci] = dv;
+            float du = p[DU + co], dv = p[DV + co];
+            du += kOmega * ((sigmaU + p[B1 + co] - dv * p[A12 + co]) / a11r[c][m] - du);
+            dv += kOmega * ((sigmaV + p[B2 + co] - du * p[A12 + co]) / a22r[c][m] - dv);
+            p[DU + co] = du;
+            p[DV + co] = dv;
             if (CLUSTER) {
+              const int y = r0 + ((cs_ >> 16) & 127), j1 = (int)(cs_ >> 23) + 1;
               if (y == r0 && crank > 0) {  // first row of the band -> bottom halo of the band above
-                st_cluster(&s_du[c * cs + (rows_per + 1) * half_w + j], crank - 1, du);
-                st_cluster(&s_dv[c * cs + (rows_per + 1) * half_w + j], crank - 1, dv);
+                st_cluster(&rs[DU + co + (rows_per + 1) * rstride + j1], crank - 1, du);
+                st_cluster(&rs[DV + co + (rows_per + 1) * rstride + j1], crank - 1, dv);
               }
               if (y == r1 - 1 && r1 < h) {  // last row -> top halo of the band below
-                st_cluster(&s_du[c * cs + j], crank + 1, du);
-                st_cluster(&s_dv[c * cs + j], crank + 1, dv);
+                st_cluster(&rs[DU + co + j1], crank + 1, du);
+                st_cluster(&rs[DV + co + j1], crank + 1, dv);
               }
             }
           }
@@ -868,11 +892,10 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
   }
   // total flow of the level = u0 + du (the update phase of the last iteration)
   RES_FOR_CELLS({
-    L.Ux[pbase + k] = u0[k] + s_du[ci];
-    L.Uy[pbase + k] = v0[k] + s_dv[ci];
+    L.Ux[pbase + k] = u0[k] + rs[DU + ci];
+    L.Uy[pbase + k] = v0[k] + rs[DV + ci];
   })
 #undef RES_FOR_CELLS
-#undef RES_CELL
 #undef RES_SYNC
 }
 
@@ -1107,13 +1130,11 @@ int vr_cluster_size(int px) {
 int vr_resident_cluster(const vstab_handle* hnd, int h, int w) {
   const char* e = getenv("VSTAB_VR_RESIDENT");
   const int mode = e ? atoi(e) : VSTAB_VR_RESIDENT_DEFAULT;
-  if (mode <= 0 || h > 1023 || w > 1022) return 0;
+  if (mode <= 0 || h > 1023 || w > 1022 || kResSmemFloats * sizeof(float) > (size_t)hnd->max_smem_optin) return 0;
   const int half_w = (w + 1) / 2;
   for (int cl = 1; cl <= 8; cl <<= 1) {
     const int rows_per = (h + cl - 1) / cl;
-    const size_t bytes = (size_t)12 * (rows_per + 2) * half_w * sizeof(float);
-    if (rows_per * half_w <= kResCells && (rows_per + 2) * half_w <= 8191 && bytes <= (size_t)hnd->max_smem_optin)
-      return (cl == 1 || mode >= 2) ? cl : 0;
+    if (rows_per * half_w <= kResCells && (rows_per + 2) * (half_w + 2) <= kResColour) return (cl == 1 || mode >= 2) ? cl : 0;
   }
   return 0;
 }
@@ -1157,8 +1178,7 @@ int dis_level(vstab_handle* hnd, const Level& Lc, const Level* finer, const VrBu
       vr_fused_kernel<true><<<P, 1024, onchip_bytes, st>>>(Lc, B, 1);
       VSTAB_LAUNCH_CHECK(hnd, "vr_fused_kernel");
     } else if (const int rcl = vr_resident_cluster(hnd, Lc.h, Lc.w)) {
-      const int rows_per = (Lc.h + rcl - 1) / rcl, half_w = (Lc.w + 1) / 2;
-      const size_t bytes = (size_t)12 * (rows_per + 2) * half_w * sizeof(float);
+      const size_t bytes = (size_t)kResSmemFloats * sizeof(float);
       const int threads = env_int("VSTAB_VR_RESIDENT_THREADS", VSTAB_VR_RESIDENT_THREADS_DEFAULT) == 512 ? 512 : 1024;
       void (*kernel)(Level, VrBuf, int) =
           rcl == 1 ? (threads == 512 ? vr_resident_kernel<false, 512> : vr_resident_kernel<false, 1024>)
