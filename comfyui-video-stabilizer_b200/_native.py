@@ -98,6 +98,8 @@ def load_library() -> C.CDLL:
         lib.vstab_host_framing.restype = i32
         lib.vstab_host_shift.argtypes = [vp, i32, C.c_float, C.c_float, vp]
         lib.vstab_host_shift.restype = i32
+        lib.vstab_host_target.argtypes = [vp, i32, i32, i32, C.c_double, i32, vp, vp]
+        lib.vstab_host_target.restype = i32
         lib.vstab_working_size.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32)]
         lib.vstab_working_size.restype = i32
         lib.vstab_gray_working.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp]
@@ -194,6 +196,19 @@ def host_framing(diffs, mode: str, width: int, height: int):
     if rc != 0:
         raise VstabNativeError(f"vstab_host_framing failed: {rc}")
     return apply, mins, maxs, box
+
+
+def host_target(path, window: int, strength: float, camera_lock: bool):
+    """vstab_host_target: (target, diffs) float64 arrays shaped like path, or None for windows numpy sums through BLAS."""
+    import numpy as np
+
+    lib = load_library()
+    path = np.ascontiguousarray(path, dtype=np.float64)
+    target = np.empty_like(path)
+    diffs = np.empty_like(path)
+    rc = lib.vstab_host_target(path.ctypes.data, int(path.shape[0]), int(path.shape[1]), int(window), float(strength), int(bool(camera_lock)),
+                               target.ctypes.data, diffs.ctypes.data)
+    return (target, diffs) if rc == 0 else None
 
 
 def host_shift(apply, off_x, off_y):

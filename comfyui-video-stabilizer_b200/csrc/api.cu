@@ -49,6 +49,8 @@ extern "C" void vstab_destroy(vstab_handle* h) {
     cudaEventDestroy(h->stagger_event[i]);
   }
   if (h->fork_event) cudaEventDestroy(h->fork_event);
+  for (int i = 0; i < h->n_level_events; ++i) cudaEventDestroy(h->level_event[i]);
+  if (h->pyramid_event) cudaEventDestroy(h->pyramid_event);
   for (int i = 0; i < h->n_area_cache; ++i)
     if (h->area_cache[i].dev) cudaFree(h->area_cache[i].dev);
   free(h);

@@ -14,6 +14,8 @@
 // equations reduced with warp shuffles.  Compiled with -fmad=false; fmaf() only where cv2 fuses.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <float.h>
 #include <math.h>
 
@@ -585,7 +587,15 @@ __global__ void __launch_bounds__(256) lk_track_kernel(LkPyr P, int n_pairs, int
 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
+int gftt_lk_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width, int max_corners,
+                float* prev_dev, float* curr_dev, int32_t* detected_dev, cudaStream_t st);
+
 }  // namespace
+
+// Pairs per pass: corner scratch, LK pyramids, Scharr derivatives and padded copies are sized for one pass
+// (~26 MB per 960x540 frame), so the workspace stays bounded however long the clip is -- like dis_run's chunks.
+// Frame p0 + kPairsPerPass is the last frame of one pass and the first of the next; its pyramid is built twice.
+static const int kPairsPerPass = 256;
 
 extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width, int max_corners,
                              float* prev_dev, float* curr_dev, int32_t* detected_dev, void* stream) {
@@ -595,6 +605,22 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
   if (n_frames < 2) return VSTAB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   VSTAB_ENTER(hnd);
+  const size_t npx = (size_t)height * width;
+  int per_pass = kPairsPerPass;
+  if (const char* e = getenv("VSTAB_LK_PAIRS_PER_PASS")) per_pass = atoi(e) > 0 ? atoi(e) : kPairsPerPass;  // tests: several passes on a short clip
+  for (int p0 = 0; p0 < n_frames - 1; p0 += per_pass) {
+    const int pairs = (n_frames - 1 - p0) < per_pass ? (n_frames - 1 - p0) : per_pass;
+    const int rc = gftt_lk_run(hnd, gray_dev + p0 * npx, pairs + 1, height, width, max_corners, prev_dev + (size_t)p0 * max_corners * 2,
+                               curr_dev + (size_t)p0 * max_corners * 2, detected_dev + p0, st);
+    if (rc != VSTAB_OK) return rc;
+  }
+  return VSTAB_OK;
+}
+
+namespace {
+
+int gftt_lk_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width, int max_corners,
+                float* prev_dev, float* curr_dev, int32_t* detected_dev, cudaStream_t st) {
   const int h = height, w = width;
   // frames per pass of the corner detector: every running-sum / selection kernel is a chain per row, column or
   // frame, so a pass costs its chain latency whatever the frame count (20.7 MB of scratch per 960x540 frame)
@@ -703,3 +729,5 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
   VSTAB_LAUNCH_CHECK(hnd, "lk_track_kernel");
   return VSTAB_OK;
 }
+
+}  // namespace

@@ -11,7 +11,8 @@
 #include "area.cuh"
 
 #define VSTAB_AREA_CACHE 32
-#define VSTAB_MAX_AUX_STREAMS 3
+#define VSTAB_MAX_AUX_STREAMS 4
+#define VSTAB_MAX_LEVEL_EVENTS 8
 struct vstab_area_cache_entry {
   int ssize, dsize;
   void* dev;
@@ -43,6 +44,10 @@ struct vstab_handle {
   cudaEvent_t stagger_event[VSTAB_MAX_AUX_STREAMS];
   cudaEvent_t fork_event;
   int n_aux;
+  // DIS: per-level "gradients and structure tensors are ready" events of the preparation stream, created on first use
+  cudaEvent_t level_event[VSTAB_MAX_LEVEL_EVENTS];
+  cudaEvent_t pyramid_event;
+  int n_level_events;
 };
 
 extern char g_vstab_err[512];

@@ -1288,17 +1288,40 @@ int dis_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height
     }
 
     // ---- per-frame pyramid, gradients, bordered copies, structure tensors ----
+    // The pyramid is a chain of INTER_AREA halvings on the caller's stream.  Gradients, bordered copies and structure
+    // tensors of a level are needed when the coarse-to-fine chain reaches that level -- the finest one, which is most of
+    // this work (~0.2 of 0.3 ms at 120 pairs), more than a millisecond after the coarsest -- so they run on a
+    // preparation stream, coarsest level first, under the (latency-bound) coarse levels of the pair groups; a group
+    // waits for a level's event right before it searches that level.  VSTAB_DIS_PREP_ASYNC=0: everything on one stream.
     for (int i = finest; i <= coarsest; i++) {
       if (i == finest) rc = vstab_area_u8(hnd, gray, F, height, width, L[i].I, L[i].h, L[i].w, st);
       else rc = vstab_area_u8(hnd, L[i - 1].I, F, L[i - 1].h, L[i - 1].w, L[i].I, L[i].h, L[i].w, st);
       if (rc != VSTAB_OK) return rc;
+    }
+    const char* prep_env = getenv("VSTAB_DIS_PREP_ASYNC");
+    const bool prep_async = !(prep_env && atoi(prep_env) == 0) && coarsest - finest + 1 <= VSTAB_MAX_LEVEL_EVENTS;
+    cudaStream_t prep = st;
+    if (prep_async) {
+      rc = vstab_aux_streams(hnd, VSTAB_MAX_AUX_STREAMS);
+      if (rc != VSTAB_OK) return rc;
+      if (!hnd->pyramid_event) VSTAB_CUDA(hnd, cudaEventCreateWithFlags(&hnd->pyramid_event, cudaEventDisableTiming));
+      while (hnd->n_level_events < VSTAB_MAX_LEVEL_EVENTS) {
+        VSTAB_CUDA(hnd, cudaEventCreateWithFlags(&hnd->level_event[hnd->n_level_events], cudaEventDisableTiming));
+        hnd->n_level_events++;
+      }
+      prep = hnd->aux_stream[VSTAB_MAX_AUX_STREAMS - 1];  // the pair groups use aux_stream[0 .. G - 2]
+      VSTAB_CUDA(hnd, cudaEventRecord(hnd->pyramid_event, st));
+      VSTAB_CUDA(hnd, cudaStreamWaitEvent(prep, hnd->pyramid_event, 0));
+    }
+    for (int i = coarsest; i >= finest; i--) {
       dim3 ge(vstab_ceil_div(L[i].w + 2 * kBorder, 32), vstab_ceil_div(L[i].h + 2 * kBorder, 8), F);
-      grad_border_kernel<<<ge, 256, 0, st>>>(L[i].I, L[i].h, L[i].w, L[i].Ix, L[i].Iy, L[i].Iext);
+      grad_border_kernel<<<ge, 256, 0, prep>>>(L[i].I, L[i].h, L[i].w, L[i].Ix, L[i].Iy, L[i].Iext);
       VSTAB_LAUNCH_CHECK(hnd, "grad_border_kernel");
-      tensor_rows_kernel<<<vstab_ceil_div(F * L[i].h, 128), 128, 0, st>>>(L[i].Ix, L[i].Iy, F, L[i].h, L[i].w, L[i].ws, aux);
+      tensor_rows_kernel<<<vstab_ceil_div(F * L[i].h, 128), 128, 0, prep>>>(L[i].Ix, L[i].Iy, F, L[i].h, L[i].w, L[i].ws, aux);
       VSTAB_LAUNCH_CHECK(hnd, "tensor_rows_kernel");
-      tensor_cols_kernel<<<vstab_ceil_div(F * 5 * L[i].ws, 128), 128, 0, st>>>(aux, F, L[i].h, L[i].ws, L[i].hs, L[i].T);
+      tensor_cols_kernel<<<vstab_ceil_div(F * 5 * L[i].ws, 128), 128, 0, prep>>>(aux, F, L[i].h, L[i].ws, L[i].hs, L[i].T);
       VSTAB_LAUNCH_CHECK(hnd, "tensor_cols_kernel");
+      if (prep_async) VSTAB_CUDA(hnd, cudaEventRecord(hnd->level_event[i - finest], prep));
     }
 
     // ---- coarse-to-fine, pair groups on their own streams ----
@@ -1309,7 +1332,7 @@ int dis_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height
       hnd->launches += 2;
     }
     int G = env_int("VSTAB_DIS_GROUPS", VSTAB_DIS_GROUPS_DEFAULT);
-    if (G > VSTAB_MAX_AUX_STREAMS + 1) G = VSTAB_MAX_AUX_STREAMS + 1;
+    if (G > VSTAB_MAX_AUX_STREAMS) G = VSTAB_MAX_AUX_STREAMS;  // the last helper stream prepares the levels
     if (G > P / 16) G = P / 16 > 0 ? P / 16 : 1;  // small batches: one chain
     cudaStream_t gs[VSTAB_MAX_AUX_STREAMS + 1];
     gs[0] = st;
@@ -1341,6 +1364,7 @@ int dis_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height
         }
         cudaEvent_t after_search = nullptr;
         if (stagger >= 0 && g + 1 < G && i == (finest + stagger < coarsest ? finest + stagger : coarsest)) after_search = hnd->stagger_event[g];
+        if (prep_async) VSTAB_CUDA(hnd, cudaStreamWaitEvent(gs[g], hnd->level_event[i - finest], 0));
         rc = dis_level(hnd, Lg, i > finest ? &finer_g : nullptr, Bg, b - a, gs[g], after_search);
         if (rc != VSTAB_OK) return rc;
         if (after_search) VSTAB_CUDA(hnd, cudaStreamWaitEvent(gs[g + 1], after_search, 0));

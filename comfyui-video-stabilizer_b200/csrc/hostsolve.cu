@@ -196,3 +196,45 @@ extern "C" int vstab_host_shift(const float* apply, int n_frames, float off_x, f
   }
   return VSTAB_OK;
 }
+
+// path -> target path and per-frame deltas (nodes/video_stabilizer_flow.py:351-374): camera lock = zero target, otherwise
+// path + strength * (box_filter(path) - path) with the edge-padded odd box filter of stabilizer_utils.py:361-383.
+// numpy evaluates that filter with np.convolve: for kernels of up to 11 taps its own scalar loop, which adds the products
+// in tap order starting from +0 (restated here, and checked against np.convolve once per process and window by
+// hostmath.native_target); longer kernels go through the BLAS dot product whose summation order belongs to the CPU it
+// runs on -- VSTAB_ERR_UNSUPPORTED, and the caller uses numpy.
+extern "C" int vstab_host_target(const double* path, int n_frames, int n_params, int window, double strength, int camera_lock,
+                                 double* target, double* diffs) {
+  if (!path || !target || !diffs || n_frames <= 0 || n_params <= 0 || n_params > 8 || window < 0) return VSTAB_ERR_INVALID;
+  const int K = n_params;
+  if (camera_lock) {
+    for (int i = 0; i < n_frames * K; ++i) {
+      target[i] = 0.0;
+      diffs[i] = target[i] - path[i];
+    }
+    return VSTAB_OK;
+  }
+  const bool filtered = window > 0 && n_frames > 2;  // smooth <= 0 or a clip of one or two frames: the filter is the identity
+  if (filtered && (window > 11 || (window & 1) == 0)) return VSTAB_ERR_UNSUPPORTED;
+  const int half = window / 2;
+  const double tap = 1.0 / (double)window;
+  for (int i = 0; i < n_frames; ++i)
+    for (int k = 0; k < K; ++k) {
+      double sm = path[(size_t)i * K + k];
+      if (filtered) {
+        double acc = 0.0;
+        for (int t = 0; t < window; ++t) {
+          int src = i + t - half;
+          src = src < 0 ? 0 : (src >= n_frames ? n_frames - 1 : src);
+          acc += path[(size_t)src * K + k] * tap;
+        }
+        sm = acc;
+      }
+      const double p = path[(size_t)i * K + k];
+      const double d = sm - p;
+      const double scaled = strength * d;
+      target[(size_t)i * K + k] = p + scaled;
+      diffs[(size_t)i * K + k] = target[(size_t)i * K + k] - p;
+    }
+  return VSTAB_OK;
+}

@@ -34,6 +34,17 @@ MODE_LADDER = {
 }
 
 
+class _GcPause:
+    """Handle of a gc_paused() block: collect_young() runs the generation-0 pass the block has been holding back."""
+
+    def __init__(self, active: bool):
+        self.active = active
+
+    def collect_young(self) -> None:
+        if self.active:
+            gc.collect(0)
+
+
 @contextlib.contextmanager
 def gc_paused():
     """Cyclic GC off while a call builds its result.  `meta` is tens of thousands of acyclic lists and
@@ -41,16 +52,19 @@ def gc_paused():
     containers, promotes the survivors and soon a full collection over every object of the process
     (tens of ms with torch loaded) -- measured 8 ms median / 125 ms worst per call for a 968-frame meta
     against 4 ms with the collector paused.  Reference counting still frees everything as usual.
-    A host application that wants its collector left alone sets VSTAB_GC_PAUSE=0."""
+    The young objects of the call still have to be looked at once: switching the collector back on makes the very
+    next allocation run that generation-0 pass (0.15 ms for a 121-frame meta) -- after the GPU has finished, on the
+    critical path.  The driver therefore calls collect_young() on the yielded handle when the meta tree is built and
+    the resampler is still running.  A host application that wants its collector left alone sets VSTAB_GC_PAUSE=0."""
     import os
 
     if os.environ.get("VSTAB_GC_PAUSE", "1") == "0":
-        yield
+        yield _GcPause(False)
         return
     was_enabled = gc.isenabled()
     gc.disable()
     try:
-        yield
+        yield _GcPause(was_enabled)
     finally:
         if was_enabled:
             gc.enable()
@@ -225,6 +239,41 @@ def native_framing(diffs: np.ndarray, mode: str, width: int, height: int):
         return None
 
 
+_TARGET_WINDOW_OK: Dict[int, bool] = {}
+
+
+def numpy_target(path: np.ndarray, strength: float, smooth: float, fps: float, camera_lock: bool):
+    """(target_path, diffs) the way the reference forms them (flow.py:351-374), in numpy."""
+    target = np.zeros_like(path) if camera_lock else path + strength * (smooth_path(path, smooth, fps) - path)
+    return target, target - path
+
+
+def native_target(path: np.ndarray, strength: float, smooth: float, fps: float, camera_lock: bool):
+    """numpy_target through libvstab's host helper (vstab_host_target) when that is known to produce numpy's bits: the box
+    filter is np.convolve, whose summation order is numpy's own loop up to 11 taps and the BLAS's beyond.  The first
+    call with a given window compares the helper with numpy on a test path; a window that disagrees (another numpy
+    build) stays on numpy for the rest of the process.  None = use numpy_target."""
+    try:
+        from . import _native
+
+        smooth_c = clip01(smooth)
+        window = 0 if (camera_lock or smooth_c <= 0.0 or len(path) <= 2) else smoothing_window(smooth_c, fps)
+        if window > 11:
+            return None
+        ok = True if window == 0 else _TARGET_WINDOW_OK.get(window)  # no filter: element-wise operations only
+        if ok is None:
+            probe = np.cumsum(np.random.default_rng(window).normal(0.0, 3.0, (40, 4)), axis=0)
+            want = numpy_target(probe, 0.7, smooth, fps, False)
+            got = _native.host_target(probe, window, 0.7, False)
+            ok = got is not None and got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes()
+            _TARGET_WINDOW_OK[window] = ok
+        if not ok:
+            return None
+        return _native.host_target(path, window, strength, camera_lock)
+    except (OSError, RuntimeError, AttributeError):  # library not built (host-only checkouts)
+        return None
+
+
 def translate_matrices(matrices: np.ndarray, off_x: float, off_y: float, affine: bool = False) -> np.ndarray:
     """[[1, 0, off_x], [0, 1, off_y], [0, 0, 1]] (float32) @ m for every m: the recentring / expand shift of the framing
     modes.  Affine stacks go through vstab_host_shift (one inexact addition per element, so independent of the BLAS);
@@ -240,6 +289,12 @@ def translate_matrices(matrices: np.ndarray, off_x: float, off_y: float, affine:
             pass
     shift = np.array([[1.0, 0.0, off_x], [0.0, 1.0, off_y], [0.0, 0.0, 1.0]], dtype=np.float32)
     return left_multiply(shift, matrices)
+
+
+def clip01(value) -> float:
+    """float(np.clip(value, 0.0, 1.0)) without the 5 us of a numpy call on a scalar (NaN stays NaN either way)."""
+    value = float(value)
+    return min(max(value, 0.0), 1.0)
 
 
 def smoothing_window(smooth: float, fps: float) -> int:

@@ -340,16 +340,16 @@ def stabilize_frames(
 ) -> StabilizationResult:
     nvtx = _Nvtx()
     try:
-        with hm.gc_paused():
+        with hm.gc_paused() as pause:
             return _stabilize_frames(context, framing_mode, transform_mode, camera_lock, strength, smooth, keep_fov, padding_rgb,
                                      frame_rate, estimator=estimator, flavour=flavour, progress_bar=progress_bar,
-                                     interrupt_check=interrupt_check, output=output, shard=shard, nvtx=nvtx)
+                                     interrupt_check=interrupt_check, output=output, shard=shard, nvtx=nvtx, gc_pause=pause)
     finally:
         nvtx.phase(None)
 
 
 def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, strength, smooth, keep_fov, padding_rgb, frame_rate, *,
-                      estimator, flavour, progress_bar, interrupt_check, output, shard, nvtx) -> StabilizationResult:
+                      estimator, flavour, progress_bar, interrupt_check, output, shard, nvtx, gc_pause=None) -> StabilizationResult:
     is_flow = flavour == "flow"
     total_frames = len(context)
     width, height = context.width, context.height
@@ -436,17 +436,15 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
     progress.advance(estimation_steps)
     check()
 
-    strength = float(np.clip(strength, 0.0, 1.0))
-    smooth = float(np.clip(smooth, 0.0, 1.0))
+    strength = hm.clip01(strength)
+    smooth = hm.clip01(smooth)
     if camera_lock:
         smooth = max(smooth, 0.85)
-        target_path = np.zeros_like(path)
-    else:
-        target_path = path + strength * (hm.smooth_path(path, smooth, fps_effective) - path)
-    diffs = target_path - path
+    solved = hm.native_target(path, strength, smooth, fps_effective, camera_lock) if use_native else None
+    target_path, diffs = solved if solved is not None else hm.numpy_target(path, strength, smooth, fps_effective, camera_lock)
     delta_full = diffs
 
-    keep_fov_clamped = float(np.clip(keep_fov, 0.0, 1.0))
+    keep_fov_clamped = hm.clip01(keep_fov)
     keep_fov_applied = framing_mode == "crop" and keep_fov_clamped > 1e-6
     stabilization_scale = 1.0
 
@@ -576,6 +574,8 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
         path[m_lo:m_hi].tolist(), target_path[m_lo:m_hi].tolist(), effective_target_path[m_lo:m_hi].tolist()
     )
 
+    if gc_pause is not None:
+        gc_pause.collect_young()  # the meta tree's generation-0 pass, while the resampler is still running
     t0 = _mark("meta build (overlaps the warp)", t0)
     nvtx.phase("finish")
     frames_out, masks_out, pad_counts = pending()
@@ -584,8 +584,9 @@ def _stabilize_frames(context, framing_mode, transform_mode, camera_lock, streng
         pad_counts = shard.unpack_pad_counts(pad_counts) if pad_gather is not None else shard.gather_pad_counts(pad_counts)
         t0 = _mark("all-gather pad counts", t0)
     pixels = int(output_size[0]) * int(output_size[1])
-    padded_ratios = hm.padded_fractions(pad_counts, pixels)
-    framing_meta["padding_detected"] = bool(np.any(np.asarray(pad_counts) > 0))
+    pad_counts = np.asarray(pad_counts)
+    padded_ratios = (pad_counts.astype(np.float32) / np.float32(pixels)).astype(np.float64)  # hm.padded_fractions as an array
+    framing_meta["padding_detected"] = bool(pad_counts.max(initial=0) > 0)
     progress.advance(total_frames)
     check()
 

@@ -210,6 +210,11 @@ VSTAB_API int vstab_host_trajectory(const double* raw, const int32_t* detected, 
 VSTAB_API int vstab_host_framing(const double* diffs, int n_frames, int mode, int width, int height, float* apply,
                                  double* mins, double* maxs, double* box);
 VSTAB_API int vstab_host_shift(const float* apply, int n_frames, float off_x, float off_y, float* out);
+/* vstab_host_target: flow.py:351-374 with the box filter of stabilizer_utils.py:361-383: path [n_frames][n_params] ->
+ * target = path + strength * (filter(path) - path) (zeros under camera lock) and diffs = target - path.  window = 0: no
+ * filter; windows of more than 11 taps return VSTAB_ERR_UNSUPPORTED (numpy sums those through the BLAS of the machine). */
+VSTAB_API int vstab_host_target(const double* path, int n_frames, int n_params, int window, double strength, int camera_lock,
+                                double* target, double* diffs);
 
 /* ---- K3 + K4 : DIS dense optical flow, batched over frame pairs ------------------------- */
 

@@ -65,3 +65,22 @@ def test_classic_matches_reference_golden(case):
     f, y, x, hh, ww = gold["patch0_at"]
     assert float(np.abs(res.frames[f, y:y + hh, x:x + ww] - gold["patch0"]).max()) <= 1e-3
     assert tuple(res.frames.shape) == tuple(gold["shape"])
+
+
+def test_long_clips_are_tracked_in_passes(handle, monkeypatch):
+    """vstab_gftt_lk works through a clip in passes of 256 pairs (bounded workspace); the frame shared by two passes gets
+    its pyramid twice.  With 4 pairs per pass on a 14-frame clip: same corners, tracks and counts as one pass."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, (96 + 40, 160 + 40), dtype=np.uint8)
+    base = np.asarray(torch.nn.functional.avg_pool2d(torch.from_numpy(base.astype(np.float32))[None, None], 3, 1, 1)[0, 0]).astype(np.uint8)
+    frames = np.stack([base[20 + (i * 3) % 7: 116 + (i * 3) % 7, 20 + (i * 5) % 9: 180 + (i * 5) % 9] for i in range(14)])
+    gray = torch.from_numpy(np.ascontiguousarray(frames)).cuda()
+    monkeypatch.delenv("VSTAB_LK_PAIRS_PER_PASS", raising=False)
+    want = [t.cpu().numpy() for t in handle.gftt_lk(gray, max_corners=200)]
+    monkeypatch.setenv("VSTAB_LK_PAIRS_PER_PASS", "4")
+    got = [t.cpu().numpy() for t in handle.gftt_lk(gray, max_corners=200)]
+    assert want[2].min() >= 12  # a real test: corners were found in every frame
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b, equal_nan=True)

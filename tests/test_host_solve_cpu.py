@@ -81,6 +81,33 @@ def test_trajectory_and_framing_helpers_equal_numpy(mode):
         assert hm.translate_matrices(apply, ox, oy, affine=affine).tobytes() == hm.left_multiply(shift, want).tobytes()
 
 
+def test_target_path_helper_equals_numpy():
+    """vstab_host_target (box filter in numpy's tap order for windows of up to 11 taps, strength blend, camera lock) against
+    hostmath.numpy_target = np.convolve; longer windows are left to numpy (their summation order is the BLAS's)."""
+    from vstab_b200 import hostmath as hm
+
+    rng = np.random.default_rng(3)
+    through_helper = 0
+    for trial in range(1500):
+        n, k = int(rng.integers(1, 300)), (2, 4, 8)[trial % 3]
+        path = np.cumsum(rng.normal(0, 5, (n, k)), axis=0)
+        path[0] = 0
+        strength, smooth = float(rng.random()), float(np.clip(rng.random() * 1.2 - 0.1, 0, 1))
+        fps, lock = float(rng.choice([1, 8, 12, 16, 24, 30, 60])), trial % 7 == 0
+        if lock:
+            smooth = max(smooth, 0.85)
+        want = hm.numpy_target(path, strength, smooth, fps, lock)
+        got = hm.native_target(path, strength, smooth, fps, lock)
+        window = hm.smoothing_window(smooth, fps)
+        if got is None:
+            assert window > 11 and not lock and smooth > 0 and n > 2
+            continue
+        through_helper += 1
+        assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes(), (trial, n, k, smooth, fps)
+    assert through_helper > 500
+    assert all(hm._TARGET_WINDOW_OK.values())  # this numpy sums short kernels in tap order; if not, the helper steps aside
+
+
 def test_fallback_pairs_are_left_to_the_ladder():
     from vstab_b200 import hostmath as hm, stabilizer_core as core
 
