@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .stabilizer_core import DeviceCandidates, PairCandidates
+from .stabilizer_core import DeviceCandidates, HostWords, PairCandidates
 
 TABLE_COLS = 43
 META_OWN_RANGE, META_EVERY_RANK = -2, -1
@@ -129,7 +129,7 @@ class FrameShard:
         host = recv.cpu().numpy()
         return np.concatenate([host[r, : counts[r]] for r in range(self.world)], axis=0)
 
-    def _gather_device_table(self, local: DeviceCandidates) -> PairCandidates:
+    def _gather_device_table(self, local: DeviceCandidates) -> "HostWords":
         """ONE all-gather (NCCL, device to device) of the fit kernels' output plus the few words every rank must agree
         on, then ONE blocking copy of the gathered buffer (~300 B per pair) to the host."""
         counts = self.pair_counts()
@@ -156,7 +156,8 @@ class FrameShard:
         detected = None
         if host[:, cap * 36 + 1].max() > 0:
             detected = np.rint(np.concatenate([host[r, cap * 36 + 2 : cap * 36 + 2 + counts[r]] for r in range(self.world)])).astype(np.int64)
-        return PairCandidates.from_raw(table, min_points, detected)
+        # the words as they are: the trajectory helper reads them directly, the columns are decoded behind the resampler launch
+        return HostWords(table, min_points, detected)
 
     def device_pad_gather(self):
         """fused_warp hook (pad_transform): all-gather the per-frame padded-pixel counts device to device on the
