@@ -715,6 +715,7 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
   const int r0 = min(crank * rows_per, h), r1 = min(r0 + rows_per, h), rows = r1 - r0;
   const int ncell = rows * half_w;
   const size_t pbase = (size_t)pair * h * w;
+  const unsigned pbase32 = (unsigned)pbase;  // 32-bit indices: one IMAD.WIDE per plane access (a chunk of 256 pairs of a 960x540 level is 1.3e8 px)
   const float* __restrict__ u0 = L.Ux + pbase;
   const float* __restrict__ v0 = L.Uy + pbase;
   // the five quotient sums live in planes the streaming kernel uses for other things
@@ -727,7 +728,8 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
 
   // own cells: cell i = tid + THREADS m of the band -> (row, column pair); the same cell in both colours.
   // packed: bits 0..12 index inside a colour (halo row and pad cell included), 13 parity of the image row, 14 / 15 the
-  //         cell is a pixel of the image in colour 0 / 1, 16..22 row of the band, 23..31 column pair
+  //         cell is a pixel of the image in colour 0 / 1, 16..22 row of the band, 23 / 24 the row is the first / last of
+  //         the band and has a band above / below it (its values are pushed into that band's halo row)
   unsigned own_s[kResPpt];
 #pragma unroll
   for (int m = 0; m < kResPpt; m++) {
@@ -736,9 +738,12 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
     if (i < ncell) {
       const int ly = i / half_w, j = i - ly * half_w, y = r0 + ly;
       const int live0 = 2 * j + (y & 1) < w, live1 = 2 * j + 1 - (y & 1) < w;
-      own_s[m] = (unsigned)((ly + 1) * rstride + j + 1) | ((y & 1) << 13) | (live0 << 14) | (live1 << 15) | (ly << 16) | ((unsigned)j << 23);
+      const int first = CLUSTER && ly == 0 && crank > 0, last = CLUSTER && ly == rows - 1 && r1 < h;
+      own_s[m] = (unsigned)((ly + 1) * rstride + j + 1) | ((y & 1) << 13) | (live0 << 14) | (live1 << 15) | (ly << 16) | (first << 23) | (last << 24);
     }
   }
+  // column pair of a cell from its plane index and band row
+#define RES_J(cs_, ly_) ((int)((cs_) & 8191) - ((ly_) + 1) * rstride - 1)
 
   // phases without per-cell register state walk the band with a rolled loop (cell -> row / column pair by division)
 #define RES_FOR_CELLS(...)                                              \
@@ -749,7 +754,7 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
     if (x < w) {                                                        \
       const int sidx = (ly + 1) * rstride + j + 1;                      \
       const int ci = c * kResColour + sidx, oi = (1 - c) * kResColour + sidx; \
-      const size_t k = (size_t)y * w + x;                               \
+      const unsigned k = (unsigned)(y * w + x);                         \
       (void)ci; (void)oi; (void)k;                                      \
       __VA_ARGS__;                                                      \
     }                                                                   \
@@ -762,7 +767,7 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
   RES_SYNC();
   RES_FOR_CELLS({
     vr_px_deriv2(L, B, pair, x, y);
-    const size_t gk = pbase + k;
+    const unsigned gk = pbase32 + k;
     const float zeta2 = 0.1f * 0.1f;
     const float ixx = B.Ixx[gk], ixy = B.Ixy[gk], iyy = B.Iyy[gk], ixz = B.Ixz[gk], iyz = B.Iyz[gk];
     const float derivNorm = ixx * ixx + ixy * ixy + zeta2;
@@ -777,22 +782,33 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
   float a11r[2][kResPpt], a22r[2][kResPpt];
   for (int it = 0; it < kVrIter; it++) {
     // ---- smoothness weights (vr_px_weight) from tu = u0 + du, tv = v0 + dv of the cell, its right and its lower neighbour
-    RES_FOR_CELLS({
-      const bool has_r = x + 1 < w, has_d = y + 1 < h;
-      const size_t kr = has_r ? k + 1 : k, kd = has_d ? k + w : k;
-      const int sr = has_r ? oi + q : ci, sd = has_d ? oi + rstride : ci;
-      float tu = u0[k], tv = v0[k], tur = u0[kr], tvr = v0[kr], tud = u0[kd], tvd = v0[kd];
-      if (it > 0) {
-        tu = tu + rs[DU + ci]; tv = tv + rs[DV + ci];
-        tur = tur + rs[DU + sr]; tvr = tvr + rs[DV + sr];
-        tud = tud + rs[DU + sd]; tvd = tvd + rs[DV + sd];
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+      for (int m = 0; m < kResPpt; m++) {
+        unsigned cs_ = own_s[m];
+        asm volatile("" : "+r"(cs_));
+        if ((cs_ >> (14 + c)) & 1) {
+          const int sidx = cs_ & 8191, ly = (cs_ >> 16) & 127, y = r0 + ly, j = RES_J(cs_, ly), q = (y + c) & 1, x = 2 * j + q;
+          const int ci = c * kResColour + sidx, oi = (1 - c) * kResColour + sidx;
+          const unsigned k = (unsigned)(y * w + x);
+          const bool has_r = x + 1 < w, has_d = y + 1 < h;
+          const unsigned kr = has_r ? k + 1 : k, kd = has_d ? k + w : k;
+          const int sr = has_r ? oi + q : ci, sd = has_d ? oi + rstride : ci;
+          float tu = u0[k], tv = v0[k], tur = u0[kr], tvr = v0[kr], tud = u0[kd], tvd = v0[kd];
+          if (it > 0) {
+            tu = tu + rs[DU + ci]; tv = tv + rs[DV + ci];
+            tur = tur + rs[DU + sr]; tvr = tvr + rs[DV + sr];
+            tud = tud + rs[DU + sd]; tvd = tvd + rs[DV + sd];
+          }
+          const float ux = tur - tu, vx = tvr - tv, uy = tud - tu, vy = tvd - tv;
+          const float eps2 = kEpsilon * kEpsilon;
+          const float wgt = (kAlpha / 2) / sqrtf(ux * ux + vx * vx + uy * uy + vy * vy + eps2);
+          rs[WG + ci] = wgt;
+          if (CLUSTER && (cs_ & (1u << 24))) st_cluster(&rs[WG + c * kResColour + j + 1], crank + 1, wgt);  // last row -> top halo of the band below
+        }
+        asm volatile("" ::: "memory");
       }
-      const float ux = tur - tu, vx = tvr - tv, uy = tud - tu, vy = tvd - tv;
-      const float eps2 = kEpsilon * kEpsilon;
-      const float wgt = (kAlpha / 2) / sqrtf(ux * ux + vx * vx + uy * uy + vy * vy + eps2);
-      rs[WG + ci] = wgt;
-      if (CLUSTER && y == r1 - 1 && r1 < h) st_cluster(&rs[WG + c * kResColour + j + 1], crank + 1, wgt);  // last row -> top halo of the band below
-    })
     RES_SYNC();
     // ---- linear system (vr_px_system): A11, A22 stay in registers, A12, b1, b2 in shared memory
 #pragma unroll
@@ -802,9 +818,9 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
         unsigned cs_ = own_s[m];
         asm volatile("" : "+r"(cs_));  // decode here, not hoisted out of the iteration loop for all cells at once
         if ((cs_ >> (14 + c)) & 1) {
-          const int sidx = cs_ & 8191, y = r0 + ((cs_ >> 16) & 127), q = (y + c) & 1, x = 2 * (int)(cs_ >> 23) + q;
+          const int sidx = cs_ & 8191, ly = (cs_ >> 16) & 127, y = r0 + ly, q = (y + c) & 1, x = 2 * RES_J(cs_, ly) + q;
           const int ci = c * kResColour + sidx, oi = (1 - c) * kResColour + sidx;
-          const size_t k = (size_t)y * w + x, gk = pbase + k;
+          const unsigned k = (unsigned)(y * w + x), gk = pbase32 + k;
           const float zeta2 = 0.1f * 0.1f, eps2 = kEpsilon * kEpsilon, gamma2 = kGamma / 2, delta2 = kDelta / 2;
           const float ix = B.Ix[gk], iy = B.Iy[gk], iz = B.Iz[gk], ixx = B.Ixx[gk], ixy = B.Ixy[gk], iyy = B.Iyy[gk];
           const float ixz = B.Ixz[gk], iyz = B.Iyz[gk], dU = rs[DU + ci], dV = rs[DV + ci];
@@ -872,13 +888,13 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
             dv += kOmega * ((sigmaV + p[B2 + co] - du * p[A12 + co]) / a22r[c][m] - dv);
             p[DU + co] = du;
             p[DV + co] = dv;
-            if (CLUSTER) {
-              const int y = r0 + ((cs_ >> 16) & 127), j1 = (int)(cs_ >> 23) + 1;
-              if (y == r0 && crank > 0) {  // first row of the band -> bottom halo of the band above
+            if (CLUSTER && (cs_ & (3u << 23))) {  // 2 of a band's ~34 rows
+              const int j1 = RES_J(cs_, (cs_ >> 16) & 127) + 1;
+              if (cs_ & (1u << 23)) {  // first row of the band -> bottom halo of the band above
                 st_cluster(&rs[DU + co + (rows_per + 1) * rstride + j1], crank - 1, du);
                 st_cluster(&rs[DV + co + (rows_per + 1) * rstride + j1], crank - 1, dv);
               }
-              if (y == r1 - 1 && r1 < h) {  // last row -> top halo of the band below
+              if (cs_ & (1u << 24)) {  // last row -> top halo of the band below
                 st_cluster(&rs[DU + co + j1], crank + 1, du);
                 st_cluster(&rs[DV + co + j1], crank + 1, dv);
               }
@@ -892,10 +908,11 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
   }
   // total flow of the level = u0 + du (the update phase of the last iteration)
   RES_FOR_CELLS({
-    L.Ux[pbase + k] = u0[k] + rs[DU + ci];
-    L.Uy[pbase + k] = v0[k] + rs[DV + ci];
+    L.Ux[pbase32 + k] = u0[k] + rs[DU + ci];
+    L.Uy[pbase32 + k] = v0[k] + rs[DV + ci];
   })
 #undef RES_FOR_CELLS
+#undef RES_J
 #undef RES_SYNC
 }
 
@@ -1134,7 +1151,8 @@ int vr_resident_cluster(const vstab_handle* hnd, int h, int w) {
   const int half_w = (w + 1) / 2;
   for (int cl = 1; cl <= 8; cl <<= 1) {
     const int rows_per = (h + cl - 1) / cl;
-    if (rows_per * half_w <= kResCells && (rows_per + 2) * (half_w + 2) <= kResColour) return (cl == 1 || mode >= 2) ? cl : 0;
+    // 127 rows per band: the row of a cell travels in 7 bits of the packed cell word
+    if (rows_per <= 127 && rows_per * half_w <= kResCells && (rows_per + 2) * (half_w + 2) <= kResColour) return (cl == 1 || mode >= 2) ? cl : 0;
   }
   return 0;
 }

@@ -100,7 +100,7 @@ static int run_case(int w, int h, int cl_old, int cl_new, int threads_new) {
       launch(vr_fused_kernel<false>, L, B, cl_old, 256, 0);
     } else {
       const int rows_per = (h + cl_new - 1) / cl_new, half_w = (w + 1) / 2;
-      if (rows_per * half_w > kResCells || (rows_per + 2) * (half_w + 2) > kResColour) { printf("case %dx%d cl %d does not fit the resident kernel\n", w, h, cl_new); exit(2); }
+      if (rows_per > 127 || rows_per * half_w > kResCells || (rows_per + 2) * (half_w + 2) > kResColour) { printf("case %dx%d cl %d does not fit the resident kernel\n", w, h, cl_new); exit(2); }
       const size_t floats = kResSmemFloats;
       Kernel k = cl_new == 1 ? (threads_new == 512 ? vr_resident_kernel<false, 512> : vr_resident_kernel<false, 1024>)
                              : (threads_new == 512 ? vr_resident_kernel<true, 512> : vr_resident_kernel<true, 1024>);

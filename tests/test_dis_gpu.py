@@ -30,7 +30,9 @@ def test_dis_matches_reference_golden(handle, case):
     assert np.array_equal(flow[0][::8, ::8], grid[0])
 
 
-@pytest.mark.parametrize("size", [(320, 180), (640, 360), (960, 540), (540, 960), (333, 187)])
+# 832x480 / 640x360: the resident refinement kernel on clusters of 4 / 2 row bands; 160x960 and 960x160: thin levels
+# (many rows per band, few cells per row and the other way round); 333x187: odd sizes, single-CTA levels only
+@pytest.mark.parametrize("size", [(320, 180), (640, 360), (832, 480), (960, 540), (540, 960), (160, 960), (960, 160), (333, 187)])
 def test_dis_bit_exact_vs_oracle_batch(handle, size):
     """Several pairs in one launch, each compared with the C oracle."""
     w, h = size
