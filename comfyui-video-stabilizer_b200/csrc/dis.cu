@@ -37,7 +37,7 @@ constexpr float kInf = 1e10f;
 constexpr float kAlpha = 20.f, kDelta = 5.f, kGamma = 10.f, kEpsilon = 0.01f, kOmega = 1.6f;
 constexpr int kMaxLevels = 8;
 #ifndef VSTAB_DIS_GROUPS_DEFAULT
-#define VSTAB_DIS_GROUPS_DEFAULT 2
+#define VSTAB_DIS_GROUPS_DEFAULT 4
 #endif
 #ifndef VSTAB_DIS_STAGGER_DEFAULT
 #define VSTAB_DIS_STAGGER_DEFAULT 0
