@@ -12,7 +12,9 @@ scaling.  One "step" = one full pass of the hot path over the (sharded) clip.
 
   value     frames/s with the clip already resident in HBM and the results left in HBM
   e2e       frames/s through the NODE (`nodes.VideoStabilizerFlow.execute`, the call ComfyUI makes) with a page-locked
-            CPU IMAGE tensor in and CPU tensors out: upload and download inside the timed region.
+            CPU IMAGE tensor in and CPU tensors out: upload and download inside the timed region.  Calls are timed one
+            by one (they return host tensors); `value` is the MEDIAN call, the mean and every sample are listed
+            (`ms_per_step_mean`, `ms_per_step_all`): on a box whose other GPUs serve other jobs the odd call is 20-90 ms slow.
             `e2e.pageable_node` is the same call with a pageable IMAGE (what a stock graph hands over),
             `e2e.pinned_driver` the driver below the node with a pinned input (what round 1 reported);
             `e2e.host_link` is the measured ceiling of this box's host link (plain pinned cudaMemcpyAsync up and
@@ -390,6 +392,29 @@ def main():
         pipeline.WARP_LAUNCH_LOG = None
         return float(t.item()), h.launch_count - launches0, log
 
+    def timed_each(step_fn, steps, warmup):
+        """End-to-end calls, one by one: every call returns host tensors, so each is bracketed by a barrier and a device
+        synchronize of its own; the per-call times are max-reduced over the ranks.  Returns (median, mean, all) in ms: the
+        host side of the link (pinned allocations, the DMA engines of a box whose other GPUs serve other jobs) produces
+        the odd call 20-90 ms slower than its neighbours (scripts/e2e_reps.py names the phase: enqueueing / running the
+        upload), so the MEDIAN is what `e2e.value` quotes and every sample is listed next to it."""
+        for _ in range(warmup):
+            step_fn()
+        settle_gc()
+        times = []
+        for _ in range(steps):
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step_fn()
+            torch.cuda.synchronize()
+            times.append((time.perf_counter() - t0) * 1e3)
+        t = torch.tensor(times, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times = [float(x) for x in t.tolist()]
+        return float(np.median(times)), float(np.mean(times)), [round(x, 2) for x in times]
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     total_ms, launches, warp_log = timed(device_step, args.steps, args.warmup, collect_warp=True)
@@ -459,9 +484,8 @@ def main():
             d2h_holder["bytes"] = pipeline.LAST_D2H_BYTES
             d2h_holder["result_bytes"] = frames_out.numel() * 4 + masks_out.numel() * 4
 
-        e2e_steps = max(2, min(args.steps, 3))
-        pin_ms, _, _ = timed(pinned_driver_step, e2e_steps, 1)
-        pin_ms /= e2e_steps
+        e2e_steps = max(2, min(args.steps, 7))
+        pin_ms, pin_mean, pin_all = timed_each(pinned_driver_step, e2e_steps, 1)
         d2h = d2h_holder["bytes"]
         ideal_ms = (h2d / (link["h2d_gbs"] * 1e9) + d2h / (link["d2h_gbs"] * 1e9)) * 1e3
         e2e = {"unit": "frames/s", "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
@@ -469,7 +493,9 @@ def main():
                "mask_on_the_link": "uint8 (binary mask, widened to float32 on the host)" if pipeline.mask_bytes_enabled() else "float32",
                "host_link": {**link, "how": "plain pinned cudaMemcpyAsync of 1 GiB each way, one copy per call, all ranks at once, best of 3",
                              "ms_for_the_step_bytes": ideal_ms, "placement": placement},
+               "statistic": f"median of {e2e_steps} calls timed one by one (host wall clock between device synchronizes, max over ranks); mean and every sample listed",
                "pinned_driver": {"value": total_frames / (pin_ms * 1e-3), "ms_per_step": pin_ms, "frac_of_link": ideal_ms / pin_ms,
+                                 "ms_per_step_mean": pin_mean, "ms_per_step_all": pin_all,
                                  "note": "pinned host clip -> flow.stabilize_frames(output='host') -> pinned results (round 1's e2e)"}}
         if world == 1:
             # the call ComfyUI makes: nodes.VideoStabilizerFlow.execute(IMAGE, widgets...) -> (IMAGE, MASK, JSON), CPU tensors both ways
@@ -478,21 +504,22 @@ def main():
                                                         PARAMS["strength"], PARAMS["smooth"], PARAMS["keep_fov"], PARAMS["padding_color"])
                 assert out[0].shape[0] == total_frames and not out[0].is_cuda and not out[1].is_cuda
 
-            node_ms, _, _ = timed(lambda: node_step(pinned_clip), e2e_steps, 1)
-            node_ms /= e2e_steps
+            node_ms, node_mean, node_all = timed_each(lambda: node_step(pinned_clip), e2e_steps, 1)
             e2e.update({"value": total_frames / (node_ms * 1e-3), "ms_per_step": node_ms, "frac_of_link": ideal_ms / node_ms,
+                        "ms_per_step_mean": node_mean, "ms_per_step_all": node_all,
                         "note": "nodes.VideoStabilizerFlow.execute(page-locked CPU IMAGE) -> CPU IMAGE + MASK + meta; upload and download inside the timed region"})
             # ... and with what a stock ComfyUI graph hands over: a PAGEABLE tensor (staged through two pinned bounce buffers)
             pageable = torch.empty(clip_dev.shape, dtype=torch.float32)
             pageable.copy_(pinned_clip)
-            page_ms, _, _ = timed(lambda: node_step(pageable), e2e_steps, 1)
-            page_ms /= e2e_steps
+            page_ms, page_mean, page_all = timed_each(lambda: node_step(pageable), e2e_steps, 1)
             e2e["pageable_node"] = {"value": total_frames / (page_ms * 1e-3), "ms_per_step": page_ms, "frac_of_link": ideal_ms / page_ms,
+                                    "ms_per_step_mean": page_mean, "ms_per_step_all": page_all,
                                     "note": "the same node call with a pageable CPU IMAGE"}
             del pageable
         else:
             # sharded runs have no single-process node call: every rank drives its frame range through the driver
             e2e.update({"value": e2e["pinned_driver"]["value"], "ms_per_step": pin_ms, "frac_of_link": ideal_ms / pin_ms,
+                        "ms_per_step_mean": pin_mean, "ms_per_step_all": pin_all,
                         "note": "per-rank pinned host shard -> flow.stabilize_frames(shard, output='host') -> pinned results"})
         del pinned_clip
 
