@@ -591,6 +591,12 @@ def fused_warp(
         step = min(step, context.chunk_frames())
     main = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(dev)
+    mask_bytes_cpu = None
+    if pack_mask:
+        try:  # page-locked like the results; when the host cannot pin it, the mask travels as float32 like before
+            mask_bytes_cpu = torch.empty((n, oh, ow), dtype=torch.uint8, pin_memory=True)
+        except RuntimeError:
+            pack_mask = False
     bufs = [
         (
             torch.empty((min(step, n), oh, ow, 3), dtype=torch.float32, device=dev),
@@ -599,7 +605,6 @@ def fused_warp(
         )
         for _ in range(2 if n > step else 1)
     ]
-    mask_bytes_cpu = torch.empty((n, oh, ow), dtype=torch.uint8, pin_memory=True) if pack_mask else None
     odd = torch.zeros((1,), dtype=torch.int32, device=dev) if pack_mask else None
     mask_ready: List[Tuple[int, int, torch.cuda.Event]] = []
     copied = [None] * len(bufs)
