@@ -218,23 +218,26 @@ extern "C" int vstab_host_target(const double* path, int n_frames, int n_params,
   if (filtered && (window > 11 || (window & 1) == 0)) return VSTAB_ERR_UNSUPPORTED;
   const int half = window / 2;
   const double tap = 1.0 / (double)window;
-  for (int i = 0; i < n_frames; ++i)
-    for (int k = 0; k < K; ++k) {
-      double sm = path[(size_t)i * K + k];
-      if (filtered) {
-        double acc = 0.0;
-        for (int t = 0; t < window; ++t) {
-          int src = i + t - half;
-          src = src < 0 ? 0 : (src >= n_frames ? n_frames - 1 : src);
-          acc += path[(size_t)src * K + k] * tap;
-        }
-        sm = acc;
+  for (int i = 0; i < n_frames; ++i) {
+    // the parameters of a frame are independent sums: their (up to 8) chains of dependent additions run side by side,
+    // each one in tap order like numpy's loop
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (filtered) {
+      for (int t = 0; t < window; ++t) {
+        int src = i + t - half;
+        src = src < 0 ? 0 : (src >= n_frames ? n_frames - 1 : src);
+        const double* row = path + (size_t)src * K;
+        for (int k = 0; k < K; ++k) acc[k] += row[k] * tap;
       }
+    }
+    for (int k = 0; k < K; ++k) {
       const double p = path[(size_t)i * K + k];
+      const double sm = filtered ? acc[k] : p;
       const double d = sm - p;
       const double scaled = strength * d;
       target[(size_t)i * K + k] = p + scaled;
       diffs[(size_t)i * K + k] = target[(size_t)i * K + k] - p;
     }
+  }
   return VSTAB_OK;
 }
