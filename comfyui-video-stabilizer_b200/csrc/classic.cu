@@ -674,6 +674,10 @@ int gftt_lk_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int he
 
   const double scale_d = 1.0 / ((double)(1 << 2) * kBlock * 255.0);
   const float s = (float)scale_d, s2 = s * 2.0f;
+  // the pass starts here for both streams (everything before it on `st`, e.g. the previous pass's tracker, is done with the workspace)
+  rc = vstab_aux_streams(hnd, 1);
+  if (rc != VSTAB_OK) return rc;
+  VSTAB_CUDA(hnd, cudaEventRecord(hnd->fork_event, st));
   // ---- corners of frames 0 .. n-2 ----
   for (int f0 = 0; f0 < P; f0 += kChunk) {
     const int F = (P - f0) < kChunk ? (P - f0) : kChunk;
@@ -701,27 +705,34 @@ int gftt_lk_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int he
                                           detected_dev + f0);
     VSTAB_LAUNCH_CHECK(hnd, "gftt_select_kernel");
   }
-  // ---- pyramids + Scharr derivatives of every frame ----
+  // ---- pyramids + Scharr derivatives of every frame: independent of the corners, so they run on a helper stream
+  // next to the corner detector (enqueued above on the caller's stream) and join it before the tracker ----
+  rc = vstab_aux_streams(hnd, 1);
+  if (rc != VSTAB_OK) return rc;
+  cudaStream_t ps = hnd->aux_stream[0];
+  VSTAB_CUDA(hnd, cudaStreamWaitEvent(ps, hnd->fork_event, 0));
   pyr.lv[0].img = gray_dev;
   for (int l = 0; l <= pyr.levels; l++) {
     if (l > 0) {
       unsigned char* dst = base + o_img[l];
       dim3 gd(vstab_ceil_div(pyr.lv[l].w, 32), vstab_ceil_div(pyr.lv[l].h, 64), n_frames);
-      pyr_down_kernel<<<gd, 256, 0, st>>>(pyr.lv[l - 1].img, pyr.lv[l - 1].h, pyr.lv[l - 1].w, dst, pyr.lv[l].h, pyr.lv[l].w);
+      pyr_down_kernel<<<gd, 256, 0, ps>>>(pyr.lv[l - 1].img, pyr.lv[l - 1].h, pyr.lv[l - 1].w, dst, pyr.lv[l].h, pyr.lv[l].w);
       VSTAB_LAUNCH_CHECK(hnd, "pyr_down_kernel");
       pyr.lv[l].img = dst;
     }
     short2* der = (short2*)(base + o_der[l]);
     dim3 gs(vstab_ceil_div(pyr.lv[l].w, 32), vstab_ceil_div(pyr.lv[l].h, kRowsPerThread * 8), n_frames);
-    scharr_kernel<<<gs, 256, 0, st>>>(pyr.lv[l].img, pyr.lv[l].h, pyr.lv[l].w, der);
+    scharr_kernel<<<gs, 256, 0, ps>>>(pyr.lv[l].img, pyr.lv[l].h, pyr.lv[l].w, der);
     VSTAB_LAUNCH_CHECK(hnd, "scharr_kernel");
     pyr.lv[l].deriv = der;
     unsigned char* ext = base + o_ext[l];
     dim3 ge(vstab_ceil_div(pyr.lv[l].w + 2 * kLkPad, 128), vstab_ceil_div(pyr.lv[l].h + 2 * kLkPad, 8), n_frames);
-    lk_pad_kernel<<<ge, 256, 0, st>>>(pyr.lv[l].img, pyr.lv[l].h, pyr.lv[l].w, ext);
+    lk_pad_kernel<<<ge, 256, 0, ps>>>(pyr.lv[l].img, pyr.lv[l].h, pyr.lv[l].w, ext);
     VSTAB_LAUNCH_CHECK(hnd, "lk_pad_kernel");
     pyr.lv[l].ext = ext;
   }
+  VSTAB_CUDA(hnd, cudaEventRecord(hnd->join_event[0], ps));
+  VSTAB_CUDA(hnd, cudaStreamWaitEvent(st, hnd->join_event[0], 0));
   // ---- track ----
   const size_t smem = (size_t)8 * kLkWarpBytes;
   VSTAB_CUDA(hnd, cudaFuncSetAttribute(lk_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
