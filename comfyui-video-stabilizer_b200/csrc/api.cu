@@ -86,6 +86,11 @@ int vstab_aux_streams(vstab_handle* h, int n) {
     VSTAB_CUDA(h, cudaEventCreateWithFlags(&h->stagger_event[h->n_aux], cudaEventDisableTiming));
     h->n_aux++;
   }
+  while (h->n_level_events < VSTAB_MAX_LEVEL_EVENTS) {
+    VSTAB_CUDA(h, cudaEventCreateWithFlags(&h->level_event[h->n_level_events], cudaEventDisableTiming));
+    h->n_level_events++;
+  }
+  if (!h->pyramid_event) VSTAB_CUDA(h, cudaEventCreateWithFlags(&h->pyramid_event, cudaEventDisableTiming));
   return VSTAB_OK;
 }
 

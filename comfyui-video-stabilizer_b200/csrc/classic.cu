@@ -587,8 +587,17 @@ __global__ void __launch_bounds__(256) lk_track_kernel(LkPyr P, int n_pairs, int
 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Streams, events and workspace of one pass.  Two slots alternate when a clip is tracked in several passes, so that the
+// tracker of pass k (issue-bound) runs under the corner detector of pass k + 1 (bandwidth-bound).
+struct PassSlot {
+  cudaStream_t main, pyr;               // corner detector + tracker | pyramids, derivatives, padded copies
+  cudaEvent_t fork, join, corners;      // pass started | pyramids done | corner detector done (releases the next pass)
+  unsigned char* base;                  // this slot's share of the handle's workspace
+};
+
+// slot == nullptr: only report the workspace one pass of n_frames needs
 int gftt_lk_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width, int max_corners,
-                float* prev_dev, float* curr_dev, int32_t* detected_dev, cudaStream_t st);
+                float* prev_dev, float* curr_dev, int32_t* detected_dev, const PassSlot* slot, size_t* bytes_out);
 
 }  // namespace
 
@@ -606,13 +615,43 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
   cudaStream_t st = (cudaStream_t)stream;
   VSTAB_ENTER(hnd);
   const size_t npx = (size_t)height * width;
+  const int P = n_frames - 1;
   int per_pass = kPairsPerPass;
-  if (const char* e = getenv("VSTAB_LK_PAIRS_PER_PASS")) per_pass = atoi(e) > 0 ? atoi(e) : kPairsPerPass;  // tests: several passes on a short clip
-  for (int p0 = 0; p0 < n_frames - 1; p0 += per_pass) {
-    const int pairs = (n_frames - 1 - p0) < per_pass ? (n_frames - 1 - p0) : per_pass;
-    const int rc = gftt_lk_run(hnd, gray_dev + p0 * npx, pairs + 1, height, width, max_corners, prev_dev + (size_t)p0 * max_corners * 2,
-                               curr_dev + (size_t)p0 * max_corners * 2, detected_dev + p0, st);
+  const char* env_pass = getenv("VSTAB_LK_PAIRS_PER_PASS");  // tests: several passes on a short clip
+  if (env_pass && atoi(env_pass) > 0) per_pass = atoi(env_pass);
+  // (a 240-pair clip split into two overlapping halves was measured: 14.8 ms against 13.6 ms in one pass -- the corner
+  // detector's kernels are chains whose latency does not halve with the frame count -- so only clips beyond one pass use the slots)
+  const int passes = (P + per_pass - 1) / per_pass;
+  const char* env_pipe = getenv("VSTAB_LK_PIPELINE");
+  const bool pipelined = passes >= 2 && !(env_pipe && atoi(env_pipe) == 0);
+  size_t bytes = 0;
+  int rc = gftt_lk_run(hnd, gray_dev, (P < per_pass ? P : per_pass) + 1, height, width, max_corners, prev_dev, curr_dev, detected_dev, nullptr, &bytes);
+  if (rc != VSTAB_OK) return rc;
+  void* wsp = nullptr;
+  rc = vstab_workspace(hnd, bytes * (pipelined ? 2 : 1), &wsp);
+  if (rc != VSTAB_OK) return rc;
+  rc = vstab_aux_streams(hnd, pipelined ? 3 : 1);
+  if (rc != VSTAB_OK) return rc;
+  PassSlot slots[2];
+  slots[0] = {st, hnd->aux_stream[0], hnd->level_event[0], hnd->level_event[1], hnd->stagger_event[0], (unsigned char*)wsp};
+  if (pipelined) {
+    slots[1] = {hnd->aux_stream[1], hnd->aux_stream[2], hnd->level_event[2], hnd->level_event[3], hnd->stagger_event[1], (unsigned char*)wsp + bytes};
+    VSTAB_CUDA(hnd, cudaEventRecord(hnd->fork_event, st));  // the second slot's stream starts behind whatever `st` holds already
+    VSTAB_CUDA(hnd, cudaStreamWaitEvent(slots[1].main, hnd->fork_event, 0));
+  }
+  for (int k = 0, p0 = 0; p0 < P; ++k, p0 += per_pass) {
+    const int pairs = (P - p0) < per_pass ? (P - p0) : per_pass;
+    const PassSlot& slot = slots[pipelined ? (k & 1) : 0];
+    // pass k starts its corner detector when pass k - 1 has finished its own (they would only share the bandwidth);
+    // from there on it runs next to the tracker of pass k - 1
+    if (pipelined && k > 0) VSTAB_CUDA(hnd, cudaStreamWaitEvent(slot.main, slots[(k - 1) & 1].corners, 0));
+    rc = gftt_lk_run(hnd, gray_dev + p0 * npx, pairs + 1, height, width, max_corners, prev_dev + (size_t)p0 * max_corners * 2,
+                     curr_dev + (size_t)p0 * max_corners * 2, detected_dev + p0, &slot, nullptr);
     if (rc != VSTAB_OK) return rc;
+  }
+  if (pipelined) {
+    VSTAB_CUDA(hnd, cudaEventRecord(hnd->join_event[1], slots[1].main));
+    VSTAB_CUDA(hnd, cudaStreamWaitEvent(st, hnd->join_event[1], 0));
   }
   return VSTAB_OK;
 }
@@ -620,7 +659,7 @@ extern "C" int vstab_gftt_lk(vstab_handle* hnd, const uint8_t* gray_dev, int n_f
 namespace {
 
 int gftt_lk_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int height, int width, int max_corners,
-                float* prev_dev, float* curr_dev, int32_t* detected_dev, cudaStream_t st) {
+                float* prev_dev, float* curr_dev, int32_t* detected_dev, const PassSlot* slot, size_t* bytes_out) {
   const int h = height, w = width;
   // frames per pass of the corner detector: every running-sum / selection kernel is a chain per row, column or
   // frame, so a pass costs its chain latency whatever the frame count (20.7 MB of scratch per 960x540 frame)
@@ -658,10 +697,12 @@ int gftt_lk_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int he
     o_der[l] = take(sizeof(short2) * (size_t)n_frames * lh * lw);
     o_ext[l] = take((size_t)n_frames * (lh + 2 * kLkPad) * (lw + 2 * kLkPad));
   }
-  void* wsp = nullptr;
-  int rc = vstab_workspace(hnd, off, &wsp);
-  if (rc != VSTAB_OK) return rc;
-  unsigned char* base = (unsigned char*)wsp;
+  if (!slot) {
+    *bytes_out = off;
+    return VSTAB_OK;
+  }
+  cudaStream_t st = slot->main;
+  unsigned char* base = slot->base;
   float* cov = (float*)(base + o_cov);
   double* rows = (double*)(base + o_rows);
   float* eig = (float*)(base + o_eig);
@@ -674,10 +715,8 @@ int gftt_lk_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int he
 
   const double scale_d = 1.0 / ((double)(1 << 2) * kBlock * 255.0);
   const float s = (float)scale_d, s2 = s * 2.0f;
-  // the pass starts here for both streams (everything before it on `st`, e.g. the previous pass's tracker, is done with the workspace)
-  rc = vstab_aux_streams(hnd, 1);
-  if (rc != VSTAB_OK) return rc;
-  VSTAB_CUDA(hnd, cudaEventRecord(hnd->fork_event, st));
+  // the pass starts here for both of its streams (everything before it on `st`, e.g. the slot's previous tracker, is done with the workspace)
+  VSTAB_CUDA(hnd, cudaEventRecord(slot->fork, st));
   // ---- corners of frames 0 .. n-2 ----
   for (int f0 = 0; f0 < P; f0 += kChunk) {
     const int F = (P - f0) < kChunk ? (P - f0) : kChunk;
@@ -707,10 +746,9 @@ int gftt_lk_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int he
   }
   // ---- pyramids + Scharr derivatives of every frame: independent of the corners, so they run on a helper stream
   // next to the corner detector (enqueued above on the caller's stream) and join it before the tracker ----
-  rc = vstab_aux_streams(hnd, 1);
-  if (rc != VSTAB_OK) return rc;
-  cudaStream_t ps = hnd->aux_stream[0];
-  VSTAB_CUDA(hnd, cudaStreamWaitEvent(ps, hnd->fork_event, 0));
+  VSTAB_CUDA(hnd, cudaEventRecord(slot->corners, st));
+  cudaStream_t ps = slot->pyr;
+  VSTAB_CUDA(hnd, cudaStreamWaitEvent(ps, slot->fork, 0));
   pyr.lv[0].img = gray_dev;
   for (int l = 0; l <= pyr.levels; l++) {
     if (l > 0) {
@@ -731,8 +769,8 @@ int gftt_lk_run(vstab_handle* hnd, const uint8_t* gray_dev, int n_frames, int he
     VSTAB_LAUNCH_CHECK(hnd, "lk_pad_kernel");
     pyr.lv[l].ext = ext;
   }
-  VSTAB_CUDA(hnd, cudaEventRecord(hnd->join_event[0], ps));
-  VSTAB_CUDA(hnd, cudaStreamWaitEvent(st, hnd->join_event[0], 0));
+  VSTAB_CUDA(hnd, cudaEventRecord(slot->join, ps));
+  VSTAB_CUDA(hnd, cudaStreamWaitEvent(st, slot->join, 0));
   // ---- track ----
   const size_t smem = (size_t)8 * kLkWarpBytes;
   VSTAB_CUDA(hnd, cudaFuncSetAttribute(lk_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
