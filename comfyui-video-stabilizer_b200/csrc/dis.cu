@@ -16,6 +16,14 @@
 // ((a0+a2)+(a1+a3)), so the float results are bit-identical to the CPU reference and so are all
 // the discrete decisions (candidate choice, early stop).  This file is compiled with
 // -fmad=false: no multiply-add contraction anywhere except where the reference itself fuses.
+//
+// Schedule of one call (dis_run): the pyramid chain on the caller's stream; gradients / bordered copies / structure
+// tensors per level on a preparation stream, coarsest level first; the pairs in four groups on forked streams, each
+// running patch search -> densification -> variational refinement -> x2 upsampling per level and waiting for a level's
+// preparation event right before it searches that level.  The refinement of a level is ONE launch: all 19 planes in one
+// CTA's shared memory for the two coarsest levels (vr_fused_kernel<true>), the SOR state in shared memory / registers
+// with row bands of a cluster exchanging halo rows through distributed shared memory where the bands fit
+// (vr_resident_kernel), a cluster streaming its planes through L2 otherwise (vr_fused_kernel<false>).
 #include "common.cuh"
 
 #include <math.h>
