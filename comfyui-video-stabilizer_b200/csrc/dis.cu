@@ -50,6 +50,9 @@ constexpr int kMaxLevels = 8;
 #ifndef VSTAB_DIS_STAGGER_DEFAULT
 #define VSTAB_DIS_STAGGER_DEFAULT 0
 #endif
+#ifndef VSTAB_VR_ONCHIP_DEFAULT
+#define VSTAB_VR_ONCHIP_DEFAULT 0
+#endif
 #ifndef VSTAB_VR_RESIDENT_DEFAULT
 #define VSTAB_VR_RESIDENT_DEFAULT 2
 #endif
@@ -1199,7 +1202,9 @@ int dis_level(vstab_handle* hnd, const Level& Lc, const Level* finer, const VrBu
   {
     const int px = Lc.w * Lc.h;
     const size_t onchip_bytes = (size_t)19 * px * sizeof(float);
-    if (onchip_bytes <= (size_t)hnd->max_smem_optin) {
+    const char* onchip_env = getenv("VSTAB_VR_ONCHIP");
+    const bool prefer_resident = (onchip_env ? atoi(onchip_env) == 0 : VSTAB_VR_ONCHIP_DEFAULT == 0) && vr_resident_cluster(hnd, Lc.h, Lc.w) == 1;
+    if (onchip_bytes <= (size_t)hnd->max_smem_optin && !prefer_resident) {
       VSTAB_CUDA(hnd, cudaFuncSetAttribute(vr_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onchip_bytes));
       vr_fused_kernel<true><<<P, 1024, onchip_bytes, st>>>(Lc, B, 1);
       VSTAB_LAUNCH_CHECK(hnd, "vr_fused_kernel");

@@ -16,7 +16,7 @@ clip = synth.render_clip_cuda(h, synth.base_texture(0, W, H).to(dev), mats, W, H
 gray = h.gray_working(clip, (960, 540))
 del clip
 KNOBS = ("VSTAB_PS_NOPACK", "VSTAB_PS_WPC", "VSTAB_DIS_GROUPS", "VSTAB_VR_CLUSTER", "VSTAB_DIS_STAGGER", "VSTAB_PS_SPW", "VSTAB_VR_RESIDENT",
-         "VSTAB_VR_RESIDENT_THREADS", "VSTAB_DIS_PREP_ASYNC")
+         "VSTAB_VR_RESIDENT_THREADS", "VSTAB_DIS_PREP_ASYNC", "VSTAB_VR_ONCHIP")
 
 def run(cfg, reps=5):
     for k in KNOBS:
