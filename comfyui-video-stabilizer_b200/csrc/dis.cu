@@ -797,6 +797,7 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
     for (int c = 0; c < 2; c++)
 #pragma unroll
       for (int m = 0; m < kResPpt; m++) {
+        if (kResThreads * m >= ncell) break;  // small levels: no thread has a cell in this slot (same answer in every thread)
         unsigned cs_ = own_s[m];
         asm volatile("" : "+r"(cs_));
         if ((cs_ >> (14 + c)) & 1) {
@@ -826,6 +827,7 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
     for (int c = 0; c < 2; c++)
 #pragma unroll
       for (int m = 0; m < kResPpt; m++) {
+        if (kResThreads * m >= ncell) break;  // small levels: no thread has a cell in this slot (same answer in every thread)
         unsigned cs_ = own_s[m];
         asm volatile("" : "+r"(cs_));  // decode here, not hoisted out of the iteration loop for all cells at once
         if ((cs_ >> (14 + c)) & 1) {
@@ -879,6 +881,7 @@ __global__ void __launch_bounds__(THREADS, 1) vr_resident_kernel(Level L, VrBuf 
       for (int c = 0; c < 2; c++) {
 #pragma unroll
         for (int m = 0; m < kResPpt; m++) {
+          if (kResThreads * m >= ncell) break;
           unsigned cs_ = own_s[m];
           asm volatile("" : "+r"(cs_));
           if ((cs_ >> (14 + c)) & 1) {

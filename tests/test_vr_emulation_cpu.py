@@ -27,6 +27,8 @@ CASES = [
     (240, 135, 8, 4, 1024),  # its finest level: four row bands, halo rows pushed through (emulated) distributed shared memory
     (101, 57, 4, 2, 512),    # odd sizes, two bands
     (50, 33, 2, 8, 512),     # more bands than rows need: thin and empty bands
+    (60, 33, 1, 1, 1024),    # the two coarsest levels: fewer cells than threads, empty cell slots are skipped
+    (30, 16, 1, 1, 1024),
     (16, 200, 4, 2, 512),    # tall and narrow: 100 rows per band (the packed cell word has 7 bits for the row)
 ]
 
