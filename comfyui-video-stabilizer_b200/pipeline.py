@@ -20,6 +20,8 @@ from . import _native
 
 # frames per host->device / device->host copy chunk (keeps staging buffers ~0.8 GB at 1080p)
 CHUNK_BYTES = 768 << 20
+# bytes per cudaMemcpyAsync of a page-locked clip on its way up (scripts/e2e_chunks.py: A/B of the enqueue behaviour)
+UPLOAD_CHUNK_BYTES = CHUNK_BYTES
 
 # bench.py sets this to a list to collect (start_event, end_event, frames, algorithmic_bytes) of
 # every vstab_warp_fused launch, recorded on the launching stream.
@@ -186,7 +188,7 @@ def _upload_batched(t: torch.Tensor, device: torch.device) -> torch.Tensor:
         return out
     frame_bytes = max(1, t[0].numel() * t.element_size())
     if t.is_pinned():
-        step = max(1, CHUNK_BYTES // frame_bytes)
+        step = max(1, UPLOAD_CHUNK_BYTES // frame_bytes)
         for a in range(0, n, step):
             out[a : a + step].copy_(t[a : a + step], non_blocking=True)
         return out
