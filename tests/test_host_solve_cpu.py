@@ -108,6 +108,36 @@ def test_target_path_helper_equals_numpy():
     assert all(hm._TARGET_WINDOW_OK.values())  # this numpy sums short kernels in tap order; if not, the helper steps aside
 
 
+def test_helpers_follow_numpy_on_non_finite_input():
+    """NaN / inf / float32-overflowing / denormal entries in the candidate table: the helpers and the numpy route still leave
+    the same bytes in every output (IEEE operations in the same order propagate them the same way)."""
+    import warnings
+
+    from vstab_b200 import hostmath as hm, stabilizer_core as core
+
+    rng = np.random.default_rng(5)
+    poison = [np.nan, np.inf, -np.inf, 1e39, -1e39, 1e-46]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for trial in range(120):
+            mode = MODES[trial % 3]
+            pairs = int(rng.integers(2, 40))
+            raw, _ = _table(rng, pairs)
+            raw[int(rng.integers(0, pairs)), int(rng.integers(0, 3)), int(rng.integers(0, 9))] = poison[trial % 6]
+            cands = core.PairCandidates.from_raw(raw, 12)
+            work = (960, 540) if trial % 2 else None
+            got = hm.native_trajectory(cands, mode, (1920, 1080), work)
+            stacked, path, _, _ = _numpy_route(core, hm, cands, mode, (1920, 1080), work)
+            assert got is not None and got[0].tobytes() == stacked.tobytes() and got[1].tobytes() == path.tobytes()
+            want = hm.numpy_target(path, 0.7, 0.5, 16.0, False)
+            target = hm.native_target(path, 0.7, 0.5, 16.0, False)
+            assert target is not None and target[0].tobytes() == want[0].tobytes() and target[1].tobytes() == want[1].tobytes()
+            apply, mins, maxs, _ = hm.native_framing(want[1], mode, 1920, 1080)
+            ref = hm.params_to_matrices(want[1], mode)
+            ref_mins, ref_maxs = hm.compute_bounding_boxes(ref, 1920, 1080)
+            assert apply.tobytes() == ref.tobytes() and mins.tobytes() == ref_mins.tobytes() and maxs.tobytes() == ref_maxs.tobytes()
+
+
 def test_fallback_pairs_are_left_to_the_ladder():
     from vstab_b200 import hostmath as hm, stabilizer_core as core
 
