@@ -3,7 +3,7 @@ through the driver (flow.stabilize_frames, pinned clip), the node (nodes.VideoSt
 with a pageable IMAGE; alternating, wall-clock per call with a device synchronize on both sides.  Also times the host's
 uint8 -> float32 widening alone and prints the host-side phase log of one call per setting.  Development aid."""
 import json, os, sys, time
-import numpy as np, torch
+import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vstab_loader; vstab_loader.load()
 import synth

@@ -1,7 +1,7 @@
 """Per-repetition host-side breakdown of the node call with a page-locked IMAGE (development aid): which phase takes the
 extra time on the slow repetitions."""
 import gc, json, os, sys, time
-import numpy as np, torch
+import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vstab_loader; vstab_loader.load()
 import synth
